@@ -1,0 +1,338 @@
+// C-ABI of the B200-native hot path (see include/esr_b200.h).  Host side: argument validation, TMA
+// descriptor encoding, tile/pipeline sizing, launches.  No torch types, no exceptions across the boundary.
+#include "../../include/esr_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "aux_kernels.cuh"
+#include "conv3x3_tc.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(ESR_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int grid_for(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  const size_t cap = 148 * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int nblock_for(int cout, int* cout_pad) {
+  int nb_n;
+  if (cout <= 64) {
+    nb_n = (cout + 15) / 16 * 16;
+    *cout_pad = nb_n;
+  } else {
+    nb_n = 64;
+    *cout_pad = (cout + 63) / 64 * 64;
+  }
+  return nb_n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* esr_last_error(void) { return g_err; }
+int esr_version(void) { return 100; }
+long long esr_launch_count(void) { return g_launches.load(); }
+
+int esr_device_check(void) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) return fail(ESR_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", major, minor);
+  if (!get_encode()) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  return ESR_OK;
+}
+
+size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out) {
+  int cout_pad = 0;
+  nblock_for(cout, &cout_pad);
+  if (cout_pad_out) *cout_pad_out = cout_pad;
+  const int nchunks = (cin_planes + kcp - 1) / kcp;
+  return (size_t)nchunks * 9 * kcp * cout_pad * 16;
+}
+
+int esr_conv3x3_cin_planes(int cin, int lead) { return (lead + 7) / 8 + (cin - lead + 7) / 8; }
+
+int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, int kcp, int dtype, int transpose_flip,
+                             void* wpacked, float* bias_out, const float* bias_in, void* stream) {
+  if (!w_oihw || !wpacked) return fail(ESR_ERR_INVALID, "pack_weights: null pointer");
+  if (lead < 0 || lead > cin || (lead && transpose_flip)) return fail(ESR_ERR_INVALID, "pack_weights: bad lead %d", lead);
+  if (kcp != 2 && kcp != 4) return fail(ESR_ERR_INVALID, "pack_weights: kcp must be 2 or 4");
+  const int lc_out = transpose_flip ? cin : cout;
+  const int lc_in = transpose_flip ? cout : cin;
+  int cout_pad = 0;
+  const int nb_n = nblock_for(lc_out, &cout_pad);
+  const int n_blocks = cout_pad / nb_n;
+  const int cin_planes = transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(cin, lead);
+  const int nchunks = (cin_planes + kcp - 1) / kcp;
+  const size_t total = (size_t)n_blocks * nchunks * 9 * kcp * nb_n * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  esr::pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(w_oihw, cout, cin, lead, kcp, nb_n, n_blocks, nchunks, dtype,
+                                                                transpose_flip, (uint16_t*)wpacked, total);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (bias_out) {
+    CUDA_TRY(cudaMemsetAsync(bias_out, 0, sizeof(float) * cout_pad, st));
+    if (bias_in && !transpose_flip)
+      CUDA_TRY(cudaMemcpyAsync(bias_out, bias_in, sizeof(float) * cout, cudaMemcpyDeviceToDevice, st));
+  }
+  return ESR_OK;
+}
+
+int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
+  if (!a) return fail(ESR_ERR_INVALID, "conv3x3: null args");
+  if (!a->in || !a->wpacked || !a->bias) return fail(ESR_ERR_INVALID, "conv3x3: null in/weights/bias");
+  if (a->n <= 0 || a->h <= 0 || a->w <= 0) return fail(ESR_ERR_INVALID, "conv3x3: bad shape %dx%dx%d", a->n, a->h, a->w);
+  if (a->kcp != 2 && a->kcp != 4) return fail(ESR_ERR_INVALID, "conv3x3: kcp must be 2 or 4");
+  if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "conv3x3: bad dtype");
+  if (!a->out16 && !a->out32 && !a->out_nchw) return fail(ESR_ERR_INVALID, "conv3x3: no output requested");
+  if (a->out16_up2 && a->out16_pixel_shuffle) return fail(ESR_ERR_INVALID, "conv3x3: up2 and pixel_shuffle are exclusive");
+  if (((uintptr_t)a->in & 15) || ((uintptr_t)a->wpacked & 15) || ((uintptr_t)a->bias & 15))
+    return fail(ESR_ERR_INVALID, "conv3x3: pointers must be 16-byte aligned");
+  EncodeTiledFn encode = get_encode();
+  if (!encode) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+
+  esr::ConvParams p;
+  memset(&p, 0, sizeof(p));
+  int cout_pad = 0;
+  p.nb_n = nblock_for(a->cout, &cout_pad);
+  if (a->cout_pad != cout_pad) return fail(ESR_ERR_INVALID, "conv3x3: cout_pad %d does not match packing (%d)", a->cout_pad, cout_pad);
+  p.n_blocks = cout_pad / p.nb_n;
+  p.n = a->n; p.h = a->h; p.w = a->w;
+  p.P = a->tile_p ? a->tile_p : 32;
+  if (p.P != 32 && p.P != 64) return fail(ESR_ERR_INVALID, "conv3x3: tile_p must be 32 or 64");
+  p.TW = p.P - 2;
+  p.MT = a->tile_mt ? a->tile_mt : 4;
+  if (p.MT != 1 && p.MT != 2 && p.MT != 4) return fail(ESR_ERR_INVALID, "conv3x3: tile_mt must be 1, 2 or 4");
+  // do not use taller tiles than the image needs
+  while (p.MT > 1 && (p.MT / 2) * 128 / p.P >= a->h) p.MT /= 2;
+  p.R = p.MT * 128 / p.P;
+  p.tiles_x = (a->w + p.TW - 1) / p.TW;
+  p.tiles_y = (a->h + p.R - 1) / p.R;
+  p.num_tiles = p.tiles_x * p.tiles_y * a->n;
+  p.kcp = a->kcp;
+  p.nchunks = (a->cin_planes + a->kcp - 1) / a->kcp;
+  p.in_plane_off = a->in_plane_off;
+  p.plane_stride = (uint32_t)(p.R + 2) * p.P * 16u;
+  p.a_bytes = p.kcp * p.plane_stride;
+  p.b_bytes = 9u * p.kcp * p.nb_n * 16u;
+  p.a_alloc = (p.a_bytes + esr::kASlack + 127u) & ~127u;
+  p.stage_bytes = p.a_alloc + ((p.b_bytes + 127u) & ~127u);
+  const uint32_t smem_max = 232448u;
+  int stages = (int)((smem_max - esr::kSmemHeader - 128u) / p.stage_bytes);
+  if (stages > esr::kMaxStages) stages = esr::kMaxStages;
+  if (stages > p.nchunks * 4) stages = p.nchunks * 4;  // no point in more buffers than a few items' worth
+  if (stages < 2) return fail(ESR_ERR_INVALID, "conv3x3: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+  p.stages = stages;
+  const uint32_t smem_bytes = esr::kSmemHeader + 128u + (uint32_t)stages * p.stage_bytes;
+  // instruction descriptor: D=f32, A/B = f16|bf16, K-major both, N, M=128
+  p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | ((uint32_t)(p.nb_n >> 3) << 17) |
+            ((uint32_t)(128 >> 4) << 24);
+  uint32_t cols = 2u * p.MT * p.nb_n, alloc = 32;
+  while (alloc < cols) alloc <<= 1;
+  if (alloc > 512) return fail(ESR_ERR_INVALID, "conv3x3: TMEM budget exceeded (%u columns)", cols);
+  p.tmem_cols = alloc;
+  p.wts = (const uint8_t*)a->wpacked;
+  p.bias = a->bias;
+  p.cout = a->cout;
+  p.dtype = a->dtype;
+  p.lrelu = a->lrelu; p.slope = a->slope; p.alpha = a->alpha;
+  p.res1 = a->res1; p.res1_pt = a->res1_planes_total; p.res1_po = a->res1_plane_off; p.beta1 = a->beta1;
+  p.res2 = a->res2; p.res2_pt = a->res2_planes_total; p.res2_po = a->res2_plane_off; p.beta2 = a->beta2;
+  p.out16 = (uint16_t*)a->out16; p.out16_pt = a->out16_planes_total; p.out16_po = a->out16_plane_off;
+  p.out16_up2 = a->out16_up2; p.out16_ps = a->out16_pixel_shuffle;
+  p.out32 = a->out32; p.out32_pt = a->out32_planes_total; p.out32_po = a->out32_plane_off;
+  p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c;
+
+  // TMA descriptor over the input planes: dims (8ch, W, H, planes, N), box (8, P, R+2, kcp, 1)
+  CUtensorMap tm;
+  cuuint64_t gdim[5] = {8, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->in_planes_total, (cuuint64_t)a->n};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16,
+                        (cuuint64_t)a->w * a->h * 16 * a->in_planes_total};
+  cuuint32_t box[5] = {8, (cuuint32_t)p.P, (cuuint32_t)(p.R + 2), (cuuint32_t)p.kcp, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(a->in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] {
+    attr_err = cudaFuncSetAttribute(esr::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  });
+  if (attr_err != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+
+  int grid = p.num_tiles * p.n_blocks;
+  if (grid > num_sms()) grid = num_sms();
+  esr::conv3x3_tc_kernel<<<grid, esr::kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_pack_nchw(const float* src, int n, int c, int h, int w, int pad, int dtype, void* dst16, float* dst32,
+                  int planes_total, int plane_off, void* stream) {
+  if (!src || (!dst16 && !dst32)) return fail(ESR_ERR_INVALID, "pack_nchw: null pointer");
+  const int planes = (c + 7) / 8;
+  if (plane_off + planes > planes_total) return fail(ESR_ERR_INVALID, "pack_nchw: planes out of range");
+  const size_t total = (size_t)n * planes * (h + 2 * pad) * (w + 2 * pad);
+  esr::pack_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, pad, dtype, (uint16_t*)dst16,
+                                                                              dst32, planes_total, plane_off, planes);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_unpack_planes16(const void* src16, int dtype, int n, int c, int h, int w, int planes_total, int plane_off,
+                        float* dst, void* stream) {
+  if (!src16 || !dst) return fail(ESR_ERR_INVALID, "unpack16: null pointer");
+  const size_t total = (size_t)n * c * h * w;
+  esr::unpack_planes_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src16, dtype, n, c, h, w,
+                                                                                       planes_total, plane_off, dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_unpack_planes32(const float* src32, int n, int c, int h, int w, int planes_total, int plane_off, float* dst,
+                        void* stream) {
+  if (!src32 || !dst) return fail(ESR_ERR_INVALID, "unpack32: null pointer");
+  const size_t total = (size_t)n * c * h * w;
+  esr::unpack_planes_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src32, 0, n, c, h, w,
+                                                                                        planes_total, plane_off, dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream) {
+  if (!src || !dst) return fail(ESR_ERR_INVALID, "upsample2x: null pointer");
+  const size_t total = (size_t)n * planes * h * w;
+  esr::upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (size_t)n * planes, h, w,
+                                                                               (uint4*)dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+static int set_smem_attr(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return ESR_OK;
+}
+
+int esr_cem_down(const float* g, int n, int c, int hh, int wh, int s, int phase, const float* kd_v, const float* kd_h,
+                 int kd_len, int rank, const float* sub_from, float* out_lr, void* stream) {
+  if (!g || !kd_v || !kd_h || !out_lr) return fail(ESR_ERR_INVALID, "cem_down: null pointer");
+  if (s < 1 || hh % s || wh % s) return fail(ESR_ERR_INVALID, "cem_down: HR size %dx%d not divisible by scale %d", hh, wh, s);
+  if (phase < 0 || phase >= s || kd_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_down: bad phase/filter");
+  const int hl = hh / s, wl = wh / s;
+  const int rows = (esr::kCemTI - 1) * s + kd_len, cols = (esr::kCemTJ - 1) * s + kd_len;
+  const size_t smem = sizeof(float) * ((size_t)rows * cols + (size_t)rows * esr::kCemTJ);
+  if (smem > 227 * 1024) return fail(ESR_ERR_INVALID, "cem_down: filter too large for shared memory");
+  int rc = set_smem_attr((const void*)esr::cem_down_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((wl + esr::kCemTJ - 1) / esr::kCemTJ, (hl + esr::kCemTI - 1) / esr::kCemTI, n * c);
+  esr::cem_down_kernel<<<grid, esr::kCemThreads, smem, (cudaStream_t)stream>>>(g, hh, wh, s, phase, kd_v, kd_h, kd_len, rank,
+                                                                             sub_from, out_lr);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_cem_inv(const float* e, int n, int c, int hl, int wl, const float* ki_v, const float* ki_h, int ki_len, int rank,
+                float* out_lr, void* stream) {
+  if (!e || !ki_v || !ki_h || !out_lr) return fail(ESR_ERR_INVALID, "cem_inv: null pointer");
+  if (ki_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_inv: bad filter");
+  const int rows = esr::kCemTI + ki_len - 1, cols = esr::kCemTJ + ki_len - 1;
+  const size_t smem = sizeof(float) * ((size_t)rows * cols + (size_t)rows * esr::kCemTJ);
+  if (smem > 227 * 1024) return fail(ESR_ERR_INVALID, "cem_inv: filter too large for shared memory");
+  int rc = set_smem_attr((const void*)esr::cem_inv_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((wl + esr::kCemTJ - 1) / esr::kCemTJ, (hl + esr::kCemTI - 1) / esr::kCemTI, n * c);
+  esr::cem_inv_kernel<<<grid, esr::kCemThreads, smem, (cudaStream_t)stream>>>(e, hl, wl, ki_v, ki_h, ki_len, rank, out_lr);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl, int s, int phase, const float* ku_v,
+                   const float* ku_h, int ku_len, int rank, int crop, float* out_hr, void* stream) {
+  if (!f || !ku_v || !ku_h || !out_hr) return fail(ESR_ERR_INVALID, "cem_up_add: null pointer");
+  if (s < 1 || phase < 0 || phase >= s || ku_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_up_add: bad scale/phase/filter");
+  const int hh = hl * s, wh = wl * s;
+  if (crop < 0 || 2 * crop >= hh || 2 * crop >= wh) return fail(ESR_ERR_INVALID, "cem_up_add: crop %d too large", crop);
+  const int ho = hh - 2 * crop, wo = wh - 2 * crop;
+  const int maxn = (esr::kUpT + ku_len) / s + 2;
+  const size_t smem = sizeof(float) * ((size_t)maxn * maxn + (size_t)maxn * esr::kUpT);
+  int rc = set_smem_attr((const void*)esr::cem_up_add_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((wo + esr::kUpT - 1) / esr::kUpT, (ho + esr::kUpT - 1) / esr::kUpT, n * c);
+  esr::cem_up_add_kernel<<<grid, esr::kCemThreads, smem, (cudaStream_t)stream>>>(f, g, hl, wl, s, phase, ku_v, ku_h, ku_len,
+                                                                               rank, crop, out_hr);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+"""ctypes binding of libesr_b200.so (include/esr_b200.h).  The product path has no fallback: if the
+shared library is missing, or the device is not sm_100, every op raises."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "libesr_b200.so")
+CSRC = os.path.join(PKG_ROOT, "csrc")
+
+ESR_F16, ESR_BF16 = 0, 1
+
+
+class EsrError(RuntimeError):
+    pass
+
+
+class ConvArgs(C.Structure):
+    """mirror of esr_conv3x3_args"""
+    _fields_ = [
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("dtype", C.c_int),
+        ("in_", C.c_void_p), ("in_planes_total", C.c_int), ("in_plane_off", C.c_int), ("cin_planes", C.c_int),
+        ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("cout", C.c_int), ("cout_pad", C.c_int), ("kcp", C.c_int),
+        ("lrelu", C.c_int), ("slope", C.c_float), ("alpha", C.c_float),
+        ("res1", C.c_void_p), ("res1_planes_total", C.c_int), ("res1_plane_off", C.c_int), ("beta1", C.c_float),
+        ("res2", C.c_void_p), ("res2_planes_total", C.c_int), ("res2_plane_off", C.c_int), ("beta2", C.c_float),
+        ("out16", C.c_void_p), ("out16_planes_total", C.c_int), ("out16_plane_off", C.c_int),
+        ("out16_up2", C.c_int), ("out16_pixel_shuffle", C.c_int),
+        ("out32", C.c_void_p), ("out32_planes_total", C.c_int), ("out32_plane_off", C.c_int),
+        ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int),
+        ("tile_p", C.c_int), ("tile_mt", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "esr_last_error": (C.c_char_p, []),
+    "esr_version": (C.c_int, []),
+    "esr_launch_count": (C.c_longlong, []),
+    "esr_device_check": (C.c_int, []),
+    "esr_conv3x3_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "esr_conv3x3_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
+    "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_pack_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "esr_unpack_planes16": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
+    "esr_unpack_planes32": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "esr_upsample2x_planes16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "esr_cem_down": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_cem_inv": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p]),
+    "esr_cem_up_add": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+              "-lineinfo", "-O3"]
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/esr_api.cu into libesr_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(REPO_ROOT, "include", "esr_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "esr_api.cu")]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (building it first if a compiler is present and it is stale/missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            build()
+        else:
+            raise EsrError("libesr_b200.so is missing and nvcc is not available: run __graft_entry__.build() first. "
+                           "There is no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EsrError("esr_b200 error %d: %s" % (rc, load().esr_last_error().decode()))
+
+
+def launch_count():
+    return int(load().esr_launch_count())

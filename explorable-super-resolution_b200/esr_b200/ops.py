@@ -1,0 +1,169 @@
+"""Tensor-level wrappers over the C-ABI (esr_b200.lib).  PyTorch is plumbing here: it owns device memory
+and the stream; every computation is a call into libesr_b200.so.
+
+Planar-8 activation tensors are torch tensors of shape [N, planes, H, W, 8] (float16 / bfloat16 operands,
+float32 residual trunk)."""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+_TORCH2ESR = {torch.float16: L.ESR_F16, torch.bfloat16: L.ESR_BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise L.EsrError("esr_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise L.EsrError("esr_b200 ops need contiguous tensors")
+
+
+def device_check():
+    L.check(L.load().esr_device_check())
+
+
+class PackedConv:
+    """Tensor-core image of one 3x3 conv's weights (+ padded fp32 bias).  `lead` = latent channels in front."""
+
+    def __init__(self, weight, bias, dtype=torch.float16, lead=0, transpose_flip=False, kcp=None):
+        lib = L.load()
+        require_cuda(weight, bias)
+        weight = weight.detach().float().contiguous()
+        cout, cin = int(weight.shape[0]), int(weight.shape[1])
+        assert tuple(weight.shape[2:]) == (3, 3), "only 3x3 kernels"
+        self.dtype = dtype
+        self.esr_dtype = _TORCH2ESR[dtype]
+        self.lead = lead
+        if transpose_flip:
+            self.cout, self.cin = cin, cout
+            self.cin_planes = (cout + 7) // 8
+        else:
+            self.cout, self.cin = cout, cin
+            self.cin_planes = int(lib.esr_conv3x3_cin_planes(cin, lead))
+        if kcp is None:
+            kcp = 4 if self.cin_planes >= 4 else 2
+        self.kcp = kcp
+        cp = C.c_int(0)
+        nbytes = int(lib.esr_conv3x3_packed_bytes(self.cin_planes, self.cout, kcp, C.byref(cp)))
+        self.cout_pad = cp.value
+        self.wpacked = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        self.bias = torch.empty(self.cout_pad, dtype=torch.float32, device=weight.device)
+        b = bias.detach().float().contiguous() if (bias is not None and not transpose_flip) else None
+        L.check(lib.esr_pack_conv3x3_weights(_ptr(weight), cout, cin, lead, kcp, self.esr_dtype, int(transpose_flip),
+                                             _ptr(self.wpacked), _ptr(self.bias), _ptr(b), _stream()))
+
+
+def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2, alpha=1.0,
+            res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0,
+            out16=None, out16_off=0, up2=False, pixel_shuffle=0, out32=None, out32_off=0,
+            out_nchw=None, tile_p=0, tile_mt=0):
+    """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor."""
+    require_cuda(x16, res1, res2, out16, out32, out_nchw)
+    n, pt, h, w, e = x16.shape
+    assert e == 8 and x16.dtype == pc.dtype
+    a = L.ConvArgs()
+    a.n, a.h, a.w, a.dtype = n, h, w, pc.esr_dtype
+    a.in_, a.in_planes_total, a.in_plane_off = x16.data_ptr(), pt, in_plane_off
+    a.cin_planes = pc.cin_planes if cin_planes is None else cin_planes
+    a.wpacked, a.bias = pc.wpacked.data_ptr(), pc.bias.data_ptr()
+    a.cout, a.cout_pad, a.kcp = pc.cout, pc.cout_pad, pc.kcp
+    a.lrelu, a.slope, a.alpha = int(lrelu), slope, alpha
+    if res1 is not None:
+        assert res1.dtype == torch.float32 and tuple(res1.shape[2:]) == (h, w, 8) and res1.shape[0] == n
+        a.res1, a.res1_planes_total, a.res1_plane_off, a.beta1 = res1.data_ptr(), res1.shape[1], res1_off, beta1
+    if res2 is not None:
+        assert res2.dtype == torch.float32 and tuple(res2.shape[2:]) == (h, w, 8) and res2.shape[0] == n
+        a.res2, a.res2_planes_total, a.res2_plane_off, a.beta2 = res2.data_ptr(), res2.shape[1], res2_off, beta2
+    if out16 is not None:
+        f = 2 if up2 else (pixel_shuffle if pixel_shuffle else 1)
+        assert out16.dtype == pc.dtype and tuple(out16.shape[2:]) == (f * h, f * w, 8) and out16.shape[0] == n
+        a.out16, a.out16_planes_total, a.out16_plane_off = out16.data_ptr(), out16.shape[1], out16_off
+        a.out16_up2, a.out16_pixel_shuffle = int(up2), int(pixel_shuffle)
+    if out32 is not None:
+        assert out32.dtype == torch.float32 and tuple(out32.shape[2:]) == (h, w, 8) and out32.shape[0] == n
+        a.out32, a.out32_planes_total, a.out32_plane_off = out32.data_ptr(), out32.shape[1], out32_off
+    if out_nchw is not None:
+        assert out_nchw.dtype == torch.float32 and out_nchw.shape[0] == n and tuple(out_nchw.shape[2:]) == (h, w)
+        a.out_nchw, a.out_nchw_c = out_nchw.data_ptr(), out_nchw.shape[1]
+    a.tile_p, a.tile_mt = tile_p, tile_mt
+    L.check(L.load().esr_conv3x3_fwd(C.byref(a), _stream()))
+
+
+def planes_for(c):
+    return (c + 7) // 8
+
+
+def pack_nchw(src, *, pad=0, dtype=torch.float16, dst16=None, dst32=None, plane_off=0, want16=True, want32=False):
+    """NCHW fp32 -> planar-8 (optionally replicate padded).  Returns (dst16, dst32)."""
+    require_cuda(src, dst16, dst32)
+    src = src.float()
+    n, c, h, w = src.shape
+    planes = planes_for(c)
+    ho, wo = h + 2 * pad, w + 2 * pad
+    if dst16 is None and want16:
+        dst16 = torch.empty((n, planes, ho, wo, 8), dtype=dtype, device=src.device)
+    if dst32 is None and want32:
+        dst32 = torch.empty((n, planes, ho, wo, 8), dtype=torch.float32, device=src.device)
+    pt = (dst16 if dst16 is not None else dst32).shape[1]
+    if dst16 is not None:
+        dtype = dst16.dtype
+    L.check(L.load().esr_pack_nchw(_ptr(src), n, c, h, w, pad, _TORCH2ESR[dtype], _ptr(dst16), _ptr(dst32), pt, plane_off,
+                                   _stream()))
+    return dst16, dst32
+
+
+def unpack_planes(src, c, plane_off=0):
+    """planar-8 -> NCHW fp32 (first c channels starting at plane_off)."""
+    require_cuda(src)
+    n, pt, h, w, _ = src.shape
+    dst = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
+    if src.dtype == torch.float32:
+        L.check(L.load().esr_unpack_planes32(_ptr(src), n, c, h, w, pt, plane_off, _ptr(dst), _stream()))
+    else:
+        L.check(L.load().esr_unpack_planes16(_ptr(src), _TORCH2ESR[src.dtype], n, c, h, w, pt, plane_off, _ptr(dst), _stream()))
+    return dst
+
+
+def upsample2x(src16):
+    require_cuda(src16)
+    n, pt, h, w, _ = src16.shape
+    dst = torch.empty((n, pt, 2 * h, 2 * w, 8), dtype=src16.dtype, device=src16.device)
+    L.check(L.load().esr_upsample2x_planes16(_ptr(src16), n, pt, h, w, _ptr(dst), _stream()))
+    return dst
+
+
+def cem_down(g, s, phase, kv, kh, sub_from=None):
+    """DownscaleOP (optionally fused `sub_from - Down(g)`).  kv/kh: [rank, len] fp32 device tensors."""
+    require_cuda(g, kv, kh, sub_from)
+    n, c, hh, wh = g.shape
+    out = torch.empty((n, c, hh // s, wh // s), dtype=torch.float32, device=g.device)
+    L.check(L.load().esr_cem_down(_ptr(g), n, c, hh, wh, s, phase, _ptr(kv), _ptr(kh), kv.shape[1], kv.shape[0],
+                                  _ptr(sub_from), _ptr(out), _stream()))
+    return out
+
+
+def cem_inv(e, kv, kh):
+    require_cuda(e, kv, kh)
+    n, c, hl, wl = e.shape
+    out = torch.empty_like(e)
+    L.check(L.load().esr_cem_inv(_ptr(e), n, c, hl, wl, _ptr(kv), _ptr(kh), kv.shape[1], kv.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def cem_up_add(f, g, s, phase, kv, kh, crop=0):
+    require_cuda(f, g, kv, kh)
+    n, c, hl, wl = f.shape
+    out = torch.empty((n, c, hl * s - 2 * crop, wl * s - 2 * crop), dtype=torch.float32, device=f.device)
+    L.check(L.load().esr_cem_up_add(_ptr(f), _ptr(g), n, c, hl, wl, s, phase, _ptr(kv), _ptr(kh), kv.shape[1], kv.shape[0],
+                                    crop, _ptr(out), _stream()))
+    return out

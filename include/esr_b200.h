@@ -1,0 +1,148 @@
+/*
+ * esr_b200.h — C-ABI of the B200-native hot path of Explorable-Super-Resolution.
+ *
+ * The reference (YuvalBahat/Explorable-Super-Resolution) is pure Python/PyTorch and has no FFI of its
+ * own; the "operator API" of the hot path is a set of torch.nn modules.  Each entry point below names
+ * the reference call site it replaces (paths relative to the reference's codes/ directory).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative esr_status otherwise; esr_last_error() returns a
+ *     human readable string for the calling thread's last failure.  No exception crosses this boundary.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.  The caller owns every buffer.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - activation tensors use the planar-8 layout  [N][C/8][H][W][8]  ("planes"): channel c of pixel
+ *     (n,y,x) lives at  (((n*planes_total + c/8)*H + y)*W + x)*8 + c%8.  16-bit planes carry the
+ *     tensor-core operands (fp16 or bf16, selected by `dtype`), fp32 planes carry the residual trunk.
+ *   - images at the boundary are NCHW fp32, exactly the reference's tensors.
+ */
+#ifndef ESR_B200_H
+#define ESR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ESR_OK = 0,
+  ESR_ERR_INVALID = -1,     /* bad argument (shape / alignment / unsupported combination) */
+  ESR_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                         */
+  ESR_ERR_UNSUPPORTED = -3  /* device is not sm_100                                        */
+} esr_status;
+
+typedef enum { ESR_F16 = 0, ESR_BF16 = 1 } esr_dtype;
+
+const char* esr_last_error(void);
+int esr_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches claim) */
+long long esr_launch_count(void);
+/* 0 if the current device can run the sm_100a kernels */
+int esr_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3x3 stride-1 zero-pad-1 convolution as a tcgen05 implicit GEMM with fused epilogue.
+ * Replaces  models/modules/block.py:129-146 (conv_block: nn.Conv2d + LeakyReLU(0.2)),
+ *           block.py:230-235 (torch.cat of the dense block + `x5*0.2 + x`),
+ *           block.py:262-270 (RRDB `out*0.2 + x`), block.py:96 (ShortcutBlock add),
+ *           block.py:299-300 (nearest x2 Upsampler, folded into the producer's store),
+ *           block.py:287 (nn.PixelShuffle, folded into the store addressing).
+ *
+ *   acc = conv3x3(in[:, in_plane_off*8 : +cin_planes*8]) + bias
+ *   if lrelu: acc = acc > 0 ? acc : slope*acc
+ *   v = alpha*acc + beta1*res1 + beta2*res2
+ *   stores (any subset): out16 planes, out32 planes, out_nchw (fp32 NCHW, first out_nchw_c channels)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, h, w;               /* batch, height, width (input == output spatial size)          */
+  int dtype;                 /* esr_dtype of `in`, `wpacked`, `out16`                        */
+  /* input (16-bit planes) */
+  const void* in;
+  int in_planes_total;       /* planes in the input buffer                                    */
+  int in_plane_off;          /* first plane consumed                                          */
+  int cin_planes;            /* planes consumed (Cin/8 rounded up)                            */
+  /* weights packed by esr_pack_conv3x3_weights, bias fp32 [cout_pad] */
+  const void* wpacked;
+  const float* bias;
+  int cout;                  /* real output channels                                          */
+  int cout_pad;              /* padded to a multiple of the n-block (16/32/64)                */
+  int kcp;                   /* planes per K chunk used when packing (2 or 4)                 */
+  /* epilogue */
+  int lrelu; float slope;
+  float alpha;
+  const float* res1; int res1_planes_total; int res1_plane_off; float beta1;
+  const float* res2; int res2_planes_total; int res2_plane_off; float beta2;
+  /* outputs */
+  void* out16; int out16_planes_total; int out16_plane_off;
+  int out16_up2;             /* 1: out16 is [N][planes][2H][2W][8], each pixel replicated 2x2 */
+  int out16_pixel_shuffle;   /* r (0 = off): out16 is [N][planes][rH][rW][8], conv channel
+                                c*r*r+i*r+j goes to channel c at (r*y+i, r*x+j)               */
+  float* out32; int out32_planes_total; int out32_plane_off;
+  float* out_nchw; int out_nchw_c;
+  /* tiling hints (0 = library default) */
+  int tile_p;                /* tile pitch 32 or 64 (valid width = pitch-2)                   */
+  int tile_mt;               /* 128-row M tiles per CTA tile: 1, 2 or 4                        */
+} esr_conv3x3_args;
+
+int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream);
+
+/* bytes of the packed weight image for (cin_planes, cout) with chunk size kcp */
+size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out);
+/* OIHW fp32 [cout][cin][3][3] (device) -> packed tensor-core image (device).
+ * Layout [n_block][chunk][tap][plane-in-chunk][cout-in-block][8 cin], zero padded.
+ * `transpose_flip` = 1 packs the dgrad operand (I/O swapped, taps rotated 180 degrees).
+ * `lead`: the first `lead` input channels (the latent z the reference concatenates IN FRONT of every
+ * conv input, block.py:92,265,268 / architecture.py:287,300) occupy their own zero-padded plane group;
+ * the remaining cin-lead channels start at the next plane boundary.  0 for plain convs. */
+int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, int kcp, int dtype,
+                             int transpose_flip, void* wpacked, float* bias_out,
+                             const float* bias_in, void* stream);
+/* planes consumed by a conv with `cin` input channels of which the first `lead` are latent */
+int esr_conv3x3_cin_planes(int cin, int lead);
+
+/* ------------------------------------------------------------------------------------------------
+ * layout conversion at the boundary (reference tensors are NCHW fp32)
+ * pack:   NCHW fp32 -> planes (16-bit and/or fp32); optional replicate padding of `pad` pixels per
+ *         side (CEM.CEMnet.py:70-71 LR_padder/HR_padder, applied at :286-295 in eval mode).
+ * unpack: planes -> NCHW fp32
+ * ---------------------------------------------------------------------------------------------- */
+int esr_pack_nchw(const float* src, int n, int c, int h, int w, int pad, int dtype,
+                  void* dst16, float* dst32, int planes_total, int plane_off, void* stream);
+int esr_unpack_planes16(const void* src16, int dtype, int n, int c, int h, int w,
+                        int planes_total, int plane_off, float* dst, void* stream);
+int esr_unpack_planes32(const float* src32, int n, int c, int h, int w,
+                        int planes_total, int plane_off, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Consistency-Enforcing Module (CEM/CEMnet.py:254-311).  Filters are the separable factors of the
+ * reference's numpy-designed kernels (CEMnet.py:22-33,186-206): ds_kernel = outer(kd_v, kd_h) and
+ * inv_hTh = outer(ki_v, ki_h), computed on the host by the Python layer.  Every filter is passed as
+ * `rank` separable terms  K[a][b] = sum_r kv[r*len + a] * kh[r*len + b]  (rank 1 for the reference's
+ * bicubic kernels; more terms represent estimated, non-separable kernels exactly).
+ *
+ * esr_cem_down : DownscaleOP, CEMnet.py:273-275 (replicate-pad k/2, correlate with rot90(ds_kernel,2),
+ *                keep phase `phase` of every s x s cell).  Optionally returns x_lr - Down(g) when
+ *                `sub_from` is given (fused residual for the projection).
+ * esr_cem_inv  : Conv_LR_with_Inv_hTh_OP, CEMnet.py:262-264 (replicate-pad, correlate).
+ * esr_cem_up_add: out = g + Upscale_OP(f) (CEMnet.py:266-272,305-310), polyphase, with optional crop
+ *                of `crop` pixels per side (HR_unpadder, CEMnet.py:72,311).  g may be NULL (pure Up).
+ * All images NCHW fp32.
+ * ---------------------------------------------------------------------------------------------- */
+int esr_cem_down(const float* g, int n, int c, int hh, int wh, int s, int phase,
+                 const float* kd_v, const float* kd_h, int kd_len, int rank,
+                 const float* sub_from, float* out_lr, void* stream);
+int esr_cem_inv(const float* e, int n, int c, int hl, int wl,
+                const float* ki_v, const float* ki_h, int ki_len, int rank, float* out_lr,
+                void* stream);
+int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl, int s, int phase,
+                   const float* ku_v, const float* ku_h, int ku_len, int rank, int crop,
+                   float* out_hr, void* stream);
+
+/* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
+int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESR_B200_H */
