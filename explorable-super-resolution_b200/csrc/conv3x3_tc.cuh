@@ -123,7 +123,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int x0 = txi * p.TW, y0 = tyi * p.R;
         const uint8_t* wsrc = p.wts + (size_t)nblk * p.nchunks * p.b_bytes;
         for (int c = 0; c < p.nchunks; ++c) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
           const uint32_t sa = stage0 + s * p.stage_bytes;
           mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
           tma_load_5d(sa, &tmA, bar_full + 8 * s, 0, x0 - 1, y0 - 1, p.in_plane_off + c * p.kcp, img);
@@ -140,10 +140,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t b_lbo = (uint32_t)p.nb_n * 16u;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
-      mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u, 2u);
       tc_fence_after();
       for (int c = 0; c < p.nchunks; ++c) {
-        mbar_wait(bar_full + 8 * s, ph);
+        mbar_wait(bar_full + 8 * s, ph, 3u);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = stage0 + s * p.stage_bytes;
@@ -183,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tyi = trem / p.tiles_x;
       const int txi = trem - tyi * p.tiles_x;
       const int x0 = txi * p.TW, y0 = tyi * p.R;
-      mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, 4u);
       tc_fence_after();
       for (int t = 0; t < p.MT; ++t) {
         const int q = t * 128 + wq * 32 + lane;

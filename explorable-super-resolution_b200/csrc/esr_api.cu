@@ -89,6 +89,15 @@ const char* esr_last_error(void) { return g_err; }
 int esr_version(void) { return 100; }
 long long esr_launch_count(void) { return g_launches.load(); }
 
+int esr_debug_watchdog(unsigned int* out8_host, int reset) {
+  CUDA_TRY(cudaMemcpyFromSymbol(out8_host, esr::g_watchdog, 8 * sizeof(unsigned int)));
+  if (reset) {
+    unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyToSymbol(esr::g_watchdog, z, sizeof(z)));
+  }
+  return ESR_OK;
+}
+
 int esr_device_check(void) {
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));

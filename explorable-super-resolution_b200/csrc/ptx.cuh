@@ -46,11 +46,28 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded spin: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
+// Watchdog state: [0] = flag, [1] = block, [2] = thread, [3] = barrier smem address, [4] = parity, [5] = tag
+__device__ unsigned int g_watchdog[8];
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug records where it was stuck and lets every role fall through (the launch
+// finishes with garbage and the host reports ESR_ERR_CUDA) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (*(volatile unsigned int*)&g_watchdog[0]) return;
+    if (globaltimer_ns() - t0 > 2000000000ull) {
+      if (atomicExch(&g_watchdog[0], 1u) == 0u) {
+        g_watchdog[1] = blockIdx.x; g_watchdog[2] = threadIdx.x; g_watchdog[3] = bar; g_watchdog[4] = parity;
+        g_watchdog[5] = tag;
+      }
+      return;
+    }
   }
 }
 

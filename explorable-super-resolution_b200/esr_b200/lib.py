@@ -40,6 +40,7 @@ SIGNATURES = {
     "esr_version": (C.c_int, []),
     "esr_launch_count": (C.c_longlong, []),
     "esr_device_check": (C.c_int, []),
+    "esr_debug_watchdog": (C.c_int, [C.POINTER(C.c_uint), C.c_int]),
     "esr_conv3x3_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "esr_conv3x3_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
@@ -100,6 +101,13 @@ def load():
 def check(rc):
     if rc != 0:
         raise EsrError("esr_b200 error %d: %s" % (rc, load().esr_last_error().decode()))
+
+
+def watchdog(reset=True):
+    """(synchronising) returns the 8-word watchdog record; word 0 != 0 means a pipeline wait timed out."""
+    buf = (C.c_uint * 8)()
+    check(load().esr_debug_watchdog(buf, int(reset)))
+    return list(buf)
 
 
 def launch_count():

@@ -38,6 +38,9 @@ const char* esr_last_error(void);
 int esr_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches claim) */
 long long esr_launch_count(void);
+/* debugging aid: copies the 8-word pipeline watchdog record (word 0 != 0: some mbarrier wait timed out;
+ * then block, thread, barrier address, parity, role tag) to host memory; optionally clears it.  Synchronises. */
+int esr_debug_watchdog(unsigned int* out8_host, int reset);
 /* 0 if the current device can run the sm_100a kernels */
 int esr_device_check(void);
 

@@ -23,9 +23,13 @@ def run(n, cin, cout, h, w, dtype=torch.float16, lrelu=False, mt=0, p=0, seed=0)
     back = ops.unpack_planes(x16, cin)
     e0 = (back - xq).abs().max().item()
     pc = ops.PackedConv(wt, b, dtype=dtype)
+    torch.cuda.synchronize(); print("  packed ok", flush=True)
     out32 = torch.zeros((n, ops.planes_for(cout), h, w, 8), dtype=torch.float32, device=dev)
     ops.conv3x3(x16, pc, lrelu=lrelu, out32=out32, tile_mt=mt, tile_p=p)
     torch.cuda.synchronize()
+    wd = lib.watchdog()
+    if wd[0]:
+        print("  WATCHDOG: block %d thread %d bar_off 0x%x parity %d tag %d (1=producer-empty 2=mma-tmem-empty 3=mma-full 4=epi-tmem-full)" % (wd[1], wd[2], wd[3], wd[4], wd[5]), flush=True)
     got = ops.unpack_planes(out32, cout)
     err = (got - ref).abs().max().item()
     rel = err / ref.abs().max().item()
