@@ -71,6 +71,32 @@ __global__ void unpack_planes_kernel(const void* __restrict__ src, int dtype, in
   }
 }
 
+// Bilinear (align_corners=False) 1/s down-scaling of the HR latent map, applied to the replicate-padded
+// map (architecture.py:284 after CEMnet.py:290-292).  NCHW fp32 in ([n*c][hh][wh], unpadded) -> NCHW fp32 out
+// ([n*c][(hh+2*pad)/s][(wh+2*pad)/s]).
+__global__ void latent_downscale_kernel(const float* __restrict__ src, size_t nc, int hh, int wh, int s, int pad,
+                                        float* __restrict__ dst) {
+  const int hp = hh + 2 * pad, wp = wh + 2 * pad;
+  const int ho = hp / s, wo = wp / s;
+  const size_t total = nc * ho * wo;
+  const float fs = 1.0f / (1.0f / (float)s);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int j = r % wo; r /= wo;
+    const int i = r % ho; r /= ho;
+    const float sy = fmaxf(((float)i + 0.5f) * fs - 0.5f, 0.f), sx = fmaxf(((float)j + 0.5f) * fs - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const int y1 = min(y0 + 1, hp - 1), x1 = min(x0 + 1, wp - 1);
+    const int ya = clampi(y0 - pad, 0, hh - 1), yb = clampi(y1 - pad, 0, hh - 1);
+    const int xa = clampi(x0 - pad, 0, wh - 1), xb = clampi(x1 - pad, 0, wh - 1);
+    const float* p = src + r * (size_t)hh * wh;
+    const float v00 = __ldg(p + (size_t)ya * wh + xa), v01 = __ldg(p + (size_t)ya * wh + xb);
+    const float v10 = __ldg(p + (size_t)yb * wh + xa), v11 = __ldg(p + (size_t)yb * wh + xb);
+    dst[idx] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
 // nearest x2 on 16-bit planes: one thread per source pixel-plane, four 16 B stores.
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, size_t nplanes, int h, int w, uint4* __restrict__ dst) {
   const size_t total = nplanes * h * w;

@@ -282,6 +282,16 @@ int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, vo
   return ESR_OK;
 }
 
+int esr_latent_downscale(const float* z_hr, int n, int c, int hh, int wh, int s, int pad_hr, float* out, void* stream) {
+  if (!z_hr || !out) return fail(ESR_ERR_INVALID, "latent_downscale: null pointer");
+  if (s < 1 || (hh + 2 * pad_hr) % s || (wh + 2 * pad_hr) % s) return fail(ESR_ERR_INVALID, "latent_downscale: size not divisible by %d", s);
+  const size_t total = (size_t)n * c * ((hh + 2 * pad_hr) / s) * ((wh + 2 * pad_hr) / s);
+  esr::latent_downscale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(z_hr, (size_t)n * c, hh, wh, s, pad_hr, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 static int set_smem_attr(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

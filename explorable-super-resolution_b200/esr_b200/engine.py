@@ -1,0 +1,179 @@
+"""RRDB generator engine: turns an `RRDBNet` parameter container into a sequence of fused conv launches.
+
+Reference control flow being replaced: architecture.py:278-302 (RRDBNet.forward), block.py:85-97
+(ShortcutBlock), block.py:262-270 (RRDB), block.py:230-235 (ResidualDenseBlock_5C), block.py:299-300 (Upsampler).
+
+Data layout in HBM (all planar-8, see include/esr_b200.h):
+  * three "dense" operand buffers D[0..2] of z+nf+4*gc channels: conv i of a dense block reads the prefix
+    [z | x | x1..x_{i}] and writes x_{i+1} into its own plane range, so block.py:234's torch.cat never happens;
+  * fp32 "trunk" buffers T[0..2] (+F for the fea_conv output) carry the residual stream x in full precision;
+    the 16-bit copy of x in D[.] exists only as tensor-core operand;
+  * conv5 of each dense block fuses `x5*0.2 + x`; the third block of an RRDB also fuses the RRDB residual:
+        out = (0.2*acc + x_rdb3)*0.2 + x_rrdb = 0.04*acc + 0.2*x_rdb3 + x_rrdb
+  * LR_conv fuses the ShortcutBlock add and writes its output already nearest-x2 replicated; every upconv
+    does the same for the next one, so the up-sampled tensor is written once and never re-read for resizing.
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+def _param_version(mods):
+    return tuple((m.weight._version, m.bias._version, m.weight.data_ptr()) for m in mods)
+
+
+class RRDBEngine:
+    def __init__(self, net, dtype=torch.float16, trunk_fp32=True):
+        self.net = net
+        self.dtype = dtype
+        self.trunk_fp32 = trunk_fp32
+        self._packed = None
+        self._packed_version = None
+        self._bufs = {}
+
+    # ---------------------------------------------------------------- weights
+    def _convs(self):
+        net = self.net
+        convs = [net.model[0]]
+        shortcut = net.model[1]
+        for blk in list(shortcut.sub)[:-1]:
+            for rdb in (blk.RDB1, blk.RDB2, blk.RDB3):
+                convs += [seq[0] for seq in rdb.convs]
+        convs.append(shortcut.sub[-1])
+        for up in net.upsamplers():
+            convs.append(up[1] if net.upsample_mode == 'upconv' else up[0])
+        convs += [net.model[-3], net.model[-1]]
+        return convs
+
+    def packed(self):
+        convs = self._convs()
+        ver = _param_version(convs)
+        if self._packed is None or ver != self._packed_version:
+            z = self.net.z_lead
+            n_up = len(self.net.upsamplers())
+            pk = []
+            for i, c in enumerate(convs):
+                is_up = len(convs) - 2 - n_up <= i < len(convs) - 2
+                lead = 0 if is_up else z
+                pk.append(ops.PackedConv(c.weight, c.bias, dtype=self.dtype, lead=lead))
+            self._packed, self._packed_version = pk, ver
+        return self._packed
+
+    # ---------------------------------------------------------------- buffers
+    def buffers(self, n, h, w, dev):
+        key = (n, h, w, str(dev))
+        b = self._bufs.get(key)
+        if b is not None:
+            return b
+        net = self.net
+        zp = 1 if net.z_lead else 0
+        nfp, gcp = net.nf // 8, net.gc // 8
+        dense_planes = zp + nfp + 4 * gcp
+        z16 = lambda *s: torch.zeros(s, dtype=self.dtype, device=dev)
+        z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        b = {
+            'in16': z16(n, zp + 1, h, w, 8),
+            'D': [z16(n, dense_planes, h, w, 8) for _ in range(3)],
+            'T': [z32(n, nfp, h, w, 8) for _ in range(3)],
+            'F': z32(n, nfp, h, w, 8),
+            'up': [],
+        }
+        s = 1
+        for r in net.up_factors():
+            s *= r
+            b['up'].append(z16(n, nfp, h * s, w * s, 8))
+        b['hr_a'] = z16(n, nfp + zp, h * s, w * s, 8)
+        b['hr_b'] = z16(n, nfp + zp, h * s, w * s, 8)
+        # keep at most two shapes alive (train + eval sizes)
+        if len(self._bufs) >= 2:
+            self._bufs.pop(next(iter(self._bufs)))
+        self._bufs[key] = b
+        return b
+
+    # ---------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, x, pad=0):
+        """x: [N, z*s^2 + 3, h, w] fp32 NCHW (reference layout).  Returns G(x): [N, out_nc, S*(h+2pad), S*(w+2pad)]."""
+        net = self.net
+        ops.require_cuda(x)
+        if net.norm_type is not None:
+            raise NotImplementedError('esr_b200: norm layers inside RRDBNet are not supported')
+        n, cin, h0, w0 = x.shape
+        h, w = h0 + 2 * pad, w0 + 2 * pad
+        dev = x.device
+        pk = self.packed()
+        B = self.buffers(n, h, w, dev)
+        z = net.z_lead
+        zp = 1 if z else 0
+        nfp, gcp = net.nf // 8, net.gc // 8
+        D, T, F = B['D'], B['T'], B['F']
+        S = net.upscale
+
+        x = x.float().contiguous()
+        if z:
+            # latent: [N, z*S^2, h, w] is a raw view of [N, z, S*h, S*w] (SRRaGAN_model.py:233, architecture.py:281-283)
+            zc = cin - 3
+            assert zc == z * S * S, 'latent channels do not match upscale^2 * num_latent_channels'
+            z_hr = x[:, :zc].contiguous().view(n, z, S * h0, S * w0)
+            # eval mode replicate-pads Z in the HR domain BEFORE the bilinear 1/S resize (CEMnet.py:290-292,
+            # architecture.py:284), so the padding is folded into the resize kernel, not applied after it
+            z_lr = ops.latent_downscale(z_hr, S, pad_hr=pad * S)
+            img = x[:, zc:].contiguous()
+            ops.pack_nchw(z_lr, dst16=B['in16'], plane_off=0)
+            ops.pack_nchw(img, pad=pad, dst16=B['in16'], plane_off=1)
+            for d in D:
+                ops.pack_nchw(z_lr, dst16=d, plane_off=0)
+            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_a'], plane_off=0)
+            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_b'], plane_off=0)
+        else:
+            ops.pack_nchw(x, pad=pad, dst16=B['in16'], plane_off=0)
+
+        it = iter(pk)
+        # fea_conv: no activation; fp32 copy kept for the ShortcutBlock add
+        ops.conv3x3(B['in16'], next(it), out16=D[0], out16_off=zp, out32=F)
+        a, b_, c = 0, 1, 2
+        Ta = F
+        nb = len(net.model[1].sub) - 1
+        for _ in range(nb):
+            src_T = Ta
+            # RDB1: a -> b ; RDB2: b -> c ; RDB3: c -> b (fused RRDB residual with x_rrdb = src_T)
+            for (di, do, Tin, last) in ((a, b_, src_T, False), (b_, c, T[b_], False), (c, b_, T[c], True)):
+                for i in range(4):
+                    ops.conv3x3(D[di], next(it), cin_planes=zp + nfp + i * gcp, lrelu=True,
+                                out16=D[di], out16_off=zp + nfp + i * gcp)
+                if not last:
+                    ops.conv3x3(D[di], next(it), alpha=0.2, res1=Tin, beta1=1.0,
+                                out16=D[do], out16_off=zp, out32=T[do])
+                else:
+                    ops.conv3x3(D[di], next(it), alpha=0.04, res1=Tin, beta1=0.2, res2=src_T, beta2=1.0,
+                                out16=D[do], out16_off=zp, out32=T[do])
+            a, b_ = b_, a
+            Ta = T[a]
+        ups = B['up']
+        factors = net.up_factors()
+        if any(r != 2 for r in factors):
+            raise NotImplementedError('esr_b200: only x2 up-sampling stages are built (scale 2/4/8)')
+        if net.upsample_mode == 'upconv':
+            # LR_conv + ShortcutBlock add, stored nearest-x2 replicated for the first upconv (block.py:299-300)
+            ops.conv3x3(D[a], next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=ups[0], up2=True)
+            for k in range(len(factors)):
+                if k < len(factors) - 1:
+                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, out16=ups[k + 1], up2=True)
+                else:  # the last upconv feeds HR_conv0, which sees the HR latent in plane 0 of hr_a
+                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, out16=B['hr_a'], out16_off=zp)
+        else:
+            # pixelshuffle_block (block.py:278-291): conv(nf -> 4nf) -> PixelShuffle(2) -> act; the shuffle is the
+            # store addressing of the conv epilogue, the (elementwise) activation is applied before it
+            ops.conv3x3(D[a], next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=D[c], out16_off=zp)
+            src, src_off = D[c], zp
+            for k in range(len(factors)):
+                dst, dst_off = (ups[k], 0) if k < len(factors) - 1 else (B['hr_a'], zp)
+                ops.conv3x3(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, out16=dst, out16_off=dst_off,
+                            pixel_shuffle=2)
+                src, src_off = dst, dst_off
+        ops.conv3x3(B['hr_a'], next(it), lrelu=True, out16=B['hr_b'], out16_off=zp)
+        out = torch.empty((n, net.out_nc, h * S, w * S), dtype=torch.float32, device=dev)
+        ops.conv3x3(B['hr_b'], next(it), out_nchw=out)
+        return out

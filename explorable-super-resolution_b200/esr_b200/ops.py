@@ -142,6 +142,14 @@ def upsample2x(src16):
     return dst
 
 
+def latent_downscale(z_hr, s, pad_hr=0):
+    require_cuda(z_hr)
+    n, c, hh, wh = z_hr.shape
+    out = torch.empty((n, c, (hh + 2 * pad_hr) // s, (wh + 2 * pad_hr) // s), dtype=torch.float32, device=z_hr.device)
+    L.check(L.load().esr_latent_downscale(_ptr(z_hr), n, c, hh, wh, s, pad_hr, _ptr(out), _stream()))
+    return out
+
+
 def cem_down(g, s, phase, kv, kh, sub_from=None):
     """DownscaleOP (optionally fused `sub_from - Down(g)`).  kv/kh: [rank, len] fp32 device tensors."""
     require_cuda(g, kv, kh, sub_from)

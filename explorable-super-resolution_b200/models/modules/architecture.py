@@ -1,0 +1,80 @@
+"""Generator architecture with the reference's constructor signature, attributes and state-dict keys
+(models/modules/architecture.py:228-302), executed by esr_b200.engine.RRDBEngine."""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import block as B
+
+
+class RRDBNet(nn.Module):
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32, upscale=4, norm_type=None, act_type='leakyrelu', mode='CNA',
+                 upsample_mode='upconv', latent_input=None, num_latent_channels=None):
+        super(RRDBNet, self).__init__()
+        self.latent_input = None
+        if num_latent_channels is not None and num_latent_channels > 0:
+            self.latent_input = latent_input
+            num_latent_channels_HR = 1 * num_latent_channels
+            if 'HR_rearranged' in latent_input:
+                num_latent_channels *= upscale ** 2
+        self.num_latent_channels = 1 * num_latent_channels
+        self.upscale = upscale
+        n_upscale = 1 if upscale == 3 else int(math.log(upscale, 2))
+        if latent_input is not None:
+            in_nc += num_latent_channels
+        if latent_input is None or 'all_layers' not in latent_input:
+            num_latent_channels, num_latent_channels_HR = 0, 0
+        if act_type != 'leakyrelu':
+            raise NotImplementedError('esr_b200 RRDBNet: only leakyrelu(0.2) is built')
+        if upsample_mode not in ('upconv', 'pixelshuffle'):
+            raise NotImplementedError('upsample mode [{:s}] is not found'.format(upsample_mode))
+        if self.latent_input is not None and ('HR_downscaled' not in self.latent_input):
+            # the reference itself only works in this domain ('LR' fails at construction, 'HR_rearranged' raises)
+            raise NotImplementedError('latent_input domain must be HR_downscaled')
+        # engine-facing description.  NOTE: like the reference (architecture.py:250) the dense blocks are
+        # built with a literal growth of 32 whatever `gc` says.
+        self.nf, self.gc, self.out_nc, self.norm_type, self.upsample_mode = nf, 32, out_nc, norm_type, upsample_mode
+        self.z_lead = num_latent_channels
+        self._n_upscale = n_upscale
+
+        fea_conv = B.conv_block(in_nc, nf, kernel_size=3, norm_type=None, act_type=None, return_module_list=True)
+        rb_blocks = [B.RRDB(nf, kernel_size=3, gc=32, stride=1, bias=True, pad_type='zero', norm_type=norm_type, act_type=act_type,
+                            mode='CNA', latent_input_channels=num_latent_channels) for _ in range(nb)]
+        LR_conv = B.conv_block(nf + num_latent_channels, nf, kernel_size=3, norm_type=norm_type, act_type=None, mode=mode,
+                               return_module_list=True)
+        upsample_block = B.upconv_blcok if upsample_mode == 'upconv' else B.pixelshuffle_block
+        if upscale == 3:
+            upsampler = [upsample_block(nf, nf, 3, act_type=act_type)]
+        else:
+            upsampler = [upsample_block(nf, nf, act_type=act_type) for _ in range(n_upscale)]
+        HR_conv0 = B.conv_block(nf + num_latent_channels_HR, nf, kernel_size=3, norm_type=None, act_type=act_type, return_module_list=True)
+        HR_conv1 = B.conv_block(nf + num_latent_channels_HR, out_nc, kernel_size=3, norm_type=None, act_type=None, return_module_list=True)
+        as_list = lambda m: m if isinstance(m, list) else [m]
+        shortcut = B.ShortcutBlock(rb_blocks + as_list(LR_conv), latent_input_channels=num_latent_channels, use_module_list=True)
+        self.model = nn.ModuleList(as_list(fea_conv) + [shortcut] + upsampler + as_list(HR_conv0) + as_list(HR_conv1))
+        self._engines = {}
+        self.compute_dtype = torch.float16
+
+    # ---- engine-facing helpers ----------------------------------------------------------------------
+    def upsamplers(self):
+        return [self.model[2 + k] for k in range(self._n_upscale)]
+
+    def up_factors(self):
+        return [3] if self.upscale == 3 else [2] * self._n_upscale
+
+    def engine(self):
+        from esr_b200.engine import RRDBEngine
+        key = self.compute_dtype
+        if key not in self._engines:
+            self._engines[key] = RRDBEngine(self, dtype=key)
+        return self._engines[key]
+
+    def forward(self, x, pad=0):
+        """x: [N, z*s^2 + in_nc, h, w] exactly as the reference feeds it (latent packed by
+        SRRaGANModel.Prepare_Input).  `pad` > 0 replicate-pads the input (CEM eval mode) inside the
+        packing kernel."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from esr_b200.autograd import rrdb_forward_with_grad
+            return rrdb_forward_with_grad(self, x, pad)
+        return self.engine().forward(x, pad=pad)

@@ -1,0 +1,103 @@
+"""Network factory with the reference's entry points (models/networks.py:85-202): define_G / define_D /
+define_F, kaiming initialisation (x0.1 for G), CEM wrapping and the DataParallel-shaped return value."""
+import functools
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+import models.modules.architecture as arch
+
+
+def weights_init_normal(m, std=0.02):
+    name = m.__class__.__name__
+    if name.find('Conv') != -1 or name.find('Linear') != -1:
+        init.normal_(m.weight.data, 0.0, std)
+        if m.bias is not None:
+            m.bias.data.zero_()
+    elif name.find('BatchNorm2d') != -1:
+        init.normal_(m.weight.data, 1.0, std)
+        init.constant_(m.bias.data, 0.0)
+
+
+def weights_init_kaiming(m, scale=1):
+    # the CEM's fixed filters are tagged and must keep their designed taps (networks.py:30-31)
+    if 'filter_layer' in m.__dict__ and m.__getattribute__('filter_layer'):
+        return
+    name = m.__class__.__name__
+    if name.find('Conv') != -1 or name.find('Linear') != -1:
+        init.kaiming_normal_(m.weight.data, a=0, mode='fan_in')
+        m.weight.data *= scale
+        if m.bias is not None:
+            m.bias.data.zero_()
+    elif 'BatchNorm2d' in name:
+        init.constant_(m.weight.data, 1.0)
+        init.constant_(m.bias.data, 0.0)
+
+
+def weights_init_orthogonal(m):
+    name = m.__class__.__name__
+    if name.find('Conv') != -1 or name.find('Linear') != -1:
+        init.orthogonal_(m.weight.data, gain=1)
+        if m.bias is not None:
+            m.bias.data.zero_()
+    elif name.find('BatchNorm2d') != -1:
+        init.constant_(m.weight.data, 1.0)
+        init.constant_(m.bias.data, 0.0)
+
+
+def init_weights(net, init_type='kaiming', scale=1, std=0.02):
+    print('initialization method [{:s}]'.format(init_type))
+    if init_type == 'normal':
+        net.apply(functools.partial(weights_init_normal, std=std))
+    elif init_type == 'kaiming':
+        net.apply(functools.partial(weights_init_kaiming, scale=scale))
+    elif init_type == 'orthogonal':
+        net.apply(weights_init_orthogonal)
+    else:
+        raise NotImplementedError('initialization method [{:s}] not implemented'.format(init_type))
+
+
+class SingleDeviceDataParallel(nn.DataParallel):
+    """What the reference returns is `nn.DataParallel(netG)` and callers reach into `.module`
+    (GUI.py:1687,2516).  esr_b200 runs one process per GPU (torch.distributed + NCCL), so the wrapper keeps
+    the DataParallel type and `.module` attribute but always runs the wrapped module on its own device —
+    no replicate / scatter / gather."""
+
+    def __init__(self, module):
+        super(SingleDeviceDataParallel, self).__init__(module, device_ids=[torch.cuda.current_device()])
+
+    def forward(self, *inputs, **kwargs):
+        return self.module(*inputs, **kwargs)
+
+
+def define_G(opt, CEM=None, num_latent_channels=None, **kwargs):
+    gpu_ids = opt['gpu_ids']
+    opt_net = opt['network_G']
+    which_model = opt_net['which_model_G']
+    opt_net['latent_input'] = opt_net['latent_input'] if opt_net['latent_input'] != "None" else None
+    if which_model == 'RRDB_net':
+        latent = (opt_net['latent_input'] + '_' + opt_net['latent_input_domain']) if opt_net['latent_input'] is not None else None
+        netG = arch.RRDBNet(in_nc=opt_net['in_nc'], out_nc=opt_net['out_nc'], nf=opt_net['nf'], nb=opt_net['nb'], gc=opt_net['gc'],
+                            upscale=opt_net['scale'], norm_type=opt_net['norm_type'], act_type='leakyrelu', mode=opt_net['mode'],
+                            upsample_mode='upconv', latent_input=latent, num_latent_channels=num_latent_channels)
+    else:
+        raise NotImplementedError('Generator model [{:s}] not recognized (esr_b200 builds RRDB_net only)'.format(which_model))
+    if opt_net['CEM_arch']:
+        netG = CEM.WrapArchitecture_PyTorch(netG, opt['datasets']['train']['patch_size'] if opt['is_train'] else None)
+    if opt['is_train']:
+        init_weights(netG, init_type='kaiming', scale=0.1)
+    if torch.cuda.is_available():
+        netG = netG.cuda()
+    if gpu_ids:
+        assert torch.cuda.is_available()
+        netG = SingleDeviceDataParallel(netG)
+    return netG
+
+
+def define_D(opt, CEM=None):
+    raise NotImplementedError('esr_b200: Discriminator_VGG_128 (SURVEY 8a-12) is not built yet in this round')
+
+
+def define_F(opt, use_bn=False, **kwargs):
+    raise NotImplementedError('esr_b200: VGGFeatureExtractor (SURVEY 8a-13) is not built yet in this round')

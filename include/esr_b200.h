@@ -142,6 +142,11 @@ int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl,
                    const float* ku_v, const float* ku_h, int ku_len, int rank, int crop,
                    float* out_hr, void* stream);
 
+/* latent map: replicate-pad `pad_hr` (eval mode, CEMnet.py:290-292) then bilinear align_corners=False
+ * resize by 1/s (models/modules/architecture.py:284).  NCHW fp32 in/out. */
+int esr_latent_downscale(const float* z_hr, int n, int c, int hh, int wh, int s, int pad_hr, float* out,
+                         void* stream);
+
 /* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
 

@@ -1,0 +1,158 @@
+"""ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement (functional PyTorch fp32 on explicit state-dict tensors) of the reference's hot path:
+RRDBNet forward, the CEM projection, and the latent packing.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this file; the product path
+(explorable-super-resolution_b200/) never does and has no CPU fallback.
+
+Parity status: PINNED.  The reference has no tests or golden vectors of its own, so the pins are
+outputs of the unmodified reference executed in the build container by oracle/make_golden.py
+(tests/golden/*.npz); tests/test_oracle.py checks this file against every one of them.
+
+Every function cites the reference lines it restates (paths relative to /root/reference/codes)."""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LRELU_SLOPE = 0.2  # models/modules/block.py:10 (act: neg_slope=0.2)
+
+
+def _conv(x, sd, key, act):
+    """conv_block, CNA order: Conv2d(k=3, s=1, zero pad 1, bias) [+ LeakyReLU(0.2)]  (block.py:129-146)."""
+    y = F.conv2d(x, sd[key + '.weight'], sd[key + '.bias'], stride=1, padding=1)
+    return F.leaky_relu(y, LRELU_SLOPE) if act else y
+
+
+def rdb_forward(x, sd, prefix, nf):
+    """ResidualDenseBlock_5C.forward (block.py:230-235): each conv sees the concatenation of the block
+    input (latent channels, if any, in front) and all previous outputs; the 5th conv has no activation in
+    CNA mode (block.py:208-209); result x5*0.2 + x[:, -nf:]."""
+    outs = [x]
+    for i in range(5):
+        outs.append(_conv(torch.cat(outs, 1), sd, '%s.convs.%d.0' % (prefix, i), act=i < 4))
+    return outs[-1] * 0.2 + outs[0][:, -nf:]
+
+
+def rrdb_forward(x, sd, prefix, nf, z):
+    """RRDB.forward (block.py:262-270): the latent channels x[:, :z] are re-concatenated in front of the
+    input of RDB2 and RDB3."""
+    out = rdb_forward(x, sd, prefix + '.RDB1', nf)
+    if z > 0:
+        out = torch.cat([x[:, :z], out], 1)
+    out = rdb_forward(out, sd, prefix + '.RDB2', nf)
+    if z > 0:
+        out = torch.cat([x[:, :z], out], 1)
+    out = rdb_forward(out, sd, prefix + '.RDB3', nf)
+    return out * 0.2 + x[:, -nf:]
+
+
+def rrdbnet_forward(x, sd, nf, nb, upscale=4, z=0, upsample_mode='upconv', prefix=''):
+    """RRDBNet.forward (architecture.py:278-302) for latent_input in {None, 'all_layers_HR_downscaled'}.
+
+    x: [N, z*upscale^2 + 3, h, w].  With a latent, the first z*s^2 channels are a raw memory view of
+    Z[N, z, s*h, s*w] (architecture.py:281-283), bilinearly resized by 1/s (align_corners=False, :284) for the
+    LR layers and used at full resolution by the two HR convs (:297-298); z goes IN FRONT of every conv
+    input except the up-sampling convs (:290-300).  Module indices: 0 fea_conv, 1 ShortcutBlock(nb RRDBs +
+    LR_conv), 2.. upsamplers, then HR_conv0, LeakyReLU, HR_conv1 (:271-273)."""
+    p = prefix + 'model.'
+    n_up = 1 if upscale == 3 else int(math.log(upscale, 2))
+    if z > 0:
+        lat, x = torch.split(x, [x.size(1) - 3, 3], dim=1)
+        z_hr = lat.reshape(lat.size(0), -1, upscale * lat.size(2), upscale * lat.size(3))
+        z_lr = F.interpolate(z_hr, scale_factor=1 / upscale, mode='bilinear', align_corners=False, recompute_scale_factor=False)
+        x = torch.cat([z_lr, x], 1)
+    fea = _conv(x, sd, p + '0', act=False)
+    # ShortcutBlock (block.py:85-97): input is cat([z, fea]); z re-concatenated before every sub-module but the first
+    out = torch.cat([z_lr, fea], 1) if z > 0 else fea
+    for b in range(nb):
+        if b > 0 and z > 0:
+            out = torch.cat([z_lr, out], 1)
+        out = rrdb_forward(out, sd, p + '1.sub.%d' % b, nf, z)
+    if z > 0:
+        out = torch.cat([z_lr, out], 1)
+    out = _conv(out, sd, p + '1.sub.%d' % nb, act=False)  # LR_conv
+    out = fea + out
+    idx = 2
+    for _ in range(n_up):
+        if upsample_mode == 'upconv':  # block.py:299-309: nearest x2 -> conv -> LeakyReLU
+            out = F.interpolate(out, scale_factor=3 if upscale == 3 else 2, mode='nearest')
+            out = _conv(out, sd, p + '%d.1' % idx, act=True)
+        else:  # block.py:278-291: conv -> PixelShuffle -> LeakyReLU
+            out = F.leaky_relu(F.pixel_shuffle(_conv(out, sd, p + '%d.0' % idx, act=False), 2), LRELU_SLOPE)
+        idx += 1
+    if z > 0:
+        out = torch.cat([z_hr, out], 1)
+    out = _conv(out, sd, p + '%d' % idx, act=True)  # HR_conv0
+    if z > 0:
+        out = torch.cat([z_hr, out], 1)
+    return _conv(out, sd, p + '%d' % (idx + 2), act=False)  # HR_conv1
+
+
+# ------------------------------------------------------------------------------------------------ CEM
+def _depthwise(x, k2d, pad):
+    """Filter_Layer (CEMnet.py:243-252): replicate-pad then depth-wise correlation with a fixed 2-D filter."""
+    c = x.size(1)
+    w = torch.as_tensor(np.ascontiguousarray(k2d), dtype=torch.float32).view(1, 1, *k2d.shape).repeat(c, 1, 1, 1)
+    return F.conv2d(F.pad(x, (pad[1], pad[1], pad[0], pad[0]), mode='replicate'), w, groups=c)
+
+
+def cem_down(g, ds_kernel, s, pre):
+    """DownscaleOP (CEMnet.py:265,270-275): replicate-pad floor(k/2), correlate with rot90(ds_kernel, 2), keep
+    sample `pre` of every s x s cell."""
+    k = np.rot90(ds_kernel, 2)
+    y = _depthwise(g, k, [k.shape[0] // 2, k.shape[1] // 2])
+    return y[:, :, pre::s, pre::s]
+
+
+def cem_inv(e, inv_hTh):
+    """Conv_LR_with_Inv_hTh_OP (CEMnet.py:262-264)."""
+    return _depthwise(e, inv_hTh, [inv_hTh.shape[0] // 2, inv_hTh.shape[1] // 2])
+
+
+def cem_up(f, ds_kernel, s, pre):
+    """Upscale_OP (CEMnet.py:266-272): zero-stuff (value at offset `pre` of each cell), replicate-pad
+    floor(k/2), correlate with ds_kernel * s^2."""
+    n, c, h, w = f.shape
+    stuffed = torch.zeros(n, c, h * s, w * s, dtype=f.dtype)
+    stuffed[:, :, pre::s, pre::s] = f
+    k = ds_kernel * s ** 2
+    return _depthwise(stuffed, k, [k.shape[0] // 2, k.shape[1] // 2])
+
+
+def cem_project(x_lr, g, ds_kernel, inv_hTh, s, pre):
+    """CEM_PyTorch.forward, consistency part (CEMnet.py:303-310):
+    ortho = Up(Inv(x));  NS = G - Up(Inv(Down(G)));  out = ortho + NS."""
+    ortho = cem_up(cem_inv(x_lr, inv_hTh), ds_kernel, s, pre)
+    ns = g - cem_up(cem_inv(cem_down(g, ds_kernel, s, pre), inv_hTh), ds_kernel, s, pre)
+    return ortho + ns
+
+
+def cem_wrapped_forward(x, sd, ds_kernel, inv_hTh, s, pre, margin_lr, eval_mode, nf, nb, z=0, upsample_mode='upconv'):
+    """CEM_PyTorch.forward around an RRDBNet (CEMnet.py:283-311).  eval mode (`pre_pad`): replicate-pad the LR
+    image by margin_lr and the HR view of the latent by s*margin_lr (:286-295), crop s*margin_lr at the end (:311)."""
+    gp = 'generated_image_model.'
+    if eval_mode:
+        if z > 0:
+            lat, img = torch.split(x, [x.size(1) - 3, 3], dim=1)
+            z_hr = lat.reshape(lat.size(0), -1, s * lat.size(2), s * lat.size(3))
+            img = F.pad(img, (margin_lr,) * 4, mode='replicate')
+            z_hr = F.pad(z_hr, (s * margin_lr,) * 4, mode='replicate')
+            lat = z_hr.reshape(z_hr.size(0), z_hr.size(1) * s * s, img.size(2), img.size(3))
+            x = torch.cat([lat, img], 1)
+        else:
+            x = F.pad(x, (margin_lr,) * 4, mode='replicate')
+    g = rrdbnet_forward(x, sd, nf, nb, upscale=s, z=z, upsample_mode=upsample_mode, prefix=gp)
+    out = cem_project(x[:, -3:], g, ds_kernel, inv_hTh, s, pre)
+    if eval_mode:
+        m = s * margin_lr
+        out = out[:, :, m:-m, m:-m]
+    return out
+
+
+def pack_latent(z_hr, x_lr, s):
+    """SRRaGANModel.Prepare_Input (SRRaGAN_model.py:230-236): Z[B,c,sH,sW] is re-viewed (raw memory) as
+    [B, c*s^2, H, W] and concatenated in front of the LR image."""
+    b, c, hh, wh = z_hr.shape
+    return torch.cat([z_hr.contiguous().view(b, c * s * s, hh // s, wh // s), x_lr], 1)

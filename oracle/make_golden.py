@@ -1,0 +1,139 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/codes, CPU, fp32) on
+seeded inputs.  Run in the build container only (`python oracle/make_golden.py`); the fixtures are committed.
+Weights and inputs are rounded to fp16-representable fp32 values BEFORE the reference runs, so that a 16-bit
+tensor-core path sees exactly the same operands at the network boundary."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+import torch  # noqa: E402
+import models.modules.architecture as arch  # noqa: E402
+import models.networks as networks  # noqa: E402
+from CEM.CEMnet import CEMnet, Get_CEM_Conf, CEM_downsampler  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(8)
+
+
+def q16(t):
+    return t.half().float()
+
+
+def build_rrdb(seed, scale=0.5, bias_std=0.05, **kw):
+    torch.manual_seed(seed)
+    net = arch.RRDBNet(**kw)
+    with contextlib.redirect_stdout(io.StringIO()):
+        networks.init_weights(net, 'kaiming', scale=scale)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith('bias'):
+                p.normal_(0, bias_std)
+            p.copy_(q16(p))
+    return net.eval()
+
+
+def sd_np(net, prefix=''):
+    return {prefix + k: v.detach().numpy().astype(np.float16) for k, v in net.state_dict().items() if 'Filter_OP' not in k}
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print('%-28s %8.1f KiB' % (name, os.path.getsize(path) / 1024), {k: getattr(v, 'shape', v) for k, v in arrays.items() if not k.startswith('w:')})
+
+
+def main():
+    g = torch.Generator().manual_seed(1234)
+    rnd = lambda *s: q16(torch.rand(*s, generator=g))
+
+    # A. plain RRDBNet x4
+    net = build_rrdb(1, in_nc=3, out_nc=3, nf=32, nb=1, upscale=4, num_latent_channels=0)
+    x = rnd(2, 3, 24, 20)
+    with torch.no_grad():
+        y = net(x)
+    save('rrdb_plain_x4', x=x.numpy(), y=y.numpy(), cfg=np.array([32, 1, 4, 0]), **{'w:' + k: v for k, v in sd_np(net).items()})
+
+    # B. latent RRDBNet x4 (all_layers, HR_downscaled, 3 channels)
+    netz = build_rrdb(2, in_nc=3, out_nc=3, nf=32, nb=1, upscale=4, latent_input='all_layers_HR_downscaled', num_latent_channels=3)
+    z_hr = q16(torch.rand(1, 3, 64, 48, generator=g) * 2 - 1)
+    x_lr = rnd(1, 3, 16, 12)
+    xz = torch.cat([z_hr.contiguous().view(1, 48, 16, 12), x_lr], 1)
+    with torch.no_grad():
+        yz = netz(xz)
+    save('rrdb_latent_x4', x=xz.numpy(), y=yz.numpy(), cfg=np.array([32, 1, 4, 3]), **{'w:' + k: v for k, v in sd_np(netz).items()})
+
+    # C. x2, x8 and pixelshuffle variants (small)
+    for name, kw in (('rrdb_plain_x2', dict(upscale=2)), ('rrdb_plain_x8', dict(upscale=8)),
+                     ('rrdb_pixelshuffle_x4', dict(upscale=4, upsample_mode='pixelshuffle'))):
+        n2 = build_rrdb(3, in_nc=3, out_nc=3, nf=32, nb=1, num_latent_channels=0, **kw)
+        x2 = rnd(1, 3, 12, 10)
+        with torch.no_grad():
+            y2 = n2(x2)
+        save(name, x=x2.numpy(), y=y2.numpy(), cfg=np.array([32, 1, kw['upscale'], 0]), **{'w:' + k: v for k, v in sd_np(n2).items()})
+
+    # D. CEM alone (given generated image), train and eval mode, scales 2/3/4; plus the individual filters
+    for s in (2, 3, 4):
+        cem = CEMnet(Get_CEM_Conf(s))
+        mod = cem.WrapArchitecture_PyTorch(None, None)
+        xl = rnd(2, 3, 18, 22)
+        gi = torch.rand(2, 3, 18 * s, 22 * s, generator=g)
+        with torch.no_grad():
+            mod.train()
+            out_train = mod([xl, gi])
+            mod.eval()
+            out_eval = mod([xl, gi])
+            down = mod.DownscaleOP(gi)
+            inv = mod.Conv_LR_with_Inv_hTh_OP(xl)
+            up = mod.Upscale_OP(xl)
+        save('cem_x%d' % s, x_lr=xl.numpy(), g=gi.numpy(), out_train=out_train.numpy(), out_eval=out_eval.numpy(), down=down.numpy(),
+             inv=inv.numpy(), up=up.numpy(), ds_kernel=cem.ds_kernel, inv_hTh=cem.inv_hTh,
+             margins=np.array([cem.invalidity_margins_LR, cem.invalidity_margins_HR, cem.ds_kernel_invalidity_half_size_LR,
+                               cem.inv_hTh_invalidity_half_size]))
+    ds = CEM_downsampler(4)
+    hr = torch.rand(1, 3, 64, 80, generator=g)
+    with torch.no_grad():
+        save('cem_downsampler_x4', hr=hr.numpy(), lr=ds(hr).numpy())
+
+    # E. CEM-wrapped generators: train mode (plain) and eval mode (latent, padded path)
+    cem = CEMnet(Get_CEM_Conf(4))
+    wrapped = cem.WrapArchitecture_PyTorch(net, None)
+    with torch.no_grad():
+        wrapped.train()
+        yt = wrapped(x)
+        wrapped.eval()
+        ye = wrapped(x)
+    save('cem_rrdb_plain_x4', x=x.numpy(), y_train=yt.numpy(), y_eval=ye.numpy())
+    cemz = CEMnet(Get_CEM_Conf(4))
+    wz = cemz.WrapArchitecture_PyTorch(netz, None)
+    with torch.no_grad():
+        wz.train()
+        yzt = wz(xz)
+        wz.eval()
+        yze = wz(xz)
+    save('cem_rrdb_latent_x4', x=xz.numpy(), y_train=yzt.numpy(), y_eval=yze.numpy())
+
+    # F. BASELINE config 1 (nf=32, nb=4, 1x3x128x128 -> 512x512): weights from the reference's own seeded
+    # training init (kaiming x0.1, networks.py:118-119) are too big to store; keep the seed and a digest.
+    torch.manual_seed(0)
+    c1 = arch.RRDBNet(3, 3, 32, 4, upscale=4, num_latent_channels=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        networks.init_weights(c1, 'kaiming', scale=0.1)
+    xc1 = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        yc1 = c1(xc1)
+    wsum = np.array([float(v.double().sum()) for v in c1.state_dict().values()])
+    save('c1_seeded', x=xc1.numpy(), y_crop=yc1[:, :, 200:264, 200:264].numpy(), y_mean=np.array(float(yc1.double().mean())),
+         y_absmax=np.array(float(yc1.abs().max())), y_rows=yc1[0, :, ::64, :].numpy(), wsum=wsum)
+
+
+if __name__ == '__main__':
+    main()
