@@ -4,8 +4,9 @@
 //
 // Data layout in HBM: planar-8 ("planes")  [N][C/8][H][W][8] 16-bit.  One pixel of one plane is exactly
 // one 16-byte row of a no-swizzle K-major UMMA core matrix, so
-//   * a TMA box (8ch, P px, R+2 rows, kcp planes) lands in shared memory as kcp halo planes whose pixels
-//     sit at a 16-byte pitch;
+//   * a TMA box (8ch*P px as ONE 512-byte inner dimension, R+2 rows, kcp planes) lands in shared memory as kcp
+//     halo planes whose pixels sit at a 16-byte pitch (a 16-byte inner box would make TMA fetch a whole 32-byte
+//     sector per pixel: measured 2x over-fetch on the L2->SM path);
 //   * a 128-row MMA operand tile is 128 consecutive pixels of the flattened (row pitch P) halo plane, and
 //     the nine filter taps are nine *address offsets* ((dy*P + dx) * 16 B) into the same halo tile — the
 //     activation tile is fetched from L2 once per CTA tile, not once per tap;
@@ -13,7 +14,7 @@
 // Columns tx >= P-2 of each flattened row are junk (they wrap into the next row) and are discarded by the
 // epilogue: M efficiency (P-2)/P.
 //
-// CTA = 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.
+// CTA = 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue.
 // Persistent over (tile, n-block) work items; TMEM accumulators are double buffered so the epilogue of
 // item i overlaps the MMAs of item i+1.
 #pragma once
@@ -23,7 +24,7 @@
 
 namespace esr {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemHeader = 1024;  // barriers + tmem pointer
 constexpr uint32_t kASlack = 128;       // junk rows of the last M tile may read a few pixels past the last plane
@@ -42,6 +43,8 @@ struct ConvParams {
   uint32_t a_alloc;       // a_bytes + slack, multiple of 128
   uint32_t stage_bytes;
   int stages;
+  int w_resident;         // 1: all K chunks of the weights are loaded once per CTA and stay in shared memory
+  uint32_t w_bytes;       // nchunks*b_bytes (resident mode)
   uint32_t idesc;
   uint32_t tmem_cols;
   const uint8_t* wts;
@@ -51,7 +54,7 @@ struct ConvParams {
   int dtype;
   int lrelu;
   float slope, alpha;
-  const float* res1; int res1_pt, res1_po; float beta1;
+  const void* res1; int res1_is16, res1_pt, res1_po; float beta1;
   const float* res2; int res2_pt, res2_po; float beta2;
   uint16_t* out16; int out16_pt, out16_po, out16_up2, out16_ps;
   float* out32; int out32_pt, out32_po;
@@ -68,6 +71,26 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
   }
 }
 
+// P (tile pitch), KCP (planes per K chunk) and NBN (MMA N) are compile-time so that every operand descriptor
+// of the 9 x KCP/2 MMAs of a (chunk, M tile) is the chunk's base descriptor plus an immediate: the single
+// issuing thread spends one 64-bit add per operand per MMA instead of rebuilding descriptors.
+__device__ __forceinline__ void unpack8(const uint4& q, int dtype, float (&a)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (dtype == 0) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[k]);
+      const float2 f = __half22float2(h);
+      a[2 * k] = f.x; a[2 * k + 1] = f.y;
+    } else {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      const float2 f = __bfloat1622float2(h);
+      a[2 * k] = f.x; a[2 * k + 1] = f.y;
+    }
+  }
+}
+
+template <int P, int KCP, int NBN>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -78,7 +101,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t bar_tfull = smem_base + 16 * kMaxStages;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t stage0 = smem_base + kSmemHeader;
+  const uint32_t bar_w = tmem_slot + 8;
+  const uint32_t wres = smem_base + kSmemHeader;                       // resident weights (if any)
+  const uint32_t stage0 = wres + (p.w_resident ? p.w_bytes : 0u);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -92,8 +117,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);
+      mbar_init(bar_tempty + 8 * b, 8);
     }
+    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -113,6 +139,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      if (p.w_resident && (int)blockIdx.x < total_items) {
+        mbar_expect_tx(bar_w, p.w_bytes);
+        for (int c = 0; c < p.nchunks; ++c) bulk_load(wres + c * p.b_bytes, p.wts + (size_t)c * p.b_bytes, p.b_bytes, bar_w);
+      }
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int nblk = item / p.num_tiles;
         const int tile = item - nblk * p.num_tiles;
@@ -125,9 +155,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
           const uint32_t sa = stage0 + s * p.stage_bytes;
-          mbar_expect_tx(bar_full + 8 * s, p.a_bytes + p.b_bytes);
-          tma_load_5d(sa, &tmA, bar_full + 8 * s, 0, x0 - 1, y0 - 1, p.in_plane_off + c * p.kcp, img);
-          bulk_load(sa + p.a_alloc, wsrc + (size_t)c * p.b_bytes, p.b_bytes, bar_full + 8 * s);
+          mbar_expect_tx(bar_full + 8 * s, p.w_resident ? p.a_bytes : p.a_bytes + p.b_bytes);
+          tma_load_4d(sa, &tmA, bar_full + 8 * s, (x0 - 1) * 8, y0 - 1, p.in_plane_off + c * p.kcp, img);
+          if (!p.w_resident) bulk_load(sa + p.a_alloc, wsrc + (size_t)c * p.b_bytes, p.b_bytes, bar_full + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -137,7 +167,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
-    const uint32_t b_lbo = (uint32_t)p.nb_n * 16u;
+    // descriptor templates: LBO/SBO/version fields; the 14-bit start-address field is added per use
+    const uint64_t adesc_t = make_smem_desc(0u, p.plane_stride, 128u);
+    const uint64_t bdesc_t = make_smem_desc(0u, (uint32_t)NBN * 16u, 128u);
+    const uint64_t a_kstep = (uint64_t)((2u * p.plane_stride) >> 4);  // two planes = one K=16 step
+    if (p.w_resident && (int)blockIdx.x < total_items) mbar_wait(bar_w, 0u, 5u);
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u, 2u);
@@ -145,20 +179,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int c = 0; c < p.nchunks; ++c) {
         mbar_wait(bar_full + 8 * s, ph, 3u);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = stage0 + s * p.stage_bytes;
-          const uint32_t sb = sa + p.a_alloc;
+          const uint64_t ad0 = adesc_t + (uint64_t)(sa >> 4);
+          const uint64_t bd0 = bdesc_t + (uint64_t)((p.w_resident ? wres + c * p.b_bytes : sa + p.a_alloc) >> 4);
+          const uint32_t acc_first = c != 0 ? 1u : 0u;
           for (int t = 0; t < p.MT; ++t) {
-            const uint32_t d = tmem_base + (uint32_t)((buf * p.MT + t) * p.nb_n);
+            const uint32_t d = tmem_base + (uint32_t)((buf * p.MT + t) * NBN);
+            const uint64_t at = ad0 + (uint64_t)(t * 128);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              const uint32_t a0 = sa + (uint32_t)(t * 128 + dy * p.P + dx) * 16u;
-              const uint32_t b0 = sb + (uint32_t)(tap * p.kcp * p.nb_n) * 16u;
-              for (int j = 0; j < (p.kcp >> 1); ++j) {
-                const uint64_t ad = make_smem_desc(a0 + (uint32_t)(2 * j) * p.plane_stride, p.plane_stride, 128u);
-                const uint64_t bd = make_smem_desc(b0 + (uint32_t)(2 * j) * b_lbo, b_lbo, 128u);
-                umma_f16(d, ad, bd, p.idesc, (c | tap | j) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < KCP / 2; ++j) {
+                const uint64_t ad = at + (uint64_t)((tap / 3) * P + (tap % 3)) + (uint64_t)j * a_kstep;
+                const uint64_t bd = bd0 + (uint64_t)((tap * KCP + 2 * j) * NBN);
+                umma_f16(d, ad, bd, p.idesc, (tap | j) != 0 ? 1u : acc_first);
               }
             }
           }
@@ -170,8 +205,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int wq = warp & 3;  // TMEM lane quarter this warp may touch
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter; they alternate over the M tiles of an item.  Per (row, unit of UW
+    // channels) every global load (residuals, bias) is issued before the first store so that a thread
+    // keeps UW/8 .. 3*UW/8 128-bit loads in flight.
+    constexpr int UW = (NBN % 32 == 0) ? 32 : 16;
+    const int wq = warp & 3;            // TMEM lane quarter this warp may touch
+    const int eh = (warp - 2) >> 2;     // which half of the M tiles this warp takes
     int it = 0;
     const size_t hw = (size_t)p.h * p.w;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -185,35 +225,62 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int x0 = txi * p.TW, y0 = tyi * p.R;
       mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u, 4u);
       tc_fence_after();
-      for (int t = 0; t < p.MT; ++t) {
+      for (int t = (p.MT > 1 ? eh : 0); t < (p.MT > 1 ? p.MT : 1 - eh); t += 2) {
         const int q = t * 128 + wq * 32 + lane;
-        const int ty = q / p.P;
-        const int tx = q - ty * p.P;
+        const int ty = q / P;
+        const int tx = q - ty * P;
         const int y = y0 + ty, x = x0 + tx;
         const bool valid = (tx < p.TW) && (x < p.w) && (y < p.h);
         const size_t pix = (size_t)y * p.w + x;
-        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * p.MT + t) * p.nb_n);
-        for (int cb = 0; cb < p.nb_n; cb += 16) {
-          uint32_t r[16];
-          tmem_ld16(trow + cb, r);
-          tc_wait_ld();
-          if (valid) {
+        const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * p.MT + t) * NBN);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int ch0 = nblk * p.nb_n + cb + hh * 8;  // first conv output channel of this group of 8
+        for (int u = 0; u < NBN / UW; ++u) {
+          uint32_t r[UW / 16][16];
+#pragma unroll
+          for (int k = 0; k < UW / 16; ++k) tmem_ld16(trow + u * UW + k * 16, r[k]);
+          const int chu = nblk * NBN + u * UW;   // first conv output channel of this unit
+          const int gu = chu >> 3;
+          constexpr int G = UW / 8;              // groups of 8 channels in a unit
+          uint4 q1[G];                           // residual 1 as 16-bit planes
+          float4 f1[G][2], f2[G][2], bb[G][2];
+          const bool on = valid;
+          if (on) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              if (chu + g * 8 < p.cout) {
+                bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
+                bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+                if (p.res1) {
+                  if (p.res1_is16) {
+                    q1[g] = __ldg(reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8));
+                  } else {
+                    const float4* rp = reinterpret_cast<const float4*>(
+                        reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8);
+                    f1[g][0] = __ldg(rp); f1[g][1] = __ldg(rp + 1);
+                  }
+                }
+                if (p.res2) {
+                  const float4* rp = reinterpret_cast<const float4*>(
+                      p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gu + g) * hw + pix) * 8);
+                  f2[g][0] = __ldg(rp); f2[g][1] = __ldg(rp + 1);
+                }
+              }
+            }
+          }
+          tc_wait_ld();
+          if (on) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int ch0 = chu + g * 8;
               if (ch0 >= p.cout) continue;
-              const int g = ch0 >> 3;
+              const int gp = gu + g;
+              const uint32_t* rg = &r[g / 2][(g & 1) * 8];
               float v[8];
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + 4));
-              v[0] = __uint_as_float(r[hh * 8 + 0]) + b0.x;
-              v[1] = __uint_as_float(r[hh * 8 + 1]) + b0.y;
-              v[2] = __uint_as_float(r[hh * 8 + 2]) + b0.z;
-              v[3] = __uint_as_float(r[hh * 8 + 3]) + b0.w;
-              v[4] = __uint_as_float(r[hh * 8 + 4]) + b1.x;
-              v[5] = __uint_as_float(r[hh * 8 + 5]) + b1.y;
-              v[6] = __uint_as_float(r[hh * 8 + 6]) + b1.z;
-              v[7] = __uint_as_float(r[hh * 8 + 7]) + b1.w;
+              v[0] = __uint_as_float(rg[0]) + bb[g][0].x; v[1] = __uint_as_float(rg[1]) + bb[g][0].y;
+              v[2] = __uint_as_float(rg[2]) + bb[g][0].z; v[3] = __uint_as_float(rg[3]) + bb[g][0].w;
+              v[4] = __uint_as_float(rg[4]) + bb[g][1].x; v[5] = __uint_as_float(rg[5]) + bb[g][1].y;
+              v[6] = __uint_as_float(rg[6]) + bb[g][1].z; v[7] = __uint_as_float(rg[7]) + bb[g][1].w;
               if (p.lrelu) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * p.slope;
@@ -221,22 +288,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
               if (p.res1) {
-                const float4* rp = reinterpret_cast<const float4*>(
-                    p.res1 + (((size_t)img * p.res1_pt + p.res1_po + g) * hw + pix) * 8);
-                const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                v[0] += p.beta1 * r0.x; v[1] += p.beta1 * r0.y; v[2] += p.beta1 * r0.z; v[3] += p.beta1 * r0.w;
-                v[4] += p.beta1 * r1.x; v[5] += p.beta1 * r1.y; v[6] += p.beta1 * r1.z; v[7] += p.beta1 * r1.w;
+                float a[8];
+                if (p.res1_is16) {
+                  unpack8(q1[g], p.dtype, a);
+                } else {
+                  a[0] = f1[g][0].x; a[1] = f1[g][0].y; a[2] = f1[g][0].z; a[3] = f1[g][0].w;
+                  a[4] = f1[g][1].x; a[5] = f1[g][1].y; a[6] = f1[g][1].z; a[7] = f1[g][1].w;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = fmaf(p.beta1, a[k], v[k]);
               }
               if (p.res2) {
-                const float4* rp = reinterpret_cast<const float4*>(
-                    p.res2 + (((size_t)img * p.res2_pt + p.res2_po + g) * hw + pix) * 8);
-                const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                v[0] += p.beta2 * r0.x; v[1] += p.beta2 * r0.y; v[2] += p.beta2 * r0.z; v[3] += p.beta2 * r0.w;
-                v[4] += p.beta2 * r1.x; v[5] += p.beta2 * r1.y; v[6] += p.beta2 * r1.z; v[7] += p.beta2 * r1.w;
+                v[0] = fmaf(p.beta2, f2[g][0].x, v[0]); v[1] = fmaf(p.beta2, f2[g][0].y, v[1]);
+                v[2] = fmaf(p.beta2, f2[g][0].z, v[2]); v[3] = fmaf(p.beta2, f2[g][0].w, v[3]);
+                v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
+                v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
               }
               if (p.out32) {
                 float4* op = reinterpret_cast<float4*>(
-                    p.out32 + (((size_t)img * p.out32_pt + p.out32_po + g) * hw + pix) * 8);
+                    p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gp) * hw + pix) * 8);
                 op[0] = make_float4(v[0], v[1], v[2], v[3]);
                 op[1] = make_float4(v[4], v[5], v[6], v[7]);
               }
@@ -256,11 +326,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   o.w = pack2(v[6], v[7], p.dtype);
                   if (!p.out16_up2) {
                     uint4* op = reinterpret_cast<uint4*>(
-                        p.out16 + (((size_t)img * p.out16_pt + p.out16_po + g) * hw + pix) * 8);
+                        p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * hw + pix) * 8);
                     *op = o;
                   } else {
                     const size_t w2 = 2 * (size_t)p.w;
-                    uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + g) * (4 * hw) +
+                    uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * (4 * hw) +
                                                  (size_t)(2 * y) * w2 + 2 * x) * 8;
                     uint4* o0 = reinterpret_cast<uint4*>(basep);
                     uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
@@ -268,16 +338,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   }
                 } else {
                   // pixel shuffle (block.py:287): conv channel c*r*r + i*r + j -> channel c at (r*y+i, r*x+j).
-                  const int rr = p.out16_ps, r2 = rr * rr;
-                  const size_t wr = (size_t)rr * p.w;
+                  const int rs = p.out16_ps, r2 = rs * rs;
+                  const size_t wr = (size_t)rs * p.w;
 #pragma unroll
                   for (int k = 0; k < 8; ++k) {
                     const int ch = ch0 + k;
                     if (ch >= p.cout) break;
                     const int oc = ch / r2, ij = ch - oc * r2;
-                    const int i = ij / rr, j = ij - i * rr;
+                    const int i = ij / rs, j = ij - i * rs;
                     uint16_t* op = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + (oc >> 3)) * (r2 * hw) +
-                                              (size_t)(rr * y + i) * wr + (rr * x + j)) * 8 + (oc & 7);
+                                              (size_t)(rs * y + i) * wr + (rs * x + j)) * 8 + (oc & 7);
                     const uint32_t pk = pack2(v[k], 0.f, p.dtype);
                     *op = (uint16_t)(pk & 0xFFFFu);
                   }

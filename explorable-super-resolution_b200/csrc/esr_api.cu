@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <set>
 
 #include "aux_kernels.cuh"
 #include "conv3x3_tc.cuh"
@@ -67,6 +68,24 @@ int num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+typedef void (*ConvKernelFn)(const CUtensorMap, const esr::ConvParams);
+
+template <int P, int KCP>
+ConvKernelFn select_n(int nb_n) {
+  switch (nb_n) {
+    case 16: return esr::conv3x3_tc_kernel<P, KCP, 16>;
+    case 32: return esr::conv3x3_tc_kernel<P, KCP, 32>;
+    case 48: return esr::conv3x3_tc_kernel<P, KCP, 48>;
+    case 64: return esr::conv3x3_tc_kernel<P, KCP, 64>;
+  }
+  return nullptr;
+}
+ConvKernelFn select_conv_kernel(int P, int kcp, int nb_n) {
+  if (P == 32 && kcp == 4) return select_n<32, 4>(nb_n);
+  if (P == 32 && kcp == 2) return select_n<32, 2>(nb_n);
+  return nullptr;
 }
 
 int nblock_for(int cout, int* cout_pad) {
@@ -166,7 +185,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.n_blocks = cout_pad / p.nb_n;
   p.n = a->n; p.h = a->h; p.w = a->w;
   p.P = a->tile_p ? a->tile_p : 32;
-  if (p.P != 32 && p.P != 64) return fail(ESR_ERR_INVALID, "conv3x3: tile_p must be 32 or 64");
+  if (p.P != 32) return fail(ESR_ERR_INVALID, "conv3x3: tile_p must be 32 (the 8*P-element TMA inner box is limited to 256 elements)");
   p.TW = p.P - 2;
   p.MT = a->tile_mt ? a->tile_mt : 4;
   if (p.MT != 1 && p.MT != 2 && p.MT != 4) return fail(ESR_ERR_INVALID, "conv3x3: tile_mt must be 1, 2 or 4");
@@ -183,14 +202,18 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.a_bytes = p.kcp * p.plane_stride;
   p.b_bytes = 9u * p.kcp * p.nb_n * 16u;
   p.a_alloc = (p.a_bytes + esr::kASlack + 127u) & ~127u;
-  p.stage_bytes = p.a_alloc + ((p.b_bytes + 127u) & ~127u);
   const uint32_t smem_max = 232448u;
-  int stages = (int)((smem_max - esr::kSmemHeader - 128u) / p.stage_bytes);
+  // weights stay resident in shared memory when all K chunks fit next to >= 3 activation stages
+  p.w_bytes = (uint32_t)p.nchunks * p.b_bytes;
+  p.w_resident = (p.n_blocks == 1 && esr::kSmemHeader + 128u + p.w_bytes + 3u * p.a_alloc <= smem_max) ? 1 : 0;
+  p.stage_bytes = p.w_resident ? p.a_alloc : p.a_alloc + ((p.b_bytes + 127u) & ~127u);
+  const uint32_t fixed = esr::kSmemHeader + 128u + (p.w_resident ? p.w_bytes : 0u);
+  int stages = (int)((smem_max - fixed) / p.stage_bytes);
   if (stages > esr::kMaxStages) stages = esr::kMaxStages;
   if (stages > p.nchunks * 4) stages = p.nchunks * 4;  // no point in more buffers than a few items' worth
   if (stages < 2) return fail(ESR_ERR_INVALID, "conv3x3: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
-  const uint32_t smem_bytes = esr::kSmemHeader + 128u + (uint32_t)stages * p.stage_bytes;
+  const uint32_t smem_bytes = fixed + (uint32_t)stages * p.stage_bytes;
   // instruction descriptor: D=f32, A/B = f16|bf16, K-major both, N, M=128
   p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | ((uint32_t)(p.nb_n >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
@@ -203,35 +226,40 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.cout = a->cout;
   p.dtype = a->dtype;
   p.lrelu = a->lrelu; p.slope = a->slope; p.alpha = a->alpha;
-  p.res1 = a->res1; p.res1_pt = a->res1_planes_total; p.res1_po = a->res1_plane_off; p.beta1 = a->beta1;
+  p.res1 = a->res1; p.res1_is16 = a->res1_is16; p.res1_pt = a->res1_planes_total; p.res1_po = a->res1_plane_off; p.beta1 = a->beta1;
   p.res2 = a->res2; p.res2_pt = a->res2_planes_total; p.res2_po = a->res2_plane_off; p.beta2 = a->beta2;
   p.out16 = (uint16_t*)a->out16; p.out16_pt = a->out16_planes_total; p.out16_po = a->out16_plane_off;
   p.out16_up2 = a->out16_up2; p.out16_ps = a->out16_pixel_shuffle;
   p.out32 = a->out32; p.out32_pt = a->out32_planes_total; p.out32_po = a->out32_plane_off;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c;
 
-  // TMA descriptor over the input planes: dims (8ch, W, H, planes, N), box (8, P, R+2, kcp, 1)
+  // TMA descriptor over the input planes: dims (8ch*W, H, planes, N), box (8*P, R+2, kcp, 1).  A pixel row of a
+  // plane is one contiguous run, so (channel-in-plane, x) is a single 512-byte inner box dimension.
   CUtensorMap tm;
-  cuuint64_t gdim[5] = {8, (cuuint64_t)a->w, (cuuint64_t)a->h, (cuuint64_t)a->in_planes_total, (cuuint64_t)a->n};
-  cuuint64_t gstr[4] = {16, (cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16,
-                        (cuuint64_t)a->w * a->h * 16 * a->in_planes_total};
-  cuuint32_t box[5] = {8, (cuuint32_t)p.P, (cuuint32_t)(p.R + 2), (cuuint32_t)p.kcp, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<void*>(a->in), gdim, gstr, box, estr,
+  cuuint64_t gdim[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->in_planes_total, (cuuint64_t)a->n};
+  cuuint64_t gstr[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->in_planes_total};
+  cuuint32_t box[4] = {(cuuint32_t)p.P * 8, (cuuint32_t)(p.R + 2), (cuuint32_t)p.kcp, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->in), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
-    attr_err = cudaFuncSetAttribute(esr::conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-  });
-  if (attr_err != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-
+  ConvKernelFn kern = select_conv_kernel(p.P, p.kcp, p.nb_n);
+  if (!kern) return fail(ESR_ERR_INVALID, "conv3x3: no kernel instance for P=%d kcp=%d N=%d", p.P, p.kcp, p.nb_n);
+  {
+    static std::mutex mu;
+    static std::set<const void*> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count((const void*)kern)) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      if (e != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      done.insert((const void*)kern);
+    }
+  }
   int grid = p.num_tiles * p.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  esr::conv3x3_tc_kernel<<<grid, esr::kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  kern<<<grid, esr::kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;

@@ -24,7 +24,7 @@ class ConvArgs(C.Structure):
         ("in_", C.c_void_p), ("in_planes_total", C.c_int), ("in_plane_off", C.c_int), ("cin_planes", C.c_int),
         ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("cout", C.c_int), ("cout_pad", C.c_int), ("kcp", C.c_int),
         ("lrelu", C.c_int), ("slope", C.c_float), ("alpha", C.c_float),
-        ("res1", C.c_void_p), ("res1_planes_total", C.c_int), ("res1_plane_off", C.c_int), ("beta1", C.c_float),
+        ("res1", C.c_void_p), ("res1_is16", C.c_int), ("res1_planes_total", C.c_int), ("res1_plane_off", C.c_int), ("beta1", C.c_float),
         ("res2", C.c_void_p), ("res2_planes_total", C.c_int), ("res2_plane_off", C.c_int), ("beta2", C.c_float),
         ("out16", C.c_void_p), ("out16_planes_total", C.c_int), ("out16_plane_off", C.c_int),
         ("out16_up2", C.c_int), ("out16_pixel_shuffle", C.c_int),

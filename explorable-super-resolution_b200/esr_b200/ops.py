@@ -79,8 +79,9 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     a.cout, a.cout_pad, a.kcp = pc.cout, pc.cout_pad, pc.kcp
     a.lrelu, a.slope, a.alpha = int(lrelu), slope, alpha
     if res1 is not None:
-        assert res1.dtype == torch.float32 and tuple(res1.shape[2:]) == (h, w, 8) and res1.shape[0] == n
+        assert res1.dtype in (torch.float32, pc.dtype) and tuple(res1.shape[2:]) == (h, w, 8) and res1.shape[0] == n
         a.res1, a.res1_planes_total, a.res1_plane_off, a.beta1 = res1.data_ptr(), res1.shape[1], res1_off, beta1
+        a.res1_is16 = int(res1.dtype != torch.float32)
     if res2 is not None:
         assert res2.dtype == torch.float32 and tuple(res2.shape[2:]) == (h, w, 8) and res2.shape[0] == n
         a.res2, a.res2_planes_total, a.res2_plane_off, a.beta2 = res2.data_ptr(), res2.shape[1], res2_off, beta2

@@ -74,7 +74,8 @@ typedef struct {
   /* epilogue */
   int lrelu; float slope;
   float alpha;
-  const float* res1; int res1_planes_total; int res1_plane_off; float beta1;
+  const void* res1; int res1_is16;   /* residual 1: fp32 planes, or 16-bit planes (`dtype`) if res1_is16 */
+  int res1_planes_total; int res1_plane_off; float beta1;
   const float* res2; int res2_planes_total; int res2_plane_off; float beta2;
   /* outputs */
   void* out16; int out16_planes_total; int out16_plane_off;

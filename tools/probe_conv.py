@@ -55,7 +55,7 @@ for c in cases:
     for mt in (1, 4):
         worst = max(worst, run(*c, mt=mt))
 worst = max(worst, run(2, 96, 32, 50, 50, dtype=torch.bfloat16, lrelu=True))
-worst = max(worst, run(1, 64, 64, 64, 130, p=64))
+worst = max(worst, run(1, 64, 64, 64, 130, mt=2))
 print("WORST", worst)
 # quick timing of the big trunk convs
 for cin, cout in [(64, 32), (192, 64)]:
