@@ -222,10 +222,37 @@ class CEM_PyTorch(nn.Module):
         f = self.Conv_LR_with_Inv_hTh_OP(e)
         return self.Upscale_OP(f, add_to=generated_image.float().contiguous(), crop=crop)
 
+    def project_backward(self, g_out, hr_full, crop=0):
+        """Gradient of `project` w.r.t. (generated_image, x_lr):  with P = Up.Inv (linear),
+              g_x = P^T g,   g_G = g - Down^T g_x,      g = crop-adjoint of g_out
+        Every factor is the exact adjoint of the clamp-addressed (replicate padded) forward filter, built from the
+        1-D adjoint kernel esr_sep_adjoint_1d.  hr_full = (H, W) of the un-cropped HR domain."""
+        ops = _ops()
+        s = int(self.ds_factor)
+        Hh, Wh = hr_full
+        hl, wl = Hh // s, Wh // s
+        dev = g_out.device
+        up, inv, down = self.Upscale_OP, self.Conv_LR_with_Inv_hTh_OP, self.DownscaleOP
+        kv, kh = up._taps(dev)
+        r = kv.shape[1] // 2
+        t = ops.sep_adjoint_2d(g_out, kv, kh, full_out=(Hh, Wh), a_stride=1, c_off=-r, n_in=(Hh, Wh), n_store=(hl, wl),
+                               m_stride=s, m_phase=up.phase, crop=crop)                       # Up^T
+        kv, kh = inv._taps(dev)
+        r = kv.shape[1] // 2
+        g_x = ops.sep_adjoint_2d(t, kv, kh, full_out=(hl, wl), a_stride=1, c_off=-r, n_in=(hl, wl), n_store=(hl, wl))   # Inv^T
+        kv, kh = down._taps(dev)
+        r = kv.shape[1] // 2
+        g_G = ops.sep_adjoint_2d(g_x, kv, kh, full_out=(hl, wl), a_stride=s, c_off=down.phase - r, n_in=(Hh, Wh), n_store=(Hh, Wh),
+                                 sub_from=g_out.float().contiguous(), sub_crop=crop)       # g - Down^T g_x
+        return g_G, g_x
+
     def forward(self, x):
         return_2_components = self.return_2_components and not self.pre_pad
         if torch.is_grad_enabled() and self._needs_grad(x):
-            raise NotImplementedError('esr_b200: backward through the CEM is not built yet; call under torch.no_grad()')
+            if (not self.using_SR_model) or self.conf.sigmoid_range_limit or return_2_components:
+                raise NotImplementedError('esr_b200: backward is built for the fused CEM(G(x)) projection only')
+            from esr_b200.autograd import cem_generator_forward_with_grad
+            return cem_generator_forward_with_grad(self, x)
         mLR = self.invalidity_margins_LR
         if self.using_SR_model:
             # eval mode pads LR by the invalidity margin before G (CEMnet.py:286-295); the generator mirror

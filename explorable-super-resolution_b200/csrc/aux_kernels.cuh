@@ -275,4 +275,174 @@ cem_up_add_kernel(const float* __restrict__ f, const float* __restrict__ g, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward helpers (gradient of the same operators; used by the Z-optimisation / training paths)
+// ------------------------------------------------------------------------------------------------
+
+// Adjoint of nearest x2 (block.py:299-300): dst[y][x] = sum of the 2x2 block of src.  Optionally multiplies by the
+// LeakyReLU derivative of the saved activation `act16` (given at the HIGH resolution, where it is stored 2x2
+// replicated) before the 16-bit store.  src fp32 planes [nplanes][2h][2w][8] -> dst32 / dst16 planes [nplanes][h][w][8].
+__global__ void downsum2x_kernel(const float4* __restrict__ src, size_t nplanes, int h, int w, const uint4* __restrict__ act16,
+                                 float slope, int dtype, float4* __restrict__ dst32, uint4* __restrict__ dst16) {
+  const size_t total = nplanes * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int y = r % h; r /= h;
+    const size_t hi = (r * (2 * (size_t)h) + 2 * y) * (2 * (size_t)w) + 2 * x;  // pixel index in the hi-res plane
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float4* sp = src + (hi + (size_t)dy * 2 * w + dx) * 2;
+        const float4 a = __ldg(sp), b = __ldg(sp + 1);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+      }
+    if (act16) {
+      const uint4 q = __ldg(act16 + hi);
+      const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float a = from16((uint16_t)((wq[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu), dtype);
+        if (!(a > 0.f)) v[k] *= slope;
+      }
+    }
+    if (dst32) {
+      dst32[idx * 2] = make_float4(v[0], v[1], v[2], v[3]);
+      dst32[idx * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (dst16) {
+      uint4 pk;
+      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
+      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
+      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
+      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
+      dst16[idx] = pk;
+    }
+  }
+}
+
+// out = a + b on fp32 planes; optional 16-bit copy
+__global__ void planes_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t n8, int dtype,
+                                  float4* __restrict__ out32, uint4* __restrict__ out16) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n8; idx += (size_t)gridDim.x * blockDim.x) {
+    const float4 a0 = __ldg(a + 2 * idx), a1 = __ldg(a + 2 * idx + 1), b0 = __ldg(b + 2 * idx), b1 = __ldg(b + 2 * idx + 1);
+    const float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+    if (out32) {
+      out32[2 * idx] = make_float4(v[0], v[1], v[2], v[3]);
+      out32[2 * idx + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (out16) {
+      uint4 pk;
+      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
+      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
+      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
+      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
+      out16[idx] = pk;
+    }
+  }
+}
+
+// Adjoint of one 1-D pass of a clamp-addressed (replicate-padded) strided filter along one axis:
+//   forward:  out[o] = sum_t k[t] * in[clamp(A*o + t + c, 0, n_in-1)]          (in: logical length n_in)
+//   adjoint:  gin[m] = sum_t k[t] * sum_{o : clamp(A*o+t+c) == m} gout[o]
+// Only the logical positions m = Am*mi + pm (mi < n_store) are produced (Am = s, pm = phase for the zero-stuffed
+// input of Upscale_OP; Am = 1, pm = 0 otherwise).  `gout` may be a crop-adjoint view: logical index o maps to
+// stored index o - crop, zero outside [0, n_out_store).  Layout: [imgs][outer][axis][inner] with inner = 1 for the
+// x axis and inner = row length for the y axis.  Optional fused epilogue: dst = sub_from_view - result (used for
+// g_G = g_out - Down^T(...)), where sub_from has the same crop convention.
+__global__ void sep_adjoint_1d_kernel(const float* __restrict__ gout, int imgs, int outer, int inner, int n_out, int o_lo,
+                                      int o_cnt, int n_in, int n_store, int A, int c, int Am, int pm,
+                                      const float* __restrict__ k, int len, const float* __restrict__ sub_from, int sub_crop,
+                                      float* __restrict__ gin) {
+  const size_t total = (size_t)imgs * outer * n_store * inner;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int in_i = r % inner; r /= inner;
+    const int mi = r % n_store; r /= n_store;
+    const int ou = r % outer; r /= outer;
+    const int img = (int)r;
+    const int m = Am * mi + pm;
+    // stored gout covers logical o in [o_lo, o_lo + o_cnt) (crop adjoint = zeros elsewhere)
+    const float* gp = gout + (((size_t)img * outer + ou) * o_cnt) * inner + in_i;
+    const int o_hi = o_lo + o_cnt;
+    float acc = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const float kt = __ldg(k + t);
+      const int num = m - t - c;  // A*o == num for the un-clamped hit
+      float ssum = 0.f;
+      if (num >= 0 && num % A == 0) {
+        const int o = num / A;
+        if (o >= o_lo && o < o_hi) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+      }
+      if (m == 0) {            // everything that fell off the low end was clamped onto index 0
+        for (int o = o_lo; o < o_hi && A * o + t + c < 0; ++o) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+      }
+      if (m == n_in - 1) {     // ... and off the high end onto index n_in-1
+        int o0 = (n_in - 1 - t - c) / A + 1;
+        if (o0 < o_lo) o0 = o_lo;
+        while (o0 > o_lo && A * (o0 - 1) + t + c > n_in - 1) --o0;
+        for (int o = o0; o < o_hi; ++o)
+          if (A * o + t + c > n_in - 1) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+      }
+      acc = fmaf(kt, ssum, acc);
+    }
+    if (sub_from) {  // x-axis pass only (inner == 1): dst = crop_adjoint(sub_from) - acc
+      const int y = ou, x = mi;
+      const int hs = outer - 2 * sub_crop, ws = n_store - 2 * sub_crop;
+      float base = 0.f;
+      if (y >= sub_crop && y < sub_crop + hs && x >= sub_crop && x < sub_crop + ws)
+        base = __ldg(sub_from + ((size_t)img * hs + (y - sub_crop)) * ws + (x - sub_crop));
+      acc = base - acc;
+    }
+    gin[idx] = acc;
+  }
+}
+
+// gradient of the latent map: scatter-add (atomics) of
+//   (a) the HR-resolution latent gradient given on the replicate-padded domain (planes32 [n][1][hp][wp][8], first c ch), and
+//   (b) the LR-resolution latent gradient through the adjoint of the bilinear 1/s resize of the padded map,
+// onto the un-padded map dst [n][c][hh][wh] (NCHW fp32, zero-initialised by the caller).
+__global__ void latent_grad_hr_kernel(const float* __restrict__ gz_hr, int n, int c, int hh, int wh, int pad, float* __restrict__ dst) {
+  const int hp = hh + 2 * pad, wp = wh + 2 * pad;
+  const size_t total = (size_t)n * hp * wp;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % wp; r /= wp;
+    const int y = r % hp; r /= hp;
+    const int img = (int)r;
+    const int sy = clampi(y - pad, 0, hh - 1), sx = clampi(x - pad, 0, wh - 1);
+    for (int ch = 0; ch < c; ++ch)
+      atomicAdd(dst + (((size_t)img * c + ch) * hh + sy) * wh + sx, gz_hr[idx * 8 + ch]);
+  }
+}
+__global__ void latent_grad_lr_kernel(const float* __restrict__ gz_lr, int n, int c, int hh, int wh, int s, int pad,
+                                      float* __restrict__ dst) {
+  const int hp = hh + 2 * pad, wp = wh + 2 * pad;
+  const int ho = hp / s, wo = wp / s;
+  const size_t total = (size_t)n * ho * wo;
+  const float fs = 1.0f / (1.0f / (float)s);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int j = r % wo; r /= wo;
+    const int i = r % ho; r /= ho;
+    const int img = (int)r;
+    const float sy = fmaxf(((float)i + 0.5f) * fs - 0.5f, 0.f), sx = fmaxf(((float)j + 0.5f) * fs - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const int y1 = min(y0 + 1, hp - 1), x1 = min(x0 + 1, wp - 1);
+    const int ya = clampi(y0 - pad, 0, hh - 1), yb = clampi(y1 - pad, 0, hh - 1);
+    const int xa = clampi(x0 - pad, 0, wh - 1), xb = clampi(x1 - pad, 0, wh - 1);
+    for (int ch = 0; ch < c; ++ch) {
+      const float g = gz_lr[idx * 8 + ch];
+      float* p = dst + ((size_t)img * c + ch) * hh * wh;
+      atomicAdd(p + (size_t)ya * wh + xa, (1.f - ly) * (1.f - lx) * g);
+      atomicAdd(p + (size_t)ya * wh + xb, (1.f - ly) * lx * g);
+      atomicAdd(p + (size_t)yb * wh + xa, ly * (1.f - lx) * g);
+      atomicAdd(p + (size_t)yb * wh + xb, ly * lx * g);
+    }
+  }
+}
+
 }  // namespace esr

@@ -56,6 +56,13 @@ struct ConvParams {
   float slope, alpha;
   const void* res1; int res1_is16, res1_pt, res1_po; float beta1;
   const float* res2; int res2_pt, res2_po; float beta2;
+  const float* res3; int res3_pt, res3_po; float beta3;
+  // dgrad helpers: the first `lead_planes` output planes (latent channels) are accumulated (+=) into lead_acc and take
+  // no other part in the epilogue; every other plane index below is relative to the first non-lead plane.
+  int lead_planes; float* lead_acc; int lead_pt;
+  // LeakyReLU derivative: planes >= tail_first are multiplied by (act > 0 ? 1 : mask_slope) before the 16-bit store;
+  // the 16-bit store itself is limited to planes >= tail_first.
+  const uint16_t* mask16; int mask_pt, mask_po; float mask_slope; int tail_first;
   uint16_t* out16; int out16_pt, out16_po, out16_up2, out16_ps;
   float* out32; int out32_pt, out32_po;
   float* out_nchw; int out_nchw_c;
@@ -209,7 +216,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Two warps per TMEM lane quarter; they alternate over the M tiles of an item.  Per (row, unit of UW
     // channels) every global load (residuals, bias) is issued before the first store so that a thread
     // keeps UW/8 .. 3*UW/8 128-bit loads in flight.
-    constexpr int UW = (NBN % 32 == 0) ? 32 : 16;
+    constexpr int UW = 16;  // 16 channels per unit keeps the prefetch registers (3 fp32 residuals + mask + bias) under the 168-register cap
     const int wq = warp & 3;            // TMEM lane quarter this warp may touch
     const int eh = (warp - 2) >> 2;     // which half of the M tiles this warp takes
     int it = 0;
@@ -239,10 +246,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < UW / 16; ++k) tmem_ld16(trow + u * UW + k * 16, r[k]);
           const int chu = nblk * NBN + u * UW;   // first conv output channel of this unit
-          const int gu = chu >> 3;
+          const int gu = chu >> 3;               // its plane index in the conv's output
           constexpr int G = UW / 8;              // groups of 8 channels in a unit
-          uint4 q1[G];                           // residual 1 as 16-bit planes
-          float4 f1[G][2], f2[G][2], bb[G][2];
+          uint4 q1[G], qm[G];                    // residual 1 as 16-bit planes, activation for the LeakyReLU mask
+          float4 f1[G][2], f2[G][2], f3[G][2], bb[G][2];
           const bool on = valid;
           if (on) {
 #pragma unroll
@@ -250,20 +257,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (chu + g * 8 < p.cout) {
                 bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
                 bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+                const int gp = gu + g - p.lead_planes;
+                if (gp < 0) {
+                  const float4* rp = reinterpret_cast<const float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
+                  f2[g][0] = rp[0]; f2[g][1] = rp[1];
+                  continue;
+                }
                 if (p.res1) {
                   if (p.res1_is16) {
                     q1[g] = __ldg(reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8));
+                        reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8));
                   } else {
                     const float4* rp = reinterpret_cast<const float4*>(
-                        reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8);
+                        reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8);
                     f1[g][0] = __ldg(rp); f1[g][1] = __ldg(rp + 1);
                   }
                 }
                 if (p.res2) {
+                  // plain loads: res2 may alias out32 (in-place accumulation of gradients)
                   const float4* rp = reinterpret_cast<const float4*>(
-                      p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gu + g) * hw + pix) * 8);
-                  f2[g][0] = __ldg(rp); f2[g][1] = __ldg(rp + 1);
+                      p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gp) * hw + pix) * 8);
+                  f2[g][0] = rp[0]; f2[g][1] = rp[1];
+                }
+                if (p.res3) {
+                  const float4* rp = reinterpret_cast<const float4*>(
+                      p.res3 + (((size_t)img * p.res3_pt + p.res3_po + gp) * hw + pix) * 8);
+                  f3[g][0] = __ldg(rp); f3[g][1] = __ldg(rp + 1);
+                }
+                if (p.mask16 && gp >= p.tail_first) {
+                  qm[g] = __ldg(reinterpret_cast<const uint4*>(p.mask16 + (((size_t)img * p.mask_pt + p.mask_po + gp) * hw + pix) * 8));
                 }
               }
             }
@@ -274,13 +296,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int g = 0; g < G; ++g) {
               const int ch0 = chu + g * 8;
               if (ch0 >= p.cout) continue;
-              const int gp = gu + g;
+              const int gp = gu + g - p.lead_planes;
               const uint32_t* rg = &r[g / 2][(g & 1) * 8];
               float v[8];
               v[0] = __uint_as_float(rg[0]) + bb[g][0].x; v[1] = __uint_as_float(rg[1]) + bb[g][0].y;
               v[2] = __uint_as_float(rg[2]) + bb[g][0].z; v[3] = __uint_as_float(rg[3]) + bb[g][0].w;
               v[4] = __uint_as_float(rg[4]) + bb[g][1].x; v[5] = __uint_as_float(rg[5]) + bb[g][1].y;
               v[6] = __uint_as_float(rg[6]) + bb[g][1].z; v[7] = __uint_as_float(rg[7]) + bb[g][1].w;
+              if (gp < 0) {  // latent planes: lead_acc += alpha * acc
+                float4* op = reinterpret_cast<float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
+                op[0] = make_float4(fmaf(p.alpha, v[0], f2[g][0].x), fmaf(p.alpha, v[1], f2[g][0].y), fmaf(p.alpha, v[2], f2[g][0].z),
+                                    fmaf(p.alpha, v[3], f2[g][0].w));
+                op[1] = make_float4(fmaf(p.alpha, v[4], f2[g][1].x), fmaf(p.alpha, v[5], f2[g][1].y), fmaf(p.alpha, v[6], f2[g][1].z),
+                                    fmaf(p.alpha, v[7], f2[g][1].w));
+                continue;
+              }
               if (p.lrelu) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * p.slope;
@@ -304,6 +334,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
                 v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
               }
+              if (p.res3) {
+                v[0] = fmaf(p.beta3, f3[g][0].x, v[0]); v[1] = fmaf(p.beta3, f3[g][0].y, v[1]);
+                v[2] = fmaf(p.beta3, f3[g][0].z, v[2]); v[3] = fmaf(p.beta3, f3[g][0].w, v[3]);
+                v[4] = fmaf(p.beta3, f3[g][1].x, v[4]); v[5] = fmaf(p.beta3, f3[g][1].y, v[5]);
+                v[6] = fmaf(p.beta3, f3[g][1].z, v[6]); v[7] = fmaf(p.beta3, f3[g][1].w, v[7]);
+              }
               if (p.out32) {
                 float4* op = reinterpret_cast<float4*>(
                     p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gp) * hw + pix) * 8);
@@ -313,11 +349,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.out_nchw) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                  const int ch = ch0 + k;
+                  const int ch = gp * 8 + k;
                   if (ch < p.out_nchw_c) p.out_nchw[((size_t)img * p.out_nchw_c + ch) * hw + pix] = v[k];
                 }
               }
-              if (p.out16) {
+              if (p.out16 && gp >= p.tail_first) {
+                if (p.mask16) {
+                  float a[8];
+                  unpack8(qm[g], p.dtype, a);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
+                }
                 if (p.out16_ps == 0) {
                   uint4 o;
                   o.x = pack2(v[0], v[1], p.dtype);
@@ -389,12 +431,19 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
     const int tap = r % 9; r /= 9;
     const int c = r % nchunks; r /= nchunks;
     const int nb = (int)r;
-    const int o = nb * nb_n + n;
-    int i = (c * kcp + j) * 8 + ci8;  // channel position in plane space -> source input channel
-    if (i < lead_pad) i = i < lead ? i : -1;
-    else i = i - lead_pad + lead;
+    int o = nb * nb_n + n;
+    int i = (c * kcp + j) * 8 + ci8;
+    // channel position in plane space -> source channel: the `lead` latent channels sit in their own zero-padded
+    // plane group in front (forward: on the input side; transpose/dgrad: on the output side)
+    if (!transpose_flip) {
+      if (i < lead_pad) i = i < lead ? i : -1;
+      else i = i - lead_pad + lead;
+    } else {
+      if (o < lead_pad) o = o < lead ? o : -1;
+      else o = o - lead_pad + lead;
+    }
     float val = 0.f;
-    if (o < lc_out && i >= 0 && i < lc_in) {
+    if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
       const int ky = tap / 3, kx = tap % 3;
       if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + kx];
       else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - kx)];

@@ -141,12 +141,14 @@ int esr_conv3x3_cin_planes(int cin, int lead) { return (lead + 7) / 8 + (cin - l
 int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, int kcp, int dtype, int transpose_flip,
                              void* wpacked, float* bias_out, const float* bias_in, void* stream) {
   if (!w_oihw || !wpacked) return fail(ESR_ERR_INVALID, "pack_weights: null pointer");
-  if (lead < 0 || lead > cin || (lead && transpose_flip)) return fail(ESR_ERR_INVALID, "pack_weights: bad lead %d", lead);
+  if (lead < 0 || lead > cin) return fail(ESR_ERR_INVALID, "pack_weights: bad lead %d", lead);
   if (kcp != 2 && kcp != 4) return fail(ESR_ERR_INVALID, "pack_weights: kcp must be 2 or 4");
   const int lc_out = transpose_flip ? cin : cout;
   const int lc_in = transpose_flip ? cout : cin;
   int cout_pad = 0;
-  const int nb_n = nblock_for(lc_out, &cout_pad);
+  // dgrad: the conv's outputs are the forward inputs, laid out in plane space ([lead pad | rest])
+  const int lc_out_planespace = transpose_flip ? esr_conv3x3_cin_planes(cin, lead) * 8 : lc_out;
+  const int nb_n = nblock_for(lc_out_planespace, &cout_pad);
   const int n_blocks = cout_pad / nb_n;
   const int cin_planes = transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(cin, lead);
   const int nchunks = (cin_planes + kcp - 1) / kcp;
@@ -170,7 +172,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   if (a->n <= 0 || a->h <= 0 || a->w <= 0) return fail(ESR_ERR_INVALID, "conv3x3: bad shape %dx%dx%d", a->n, a->h, a->w);
   if (a->kcp != 2 && a->kcp != 4) return fail(ESR_ERR_INVALID, "conv3x3: kcp must be 2 or 4");
   if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "conv3x3: bad dtype");
-  if (!a->out16 && !a->out32 && !a->out_nchw) return fail(ESR_ERR_INVALID, "conv3x3: no output requested");
+  if (!a->out16 && !a->out32 && !a->out_nchw && !a->lead_acc) return fail(ESR_ERR_INVALID, "conv3x3: no output requested");
   if (a->out16_up2 && a->out16_pixel_shuffle) return fail(ESR_ERR_INVALID, "conv3x3: up2 and pixel_shuffle are exclusive");
   if (((uintptr_t)a->in & 15) || ((uintptr_t)a->wpacked & 15) || ((uintptr_t)a->bias & 15))
     return fail(ESR_ERR_INVALID, "conv3x3: pointers must be 16-byte aligned");
@@ -228,6 +230,11 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.lrelu = a->lrelu; p.slope = a->slope; p.alpha = a->alpha;
   p.res1 = a->res1; p.res1_is16 = a->res1_is16; p.res1_pt = a->res1_planes_total; p.res1_po = a->res1_plane_off; p.beta1 = a->beta1;
   p.res2 = a->res2; p.res2_pt = a->res2_planes_total; p.res2_po = a->res2_plane_off; p.beta2 = a->beta2;
+  p.res3 = a->res3; p.res3_pt = a->res3_planes_total; p.res3_po = a->res3_plane_off; p.beta3 = a->beta3;
+  p.lead_planes = a->lead_planes; p.lead_acc = a->lead_acc; p.lead_pt = a->lead_planes_total;
+  if (p.lead_planes && !p.lead_acc) return fail(ESR_ERR_INVALID, "conv3x3: lead_planes without lead_acc");
+  p.mask16 = (const uint16_t*)a->mask16; p.mask_pt = a->mask_planes_total; p.mask_po = a->mask_plane_off; p.mask_slope = a->mask_slope;
+  p.tail_first = a->tail_first_plane;
   p.out16 = (uint16_t*)a->out16; p.out16_pt = a->out16_planes_total; p.out16_po = a->out16_plane_off;
   p.out16_up2 = a->out16_up2; p.out16_ps = a->out16_pixel_shuffle;
   p.out32 = a->out32; p.out32_pt = a->out32_planes_total; p.out32_po = a->out32_plane_off;
@@ -316,6 +323,62 @@ int esr_latent_downscale(const float* z_hr, int n, int c, int hh, int wh, int s,
   const size_t total = (size_t)n * c * ((hh + 2 * pad_hr) / s) * ((wh + 2 * pad_hr) / s);
   esr::latent_downscale_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(z_hr, (size_t)n * c, hh, wh, s, pad_hr, out);
   g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_downsum2x_planes(const float* src32, int n, int planes, int h, int w, const void* act16_hi, float slope, int dtype,
+                         float* dst32, void* dst16, void* stream) {
+  if (!src32 || (!dst32 && !dst16)) return fail(ESR_ERR_INVALID, "downsum2x: null pointer");
+  const size_t total = (size_t)n * planes * h * w;
+  esr::downsum2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src32, (size_t)n * planes, h, w,
+                                                                              (const uint4*)act16_hi, slope, dtype, (float4*)dst32,
+                                                                              (uint4*)dst16);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_planes_add(const float* a32, const float* b32, size_t n_groups8, int dtype, float* out32, void* out16, void* stream) {
+  if (!a32 || !b32 || (!out32 && !out16)) return fail(ESR_ERR_INVALID, "planes_add: null pointer");
+  esr::planes_add_kernel<<<grid_for(n_groups8, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a32, (const float4*)b32, n_groups8,
+                                                                                   dtype, (float4*)out32, (uint4*)out16);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_sep_adjoint_1d(const float* gout, int imgs, int outer, int inner, int n_out, int o_lo, int o_cnt, int n_in, int n_store,
+                       int a_stride, int c_off, int m_stride, int m_phase, const float* taps, int len, const float* sub_from,
+                       int sub_crop, float* gin, void* stream) {
+  if (!gout || !taps || !gin) return fail(ESR_ERR_INVALID, "sep_adjoint_1d: null pointer");
+  if (a_stride < 1 || m_stride < 1 || len < 1) return fail(ESR_ERR_INVALID, "sep_adjoint_1d: bad strides");
+  if (o_lo < 0 || o_cnt < 0 || o_lo + o_cnt > n_out) return fail(ESR_ERR_INVALID, "sep_adjoint_1d: bad stored range");
+  if (sub_from && inner != 1) return fail(ESR_ERR_INVALID, "sep_adjoint_1d: sub_from needs the x-axis pass");
+  const size_t total = (size_t)imgs * outer * n_store * inner;
+  esr::sep_adjoint_1d_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(gout, imgs, outer, inner, n_out, o_lo, o_cnt, n_in,
+                                                                                   n_store, a_stride, c_off, m_stride, m_phase, taps, len,
+                                                                                   sub_from, sub_crop, gin);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, int n, int c, int hh, int wh, int s, int pad_hr,
+                    float* dst_nchw, void* stream) {
+  if (!dst_nchw || c > 8) return fail(ESR_ERR_INVALID, "latent_grad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(dst_nchw, 0, sizeof(float) * (size_t)n * c * hh * wh, st));
+  if (gz_hr_planes32) {
+    const size_t total = (size_t)n * (hh + 2 * pad_hr) * (wh + 2 * pad_hr);
+    esr::latent_grad_hr_kernel<<<grid_for(total, 256), 256, 0, st>>>(gz_hr_planes32, n, c, hh, wh, pad_hr, dst_nchw);
+    g_launches++;
+  }
+  if (gz_lr_planes32) {
+    const size_t total = (size_t)n * ((hh + 2 * pad_hr) / s) * ((wh + 2 * pad_hr) / s);
+    esr::latent_grad_lr_kernel<<<grid_for(total, 256), 256, 0, st>>>(gz_lr_planes32, n, c, hh, wh, s, pad_hr, dst_nchw);
+    g_launches++;
+  }
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
 }

@@ -4,36 +4,43 @@ Reference control flow being replaced: architecture.py:278-302 (RRDBNet.forward)
 (ShortcutBlock), block.py:262-270 (RRDB), block.py:230-235 (ResidualDenseBlock_5C), block.py:299-300 (Upsampler).
 
 Data layout in HBM (all planar-8, see include/esr_b200.h):
-  * three "dense" operand buffers D[0..2] of z+nf+4*gc channels: conv i of a dense block reads the prefix
-    [z | x | x1..x_{i}] and writes x_{i+1} into its own plane range, so block.py:234's torch.cat never happens;
-  * fp32 "trunk" buffers T[0..2] (+F for the fea_conv output) carry the residual stream x in full precision;
-    the 16-bit copy of x in D[.] exists only as tensor-core operand;
+  * "dense" operand buffers of z+nf+4*gc channels: conv i of a dense block reads the prefix [z | x | x1..x_i] and writes
+    x_{i+1} into its own plane range, so block.py:234's torch.cat never happens.  Inference rotates three of them;
+    when a backward pass will follow, every dense block keeps its own (the saved activations ARE these buffers);
+  * fp32 "trunk" buffers carry the residual stream x in full precision at RRDB boundaries; inside an RRDB the
+    0.2-scaled dense-block residuals use the 16-bit copy of x (the tensor-core operand);
   * conv5 of each dense block fuses `x5*0.2 + x`; the third block of an RRDB also fuses the RRDB residual:
         out = (0.2*acc + x_rdb3)*0.2 + x_rrdb = 0.04*acc + 0.2*x_rdb3 + x_rrdb
-  * LR_conv fuses the ShortcutBlock add and writes its output already nearest-x2 replicated; every upconv
-    does the same for the next one, so the up-sampled tensor is written once and never re-read for resizing.
-"""
-import math
+  * LR_conv fuses the ShortcutBlock add and writes its output already nearest-x2 replicated; every upconv does the
+    same for the next one, so the up-sampled tensor is written once and never re-read for resizing.
 
+Backward (input gradient: what Z_optimization.py:747 needs; weights frozen): every conv's dgrad is the same tcgen05
+kernel with transposed/rotated weights (`transpose_flip`), the dense-block gradient accumulates in one fp32 buffer
+(in-place `res2 == out32`), LeakyReLU derivatives come from the saved 16-bit activations (`mask16`), and the latent
+channels' gradient is accumulated by every launch into one plane (`lead_acc`).
+"""
 import torch
 
 from . import ops
+
+SLOPE = 0.2
 
 
 def _param_version(mods):
     return tuple((m.weight._version, m.bias._version, m.weight.data_ptr()) for m in mods)
 
 
+class _Saved:
+    """activations kept by a forward pass that a backward pass will use"""
+    pass
+
+
 class RRDBEngine:
-    def __init__(self, net, dtype=torch.float16, trunk='rrdb'):
-        """trunk: granularity of the fp32 residual stream.  'rrdb' keeps x in fp32 at RRDB boundaries (the 0.2-scaled
-        dense-block residuals inside an RRDB use the 16-bit copy: +6 % error, -30 % conv5 HBM traffic);
-        'rdb' keeps it in fp32 after every dense block."""
-        assert trunk in ('rrdb', 'rdb')
+    def __init__(self, net, dtype=torch.float16):
         self.net = net
         self.dtype = dtype
-        self.trunk = trunk
         self._packed = None
+        self._packed_t = None
         self._packed_version = None
         self._bufs = {}
 
@@ -51,36 +58,48 @@ class RRDBEngine:
         convs += [net.model[-3], net.model[-1]]
         return convs
 
-    def packed(self):
+    def _leads(self, convs):
+        z, n_up = self.net.z_lead, len(self.net.upsamplers())
+        return [0 if (len(convs) - 2 - n_up <= i < len(convs) - 2) else z for i in range(len(convs))]
+
+    def _check_version(self):
         convs = self._convs()
         ver = _param_version(convs)
-        if self._packed is None or ver != self._packed_version:
-            z = self.net.z_lead
-            n_up = len(self.net.upsamplers())
-            pk = []
-            for i, c in enumerate(convs):
-                is_up = len(convs) - 2 - n_up <= i < len(convs) - 2
-                lead = 0 if is_up else z
-                pk.append(ops.PackedConv(c.weight, c.bias, dtype=self.dtype, lead=lead))
-            self._packed, self._packed_version = pk, ver
+        if ver != self._packed_version:
+            self._packed, self._packed_t, self._packed_version = None, None, ver
+        return convs
+
+    def packed(self):
+        convs = self._check_version()
+        if self._packed is None:
+            self._packed = [ops.PackedConv(c.weight, c.bias, dtype=self.dtype, lead=l) for c, l in zip(convs, self._leads(convs))]
         return self._packed
 
+    def packed_t(self):
+        """dgrad operands: I/O swapped, taps rotated by 180 degrees, no bias"""
+        convs = self._check_version()
+        if self._packed_t is None:
+            self._packed_t = [ops.PackedConv(c.weight, None, dtype=self.dtype, lead=l, transpose_flip=True)
+                              for c, l in zip(convs, self._leads(convs))]
+        return self._packed_t
+
     # ---------------------------------------------------------------- buffers
-    def buffers(self, n, h, w, dev):
-        key = (n, h, w, str(dev))
+    def buffers(self, n, h, w, dev, save):
+        key = (n, h, w, str(dev), bool(save))
         b = self._bufs.get(key)
         if b is not None:
             return b
         net = self.net
         zp = 1 if net.z_lead else 0
         nfp, gcp = net.nf // 8, net.gc // 8
+        nb = len(net.model[1].sub) - 1
         dense_planes = zp + nfp + 4 * gcp
         z16 = lambda *s: torch.zeros(s, dtype=self.dtype, device=dev)
         z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         b = {
             'in16': z16(n, zp + 1, h, w, 8),
-            'D': [z16(n, dense_planes, h, w, 8) for _ in range(3)],
-            'T': [z32(n, nfp, h, w, 8) for _ in range(3)],
+            'D': [z16(n, dense_planes, h, w, 8) for _ in range(3 * nb + 1 if save else 3)],
+            'T': [z32(n, nfp, h, w, 8) for _ in range(2)],
             'F': z32(n, nfp, h, w, 8),
             'up': [],
         }
@@ -90,16 +109,23 @@ class RRDBEngine:
             b['up'].append(z16(n, nfp, h * s, w * s, 8))
         b['hr_a'] = z16(n, nfp + zp, h * s, w * s, 8)
         b['hr_b'] = z16(n, nfp + zp, h * s, w * s, 8)
-        # keep at most two shapes alive (train + eval sizes)
-        if len(self._bufs) >= 2:
+        if len(self._bufs) >= 2:  # keep at most two shapes alive (train + eval sizes)
             self._bufs.pop(next(iter(self._bufs)))
         self._bufs[key] = b
         return b
 
+    def _dense(self, B, save, k, j):
+        """operand buffer holding the input of dense block j (0..2) of RRDB k; j == 3 -> where the RRDB output goes"""
+        if save:
+            return B['D'][3 * k + j]
+        a, b_ = (0, 1) if k % 2 == 0 else (1, 0)
+        return B['D'][(a, b_, 2, b_)[j]]
+
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, x, pad=0):
-        """x: [N, z*s^2 + 3, h, w] fp32 NCHW (reference layout).  Returns G(x): [N, out_nc, S*(h+2pad), S*(w+2pad)]."""
+    def forward(self, x, pad=0, save=False):
+        """x: [N, z*s^2 + 3, h, w] fp32 NCHW (reference layout).  Returns G(x): [N, out_nc, S*(h+2pad), S*(w+2pad)]
+        (and the saved-activation record when `save`)."""
         net = self.net
         ops.require_cuda(x)
         if net.norm_type is not None:
@@ -108,12 +134,13 @@ class RRDBEngine:
         h, w = h0 + 2 * pad, w0 + 2 * pad
         dev = x.device
         pk = self.packed()
-        B = self.buffers(n, h, w, dev)
+        B = self.buffers(n, h, w, dev, save)
         z = net.z_lead
         zp = 1 if z else 0
         nfp, gcp = net.nf // 8, net.gc // 8
-        D, T, F = B['D'], B['T'], B['F']
+        T, F = B['T'], B['F']
         S = net.upscale
+        nb = len(net.model[1].sub) - 1
 
         x = x.float().contiguous()
         if z:
@@ -127,7 +154,7 @@ class RRDBEngine:
             img = x[:, zc:].contiguous()
             ops.pack_nchw(z_lr, dst16=B['in16'], plane_off=0)
             ops.pack_nchw(img, pad=pad, dst16=B['in16'], plane_off=1)
-            for d in D:
+            for d in B['D']:
                 ops.pack_nchw(z_lr, dst16=d, plane_off=0)
             ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_a'], plane_off=0)
             ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_b'], plane_off=0)
@@ -136,52 +163,143 @@ class RRDBEngine:
 
         it = iter(pk)
         # fea_conv: no activation; fp32 copy kept for the ShortcutBlock add
-        ops.conv3x3(B['in16'], next(it), out16=D[0], out16_off=zp, out32=F)
-        a, b_, c = 0, 1, 2
-        Ta = F
-        nb = len(net.model[1].sub) - 1
-        for _ in range(nb):
-            src_T = Ta
-            # RDB1: a -> b ; RDB2: b -> c ; RDB3: c -> b (fused RRDB residual with x_rrdb = src_T)
-            for (di, do, Tin, last) in ((a, b_, src_T, False), (b_, c, T[b_], False), (c, b_, T[c], True)):
+        ops.conv3x3(B['in16'], next(it), out16=self._dense(B, save, 0, 0), out16_off=zp, out32=F)
+        for k in range(nb):
+            src_T = F if k == 0 else T[k % 2]
+            dst_T = T[(k + 1) % 2]
+            for j in range(3):
+                Di, Do = self._dense(B, save, k, j), self._dense(B, save, k, j + 1)
                 for i in range(4):
-                    ops.conv3x3(D[di], next(it), cin_planes=zp + nfp + i * gcp, lrelu=True,
-                                out16=D[di], out16_off=zp + nfp + i * gcp)
-                if self.trunk == 'rdb':
-                    r1, r1_off, o32 = Tin, 0, T[do]
-                else:  # dense-block residual from the 16-bit copy of x (planes zp.. of the block's own buffer)
-                    r1, r1_off, o32 = D[di], zp, (T[do] if last else None)
-                if not last:
-                    ops.conv3x3(D[di], next(it), alpha=0.2, res1=r1, res1_off=r1_off, beta1=1.0,
-                                out16=D[do], out16_off=zp, out32=o32)
-                else:
-                    ops.conv3x3(D[di], next(it), alpha=0.04, res1=r1, res1_off=r1_off, beta1=0.2, res2=src_T, beta2=1.0,
-                                out16=D[do], out16_off=zp, out32=o32)
-            a, b_ = b_, a
-            Ta = T[a]
+                    ops.conv3x3(Di, next(it), cin_planes=zp + nfp + i * gcp, lrelu=True, slope=SLOPE,
+                                out16=Di, out16_off=zp + nfp + i * gcp)
+                if j < 2:   # x5*0.2 + x, residual from the 16-bit copy of x in the block's own buffer
+                    ops.conv3x3(Di, next(it), alpha=0.2, res1=Di, res1_off=zp, beta1=1.0, out16=Do, out16_off=zp)
+                else:       # ... and the RRDB residual from the fp32 trunk
+                    ops.conv3x3(Di, next(it), alpha=0.04, res1=Di, res1_off=zp, beta1=0.2, res2=src_T, beta2=1.0,
+                                out16=Do, out16_off=zp, out32=dst_T)
+        Dlast = self._dense(B, save, nb - 1, 3) if nb > 0 else self._dense(B, save, 0, 0)
         ups = B['up']
         factors = net.up_factors()
         if any(r != 2 for r in factors):
             raise NotImplementedError('esr_b200: only x2 up-sampling stages are built (scale 2/4/8)')
         if net.upsample_mode == 'upconv':
             # LR_conv + ShortcutBlock add, stored nearest-x2 replicated for the first upconv (block.py:299-300)
-            ops.conv3x3(D[a], next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=ups[0], up2=True)
+            ops.conv3x3(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=ups[0], up2=True)
             for k in range(len(factors)):
                 if k < len(factors) - 1:
-                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, out16=ups[k + 1], up2=True)
+                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=ups[k + 1], up2=True)
                 else:  # the last upconv feeds HR_conv0, which sees the HR latent in plane 0 of hr_a
-                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, out16=B['hr_a'], out16_off=zp)
+                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=B['hr_a'], out16_off=zp)
         else:
+            if save:
+                raise NotImplementedError('esr_b200: backward through the pixelshuffle upsampler is not built')
             # pixelshuffle_block (block.py:278-291): conv(nf -> 4nf) -> PixelShuffle(2) -> act; the shuffle is the
             # store addressing of the conv epilogue, the (elementwise) activation is applied before it
-            ops.conv3x3(D[a], next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=D[c], out16_off=zp)
-            src, src_off = D[c], zp
+            tmp = B['D'][2] if Dlast is not B['D'][2] else B['D'][0]
+            ops.conv3x3(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=tmp, out16_off=zp)
+            src, src_off = tmp, zp
             for k in range(len(factors)):
                 dst, dst_off = (ups[k], 0) if k < len(factors) - 1 else (B['hr_a'], zp)
-                ops.conv3x3(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, out16=dst, out16_off=dst_off,
+                ops.conv3x3(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, slope=SLOPE, out16=dst, out16_off=dst_off,
                             pixel_shuffle=2)
                 src, src_off = dst, dst_off
-        ops.conv3x3(B['hr_a'], next(it), lrelu=True, out16=B['hr_b'], out16_off=zp)
+        ops.conv3x3(B['hr_a'], next(it), lrelu=True, slope=SLOPE, out16=B['hr_b'], out16_off=zp)
         out = torch.empty((n, net.out_nc, h * S, w * S), dtype=torch.float32, device=dev)
         ops.conv3x3(B['hr_b'], next(it), out_nchw=out)
-        return out
+        if not save:
+            return out
+        sv = _Saved()
+        sv.B, sv.n, sv.h, sv.w, sv.h0, sv.w0, sv.pad, sv.cin = B, n, h, w, h0, w0, pad, cin
+        return out, sv
+
+    # ---------------------------------------------------------------- backward (input gradient)
+    @torch.no_grad()
+    def backward_input(self, g_out, sv):
+        """g_out: dL/dG on the padded HR domain [N, out_nc, S*h, S*w].  Returns dL/dx with x's layout
+        [N, z*S^2 + 3, h0, w0] (latent part exact; the LR-image part is returned only when pad == 0)."""
+        net = self.net
+        B, n, h, w, pad = sv.B, sv.n, sv.h, sv.w, sv.pad
+        dev = g_out.device
+        wt = self.packed_t()
+        z = net.z_lead
+        zp = 1 if z else 0
+        nfp, gcp = net.nf // 8, net.gc // 8
+        S = net.upscale
+        nb = len(net.model[1].sub) - 1
+        n_up = len(net.up_factors())
+        H, W = h * S, w * S
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        f16 = lambda *s: torch.zeros(s, dtype=self.dtype, device=dev)
+        gz_hr = f32(n, 1, H, W, 8) if z else None
+        gz_lr = f32(n, 1, h, w, 8) if z else None
+        lead = dict(lead_planes=zp, lead_acc=gz_hr) if z else {}
+        idx_lr = 1 + 15 * nb
+        idx_hr0 = idx_lr + 1 + n_up
+
+        # HR_conv1^T, HR_conv0^T (LeakyReLU derivative of the conv below comes from its saved output)
+        g16, _ = ops.pack_nchw(g_out.float().contiguous(), dtype=self.dtype)
+        g_b = f16(n, nfp, H, W, 8)
+        ops.conv3x3(g16, wt[idx_hr0 + 1], mask16=B['hr_b'], mask_off=zp, mask_slope=SLOPE, out16=g_b, **lead)
+        g_a = f16(n, nfp, H, W, 8)
+        ops.conv3x3(g_b, wt[idx_hr0], mask16=B['hr_a'], mask_off=zp, mask_slope=SLOPE, out16=g_a, **lead)
+        del g_b, g16
+        # upconvs: conv^T at the high resolution, then the adjoint of nearest x2 (2x2 sum)
+        cur = g_a
+        g_t32 = None
+        for k in range(n_up - 1, -1, -1):
+            hk, wk = h * 2 ** (k + 1), w * 2 ** (k + 1)
+            gu = f32(n, nfp, hk, wk, 8)
+            ops.conv3x3(cur, wt[idx_lr + 1 + k], out32=gu)
+            if k > 0:   # B['up'][k] is the (replicated) LeakyReLU output of upconv k-1
+                _, cur = ops.downsum2x(gu, act16_hi=B['up'][k], slope=SLOPE, dtype=self.dtype, want32=False)
+            else:       # B['up'][0] is LR_conv + fea, no activation
+                g_t32, cur = ops.downsum2x(gu, dtype=self.dtype)
+            del gu
+        lead = dict(lead_planes=zp, lead_acc=gz_lr) if z else {}
+        # LR_conv^T -> gradient w.r.t. the last RRDB's output
+        go32, go16 = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
+        ops.conv3x3(cur, wt[idx_lr], out32=go32, out16=go16, **lead)
+        gS = f32(n, nfp + 4 * gcp, h, w, 8)
+        G16 = f16(n, nfp + 4 * gcp, h, w, 8)
+        gy32 = [f32(n, nfp, h, w, 8) for _ in range(2)]
+        gy16 = [f16(n, nfp, h, w, 8) for _ in range(2)]
+        gi32, gi16 = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
+        for k in range(nb - 1, -1, -1):
+            for j in (2, 1, 0):
+                Sb = self._dense(B, True, k, j)
+                base = 1 + (3 * k + j) * 5
+                if j == 2:
+                    gin16, a5 = go16, 0.04
+                else:
+                    gin16, a5 = gy16[j % 2], 0.2
+                # conv5^T: gS = alpha * conv5^T(g); x4's slice is final -> masked 16-bit copy
+                ops.conv3x3(gin16, wt[base + 4], alpha=a5, out32=gS, mask16=Sb, mask_off=zp, mask_slope=SLOPE,
+                            tail_first=nfp + 3 * gcp, out16=G16, **lead)
+                for i in (3, 2, 1):
+                    # conv_{i+1}^T: consumes the masked gradient of x_{i+1}, accumulates into gS[0 : nfp+i*gcp) in place,
+                    # finalises x_i's slice
+                    ops.conv3x3(G16, wt[base + i], in_plane_off=nfp + i * gcp, cin_planes=gcp, res2=gS, beta2=1.0, out32=gS,
+                                mask16=Sb, mask_off=zp, mask_slope=SLOPE, tail_first=nfp + (i - 1) * gcp, out16=G16, **lead)
+                # conv1^T closes the block: g_x = acc + gS[x] + (gradient arriving at the block's output)
+                if j == 2:
+                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=go32, beta3=0.2,
+                                out32=gy32[1], out16=gy16[1], **lead)
+                elif j == 1:
+                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=gy32[1], beta3=1.0,
+                                out32=gy32[0], out16=gy16[0], **lead)
+                else:   # ... plus the RRDB skip connection
+                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=gy32[0], beta3=1.0,
+                                res1=go32, beta1=1.0, out32=gi32, out16=gi16, **lead)
+            go32, gi32 = gi32, go32
+            go16, gi16 = gi16, go16
+        # ShortcutBlock: the fea_conv output feeds the first RRDB and the skip
+        _, gf16 = ops.planes_add(go32, g_t32, dtype=self.dtype, want32=False)
+        g_img = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+        ops.conv3x3(gf16, wt[0], out_nchw=g_img, **lead)
+        gx = torch.zeros((n, sv.cin, sv.h0, sv.w0), dtype=torch.float32, device=dev)
+        if z:
+            gz = ops.latent_grad(gz_hr, gz_lr, n, z, S * sv.h0, S * sv.w0, S, pad * S)
+            gx[:, :sv.cin - 3] = gz.view(n, z * S * S, sv.h0, sv.w0)
+        if pad == 0:
+            gx[:, sv.cin - 3:] = g_img
+        return gx

@@ -26,6 +26,10 @@ class ConvArgs(C.Structure):
         ("lrelu", C.c_int), ("slope", C.c_float), ("alpha", C.c_float),
         ("res1", C.c_void_p), ("res1_is16", C.c_int), ("res1_planes_total", C.c_int), ("res1_plane_off", C.c_int), ("beta1", C.c_float),
         ("res2", C.c_void_p), ("res2_planes_total", C.c_int), ("res2_plane_off", C.c_int), ("beta2", C.c_float),
+        ("res3", C.c_void_p), ("res3_planes_total", C.c_int), ("res3_plane_off", C.c_int), ("beta3", C.c_float),
+        ("lead_planes", C.c_int), ("lead_acc", C.c_void_p), ("lead_planes_total", C.c_int),
+        ("mask16", C.c_void_p), ("mask_planes_total", C.c_int), ("mask_plane_off", C.c_int), ("mask_slope", C.c_float),
+        ("tail_first_plane", C.c_int),
         ("out16", C.c_void_p), ("out16_planes_total", C.c_int), ("out16_plane_off", C.c_int),
         ("out16_up2", C.c_int), ("out16_pixel_shuffle", C.c_int),
         ("out32", C.c_void_p), ("out32_planes_total", C.c_int), ("out32_plane_off", C.c_int),
@@ -51,6 +55,11 @@ SIGNATURES = {
     "esr_unpack_planes32": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "esr_upsample2x_planes16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_latent_downscale": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "esr_downsum2x_planes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "esr_planes_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_sep_adjoint_1d": (C.c_int, [C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "esr_latent_grad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "esr_cem_down": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "esr_cem_inv": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -45,7 +45,8 @@ class PackedConv:
         self.esr_dtype = _TORCH2ESR[dtype]
         self.lead = lead
         if transpose_flip:
-            self.cout, self.cin = cin, cout
+            # dgrad: outputs are the forward inputs in plane space ([latent plane | rest]), inputs the forward outputs
+            self.cout, self.cin = int(lib.esr_conv3x3_cin_planes(cin, lead)) * 8, cout
             self.cin_planes = (cout + 7) // 8
         else:
             self.cout, self.cin = cout, cin
@@ -64,11 +65,12 @@ class PackedConv:
 
 
 def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2, alpha=1.0,
-            res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0,
+            res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0, res3=None, res3_off=0, beta3=1.0,
             out16=None, out16_off=0, up2=False, pixel_shuffle=0, out32=None, out32_off=0,
-            out_nchw=None, tile_p=0, tile_mt=0):
+            out_nchw=None, lead_planes=0, lead_acc=None, mask16=None, mask_off=0, mask_slope=0.2, tail_first=0,
+            tile_p=0, tile_mt=0):
     """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor."""
-    require_cuda(x16, res1, res2, out16, out32, out_nchw)
+    require_cuda(x16, res1, res2, res3, out16, out32, out_nchw, lead_acc, mask16)
     n, pt, h, w, e = x16.shape
     assert e == 8 and x16.dtype == pc.dtype
     a = L.ConvArgs()
@@ -85,6 +87,16 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     if res2 is not None:
         assert res2.dtype == torch.float32 and tuple(res2.shape[2:]) == (h, w, 8) and res2.shape[0] == n
         a.res2, a.res2_planes_total, a.res2_plane_off, a.beta2 = res2.data_ptr(), res2.shape[1], res2_off, beta2
+    if res3 is not None:
+        assert res3.dtype == torch.float32 and tuple(res3.shape[2:]) == (h, w, 8) and res3.shape[0] == n
+        a.res3, a.res3_planes_total, a.res3_plane_off, a.beta3 = res3.data_ptr(), res3.shape[1], res3_off, beta3
+    if lead_planes:
+        assert lead_acc is not None and lead_acc.dtype == torch.float32 and tuple(lead_acc.shape[2:]) == (h, w, 8)
+        a.lead_planes, a.lead_acc, a.lead_planes_total = lead_planes, lead_acc.data_ptr(), lead_acc.shape[1]
+    if mask16 is not None:
+        assert mask16.dtype == pc.dtype and tuple(mask16.shape[2:]) == (h, w, 8)
+        a.mask16, a.mask_planes_total, a.mask_plane_off, a.mask_slope = mask16.data_ptr(), mask16.shape[1], mask_off, mask_slope
+    a.tail_first_plane = tail_first
     if out16 is not None:
         f = 2 if up2 else (pixel_shuffle if pixel_shuffle else 1)
         assert out16.dtype == pc.dtype and tuple(out16.shape[2:]) == (f * h, f * w, 8) and out16.shape[0] == n
@@ -176,3 +188,61 @@ def cem_up_add(f, g, s, phase, kv, kh, crop=0):
     L.check(L.load().esr_cem_up_add(_ptr(f), _ptr(g), n, c, hl, wl, s, phase, _ptr(kv), _ptr(kh), kv.shape[1], kv.shape[0],
                                     crop, _ptr(out), _stream()))
     return out
+
+
+def downsum2x(src32, act16_hi=None, slope=0.2, dtype=torch.float16, want32=True, want16=True):
+    """adjoint of nearest x2 on fp32 planes [N,P,2h,2w,8] (+ LeakyReLU derivative from the hi-res saved activation)."""
+    require_cuda(src32, act16_hi)
+    n, pt, h2, w2, _ = src32.shape
+    h, w = h2 // 2, w2 // 2
+    d32 = torch.empty((n, pt, h, w, 8), dtype=torch.float32, device=src32.device) if want32 else None
+    d16 = torch.empty((n, pt, h, w, 8), dtype=dtype, device=src32.device) if want16 else None
+    if act16_hi is not None:
+        assert act16_hi.shape == src32.shape and act16_hi.dtype == dtype
+    L.check(L.load().esr_downsum2x_planes(_ptr(src32), n, pt, h, w, _ptr(act16_hi), slope, _TORCH2ESR[dtype], _ptr(d32), _ptr(d16),
+                                          _stream()))
+    return d32, d16
+
+
+def planes_add(a32, b32, dtype=torch.float16, want32=True, want16=True):
+    require_cuda(a32, b32)
+    assert a32.shape == b32.shape and a32.dtype == b32.dtype == torch.float32
+    o32 = torch.empty_like(a32) if want32 else None
+    o16 = torch.empty(a32.shape, dtype=dtype, device=a32.device) if want16 else None
+    L.check(L.load().esr_planes_add(_ptr(a32), _ptr(b32), a32.numel() // 8, _TORCH2ESR[dtype], _ptr(o32), _ptr(o16), _stream()))
+    return o32, o16
+
+
+def sep_adjoint_2d(gout, taps_v, taps_h, *, full_out, a_stride, c_off, n_in, n_store, m_stride=1, m_phase=0, crop=0,
+                   sub_from=None, sub_crop=0):
+    """Adjoint of a separable, clamp-addressed, strided 2-D filter (sum over `rank` separable terms).
+    gout: [N,C,Ho_store,Wo_store] (logical output size full_out=(Ho,Wo); stored = logical cropped by `crop`).
+    Returns the gradient at the stored input positions [N,C,n_store[0],n_store[1]]."""
+    require_cuda(gout, taps_v, taps_h, sub_from)
+    gout = gout.float().contiguous()
+    n, c, hs, ws = gout.shape
+    Ho, Wo = full_out
+    lib = L.load()
+    rank, ln = taps_v.shape
+    total = None
+    for r in range(rank):
+        tmp = torch.empty((n, c, n_store[0], ws), dtype=torch.float32, device=gout.device)
+        L.check(lib.esr_sep_adjoint_1d(_ptr(gout), n * c, 1, ws, Ho, crop, hs, n_in[0], n_store[0], a_stride, c_off, m_stride, m_phase,
+                                       _ptr(taps_v[r]), ln, None, 0, _ptr(tmp), _stream()))
+        out = torch.empty((n, c, n_store[0], n_store[1]), dtype=torch.float32, device=gout.device)
+        last = r == rank - 1 and total is None
+        L.check(lib.esr_sep_adjoint_1d(_ptr(tmp), n * c, n_store[0], 1, Wo, crop, ws, n_in[1], n_store[1], a_stride, c_off, m_stride,
+                                       m_phase, _ptr(taps_h[r]), ln, _ptr(sub_from) if (sub_from is not None and rank == 1) else None,
+                                       sub_crop, _ptr(out), _stream()))
+        total = out if total is None else total + out
+    if sub_from is not None and rank > 1:
+        raise L.EsrError('sep_adjoint_2d: fused subtraction supports rank-1 filters only')
+    return total
+
+
+def latent_grad(gz_hr, gz_lr, n, c, hh, wh, s, pad_hr):
+    require_cuda(gz_hr, gz_lr)
+    dev = (gz_hr if gz_hr is not None else gz_lr).device
+    dst = torch.empty((n, c, hh, wh), dtype=torch.float32, device=dev)
+    L.check(L.load().esr_latent_grad(_ptr(gz_hr), _ptr(gz_lr), n, c, hh, wh, s, pad_hr, _ptr(dst), _stream()))
+    return dst

@@ -76,7 +76,16 @@ typedef struct {
   float alpha;
   const void* res1; int res1_is16;   /* residual 1: fp32 planes, or 16-bit planes (`dtype`) if res1_is16 */
   int res1_planes_total; int res1_plane_off; float beta1;
-  const float* res2; int res2_planes_total; int res2_plane_off; float beta2;
+  const float* res2; int res2_planes_total; int res2_plane_off; float beta2;  /* may alias out32 (in-place +=) */
+  const float* res3; int res3_planes_total; int res3_plane_off; float beta3;
+  /* dgrad helpers (backward of the same convs, weights packed with transpose_flip=1):
+   *  - the first `lead_planes` output planes (gradient of the latent channels every conv sees) are accumulated,
+   *    lead_acc[plane] += alpha*acc, and skip the rest of the epilogue; all other plane offsets in this struct
+   *    are relative to the first non-lead plane;
+   *  - planes >= tail_first_plane are multiplied by the LeakyReLU derivative taken from the saved activation
+   *    `mask16` (act > 0 ? 1 : mask_slope) before the 16-bit store, and the 16-bit store is limited to them. */
+  int lead_planes; float* lead_acc; int lead_planes_total;
+  const void* mask16; int mask_planes_total; int mask_plane_off; float mask_slope; int tail_first_plane;
   /* outputs */
   void* out16; int out16_planes_total; int out16_plane_off;
   int out16_up2;             /* 1: out16 is [N][planes][2H][2W][8], each pixel replicated 2x2 */
@@ -147,6 +156,28 @@ int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl,
  * resize by 1/s (models/modules/architecture.py:284).  NCHW fp32 in/out. */
 int esr_latent_downscale(const float* z_hr, int n, int c, int hh, int wh, int s, int pad_hr, float* out,
                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * backward helpers (gradients of the operators above; Z_optimization.py:673-749 drives them through autograd)
+ * ---------------------------------------------------------------------------------------------- */
+/* adjoint of nearest x2 (+ optional LeakyReLU derivative from the saved hi-res activation) */
+int esr_downsum2x_planes(const float* src32, int n, int planes, int h, int w, const void* act16_hi, float slope,
+                         int dtype, float* dst32, void* dst16, void* stream);
+/* out = a + b on fp32 planes (n_groups8 groups of 8 floats), optional 16-bit copy */
+int esr_planes_add(const float* a32, const float* b32, size_t n_groups8, int dtype, float* out32, void* out16,
+                   void* stream);
+/* adjoint of one 1-D pass of a clamp-addressed strided filter (the building block of the CEM backward):
+ *   forward out[o] = sum_t k[t]*in[clamp(a_stride*o + t + c_off, 0, n_in-1)];  produces gin at logical positions
+ *   m = m_stride*mi + m_phase, mi < n_store.  Tensor viewed as [imgs][outer][axis][inner].
+ *   The stored gout covers logical o in [o_lo, o_lo+o_cnt) only (adjoint of the HR_unpadder crop: zeros elsewhere).
+ *   sub_from (x-axis pass only): gin = crop_adjoint(sub_from, sub_crop) - result, i.e. g_G = g_out - Down^T(...). */
+int esr_sep_adjoint_1d(const float* gout, int imgs, int outer, int inner, int n_out, int o_lo, int o_cnt, int n_in,
+                       int n_store, int a_stride, int c_off, int m_stride, int m_phase, const float* taps, int len,
+                       const float* sub_from, int sub_crop, float* gin, void* stream);
+/* gradient of the latent map Z[n][c][hh][wh] from the HR-resolution (padded planes32) and LR-resolution latent
+ * gradients accumulated by the dgrad convs (adjoint of replicate pad + bilinear 1/s resize) */
+int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, int n, int c, int hh, int wh, int s,
+                    int pad_hr, float* dst_nchw, void* stream);
 
 /* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);

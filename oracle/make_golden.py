@@ -121,6 +121,25 @@ def main():
         yze = wz(xz)
     save('cem_rrdb_latent_x4', x=xz.numpy(), y_train=yzt.numpy(), y_eval=yze.numpy())
 
+    # E2. input gradients through the reference's own autograd (what Z_optimizer.optimize back-propagates):
+    #     loss = sum(out * Wt) with a fixed seeded Wt; gradient w.r.t. the packed [Z | LR] input.
+    for name, mod, xin in (('grad_cem_rrdb_latent_eval', wz, xz), ('grad_cem_rrdb_plain_train', wrapped, x)):
+        for p in mod.parameters():
+            p.requires_grad_(False)
+        mod.eval() if 'eval' in name else mod.train()
+        xi = xin.clone().requires_grad_(True)
+        out = mod(xi)
+        wt = torch.randn(out.shape, generator=g)
+        (out * wt).sum().backward()
+        save(name, x=xin.numpy(), wt=wt.numpy(), out=out.detach().numpy(), gx=xi.grad.numpy())
+    netz_g = xz.clone().requires_grad_(True)
+    for p in netz.parameters():
+        p.requires_grad_(False)
+    outz = netz(netz_g)
+    wtz = torch.randn(outz.shape, generator=g)
+    (outz * wtz).sum().backward()
+    save('grad_rrdb_latent', x=xz.numpy(), wt=wtz.numpy(), gx=netz_g.grad.numpy())
+
     # F. BASELINE config 1 (nf=32, nb=4, 1x3x128x128 -> 512x512): weights from the reference's own seeded
     # training init (kaiming x0.1, networks.py:118-119) are too big to store; keep the seed and a digest.
     torch.manual_seed(0)

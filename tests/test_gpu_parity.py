@@ -242,3 +242,98 @@ def test_full_size_invariants_config2_shape():
     assert y.shape == (1, 3, 1024, 1024) and torch.isfinite(y).all()
     assert (back - x)[:, :, m:-m, m:-m].abs().max().item() < 2e-5
     assert (again - y)[:, :, 4 * m:-4 * m, 4 * m:-4 * m].abs().max().item() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ backward
+def test_dgrad_conv_matches_autograd():
+    """the dgrad operand packing (transpose_flip) reproduces conv2d's input gradient, incl. the latent lead plane"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    n, cin, cout, h, w, z = 2, 3 + 64, 32, 19, 41, 3
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / 20).half().float().to(DEV)
+    gy = torch.randn(n, cout, h, w, generator=g).half().float().to(DEV)
+    x = torch.zeros(n, cin, h, w, device=DEV, requires_grad=True)
+    F.conv2d(x.double(), wt.double(), None, padding=1).backward(gy.double())
+    ref = x.grad.float()
+    pct = ops.PackedConv(wt, None, lead=z, transpose_flip=True)
+    g16, _ = ops.pack_nchw(gy)
+    lead_acc = torch.zeros(n, 1, h, w, 8, device=DEV)
+    out32 = torch.zeros(n, 8, h, w, 8, device=DEV)
+    ops.conv3x3(g16, pct, out32=out32, lead_planes=1, lead_acc=lead_acc)
+    ops.conv3x3(g16, pct, out32=out32, lead_planes=1, lead_acc=lead_acc)   # second call: lead plane accumulates
+    assert rel_err(ops.unpack_planes(out32, 64), ref[:, z:])[0] < 1e-5
+    assert rel_err(ops.unpack_planes(lead_acc, z), 2 * ref[:, :z])[0] < 1e-5
+
+
+def test_cem_projection_adjoint_matches_autograd():
+    """<g, J v> structure: gradient of sum(out*Wt) w.r.t. (G, x_lr) vs torch autograd on the oracle, train + eval crop"""
+    _ops()
+    from oracle import esr_oracle as O
+    from CEM.CEMnet import CEMnet, Get_CEM_Conf
+    for s, pre in ((4, 1), (2, 0), (3, 1)):
+        cem = CEMnet(Get_CEM_Conf(s))
+        mod = cem.WrapArchitecture_PyTorch(None, None).to(DEV)
+        gen = torch.Generator().manual_seed(30 + s)
+        m_lr = int(cem.invalidity_margins_LR)
+        hl, wl = 16 + 2 * m_lr, 12 + 2 * m_lr
+        for crop in (0, s * m_lr):
+            x = torch.rand(1, 3, hl, wl, generator=gen, requires_grad=True)
+            G = torch.rand(1, 3, hl * s, wl * s, generator=gen, requires_grad=True)
+            out = O.cem_project(x, G, cem.ds_kernel, cem.inv_hTh, s, pre)
+            if crop:
+                out = out[:, :, crop:-crop, crop:-crop]
+            wt = torch.randn(out.shape, generator=gen)
+            (out * wt).sum().backward()
+            g_G, g_x = mod.project_backward(wt.to(DEV), (hl * s, wl * s), crop=crop)
+            assert rel_err(g_G.cpu(), G.grad)[0] < 2e-5, (s, crop)
+            assert rel_err(g_x.cpu(), x.grad)[0] < 2e-5, (s, crop)
+
+
+@pytest.mark.parametrize('name,fixture,eval_mode', [('grad_cem_rrdb_latent_eval', 'rrdb_latent_x4', True),
+                                                    ('grad_cem_rrdb_plain_train', 'rrdb_plain_x4', False)])
+def test_input_gradient_matches_reference_autograd(name, fixture, eval_mode):
+    """Z-optimisation's backward: d(sum(out*Wt))/d[Z|LR] through CEM(G(.)) vs the reference's own autograd.
+    Tolerance: rel-L2 <= 2e-3 / max <= 4e-3 of the gradient range (two passes through fp16-operand convs)."""
+    _ops()
+    from CEM.CEMnet import CEMnet, Get_CEM_Conf
+    g, gw = golden(name), golden(fixture)
+    wrapped = CEMnet(Get_CEM_Conf(4)).WrapArchitecture_PyTorch(mirror_rrdb(gw), None).to(DEV)
+    for p in wrapped.parameters():
+        p.requires_grad_(False)
+    wrapped.eval() if eval_mode else wrapped.train()
+    x = torch.from_numpy(g['x']).to(DEV).requires_grad_(True)
+    out = wrapped(x)
+    assert (out.detach().cpu() - torch.from_numpy(g['out'])).abs().max().item() < 1e-3
+    (out * torch.from_numpy(g['wt']).to(DEV)).sum().backward()
+    ref = torch.from_numpy(g['gx'])
+    got = x.grad.cpu()
+    zc = ref.shape[1] - 3
+    if zc:   # latent part (always exact); LR-image part only in train mode
+        emax, el2 = rel_err(got[:, :zc], ref[:, :zc])
+        print(name, 'latent grad: max %.2e l2 %.2e' % (emax, el2))
+        assert el2 < 2e-3 and emax < 4e-3, (emax, el2)
+    if not eval_mode:
+        emax, el2 = rel_err(got[:, zc:], ref[:, zc:])
+        print(name, 'image grad: max %.2e l2 %.2e' % (emax, el2))
+        assert el2 < 2e-3 and emax < 4e-3, (emax, el2)
+
+
+def test_rrdb_latent_input_gradient_matches_reference_autograd():
+    _ops()
+    g, gw = golden('grad_rrdb_latent'), golden('rrdb_latent_x4')
+    net = mirror_rrdb(gw).to(DEV)
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x = torch.from_numpy(g['x']).to(DEV).requires_grad_(True)
+    (net(x) * torch.from_numpy(g['wt']).to(DEV)).sum().backward()
+    emax, el2 = rel_err(x.grad.cpu(), torch.from_numpy(g['gx']))
+    print('rrdb latent grad: max %.2e l2 %.2e' % (emax, el2))
+    assert el2 < 2e-3 and emax < 4e-3, (emax, el2)
+
+
+def test_wgrad_is_refused_loudly():
+    _ops()
+    g = golden('rrdb_plain_x4')
+    net = mirror_rrdb(g).to(DEV)       # parameters require grad by default
+    with pytest.raises(NotImplementedError):
+        net(torch.from_numpy(g['x']).to(DEV))

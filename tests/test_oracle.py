@@ -73,3 +73,17 @@ def test_cem_invariants_on_the_oracle():
     again = O.cem_project(x, out, dk, ih, 4, 1)
     assert (again - out)[:, :, 4 * m:-4 * m, 4 * m:-4 * m].abs().max() < 5e-5
     assert abs(float(dk.sum()) - 1) < 1e-6
+
+
+@pytest.mark.parametrize('name,fixture,eval_mode', [('grad_cem_rrdb_latent_eval', 'rrdb_latent_x4', True),
+                                                    ('grad_cem_rrdb_plain_train', 'rrdb_plain_x4', False)])
+def test_input_gradient_matches_reference_autograd(name, fixture, eval_mode):
+    """d(sum(out*Wt))/dx through the oracle (torch autograd on the restatement) vs the reference's own autograd."""
+    g, gw, gc = golden(name), golden(fixture), golden('cem_x4')
+    nf, nb, s, z = [int(v) for v in gw['cfg']]
+    sd = golden_state_dict(gw, prefix='generated_image_model.')
+    x = torch.from_numpy(g['x']).clone().requires_grad_(True)
+    out = O.cem_wrapped_forward(x, sd, gc['ds_kernel'], gc['inv_hTh'], s, 1, int(gc['margins'][0]), eval_mode, nf, nb, z=z)
+    (out * torch.from_numpy(g['wt'])).sum().backward()
+    emax, el2 = rel_err(x.grad, torch.from_numpy(g['gx']))
+    assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
