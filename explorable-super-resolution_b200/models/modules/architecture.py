@@ -55,7 +55,6 @@ class RRDBNet(nn.Module):
         self.model = nn.ModuleList(as_list(fea_conv) + [shortcut] + upsampler + as_list(HR_conv0) + as_list(HR_conv1))
         self._engines = {}
         self.compute_dtype = torch.float16
-        self.trunk_mode = 'rrdb'
 
     # ---- engine-facing helpers ----------------------------------------------------------------------
     def upsamplers(self):
@@ -66,9 +65,9 @@ class RRDBNet(nn.Module):
 
     def engine(self):
         from esr_b200.engine import RRDBEngine
-        key = (self.compute_dtype, self.trunk_mode)
+        key = self.compute_dtype
         if key not in self._engines:
-            self._engines[key] = RRDBEngine(self, dtype=key[0], trunk=key[1])
+            self._engines[key] = RRDBEngine(self, dtype=key)
         return self._engines[key]
 
     def forward(self, x, pad=0):

@@ -140,6 +140,41 @@ def main():
     (outz * wtz).sum().backward()
     save('grad_rrdb_latent', x=xz.numpy(), wt=wtz.numpy(), gx=netz_g.grad.numpy())
 
+    # E3. "kink-free" gradient fixture.  LeakyReLU's derivative jumps at 0, so wherever a pre-activation is smaller than
+    #     the forward rounding error a reduced-precision implementation may legitimately pick the other slope; the
+    #     resulting outliers say nothing about the backward arithmetic.  Here every LeakyReLU input is kept far from 0
+    #     (per-channel biases of magnitude 2..3 with random signs, small weights), so both slopes are exercised and the
+    #     gradient is comparable element-wise at operand precision.
+    netk = build_rrdb(7, scale=0.1, in_nc=3, out_nc=3, nf=32, nb=2, upscale=4, latent_input='all_layers_HR_downscaled',
+                      num_latent_channels=3)
+    with torch.no_grad():
+        for name, p in netk.named_parameters():
+            if name.endswith('bias'):
+                sign = torch.where(torch.rand(p.shape, generator=g) < 0.5, -1.0, 1.0)
+                p.copy_(q16(sign * (2.0 + torch.rand(p.shape, generator=g))))
+    margins = []
+    hooks = [m.register_forward_pre_hook(lambda mod, inp: margins.append(float(inp[0].abs().min())))
+             for m in netk.modules() if isinstance(m, torch.nn.LeakyReLU)]
+    cemk = CEMnet(Get_CEM_Conf(4))
+    wk = cemk.WrapArchitecture_PyTorch(netk, None)
+    for p in wk.parameters():
+        p.requires_grad_(False)
+    zk = q16(torch.rand(1, 3, 80, 64, generator=g) * 2 - 1)
+    xk = torch.cat([zk.contiguous().view(1, 48, 20, 16), rnd(1, 3, 20, 16)], 1)
+    for mode in ('eval', 'train'):
+        wk.eval() if mode == 'eval' else wk.train()
+        xi = xk.clone().requires_grad_(True)
+        out = wk(xi)
+        wt = torch.randn(out.shape, generator=g)
+        (out * wt).sum().backward()
+        extra = {'w:' + k: v for k, v in sd_np(netk).items()} if mode == 'eval' else {}
+        save('grad_kinkfree_latent_' + mode, x=xk.numpy(), wt=wt.numpy(), out=out.detach().numpy(), gx=xi.grad.numpy(),
+             cfg=np.array([32, 2, 4, 3]), min_preact=np.array(min(margins)), **extra)
+    for hk in hooks:
+        hk.remove()
+    print('kink-free fixture: min |LeakyReLU input| = %.3f' % min(margins))
+    assert min(margins) > 0.05
+
     # F. BASELINE config 1 (nf=32, nb=4, 1x3x128x128 -> 512x512): weights from the reference's own seeded
     # training init (kaiming x0.1, networks.py:118-119) are too big to store; keep the seed and a digest.
     torch.manual_seed(0)

@@ -76,7 +76,9 @@ def test_cem_invariants_on_the_oracle():
 
 
 @pytest.mark.parametrize('name,fixture,eval_mode', [('grad_cem_rrdb_latent_eval', 'rrdb_latent_x4', True),
-                                                    ('grad_cem_rrdb_plain_train', 'rrdb_plain_x4', False)])
+                                                    ('grad_cem_rrdb_plain_train', 'rrdb_plain_x4', False),
+                                                    ('grad_kinkfree_latent_eval', 'grad_kinkfree_latent_eval', True),
+                                                    ('grad_kinkfree_latent_train', 'grad_kinkfree_latent_eval', False)])
 def test_input_gradient_matches_reference_autograd(name, fixture, eval_mode):
     """d(sum(out*Wt))/dx through the oracle (torch autograd on the restatement) vs the reference's own autograd."""
     g, gw, gc = golden(name), golden(fixture), golden('cem_x4')
