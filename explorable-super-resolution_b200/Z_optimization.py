@@ -1,0 +1,277 @@
+"""Latent-exploration inner loop with the reference's surface (Z_optimization.py): `Optimizable_Z`, `ArcTanH`,
+`TV_Loss`, `Z_optimizer`.
+
+The loop itself (Z_optimization.py:647-797) is host code, as in the reference: Adam over a tanh-parametrised latent map,
+one generator+CEM forward WITH gradient per iteration, loss on the clamped output, backward to Z only.  What changes is
+underneath `model.test(prevent_grads_calc=False)` / `Z_loss.backward()`: a single autograd node that runs the fused
+tcgen05 forward launches and, in backward, the dgrad launches + the exact CEM adjoint (esr_b200.autograd) instead of
+~1800 autograd nodes over cuDNN calls.
+
+Objectives built: 'l1' (optionally masked), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' / 'STD_decrease' (global),
+'random_l1' (+ '_limited').  The patch-based ('local', 'Mag', 'periodicity'), histogram/dictionary, scribble, VGG,
+Adversarial, desired_SVD and digit objectives are SURVEY §8(f)-1 and raise NotImplementedError."""
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _dev():
+    return torch.device('cuda')
+
+
+class Optimizable_Z(torch.nn.Module):
+    """Z = Z_range * tanh(pre_tanh_Z), optionally frozen to its initial value outside Z_mask (Z_optimization.py:273-319)."""
+
+    def __init__(self, Z_shape, Z_range=None, initial_pre_tanh_Z=None, Z_mask=None, random_perturbations=False):
+        super(Optimizable_Z, self).__init__()
+        self.Z = torch.nn.Parameter(data=torch.zeros(Z_shape, dtype=torch.float32, device=_dev()))
+        self.mask = None
+        if Z_mask is not None and not np.all(Z_mask):
+            self.mask = torch.from_numpy(np.asarray(Z_mask)).float().to(self.Z.device)
+            self.initial_pre_tanh_Z = (1 * initial_pre_tanh_Z).float().to(self.Z.device)
+        if initial_pre_tanh_Z is not None:
+            assert initial_pre_tanh_Z.size()[1:] == self.Z.data.size()[1:] and (initial_pre_tanh_Z.size(0) in [1, self.Z.data.size(0)]), \
+                'Initilizer size does not match desired Z size'
+            if random_perturbations:
+                initial_pre_tanh_Z = initial_pre_tanh_Z + 0.001 * torch.randn_like(initial_pre_tanh_Z)
+            self.Z.data[:initial_pre_tanh_Z.size(0), ...] = initial_pre_tanh_Z.to(self.Z.device)
+        self.Z_range = Z_range
+
+    def forward(self):
+        if self.Z_range is not None:
+            big = torch.finfo(self.Z.dtype).max
+            self.Z.data = torch.clamp(self.Z.data, -big, big)
+        if self.mask is not None:
+            self.Z.data = self.mask * self.Z.data + (1 - self.mask) * self.initial_pre_tanh_Z
+        return self.Z_range * torch.tanh(self.Z) if self.Z_range is not None else self.Z
+
+    def PreTanhZ(self):
+        if self.mask is not None:
+            return self.mask * self.Z.data + (1 - self.mask) * self.initial_pre_tanh_Z
+        return self.Z.data
+
+    def Randomize_Z(self, what_2_shuffle):
+        assert what_2_shuffle in ['all', 'allButFirst']
+        torch.nn.init.xavier_uniform_(self.Z.data if what_2_shuffle == 'all' else self.Z.data[1:], gain=100)
+
+    def Return_Detached_Z(self):
+        return self.forward().detach()
+
+    def Assign_Z(self, Z):
+        self.Z.data = 1 * Z
+
+
+def ArcTanH(input_tensor):
+    eps = torch.finfo(input_tensor.dtype).eps
+    return 0.5 * torch.log((1 + input_tensor + eps) / (1 - input_tensor + eps))
+
+
+def TV_Loss(image):
+    return (image[:, :, :, :-1] - image[:, :, :, 1:]).abs().mean(dim=(1, 2, 3)) + (image[:, :, :-1, :] - image[:, :, 1:, :]).abs().mean(dim=(1, 2, 3))
+
+
+_UNBUILT = ['local', 'Mag', 'periodicity', 'hist', 'dict', 'scribble', 'VGG', 'Adversarial', 'desired_SVD', 'digit']
+
+
+class Z_optimizer():
+    MIN_LR = 1e-5
+    PATCH_SIZE_4_STD = 7
+
+    def __init__(self, objective, Z_size, model, Z_range, max_iters, data=None, loggers=None, image_mask=None, Z_mask=None, initial_Z=None,
+                 initial_LR=None, existing_optimizer=None, batch_size=1, HR_unpadder=None, auto_set_hist_temperature=False, random_Z_inits=False,
+                 jpeg_extractor=None, non_local_Z_optimization=False):
+        if jpeg_extractor is not None:
+            raise NotImplementedError('esr_b200: the JPEG sibling project is out of scope')
+        for word in _UNBUILT:
+            if word in objective:
+                raise NotImplementedError('esr_b200: Z_optimizer objective [%s] is not built yet (SURVEY 8f-1)' % objective)
+        self.jpeg_mode = False
+        self.data_keys = {'reconstructed': 'SR'}
+        if initial_Z is not None or 'cur_Z' in model.__dict__.keys():
+            if initial_Z is None:
+                initial_Z = 1 * model.GetLatent()
+            eps = torch.finfo(initial_Z.dtype).eps
+            initial_pre_tanh_Z = ArcTanH(torch.clamp(initial_Z / Z_range, min=-1 + eps, max=1. - eps))
+        else:
+            initial_pre_tanh_Z = None
+        self.non_local_Z_optimization = non_local_Z_optimization and image_mask is not None and image_mask.mean() < 1
+        self.model_training = HR_unpadder is not None
+        assert not (self.non_local_Z_optimization and self.model_training), 'Shouldn''t happen...'
+        if not self.model_training:
+            self.initial_output = model.Output_Batch(within_0_1=True)
+        if self.non_local_Z_optimization:
+            from cv2 import dilate
+            NON_EDIT_MARGINS = 24
+            new_Z_mask = np.zeros_like(Z_mask)
+            new_Z_mask[NON_EDIT_MARGINS:-NON_EDIT_MARGINS, NON_EDIT_MARGINS:-NON_EDIT_MARGINS] = 1
+            Z_mask = np.minimum(1, new_Z_mask + dilate(image_mask, np.ones([16, 16])))
+        self.Z_model = Optimizable_Z(Z_shape=[batch_size, model.num_latent_channels] + list(Z_size), Z_range=Z_range,
+                                     initial_pre_tanh_Z=initial_pre_tanh_Z, Z_mask=Z_mask,
+                                     random_perturbations=(random_Z_inits and 'random' not in objective) or ('random' in objective and 'limited' in objective))
+        assert (initial_LR is not None) or (existing_optimizer is not None), \
+            'Should either supply optimizer from previous iterations or initial LR for new optimizer'
+        self.objective = objective
+        self.data = data
+        self.device = _dev()
+        self.model = model
+        if image_mask is None:
+            self.image_mask = torch.ones(list(model.fake_H.size()[2:]), dtype=model.fake_H.dtype, device=self.device) \
+                if 'fake_H' in model.__dict__.keys() else None
+            self.Z_mask = None
+        else:
+            assert Z_mask is not None, 'Should either supply both masks or niether'
+            self.image_mask = torch.from_numpy(image_mask).type(model.fake_H.dtype).to(self.device)
+            self.Z_mask = torch.from_numpy(Z_mask).type(model.fake_H.dtype).to(self.device)
+            self.initial_Z = 1. * model.GetLatent()
+            if self.non_local_Z_optimization:
+                self.constraining_mask = 1 - (self.image_mask > 0).type(self.image_mask.dtype)
+                self.constraining_loss = lambda produced_im: F.l1_loss(input=produced_im * self.constraining_mask,
+                                                                       target=self.initial_output * self.constraining_mask)
+                self.constraining_loss_weight = 0.1
+        if not self.model_training:
+            self.initial_STD = self.Masked_STD(first_image_only=True)
+            print('Initial STD: %.3e' % (self.initial_STD.mean().item()))
+        if existing_optimizer is None:
+            if 'l1' in objective and 'random' not in objective:
+                if data is not None and 'desired' in data.keys():
+                    self.desired_im = data['desired']
+                if self.image_mask is None:
+                    self.loss = torch.nn.L1Loss()
+                else:
+                    loss_mask = (self.image_mask > 0).type(self.image_mask.dtype)
+                    self.loss = lambda produced_im, GT_im: torch.stack(
+                        [F.l1_loss(input=produced_im[i].unsqueeze(0) * loss_mask, target=GT_im * loss_mask) for i in range(produced_im.size(0))], 0)
+                    self.constraining_loss_weight = 1
+            elif 'STD' in objective and 'TV' not in objective:
+                assert self.objective in ['max_STD', 'min_STD', 'STD_increase', 'STD_decrease']
+                if any(p in objective for p in ['increase', 'decrease']):
+                    STD_CHANGE_FACTOR = 1.05
+                    self.desired_STD = self.initial_STD
+                    if data['STD_increment'] is None:
+                        self.desired_STD = self.desired_STD * (STD_CHANGE_FACTOR if 'increase' in objective else 1 / STD_CHANGE_FACTOR)
+                    else:
+                        self.desired_STD = self.desired_STD + (data['STD_increment'] if 'increase' in objective else -data['STD_increment'])
+                        self.constraining_loss_weight = 255 / 10 * data['STD_increment'] ** 2
+            elif 'TV' in objective:
+                self.STD_PRESERVING_WEIGHT = 100
+            elif 'limited' in objective:
+                self.initial_image = 1 * model.output_image.detach()
+                self.rmse_weight = data['rmse_weight']
+            elif 'random' in objective:
+                self.STD_PRESERVING_WEIGHT = 1e3
+            self.optimizer = torch.optim.Adam(self.Z_model.parameters(), lr=initial_LR)
+        else:
+            self.optimizer = existing_optimizer
+        self.LR = initial_LR
+        self.scheduler = None
+        self.loggers = loggers
+        self.cur_iter = 0
+        self.max_iters = max_iters
+        self.random_Z_inits = 'all' if (random_Z_inits or self.model_training) \
+            else 'allButFirst' if (initial_pre_tanh_Z is not None and initial_pre_tanh_Z.size(0) < batch_size) else False
+        self.HR_unpadder = HR_unpadder
+
+    def Masked_STD(self, first_image_only=False):
+        model_output = self.model.Output_Batch(within_0_1=True)
+        return torch.std(model_output * self.image_mask, dim=(1, 2, 3)).view(1, -1)
+
+    def feed_data(self, data):
+        self.data = data
+        self.cur_iter = 0
+        if 'l1' in self.objective:
+            self.desired_im = data['desired'].to(self.device)
+
+    def Manage_Model_Grad_Requirements(self, verify_disabled):
+        if verify_disabled:
+            self.original_requires_grad_status = []
+            for p in self.model.netG.parameters():
+                self.original_requires_grad_status.append(p.requires_grad)
+                p.requires_grad = False
+        else:
+            for i, p in enumerate(self.model.netG.parameters()):
+                p.requires_grad = self.original_requires_grad_status[i]
+
+    def optimize(self):
+        USE_MIN_LOSS_Z = not self.model_training
+        self.Manage_Model_Grad_Requirements(verify_disabled=True)
+        self.loss_values, per_iter_pre_tanh_Z = [], []
+        if self.random_Z_inits and self.cur_iter == 0:
+            self.Z_model.Randomize_Z(what_2_shuffle=self.random_Z_inits)
+        z_iter = self.cur_iter
+        while True:
+            if self.max_iters > 0:
+                if z_iter == (self.cur_iter + self.max_iters):
+                    break
+            elif len(self.loss_values) >= -self.max_iters:  # stop when the loss stops decreasing, or after 5*|max_iters|
+                if z_iter == (self.cur_iter - 5 * self.max_iters):
+                    break
+                if (self.loss_values[self.max_iters] - self.loss_values[-1]) / np.abs(self.loss_values[self.max_iters]) < 1e-2 * self.LR:
+                    break
+            self.optimizer.zero_grad()
+            self.data['Z'] = self.Z_model()
+            if USE_MIN_LOSS_Z:
+                per_iter_pre_tanh_Z.append(1 * self.Z_model.PreTanhZ())
+            self.model.feed_data(self.data, need_GT=False)
+            self.model.test(prevent_grads_calc=False)
+            self.output_image = self.model.Output_Batch(within_0_1=True)
+            if self.model_training:
+                self.output_image = self.HR_unpadder(self.output_image)
+            if 'random' in self.objective:
+                dom = self.output_image
+                Z_loss = torch.min((dom.unsqueeze(0) - dom.unsqueeze(1)).abs() +
+                                   torch.eye(dom.size(0), device=dom.device).unsqueeze(2).unsqueeze(3).unsqueeze(4), dim=0)[0]
+                if 'limited' in self.objective:
+                    Z_loss = Z_loss - self.rmse_weight * (dom - self.initial_image).abs()
+                if self.Z_mask is not None:
+                    Z_loss = Z_loss * self.image_mask
+                Z_loss = -1 * Z_loss.mean(dim=(1, 2, 3))
+            elif 'l1' in self.objective:
+                Z_loss = self.loss(self.output_image.to(self.device), self.desired_im.to(self.device))
+            elif 'STD' in self.objective and 'TV' not in self.objective:
+                Z_loss = self.Masked_STD(first_image_only=False)
+                if any(p in self.objective for p in ['increase', 'decrease']):
+                    Z_loss = (Z_loss - self.desired_STD) ** 2
+                Z_loss = Z_loss.mean(0)
+            elif 'TV' in self.objective:
+                Z_loss = (self.STD_PRESERVING_WEIGHT * (self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean(0) + \
+                    TV_Loss(self.output_image * self.image_mask)
+            if 'max' in self.objective:
+                Z_loss = -1 * Z_loss
+            cur_LR = self.optimizer.param_groups[0]['lr']
+            if self.loggers is not None:
+                for logger_num, logger in enumerate(self.loggers):
+                    cur_value = Z_loss[logger_num].mean().item() if Z_loss.dim() > 0 else Z_loss.mean().item()
+                    logger.print_format_results('val', {'epoch': 0, 'iters': z_iter, 'time': time.time(), 'model': '', 'lr': cur_LR,
+                                                        'Z_loss': cur_value}, dont_print=True)
+            if not self.model_training:
+                self.latest_Z_loss_values = [val.mean().item() for val in Z_loss] if Z_loss.dim() > 0 else [Z_loss.item()]
+            Z_loss = Z_loss.mean()
+            if self.non_local_Z_optimization:
+                Z_loss = Z_loss + self.constraining_loss_weight * self.constraining_loss(self.output_image.to(self.device))
+            Z_loss.backward()
+            self.loss_values.append(Z_loss.item())
+            self.optimizer.step()
+            z_iter += 1
+        if USE_MIN_LOSS_Z:
+            if np.min(self.loss_values) != self.loss_values[-1]:
+                min_loss_iter = int(np.argmin(self.loss_values))
+                print('Minimum loss observed in %d/%d iteration, discarding subsequent iterations.' % (min_loss_iter + 1, len(self.loss_values)))
+                self.Z_model.Z.data = 1 * per_iter_pre_tanh_Z[min_loss_iter]
+                self.loss_values = self.loss_values[:min_loss_iter + 1]
+        if 'random' in self.objective and 'limited' in self.objective:
+            self.loss_values[0] = self.loss_values[1]
+        self.cur_iter = z_iter + 1
+        Z_2_return = self.Z_model.Return_Detached_Z()
+        self.Manage_Model_Grad_Requirements(verify_disabled=False)
+        if not self.model_training:
+            print('Final STDs: ', ['%.3e' % (val.item()) for val in self.Masked_STD(first_image_only=False).mean(0)])
+        if self.model_training:
+            self.data['Z'] = Z_2_return
+            self.model.feed_data(self.data, need_GT=False)
+            self.model.fake_H = self.model.netG(self.model.model_input)
+        return Z_2_return
+
+    def ReturnStatus(self):
+        return self.cur_iter, self.Z_model.PreTanhZ()

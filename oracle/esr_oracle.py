@@ -156,3 +156,27 @@ def pack_latent(z_hr, x_lr, s):
     [B, c*s^2, H, W] and concatenated in front of the LR image."""
     b, c, hh, wh = z_hr.shape
     return torch.cat([z_hr.contiguous().view(b, c * s * s, hh // s, wh // s), x_lr], 1)
+
+
+def z_optimize_l1(sd, ds_kernel, inv_hTh, s, pre, margin_lr, nf, nb, z, x_lr, desired, Z_range, lr, iters, batch=1):
+    """Z_optimizer.optimize for objective 'l1' with all-ones masks (Z_optimization.py:647-797 with :292-300, :683-734):
+    Adam on the pre-tanh latent map (init 0), Z = Z_range*tanh(.), eval-mode CEM(G([Z | LR])), output clamped to [0,1]
+    (SRRaGAN_model.py:224-228), per-image L1 to `desired`, mean over the batch.  The iterate with the minimum loss is kept
+    (:755-762).  Returns (loss values, final Z)."""
+    zp = torch.zeros(batch, z, s * x_lr.size(2), s * x_lr.size(3), requires_grad=True)
+    opt = torch.optim.Adam([zp], lr=lr)
+    losses, iterates = [], []
+    lr_b = x_lr.expand(batch, -1, -1, -1)
+    for _ in range(iters):
+        opt.zero_grad()
+        iterates.append(zp.detach().clone())
+        Z = Z_range * torch.tanh(zp)
+        out = cem_wrapped_forward(pack_latent(Z, lr_b, s), sd, ds_kernel, inv_hTh, s, pre, margin_lr, True, nf, nb, z=z)
+        out = torch.clamp(out, 0, 1)
+        loss = torch.stack([F.l1_loss(out[i:i + 1], desired) for i in range(batch)], 0).mean()
+        loss.backward()
+        losses.append(loss.item())
+        opt.step()
+    best = int(np.argmin(losses))
+    final = zp.detach() if losses[best] == losses[-1] else iterates[best]
+    return losses if losses[best] == losses[-1] else losses[:best + 1], Z_range * torch.tanh(final)
