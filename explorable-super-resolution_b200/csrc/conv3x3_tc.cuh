@@ -14,7 +14,8 @@
 // Columns tx >= P-2 of each flattened row are junk (they wrap into the next row) and are discarded by the
 // epilogue: M efficiency (P-2)/P.
 //
-// CTA = 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue.
+// CTA = 12 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 4..11 = epilogue; setmaxnreg moves
+// the registers the first warpgroup does not need (56/thread) to the epilogue warpgroups (224/thread).
 // Persistent over (tile, n-block) work items; TMEM accumulators are double buffered so the epilogue of
 // item i overlaps the MMAs of item i+1.
 #pragma once
@@ -24,7 +25,7 @@
 
 namespace esr {
 
-constexpr int kConvThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kConvThreads = 384;  // warpgroup 0: TMA warp, MMA warp (+2 idle); warpgroups 1,2: 8 epilogue warps
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemHeader = 1024;  // barriers + tmem pointer
 constexpr uint32_t kASlack = 128;       // junk rows of the last M tile may read a few pixels past the last plane
@@ -81,6 +82,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
 // P (tile pitch), KCP (planes per K chunk) and NBN (MMA N) are compile-time so that every operand descriptor
 // of the 9 x KCP/2 MMAs of a (chunk, M tile) is the chunk's base descriptor plus an immediate: the single
 // issuing thread spends one 64-bit add per operand per MMA instead of rebuilding descriptors.
+// kBwd selects the epilogue: false = forward (bias/LeakyReLU/two residuals, 32-channel units), true = adds the dgrad
+// features (latent lead planes, LeakyReLU-derivative mask, third residual) with 16-channel units to stay in registers.
 __device__ __forceinline__ void unpack8(const uint4& q, int dtype, float (&a)[8]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -97,7 +100,7 @@ __device__ __forceinline__ void unpack8(const uint4& q, int dtype, float (&a)[8]
   }
 }
 
-template <int P, int KCP, int NBN>
+template <int P, int KCP, int NBN, bool kBwd>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -141,6 +144,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int total_items = p.num_tiles * p.n_blocks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -211,14 +216,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
+  }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ------------------------------------------------------------------ epilogue (warps 4..11)
     // Two warps per TMEM lane quarter; they alternate over the M tiles of an item.  Per (row, unit of UW
     // channels) every global load (residuals, bias) is issued before the first store so that a thread
     // keeps UW/8 .. 3*UW/8 128-bit loads in flight.
-    constexpr int UW = 16;  // 16 channels per unit keeps the prefetch registers (3 fp32 residuals + mask + bias) under the 168-register cap
+    constexpr int UW = (!kBwd && NBN % 32 == 0) ? 32 : 16;  // dgrad prefetches more (3 residuals + mask): smaller units
     const int wq = warp & 3;            // TMEM lane quarter this warp may touch
-    const int eh = (warp - 2) >> 2;     // which half of the M tiles this warp takes
+    const int eh = (warp - 4) >> 2;     // which half of the M tiles this warp takes
     int it = 0;
     const size_t hw = (size_t)p.h * p.w;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -255,10 +262,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               if (chu + g * 8 < p.cout) {
-                bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
-                bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
-                const int gp = gu + g - p.lead_planes;
-                if (gp < 0) {
+                if (!kBwd) {  // forward: bias prefetched with the residuals (dgrad has no bias and fewer spare registers)
+                  bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
+                  bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+                }
+                const int gp = gu + g - (kBwd ? p.lead_planes : 0);
+                if (kBwd && gp < 0) {
                   const float4* rp = reinterpret_cast<const float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
                   f2[g][0] = rp[0]; f2[g][1] = rp[1];
                   continue;
@@ -277,14 +286,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   // plain loads: res2 may alias out32 (in-place accumulation of gradients)
                   const float4* rp = reinterpret_cast<const float4*>(
                       p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gp) * hw + pix) * 8);
-                  f2[g][0] = rp[0]; f2[g][1] = rp[1];
+                  if (kBwd) { f2[g][0] = rp[0]; f2[g][1] = rp[1]; }
+                  else { f2[g][0] = __ldg(rp); f2[g][1] = __ldg(rp + 1); }
                 }
-                if (p.res3) {
+                if (kBwd && p.res3) {
                   const float4* rp = reinterpret_cast<const float4*>(
                       p.res3 + (((size_t)img * p.res3_pt + p.res3_po + gp) * hw + pix) * 8);
                   f3[g][0] = __ldg(rp); f3[g][1] = __ldg(rp + 1);
                 }
-                if (p.mask16 && gp >= p.tail_first) {
+                if (kBwd && p.mask16 && gp >= p.tail_first) {
                   qm[g] = __ldg(reinterpret_cast<const uint4*>(p.mask16 + (((size_t)img * p.mask_pt + p.mask_po + gp) * hw + pix) * 8));
                 }
               }
@@ -296,14 +306,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int g = 0; g < G; ++g) {
               const int ch0 = chu + g * 8;
               if (ch0 >= p.cout) continue;
-              const int gp = gu + g - p.lead_planes;
+              const int gp = gu + g - (kBwd ? p.lead_planes : 0);
               const uint32_t* rg = &r[g / 2][(g & 1) * 8];
               float v[8];
-              v[0] = __uint_as_float(rg[0]) + bb[g][0].x; v[1] = __uint_as_float(rg[1]) + bb[g][0].y;
-              v[2] = __uint_as_float(rg[2]) + bb[g][0].z; v[3] = __uint_as_float(rg[3]) + bb[g][0].w;
-              v[4] = __uint_as_float(rg[4]) + bb[g][1].x; v[5] = __uint_as_float(rg[5]) + bb[g][1].y;
-              v[6] = __uint_as_float(rg[6]) + bb[g][1].z; v[7] = __uint_as_float(rg[7]) + bb[g][1].w;
-              if (gp < 0) {  // latent planes: lead_acc += alpha * acc
+              {
+                float4 b0, b1;
+                if (kBwd) { b0 = make_float4(0.f, 0.f, 0.f, 0.f); b1 = b0; }   // transposed convs carry no bias
+                else { b0 = bb[g][0]; b1 = bb[g][1]; }
+                v[0] = __uint_as_float(rg[0]) + b0.x; v[1] = __uint_as_float(rg[1]) + b0.y;
+                v[2] = __uint_as_float(rg[2]) + b0.z; v[3] = __uint_as_float(rg[3]) + b0.w;
+                v[4] = __uint_as_float(rg[4]) + b1.x; v[5] = __uint_as_float(rg[5]) + b1.y;
+                v[6] = __uint_as_float(rg[6]) + b1.z; v[7] = __uint_as_float(rg[7]) + b1.w;
+              }
+              if (kBwd && gp < 0) {  // latent planes: lead_acc += alpha * acc
                 float4* op = reinterpret_cast<float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
                 op[0] = make_float4(fmaf(p.alpha, v[0], f2[g][0].x), fmaf(p.alpha, v[1], f2[g][0].y), fmaf(p.alpha, v[2], f2[g][0].z),
                                     fmaf(p.alpha, v[3], f2[g][0].w));
@@ -334,7 +349,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
                 v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
               }
-              if (p.res3) {
+              if (kBwd && p.res3) {
                 v[0] = fmaf(p.beta3, f3[g][0].x, v[0]); v[1] = fmaf(p.beta3, f3[g][0].y, v[1]);
                 v[2] = fmaf(p.beta3, f3[g][0].z, v[2]); v[3] = fmaf(p.beta3, f3[g][0].w, v[3]);
                 v[4] = fmaf(p.beta3, f3[g][1].x, v[4]); v[5] = fmaf(p.beta3, f3[g][1].y, v[5]);
@@ -353,8 +368,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   if (ch < p.out_nchw_c) p.out_nchw[((size_t)img * p.out_nchw_c + ch) * hw + pix] = v[k];
                 }
               }
-              if (p.out16 && gp >= p.tail_first) {
-                if (p.mask16) {
+              if (p.out16 && (!kBwd || gp >= p.tail_first)) {
+                if (kBwd && p.mask16) {
                   float a[8];
                   unpack8(qm[g], p.dtype, a);
 #pragma unroll

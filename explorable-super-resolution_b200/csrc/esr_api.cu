@@ -72,19 +72,20 @@ int num_sms() {
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const esr::ConvParams);
 
-template <int P, int KCP>
+template <int P, int KCP, bool kBwd>
 ConvKernelFn select_n(int nb_n) {
   switch (nb_n) {
-    case 16: return esr::conv3x3_tc_kernel<P, KCP, 16>;
-    case 32: return esr::conv3x3_tc_kernel<P, KCP, 32>;
-    case 48: return esr::conv3x3_tc_kernel<P, KCP, 48>;
-    case 64: return esr::conv3x3_tc_kernel<P, KCP, 64>;
+    case 16: return esr::conv3x3_tc_kernel<P, KCP, 16, kBwd>;
+    case 32: return esr::conv3x3_tc_kernel<P, KCP, 32, kBwd>;
+    case 48: return esr::conv3x3_tc_kernel<P, KCP, 48, kBwd>;
+    case 64: return esr::conv3x3_tc_kernel<P, KCP, 64, kBwd>;
   }
   return nullptr;
 }
-ConvKernelFn select_conv_kernel(int P, int kcp, int nb_n) {
-  if (P == 32 && kcp == 4) return select_n<32, 4>(nb_n);
-  if (P == 32 && kcp == 2) return select_n<32, 2>(nb_n);
+ConvKernelFn select_conv_kernel(int P, int kcp, int nb_n, bool bwd) {
+  if (P != 32) return nullptr;
+  if (kcp == 4) return bwd ? select_n<32, 4, true>(nb_n) : select_n<32, 4, false>(nb_n);
+  if (kcp == 2) return bwd ? select_n<32, 2, true>(nb_n) : select_n<32, 2, false>(nb_n);
   return nullptr;
 }
 
@@ -252,7 +253,8 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
-  ConvKernelFn kern = select_conv_kernel(p.P, p.kcp, p.nb_n);
+  const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
+  ConvKernelFn kern = select_conv_kernel(p.P, p.kcp, p.nb_n, bwd);
   if (!kern) return fail(ESR_ERR_INVALID, "conv3x3: no kernel instance for P=%d kcp=%d N=%d", p.P, p.kcp, p.nb_n);
   {
     static std::mutex mu;
