@@ -143,6 +143,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int total_items = p.num_tiles * p.n_blocks;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  // PDL: the next conv of the stream may begin its prologue (barriers, TMEM, weight loads) while this grid drains;
+  // every access to activations below is preceded by pdl_wait().
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -155,6 +158,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_expect_tx(bar_w, p.w_bytes);
         for (int c = 0; c < p.nchunks; ++c) bulk_load(wres + c * p.b_bytes, p.wts + (size_t)c * p.b_bytes, p.b_bytes, bar_w);
       }
+      pdl_wait();  // weights do not depend on the previous launch, activations do
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int nblk = item / p.num_tiles;
         const int tile = item - nblk * p.num_tiles;
@@ -228,6 +232,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int eh = (warp - 4) >> 2;     // which half of the M tiles this warp takes
     int it = 0;
     const size_t hw = (size_t)p.h * p.w;
+    pdl_wait();  // residual reads and all stores must not overtake the previous launch
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
       const int nblk = item / p.num_tiles;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -268,7 +269,21 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   }
   int grid = p.num_tiles * p.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, esr::kConvThreads, smem_bytes, (cudaStream_t)stream>>>(tm, p);
+  {
+    static const bool use_pdl = [] { const char* e = getenv("ESR_PDL"); return !(e && e[0] == '0'); }();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(esr::kConvThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p));
+  }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
