@@ -294,7 +294,7 @@ def main():
             'clocks': clocks, 'gpu_launches': launches,
             'e2e': {'value': mp_step / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': x_host.numel() * 4,
                     'd2h_bytes_per_step': y_host.numel() * 4},
-            'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel (%d launches/step)' % n_conv, 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_rows_kernel + conv3x3_tc_kernel (%d conv launches/step)' % n_conv, 'achieved': achieved, 'peak': peak,
                          'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': pk_src + ', sustained bf16',
                          'kernel_ms_per_step': conv_ms, 'algorithmic_tflop_per_step': flops_step / 1e12},
         }

@@ -48,6 +48,12 @@ struct ConvParams {
   uint32_t w_bytes;       // nchunks*b_bytes (resident mode)
   uint32_t idesc;
   uint32_t tmem_cols;
+  // row-streaming kernel (conv3x3_rows.cuh): work = n*strips*h output rows of 128 pixels, split into `ranges`
+  // contiguous ranges (one per CTA and n-block); accumulators live in a ring of `slots` TMEM slots of nb_n columns
+  const uint8_t* in; int in_pt;
+  int strips, ranges, slots, cin_planes;
+  long long units;
+  uint32_t idesc_n[3];    // instruction descriptors for N = 1, 2, 3 x nb_n
   const uint8_t* wts;
   const float* bias;
   int cout;
@@ -96,6 +102,269 @@ __device__ __forceinline__ void unpack8(const uint4& q, int dtype, float (&a)[8]
       const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
       const float2 f = __bfloat1622float2(h);
       a[2 * k] = f.x; a[2 * k + 1] = f.y;
+    }
+  }
+}
+
+// Epilogue of one accumulator row of one thread (= one output pixel): TMEM -> registers -> bias / LeakyReLU /
+// residuals -> stores.  `trow` addresses the thread's TMEM lane and the first of the NBN accumulator columns.
+// Shared by the tile kernel below and the row-streaming kernel (conv3x3_rows.cuh).
+template <int NBN, bool kBwd>
+__device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid, int nblk) {
+  constexpr int UW = (!kBwd && NBN % 32 == 0) ? 32 : 16;  // dgrad prefetches more (3 residuals + mask): smaller units
+  const size_t hw = (size_t)p.h * p.w;
+  const size_t pix = (size_t)y * p.w + x;
+#pragma unroll
+  for (int u = 0; u < NBN / UW; ++u) {
+    uint32_t r[UW / 16][16];
+#pragma unroll
+    for (int k = 0; k < UW / 16; ++k) tmem_ld16(trow + u * UW + k * 16, r[k]);
+    const int chu = nblk * NBN + u * UW;   // first conv output channel of this unit
+    const int gu = chu >> 3;               // its plane index in the conv's output
+    constexpr int G = UW / 8;              // groups of 8 channels in a unit
+    uint4 q1[G], qm[G];                    // residual 1 as 16-bit planes, activation for the LeakyReLU mask
+    float4 f1[G][2], f2[G][2], f3[G][2], bb[G][2];
+    const bool on = valid;
+    if (on) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (chu + g * 8 < p.cout) {
+          if (!kBwd) {  // forward: bias prefetched with the residuals (dgrad has no bias and fewer spare registers)
+            bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
+            bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+          }
+          const int gp = gu + g - (kBwd ? p.lead_planes : 0);
+          if (kBwd && gp < 0) {
+            const float4* rp = reinterpret_cast<const float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
+            f2[g][0] = rp[0]; f2[g][1] = rp[1];
+            continue;
+          }
+          if (p.res1) {
+            if (p.res1_is16) {
+              q1[g] = __ldg(reinterpret_cast<const uint4*>(
+                  reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8));
+            } else {
+              const float4* rp = reinterpret_cast<const float4*>(
+                  reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8);
+              f1[g][0] = __ldg(rp); f1[g][1] = __ldg(rp + 1);
+            }
+          }
+          if (p.res2) {
+            // plain loads: res2 may alias out32 (in-place accumulation of gradients)
+            const float4* rp = reinterpret_cast<const float4*>(
+                p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gp) * hw + pix) * 8);
+            if (kBwd) { f2[g][0] = rp[0]; f2[g][1] = rp[1]; }
+            else { f2[g][0] = __ldg(rp); f2[g][1] = __ldg(rp + 1); }
+          }
+          if (kBwd && p.res3) {
+            const float4* rp = reinterpret_cast<const float4*>(
+                p.res3 + (((size_t)img * p.res3_pt + p.res3_po + gp) * hw + pix) * 8);
+            f3[g][0] = __ldg(rp); f3[g][1] = __ldg(rp + 1);
+          }
+          if (kBwd && p.mask16 && gp >= p.tail_first) {
+            qm[g] = __ldg(reinterpret_cast<const uint4*>(p.mask16 + (((size_t)img * p.mask_pt + p.mask_po + gp) * hw + pix) * 8));
+          }
+        }
+      }
+    }
+    tc_wait_ld();
+    if (on) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int ch0 = chu + g * 8;
+        if (ch0 >= p.cout) continue;
+        const int gp = gu + g - (kBwd ? p.lead_planes : 0);
+        const uint32_t* rg = &r[g / 2][(g & 1) * 8];
+        float v[8];
+        {
+          float4 b0, b1;
+          if (kBwd) { b0 = make_float4(0.f, 0.f, 0.f, 0.f); b1 = b0; }   // transposed convs carry no bias
+          else { b0 = bb[g][0]; b1 = bb[g][1]; }
+          v[0] = __uint_as_float(rg[0]) + b0.x; v[1] = __uint_as_float(rg[1]) + b0.y;
+          v[2] = __uint_as_float(rg[2]) + b0.z; v[3] = __uint_as_float(rg[3]) + b0.w;
+          v[4] = __uint_as_float(rg[4]) + b1.x; v[5] = __uint_as_float(rg[5]) + b1.y;
+          v[6] = __uint_as_float(rg[6]) + b1.z; v[7] = __uint_as_float(rg[7]) + b1.w;
+        }
+        if (kBwd && gp < 0) {  // latent planes: lead_acc += alpha * acc
+          float4* op = reinterpret_cast<float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
+          op[0] = make_float4(fmaf(p.alpha, v[0], f2[g][0].x), fmaf(p.alpha, v[1], f2[g][0].y), fmaf(p.alpha, v[2], f2[g][0].z),
+                              fmaf(p.alpha, v[3], f2[g][0].w));
+          op[1] = make_float4(fmaf(p.alpha, v[4], f2[g][1].x), fmaf(p.alpha, v[5], f2[g][1].y), fmaf(p.alpha, v[6], f2[g][1].z),
+                              fmaf(p.alpha, v[7], f2[g][1].w));
+          continue;
+        }
+        if (p.lrelu) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * p.slope;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
+        if (p.res1) {
+          float a[8];
+          if (p.res1_is16) {
+            unpack8(q1[g], p.dtype, a);
+          } else {
+            a[0] = f1[g][0].x; a[1] = f1[g][0].y; a[2] = f1[g][0].z; a[3] = f1[g][0].w;
+            a[4] = f1[g][1].x; a[5] = f1[g][1].y; a[6] = f1[g][1].z; a[7] = f1[g][1].w;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(p.beta1, a[k], v[k]);
+        }
+        if (p.res2) {
+          v[0] = fmaf(p.beta2, f2[g][0].x, v[0]); v[1] = fmaf(p.beta2, f2[g][0].y, v[1]);
+          v[2] = fmaf(p.beta2, f2[g][0].z, v[2]); v[3] = fmaf(p.beta2, f2[g][0].w, v[3]);
+          v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
+          v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
+        }
+        if (kBwd && p.res3) {
+          v[0] = fmaf(p.beta3, f3[g][0].x, v[0]); v[1] = fmaf(p.beta3, f3[g][0].y, v[1]);
+          v[2] = fmaf(p.beta3, f3[g][0].z, v[2]); v[3] = fmaf(p.beta3, f3[g][0].w, v[3]);
+          v[4] = fmaf(p.beta3, f3[g][1].x, v[4]); v[5] = fmaf(p.beta3, f3[g][1].y, v[5]);
+          v[6] = fmaf(p.beta3, f3[g][1].z, v[6]); v[7] = fmaf(p.beta3, f3[g][1].w, v[7]);
+        }
+        if (p.out32) {
+          float4* op = reinterpret_cast<float4*>(
+              p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gp) * hw + pix) * 8);
+          op[0] = make_float4(v[0], v[1], v[2], v[3]);
+          op[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (p.out_nchw) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ch = gp * 8 + k;
+            if (ch < p.out_nchw_c) p.out_nchw[((size_t)img * p.out_nchw_c + ch) * hw + pix] = v[k];
+          }
+        }
+        if (p.out16 && (!kBwd || gp >= p.tail_first)) {
+          if (kBwd && p.mask16) {
+            float a[8];
+            unpack8(qm[g], p.dtype, a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
+          }
+          if (p.out16_ps == 0) {
+            uint4 o;
+            o.x = pack2(v[0], v[1], p.dtype);
+            o.y = pack2(v[2], v[3], p.dtype);
+            o.z = pack2(v[4], v[5], p.dtype);
+            o.w = pack2(v[6], v[7], p.dtype);
+            if (!p.out16_up2) {
+              uint4* op = reinterpret_cast<uint4*>(
+                  p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * hw + pix) * 8);
+              *op = o;
+            } else {
+              const size_t w2 = 2 * (size_t)p.w;
+              uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * (4 * hw) +
+                                           (size_t)(2 * y) * w2 + 2 * x) * 8;
+              uint4* o0 = reinterpret_cast<uint4*>(basep);
+              uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
+              o0[0] = o; o0[1] = o; o1[0] = o; o1[1] = o;
+            }
+          } else {
+            // pixel shuffle (block.py:287): conv channel c*r*r + i*r + j -> channel c at (r*y+i, r*x+j).
+            const int rs = p.out16_ps, r2 = rs * rs;
+            const size_t wr = (size_t)rs * p.w;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int ch = ch0 + k;
+              if (ch >= p.cout) break;
+              const int oc = ch / r2, ij = ch - oc * r2;
+              const int i = ij / rs, j = ij - i * rs;
+              uint16_t* op = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + (oc >> 3)) * (r2 * hw) +
+                                        (size_t)(rs * y + i) * wr + (rs * x + j)) * 8 + (oc & 7);
+              const uint32_t pk = pack2(v[k], 0.f, p.dtype);
+              *op = (uint16_t)(pk & 0xFFFFu);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Specialised epilogues of the row-streaming kernel for the launches that make up a generator step; everything the
+// generic epilogue decides at run time is fixed here (cout % 32 == 0, forward only), which cuts the instruction count
+// per output row ~3x (the generic epilogue is what bounds the row kernel otherwise).
+//   kMode 1: out16 = lrelu(acc + bias)                      plain or nearest-x2 replicated store   (growth convs, HR convs)
+//   kMode 2: v = alpha*(acc + bias) + beta1*res1(16-bit) [+ beta2*res2(fp32)] -> out16 [+ out32]   (conv5 of a dense block)
+template <int NBN, int kMode>
+__device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid, int nblk) {
+  const size_t hw = (size_t)p.h * p.w;
+  const size_t pix = (size_t)y * p.w + x;
+#pragma unroll
+  for (int u = 0; u < NBN / 32; ++u) {
+    uint32_t r[2][16];
+    tmem_ld16(trow + u * 32, r[0]);
+    tmem_ld16(trow + u * 32 + 16, r[1]);
+    const int chu = nblk * NBN + u * 32;
+    const int gu = chu >> 3;
+    uint4 q1[4];
+    float4 f2[4][2], bb[4][2];
+    const bool has2 = kMode == 2 && p.res2 != nullptr;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
+      bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+    }
+    if (kMode == 2 && valid) {
+      const uint16_t* r1 = reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu) * hw + pix) * 8;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) q1[g] = __ldg(reinterpret_cast<const uint4*>(r1 + (size_t)g * hw * 8));
+      if (has2) {
+        const float* r2 = p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gu) * hw + pix) * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          f2[g][0] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8));
+          f2[g][1] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8) + 1);
+        }
+      }
+    }
+    tc_wait_ld();
+    if (valid) {
+      const float slope = p.lrelu ? p.slope : 1.0f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t* rg = &r[g / 2][(g & 1) * 8];
+        float v[8];
+        v[0] = __uint_as_float(rg[0]) + bb[g][0].x; v[1] = __uint_as_float(rg[1]) + bb[g][0].y;
+        v[2] = __uint_as_float(rg[2]) + bb[g][0].z; v[3] = __uint_as_float(rg[3]) + bb[g][0].w;
+        v[4] = __uint_as_float(rg[4]) + bb[g][1].x; v[5] = __uint_as_float(rg[5]) + bb[g][1].y;
+        v[6] = __uint_as_float(rg[6]) + bb[g][1].z; v[7] = __uint_as_float(rg[7]) + bb[g][1].w;
+        if (kMode == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+        } else {
+          float a[8];
+          unpack8(q1[g], p.dtype, a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(p.beta1, a[k], v[k] * p.alpha);
+          if (has2) {
+            v[0] = fmaf(p.beta2, f2[g][0].x, v[0]); v[1] = fmaf(p.beta2, f2[g][0].y, v[1]);
+            v[2] = fmaf(p.beta2, f2[g][0].z, v[2]); v[3] = fmaf(p.beta2, f2[g][0].w, v[3]);
+            v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
+            v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
+          }
+          if (p.out32) {
+            float4* op = reinterpret_cast<float4*>(p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gu + g) * hw + pix) * 8);
+            op[0] = make_float4(v[0], v[1], v[2], v[3]);
+            op[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+        uint4 o;
+        o.x = pack2(v[0], v[1], p.dtype);
+        o.y = pack2(v[2], v[3], p.dtype);
+        o.z = pack2(v[4], v[5], p.dtype);
+        o.w = pack2(v[6], v[7], p.dtype);
+        if (kMode == 1 && p.out16_up2) {
+          const size_t w2 = 2 * (size_t)p.w;
+          uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * (4 * hw) + (size_t)(2 * y) * w2 + 2 * x) * 8;
+          uint4* o0 = reinterpret_cast<uint4*>(basep);
+          uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
+          o0[0] = o; o0[1] = o; o1[0] = o; o1[1] = o;
+        } else {
+          *reinterpret_cast<uint4*>(p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * hw + pix) * 8) = o;
+        }
+      }
     }
   }
 }
@@ -227,11 +496,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Two warps per TMEM lane quarter; they alternate over the M tiles of an item.  Per (row, unit of UW
     // channels) every global load (residuals, bias) is issued before the first store so that a thread
     // keeps UW/8 .. 3*UW/8 128-bit loads in flight.
-    constexpr int UW = (!kBwd && NBN % 32 == 0) ? 32 : 16;  // dgrad prefetches more (3 residuals + mask): smaller units
     const int wq = warp & 3;            // TMEM lane quarter this warp may touch
     const int eh = (warp - 4) >> 2;     // which half of the M tiles this warp takes
     int it = 0;
-    const size_t hw = (size_t)p.h * p.w;
     pdl_wait();  // residual reads and all stores must not overtake the previous launch
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -250,174 +517,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tx = q - ty * P;
         const int y = y0 + ty, x = x0 + tx;
         const bool valid = (tx < p.TW) && (x < p.w) && (y < p.h);
-        const size_t pix = (size_t)y * p.w + x;
         const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((buf * p.MT + t) * NBN);
-#pragma unroll
-        for (int u = 0; u < NBN / UW; ++u) {
-          uint32_t r[UW / 16][16];
-#pragma unroll
-          for (int k = 0; k < UW / 16; ++k) tmem_ld16(trow + u * UW + k * 16, r[k]);
-          const int chu = nblk * NBN + u * UW;   // first conv output channel of this unit
-          const int gu = chu >> 3;               // its plane index in the conv's output
-          constexpr int G = UW / 8;              // groups of 8 channels in a unit
-          uint4 q1[G], qm[G];                    // residual 1 as 16-bit planes, activation for the LeakyReLU mask
-          float4 f1[G][2], f2[G][2], f3[G][2], bb[G][2];
-          const bool on = valid;
-          if (on) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              if (chu + g * 8 < p.cout) {
-                if (!kBwd) {  // forward: bias prefetched with the residuals (dgrad has no bias and fewer spare registers)
-                  bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
-                  bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
-                }
-                const int gp = gu + g - (kBwd ? p.lead_planes : 0);
-                if (kBwd && gp < 0) {
-                  const float4* rp = reinterpret_cast<const float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
-                  f2[g][0] = rp[0]; f2[g][1] = rp[1];
-                  continue;
-                }
-                if (p.res1) {
-                  if (p.res1_is16) {
-                    q1[g] = __ldg(reinterpret_cast<const uint4*>(
-                        reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8));
-                  } else {
-                    const float4* rp = reinterpret_cast<const float4*>(
-                        reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8);
-                    f1[g][0] = __ldg(rp); f1[g][1] = __ldg(rp + 1);
-                  }
-                }
-                if (p.res2) {
-                  // plain loads: res2 may alias out32 (in-place accumulation of gradients)
-                  const float4* rp = reinterpret_cast<const float4*>(
-                      p.res2 + (((size_t)img * p.res2_pt + p.res2_po + gp) * hw + pix) * 8);
-                  if (kBwd) { f2[g][0] = rp[0]; f2[g][1] = rp[1]; }
-                  else { f2[g][0] = __ldg(rp); f2[g][1] = __ldg(rp + 1); }
-                }
-                if (kBwd && p.res3) {
-                  const float4* rp = reinterpret_cast<const float4*>(
-                      p.res3 + (((size_t)img * p.res3_pt + p.res3_po + gp) * hw + pix) * 8);
-                  f3[g][0] = __ldg(rp); f3[g][1] = __ldg(rp + 1);
-                }
-                if (kBwd && p.mask16 && gp >= p.tail_first) {
-                  qm[g] = __ldg(reinterpret_cast<const uint4*>(p.mask16 + (((size_t)img * p.mask_pt + p.mask_po + gp) * hw + pix) * 8));
-                }
-              }
-            }
-          }
-          tc_wait_ld();
-          if (on) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int ch0 = chu + g * 8;
-              if (ch0 >= p.cout) continue;
-              const int gp = gu + g - (kBwd ? p.lead_planes : 0);
-              const uint32_t* rg = &r[g / 2][(g & 1) * 8];
-              float v[8];
-              {
-                float4 b0, b1;
-                if (kBwd) { b0 = make_float4(0.f, 0.f, 0.f, 0.f); b1 = b0; }   // transposed convs carry no bias
-                else { b0 = bb[g][0]; b1 = bb[g][1]; }
-                v[0] = __uint_as_float(rg[0]) + b0.x; v[1] = __uint_as_float(rg[1]) + b0.y;
-                v[2] = __uint_as_float(rg[2]) + b0.z; v[3] = __uint_as_float(rg[3]) + b0.w;
-                v[4] = __uint_as_float(rg[4]) + b1.x; v[5] = __uint_as_float(rg[5]) + b1.y;
-                v[6] = __uint_as_float(rg[6]) + b1.z; v[7] = __uint_as_float(rg[7]) + b1.w;
-              }
-              if (kBwd && gp < 0) {  // latent planes: lead_acc += alpha * acc
-                float4* op = reinterpret_cast<float4*>(p.lead_acc + (((size_t)img * p.lead_pt + gu + g) * hw + pix) * 8);
-                op[0] = make_float4(fmaf(p.alpha, v[0], f2[g][0].x), fmaf(p.alpha, v[1], f2[g][0].y), fmaf(p.alpha, v[2], f2[g][0].z),
-                                    fmaf(p.alpha, v[3], f2[g][0].w));
-                op[1] = make_float4(fmaf(p.alpha, v[4], f2[g][1].x), fmaf(p.alpha, v[5], f2[g][1].y), fmaf(p.alpha, v[6], f2[g][1].z),
-                                    fmaf(p.alpha, v[7], f2[g][1].w));
-                continue;
-              }
-              if (p.lrelu) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * p.slope;
-              }
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] *= p.alpha;
-              if (p.res1) {
-                float a[8];
-                if (p.res1_is16) {
-                  unpack8(q1[g], p.dtype, a);
-                } else {
-                  a[0] = f1[g][0].x; a[1] = f1[g][0].y; a[2] = f1[g][0].z; a[3] = f1[g][0].w;
-                  a[4] = f1[g][1].x; a[5] = f1[g][1].y; a[6] = f1[g][1].z; a[7] = f1[g][1].w;
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = fmaf(p.beta1, a[k], v[k]);
-              }
-              if (p.res2) {
-                v[0] = fmaf(p.beta2, f2[g][0].x, v[0]); v[1] = fmaf(p.beta2, f2[g][0].y, v[1]);
-                v[2] = fmaf(p.beta2, f2[g][0].z, v[2]); v[3] = fmaf(p.beta2, f2[g][0].w, v[3]);
-                v[4] = fmaf(p.beta2, f2[g][1].x, v[4]); v[5] = fmaf(p.beta2, f2[g][1].y, v[5]);
-                v[6] = fmaf(p.beta2, f2[g][1].z, v[6]); v[7] = fmaf(p.beta2, f2[g][1].w, v[7]);
-              }
-              if (kBwd && p.res3) {
-                v[0] = fmaf(p.beta3, f3[g][0].x, v[0]); v[1] = fmaf(p.beta3, f3[g][0].y, v[1]);
-                v[2] = fmaf(p.beta3, f3[g][0].z, v[2]); v[3] = fmaf(p.beta3, f3[g][0].w, v[3]);
-                v[4] = fmaf(p.beta3, f3[g][1].x, v[4]); v[5] = fmaf(p.beta3, f3[g][1].y, v[5]);
-                v[6] = fmaf(p.beta3, f3[g][1].z, v[6]); v[7] = fmaf(p.beta3, f3[g][1].w, v[7]);
-              }
-              if (p.out32) {
-                float4* op = reinterpret_cast<float4*>(
-                    p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gp) * hw + pix) * 8);
-                op[0] = make_float4(v[0], v[1], v[2], v[3]);
-                op[1] = make_float4(v[4], v[5], v[6], v[7]);
-              }
-              if (p.out_nchw) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const int ch = gp * 8 + k;
-                  if (ch < p.out_nchw_c) p.out_nchw[((size_t)img * p.out_nchw_c + ch) * hw + pix] = v[k];
-                }
-              }
-              if (p.out16 && (!kBwd || gp >= p.tail_first)) {
-                if (kBwd && p.mask16) {
-                  float a[8];
-                  unpack8(qm[g], p.dtype, a);
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
-                }
-                if (p.out16_ps == 0) {
-                  uint4 o;
-                  o.x = pack2(v[0], v[1], p.dtype);
-                  o.y = pack2(v[2], v[3], p.dtype);
-                  o.z = pack2(v[4], v[5], p.dtype);
-                  o.w = pack2(v[6], v[7], p.dtype);
-                  if (!p.out16_up2) {
-                    uint4* op = reinterpret_cast<uint4*>(
-                        p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * hw + pix) * 8);
-                    *op = o;
-                  } else {
-                    const size_t w2 = 2 * (size_t)p.w;
-                    uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * (4 * hw) +
-                                                 (size_t)(2 * y) * w2 + 2 * x) * 8;
-                    uint4* o0 = reinterpret_cast<uint4*>(basep);
-                    uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
-                    o0[0] = o; o0[1] = o; o1[0] = o; o1[1] = o;
-                  }
-                } else {
-                  // pixel shuffle (block.py:287): conv channel c*r*r + i*r + j -> channel c at (r*y+i, r*x+j).
-                  const int rs = p.out16_ps, r2 = rs * rs;
-                  const size_t wr = (size_t)rs * p.w;
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const int ch = ch0 + k;
-                    if (ch >= p.cout) break;
-                    const int oc = ch / r2, ij = ch - oc * r2;
-                    const int i = ij / rs, j = ij - i * rs;
-                    uint16_t* op = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + (oc >> 3)) * (r2 * hw) +
-                                              (size_t)(rs * y + i) * wr + (rs * x + j)) * 8 + (oc & 7);
-                    const uint32_t pk = pack2(v[k], 0.f, p.dtype);
-                    *op = (uint16_t)(pk & 0xFFFFu);
-                  }
-                }
-              }
-            }
-          }
-        }
+        conv_epilogue_px<NBN, kBwd>(p, trow, img, y, x, valid, nblk);
       }
       tc_fence_before();
       __syncwarp();

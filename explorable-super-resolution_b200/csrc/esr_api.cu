@@ -15,6 +15,7 @@
 
 #include "aux_kernels.cuh"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_rows.cuh"
 
 namespace {
 
@@ -100,6 +101,81 @@ int nblock_for(int cout, int* cout_pad) {
     *cout_pad = (cout + 63) / 64 * 64;
   }
   return nb_n;
+}
+
+const uint32_t kSmemMax = 232448u;
+
+// n-block of the row-streaming kernel for (cin_planes, cout); 0 = this conv cannot use it
+int rows_nbn_for(int cin_planes, int cout) {
+  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+  auto fits = [&](int nbn, int min_stages) {
+    const size_t wb = (size_t)nchunks * 3 * esr::kRowsKch * 3 * nbn * 16;
+    return esr::kSmemHeader + 128u + wb + (size_t)min_stages * esr::kRowsStageBytes <= kSmemMax;
+  };
+  if (cout <= 16) return fits(16, 6) ? 16 : 0;
+  if (cout > 32 && cout <= 64 && fits(64, 8)) return 64;
+  return fits(32, 4) ? 32 : 0;
+}
+
+typedef void (*RowsKernelFn)(const esr::ConvParams);
+// epi: 0 generic epilogue, 1 / 2 the specialised forward epilogues (conv_epilogue_fast)
+RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
+  if (bwd) {
+    switch (nbn) {
+      case 16: return esr::conv3x3_rows_kernel<16, true, 0>;
+      case 32: return esr::conv3x3_rows_kernel<32, true, 0>;
+      case 64: return esr::conv3x3_rows_kernel<64, true, 0>;
+    }
+    return nullptr;
+  }
+  switch (nbn * 4 + epi) {
+    case 16 * 4 + 0: return esr::conv3x3_rows_kernel<16, false, 0>;
+    case 32 * 4 + 0: return esr::conv3x3_rows_kernel<32, false, 0>;
+    case 32 * 4 + 1: return esr::conv3x3_rows_kernel<32, false, 1>;
+    case 32 * 4 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
+    case 64 * 4 + 0: return esr::conv3x3_rows_kernel<64, false, 0>;
+    case 64 * 4 + 1: return esr::conv3x3_rows_kernel<64, false, 1>;
+    case 64 * 4 + 2: return esr::conv3x3_rows_kernel<64, false, 2>;
+  }
+  return nullptr;
+}
+
+int set_max_smem_once(const void* kern) {
+  static std::mutex mu;
+  static std::set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!done.count(kern)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+    if (e != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    done.insert(kern);
+  }
+  return ESR_OK;
+}
+
+int launch_conv(const void* kern, int grid, uint32_t smem_bytes, void* stream, void** kargs) {
+  static const bool use_pdl = [] { const char* e = getenv("ESR_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(esr::kConvThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelExC(&cfg, kern, kargs));
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+// the row-streaming kernel pays off when its 128-pixel strips are mostly real pixels
+bool rows_shape_ok(int w) {
+  static const bool enabled = [] { const char* e = getenv("ESR_ROWS"); return !(e && e[0] == '0'); }();
+  const int strips = (w + 127) / 128;
+  return enabled && w * 100 >= strips * 128 * 80;
 }
 
 }  // namespace
@@ -242,6 +318,48 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.out32 = a->out32; p.out32_pt = a->out32_planes_total; p.out32_po = a->out32_plane_off;
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c;
 
+  const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
+  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w))) {
+    // ---- row-streaming kernel (conv3x3_rows.cuh)
+    const int nbn = a->rows_nbn;
+    if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "conv3x3: rows_nbn must be 16, 32 or 64");
+    if ((uintptr_t)a->wpacked_rows & 15) return fail(ESR_ERR_INVALID, "conv3x3: wpacked_rows must be 16-byte aligned");
+    int epi = 0;
+    if (!bwd && nbn >= 32 && a->cout % 32 == 0 && p.out16 && !p.out_nchw && !p.out16_ps && !p.res3) {
+      if (!p.res1 && !p.res2 && !p.out32 && p.alpha == 1.0f) epi = 1;
+      else if (p.res1 && p.res1_is16 && !p.lrelu && !p.out16_up2) epi = 2;
+    }
+    RowsKernelFn rk = select_rows_kernel(nbn, bwd, epi);
+    if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
+    p.nb_n = nbn;
+    p.n_blocks = (a->cout + nbn - 1) / nbn;
+    p.nchunks = (a->cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+    p.cin_planes = a->cin_planes;
+    p.w_bytes = (uint32_t)p.nchunks * 3u * esr::kRowsKch * 3u * nbn * 16u;
+    const uint32_t fixed = esr::kSmemHeader + 128u + p.w_bytes;
+    int stages = (int)((kSmemMax - fixed) / esr::kRowsStageBytes);
+    if (stages > esr::kRowsMaxStages) stages = esr::kRowsMaxStages;
+    if (stages < 4) return fail(ESR_ERR_INVALID, "conv3x3: row kernel weights (%u bytes) leave no room for the pipeline", p.w_bytes);
+    p.stages = stages;
+    p.slots = 512 / nbn < esr::kRowsMaxSlots ? 512 / nbn : esr::kRowsMaxSlots;
+    p.strips = (a->w + 127) / 128;
+    p.units = (long long)a->n * p.strips * a->h;
+    int ranges = num_sms() / p.n_blocks;
+    if (ranges < 1) return fail(ESR_ERR_INVALID, "conv3x3: too many n-blocks (%d) for the row kernel", p.n_blocks);
+    if ((long long)ranges > p.units) ranges = (int)p.units;
+    p.ranges = ranges;
+    p.in = (const uint8_t*)a->in;
+    p.in_pt = a->in_planes_total;
+    p.wts = (const uint8_t*)a->wpacked_rows;
+    for (int k = 0; k < 3; ++k)
+      p.idesc_n[k] = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | ((uint32_t)(((k + 1) * nbn) >> 3) << 17) |
+                     ((uint32_t)(128 >> 4) << 24);
+    int rc = set_max_smem_once((const void*)rk);
+    if (rc) return rc;
+    void* kargs[1] = {(void*)&p};
+    return launch_conv((const void*)rk, ranges * p.n_blocks, fixed + (uint32_t)stages * esr::kRowsStageBytes, stream, kargs);
+  }
+
   // TMA descriptor over the input planes: dims (8ch*W, H, planes, N), box (8*P, R+2, kcp, 1).  A pixel row of a
   // plane is one contiguous run, so (channel-in-plane, x) is a single 512-byte inner box dimension.
   CUtensorMap tm;
@@ -254,36 +372,39 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
-  const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
   ConvKernelFn kern = select_conv_kernel(p.P, p.kcp, p.nb_n, bwd);
   if (!kern) return fail(ESR_ERR_INVALID, "conv3x3: no kernel instance for P=%d kcp=%d N=%d", p.P, p.kcp, p.nb_n);
-  {
-    static std::mutex mu;
-    static std::set<const void*> done;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!done.count((const void*)kern)) {
-      cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-      if (e != cudaSuccess) return fail(ESR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      done.insert((const void*)kern);
-    }
-  }
+  int rc = set_max_smem_once((const void*)kern);
+  if (rc) return rc;
   int grid = p.num_tiles * p.n_blocks;
   if (grid > num_sms()) grid = num_sms();
-  {
-    static const bool use_pdl = [] { const char* e = getenv("ESR_PDL"); return !(e && e[0] == '0'); }();
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(esr::kConvThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p));
-  }
+  void* kargs[2] = {(void*)&tm, (void*)&p};
+  return launch_conv((const void*)kern, grid, smem_bytes, stream, kargs);
+}
+
+int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out) {
+  const int nbn = rows_nbn_for(cin_planes, cout);
+  if (nbn_out) *nbn_out = nbn;
+  if (!nbn) return fail(ESR_ERR_INVALID, "conv3x3 rows: weights of (cin_planes %d, cout %d) do not fit in shared memory", cin_planes, cout);
+  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+  const int n_blocks = (cout + nbn - 1) / nbn;
+  if (bytes_out) *bytes_out = (size_t)n_blocks * nchunks * 3 * esr::kRowsKch * 3 * nbn * 16;
+  return ESR_OK;
+}
+
+int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int lead, int dtype, int transpose_flip, int nbn,
+                                  void* wpacked_rows, void* stream) {
+  if (!w_oihw || !wpacked_rows) return fail(ESR_ERR_INVALID, "pack_weights_rows: null pointer");
+  if (lead < 0 || lead > cin) return fail(ESR_ERR_INVALID, "pack_weights_rows: bad lead %d", lead);
+  if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "pack_weights_rows: n-block must be 16, 32 or 64");
+  const int lc_out = transpose_flip ? esr_conv3x3_cin_planes(cin, lead) * 8 : cout;
+  const int lc_in = transpose_flip ? cout : cin;
+  const int cin_planes = transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(cin, lead);
+  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+  const int n_blocks = (lc_out + nbn - 1) / nbn;
+  const size_t total = (size_t)n_blocks * nchunks * 3 * esr::kRowsKch * 3 * nbn * 8;
+  esr::pack_weights_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, lead, nbn, nchunks, dtype,
+                                                                                      transpose_flip, (uint16_t*)wpacked_rows, total);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;

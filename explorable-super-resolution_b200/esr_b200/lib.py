@@ -35,6 +35,7 @@ class ConvArgs(C.Structure):
         ("out32", C.c_void_p), ("out32_planes_total", C.c_int), ("out32_plane_off", C.c_int),
         ("out_nchw", C.c_void_p), ("out_nchw_c", C.c_int),
         ("tile_p", C.c_int), ("tile_mt", C.c_int),
+        ("wpacked_rows", C.c_void_p), ("rows_nbn", C.c_int), ("rows_mode", C.c_int),
     ]
 
 
@@ -50,6 +51,8 @@ SIGNATURES = {
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
     "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_conv3x3_rows_config": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_pack_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "esr_unpack_planes16": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "esr_unpack_planes32": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),

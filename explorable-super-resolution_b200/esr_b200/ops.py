@@ -35,7 +35,7 @@ def device_check():
 class PackedConv:
     """Tensor-core image of one 3x3 conv's weights (+ padded fp32 bias).  `lead` = latent channels in front."""
 
-    def __init__(self, weight, bias, dtype=torch.float16, lead=0, transpose_flip=False, kcp=None):
+    def __init__(self, weight, bias, dtype=torch.float16, lead=0, transpose_flip=False, kcp=None, rows=True):
         lib = L.load()
         require_cuda(weight, bias)
         weight = weight.detach().float().contiguous()
@@ -62,13 +62,21 @@ class PackedConv:
         b = bias.detach().float().contiguous() if (bias is not None and not transpose_flip) else None
         L.check(lib.esr_pack_conv3x3_weights(_ptr(weight), cout, cin, lead, kcp, self.esr_dtype, int(transpose_flip),
                                              _ptr(self.wpacked), _ptr(self.bias), _ptr(b), _stream()))
+        # second image for the row-streaming kernel (used for images wide enough for 128-pixel strips)
+        nbn, nb = C.c_int(0), C.c_size_t(0)
+        self.wrows, self.rows_nbn = None, 0
+        if rows and lib.esr_conv3x3_rows_config(self.cin_planes, self.cout, C.byref(nbn), C.byref(nb)) == 0:
+            self.rows_nbn = nbn.value
+            self.wrows = torch.empty(nb.value, dtype=torch.uint8, device=weight.device)
+            L.check(lib.esr_pack_conv3x3_weights_rows(_ptr(weight), cout, cin, lead, self.esr_dtype, int(transpose_flip),
+                                                      self.rows_nbn, _ptr(self.wrows), _stream()))
 
 
 def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2, alpha=1.0,
             res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0, res3=None, res3_off=0, beta3=1.0,
             out16=None, out16_off=0, up2=False, pixel_shuffle=0, out32=None, out32_off=0,
             out_nchw=None, lead_planes=0, lead_acc=None, mask16=None, mask_off=0, mask_slope=0.2, tail_first=0,
-            tile_p=0, tile_mt=0):
+            tile_p=0, tile_mt=0, rows=True):
     """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor."""
     require_cuda(x16, res1, res2, res3, out16, out32, out_nchw, lead_acc, mask16)
     n, pt, h, w, e = x16.shape
@@ -109,6 +117,8 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
         assert out_nchw.dtype == torch.float32 and out_nchw.shape[0] == n and tuple(out_nchw.shape[2:]) == (h, w)
         a.out_nchw, a.out_nchw_c = out_nchw.data_ptr(), out_nchw.shape[1]
     a.tile_p, a.tile_mt = tile_p, tile_mt
+    if pc.wrows is not None and rows:   # rows: True = library decides by width, 'force' = always, False = tile kernel
+        a.wpacked_rows, a.rows_nbn, a.rows_mode = pc.wrows.data_ptr(), pc.rows_nbn, (1 if rows == 'force' else 0)
     L.check(L.load().esr_conv3x3_fwd(C.byref(a), _stream()))
 
 

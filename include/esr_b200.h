@@ -96,6 +96,11 @@ typedef struct {
   /* tiling hints (0 = library default) */
   int tile_p;                /* tile pitch 32 or 64 (valid width = pitch-2)                   */
   int tile_mt;               /* 128-row M tiles per CTA tile: 1, 2 or 4                        */
+  /* optional second weight image for the row-streaming kernel (esr_pack_conv3x3_weights_rows); when given and the
+   * image is wide enough for 128-pixel strips the launch uses that kernel, otherwise the tile kernel above */
+  const void* wpacked_rows;
+  int rows_nbn;              /* n-block the row image was packed with (esr_conv3x3_rows_config) */
+  int rows_mode;             /* 0: library decides by image width; 1: always the row kernel; -1: never */
 } esr_conv3x3_args;
 
 int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream);
@@ -111,6 +116,14 @@ size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad
 int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, int kcp, int dtype,
                              int transpose_flip, void* wpacked, float* bias_out,
                              const float* bias_in, void* stream);
+/* Row-streaming variant of the same convolution (csrc/conv3x3_rows.cuh): the three vertical taps are merged into the
+ * MMA's N dimension (N = 3 x n-block), the weights of one n-block stay resident in shared memory and a CTA marches
+ * down a 128-pixel column strip.  rows_config reports the n-block (16/32/64; 0 = the weights do not fit, use the tile
+ * kernel) and the size of the packed image [n_block][chunk][dx][plane-in-chunk (4)][ky*nbn + cout-in-block][8 cin];
+ * for a dgrad operand pass cout = 8 * esr_conv3x3_cin_planes(cin, lead) and cin_planes = ceil(cout_fwd / 8). */
+int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out);
+int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int lead, int dtype, int transpose_flip,
+                                  int nbn, void* wpacked_rows, void* stream);
 /* planes consumed by a conv with `cin` input channels of which the first `lead` are latent */
 int esr_conv3x3_cin_planes(int cin, int lead);
 
