@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_rfull + 8 * s, 1);
+      mbar_init(bar_rfull + 8 * s, (uint32_t)p.issuers);
       mbar_init(bar_rempty + 8 * s, 4);
     }
     mbar_init(bar_w, 1);
@@ -184,9 +184,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
           }
         }
       }
-    } else if (warp == 1) {
-      // ------------------------------------------------------------------ MMA issuer: ONE thread runs the whole role
-      if (elect_one()) {
+    } else {
+      // ------------------------------------------------------------------ MMA issuers: ONE thread per warp runs the role.
+      // A single thread cannot issue (and book-keep) as fast as the tensor pipe retires N=96 MMAs, so up to three warps
+      // share the stream of K chunks round-robin.  All of them walk the same (row, chunk) sequence; each waits for and
+      // issues only the chunks it owns.  Every MMA accumulates (the epilogue hands slots back zeroed), so MMAs of
+      // different issuers on the same accumulator commute; a row is complete when every issuer has committed it.
+      const int iw = warp - 1, NI = p.issuers;
+      if (iw < NI && elect_one()) {
         const uint64_t adesc_t = make_smem_desc(0u, kRowBytes, 128u);
         const uint64_t bdesc_t = make_smem_desc(0u, (uint32_t)N3 * 16u, 128u) + (uint64_t)(wres >> 4);
         const int nchunks = p.nchunks, stages = p.stages;
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
           mbar_wait(bar_zero, 0u, 6u);
         }
         tc_fence_after();
-        int s = 0;
+        int s = 0, kmod = 0;
         uint32_t ph = 0;
         int g0 = 0;   // index of the segment's first output row in this CTA's sequence of rows: row g uses slot S-1-g%S
         long long u = u0;
@@ -228,14 +233,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
             const uint32_t idA = nA == 3 ? id3 : (nA == 2 ? id2 : id1), idB = nB == 2 ? id2 : id1;
             const uint64_t bA = bdesc_t + (uint64_t)(ky_lo * NBN), bB = bdesc_t + (uint64_t)((ky_lo + nA) * NBN);
             for (int c = 0; c < nchunks; ++c) {
-              mbar_wait(bar_full + 8 * s, ph, 3u);
-              tc_fence_after();
-              const uint64_t ad0 = adesc_t + (uint64_t)((stage0 + s * kRowsStageBytes) >> 4);
-              const uint64_t wo = (uint64_t)(c * (kChunkW >> 4));
-              const int nk = c == nchunks - 1 ? nk_last : kRowsKch / 2;
-              if (nB == 0) rows_issue_chunk<N3, false>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
-              else rows_issue_chunk<N3, true>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
-              umma_commit(bar_empty + 8 * s);
+              if (kmod == iw) {
+                mbar_wait(bar_full + 8 * s, ph, 3u);
+                tc_fence_after();
+                const uint64_t ad0 = adesc_t + (uint64_t)((stage0 + s * kRowsStageBytes) >> 4);
+                const uint64_t wo = (uint64_t)(c * (kChunkW >> 4));
+                const int nk = c == nchunks - 1 ? nk_last : kRowsKch / 2;
+                if (nB == 0) rows_issue_chunk<N3, false>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
+                else rows_issue_chunk<N3, true>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
+                umma_commit(bar_empty + 8 * s);
+              }
+              if (++kmod == NI) kmod = 0;
               if (++s == stages) { s = 0; ph ^= 1u; }
             }
             // output row yi-1 has now seen all three input rows; the last row of the image completes with yi itself
@@ -275,6 +283,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
         tc_fence_after();
         const uint32_t trow = tq + (uint32_t)(slot * NBN);
         if (kEpi == 0) conv_epilogue_px<NBN, kBwd>(p, trow, img, y, x, valid, nblk);
+        else if (kEpi == 3) conv_epilogue_nchw<NBN>(p, trow, img, y, x, valid);
         else conv_epilogue_fast<NBN, kEpi>(p, trow, img, y, x, valid, nblk);
         // hand the slot back zeroed: the next output row that uses it accumulates from its first MMA on
 #pragma unroll

@@ -51,7 +51,7 @@ struct ConvParams {
   // row-streaming kernel (conv3x3_rows.cuh): work = n*strips*h output rows of 128 pixels, split into `ranges`
   // contiguous ranges (one per CTA and n-block); accumulators live in a ring of `slots` TMEM slots of nb_n columns
   const uint8_t* in; int in_pt;
-  int strips, ranges, slots, cin_planes;
+  int strips, ranges, slots, cin_planes, issuers;
   long long units;
   uint32_t idesc_n[3];    // instruction descriptors for N = 1, 2, 3 x nb_n
   const uint8_t* wts;
@@ -285,7 +285,8 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
 // Specialised epilogues of the row-streaming kernel for the launches that make up a generator step; everything the
 // generic epilogue decides at run time is fixed here (cout % 32 == 0, forward only), which cuts the instruction count
 // per output row ~3x (the generic epilogue is what bounds the row kernel otherwise).
-//   kMode 1: out16 = lrelu(acc + bias)                      plain or nearest-x2 replicated store   (growth convs, HR convs)
+//   kMode 1: out16 = lrelu(acc + bias) [+ beta1*res1(fp32)]  plain or nearest-x2 replicated store   (growth convs, HR convs,
+//            LR_conv + ShortcutBlock add)
 //   kMode 2: v = alpha*(acc + bias) + beta1*res1(16-bit) [+ beta2*res2(fp32)] -> out16 [+ out32]   (conv5 of a dense block)
 template <int NBN, int kMode>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid, int nblk) {
@@ -300,11 +301,19 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
     const int gu = chu >> 3;
     uint4 q1[4];
     float4 f2[4][2], bb[4][2];
-    const bool has2 = kMode == 2 && p.res2 != nullptr;
+    const bool has2 = (kMode == 2 && p.res2 != nullptr) || (kMode == 1 && p.res1 != nullptr);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
       bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+    }
+    if (kMode == 1 && has2 && valid) {   // fp32 residual (the ShortcutBlock's skip) rides in the f2 registers
+      const float* r2 = reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu) * hw + pix) * 8;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        f2[g][0] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8));
+        f2[g][1] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8) + 1);
+      }
     }
     if (kMode == 2 && valid) {
       const uint16_t* r1 = reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu) * hw + pix) * 8;
@@ -333,6 +342,12 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
         if (kMode == 1) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+          if (has2) {
+            v[0] = fmaf(p.beta1, f2[g][0].x, v[0]); v[1] = fmaf(p.beta1, f2[g][0].y, v[1]);
+            v[2] = fmaf(p.beta1, f2[g][0].z, v[2]); v[3] = fmaf(p.beta1, f2[g][0].w, v[3]);
+            v[4] = fmaf(p.beta1, f2[g][1].x, v[4]); v[5] = fmaf(p.beta1, f2[g][1].y, v[5]);
+            v[6] = fmaf(p.beta1, f2[g][1].z, v[6]); v[7] = fmaf(p.beta1, f2[g][1].w, v[7]);
+          }
         } else {
           float a[8];
           unpack8(q1[g], p.dtype, a);
@@ -364,6 +379,30 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
         } else {
           *reinterpret_cast<uint4*>(p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * hw + pix) * 8) = o;
         }
+      }
+    }
+  }
+}
+
+//   kMode 3: out_nchw[c] = lrelu?(acc + bias), c < out_nchw_c <= 8                                    (HR_conv1 -> image)
+template <int NBN>
+__device__ __forceinline__ void conv_epilogue_nchw(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid) {
+  uint32_t r[16];
+  tmem_ld16(trow, r);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + 4));
+  tc_wait_ld();
+  if (valid) {
+    const float slope = p.lrelu ? p.slope : 1.0f;
+    const size_t hw = (size_t)p.h * p.w;
+    float* op = p.out_nchw + (size_t)img * p.out_nchw_c * hw + (size_t)y * p.w + x;
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < p.out_nchw_c) {
+        float v = __uint_as_float(r[k]) + bb[k];
+        v = v > 0.f ? v : v * slope;
+        op[(size_t)k * hw] = v * p.alpha;
       }
     }
   }

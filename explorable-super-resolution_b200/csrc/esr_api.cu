@@ -130,6 +130,7 @@ RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
   }
   switch (nbn * 4 + epi) {
     case 16 * 4 + 0: return esr::conv3x3_rows_kernel<16, false, 0>;
+    case 16 * 4 + 3: return esr::conv3x3_rows_kernel<16, false, 3>;
     case 32 * 4 + 0: return esr::conv3x3_rows_kernel<32, false, 0>;
     case 32 * 4 + 1: return esr::conv3x3_rows_kernel<32, false, 1>;
     case 32 * 4 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
@@ -326,9 +327,10 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     if ((uintptr_t)a->wpacked_rows & 15) return fail(ESR_ERR_INVALID, "conv3x3: wpacked_rows must be 16-byte aligned");
     int epi = 0;
     if (!bwd && nbn >= 32 && a->cout % 32 == 0 && p.out16 && !p.out_nchw && !p.out16_ps && !p.res3) {
-      if (!p.res1 && !p.res2 && !p.out32 && p.alpha == 1.0f) epi = 1;
+      if ((!p.res1 || !p.res1_is16) && !p.res2 && !p.out32 && p.alpha == 1.0f) epi = 1;
       else if (p.res1 && p.res1_is16 && !p.lrelu && !p.out16_up2) epi = 2;
     }
+    if (!bwd && nbn == 16 && p.out_nchw && p.out_nchw_c <= 8 && !p.out16 && !p.out32 && !p.res1 && !p.res2 && !p.res3) epi = 3;
     RowsKernelFn rk = select_rows_kernel(nbn, bwd, epi);
     if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
     p.nb_n = nbn;
@@ -342,6 +344,10 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     if (stages < 4) return fail(ESR_ERR_INVALID, "conv3x3: row kernel weights (%u bytes) leave no room for the pipeline", p.w_bytes);
     p.stages = stages;
     p.slots = 512 / nbn < esr::kRowsMaxSlots ? 512 / nbn : esr::kRowsMaxSlots;
+    {
+      static const int issuers = [] { const char* e = getenv("ESR_ISSUERS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 3 ? 3 : v); }();
+      p.issuers = issuers;
+    }
     p.strips = (a->w + 127) / 128;
     p.units = (long long)a->n * p.strips * a->h;
     int ranges = num_sms() / p.n_blocks;

@@ -141,3 +141,27 @@ def test_rows_fast_epilogue_residuals():
     got = ops.unpack_planes(o32, cout)
     assert rel_err(got, ref)[0] < 1e-5
     assert torch.equal(ops.unpack_planes(o16, cout), got.half().float())
+
+
+def test_rows_fast_epilogue_shortcut_add_and_image_store():
+    """LR_conv (+ fp32 ShortcutBlock residual, nearest-x2 store) and HR_conv1 (NCHW fp32 image) epilogues == tile kernel"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(41)
+    n, h, w = 2, 37, 256
+    x16, _ = ops.pack_nchw(torch.randn(n, 64, h, w, generator=g).to(DEV))
+    _, f32 = ops.pack_nchw(torch.randn(n, 64, h, w, generator=g).to(DEV), want16=False, want32=True)
+    pc = ops.PackedConv((torch.randn(64, 64, 3, 3, generator=g) / 24).to(DEV), (torch.randn(64, generator=g) * 0.1).to(DEV))
+    outs = []
+    for mode in ('force', False):
+        o16 = torch.zeros((n, 8, 2 * h, 2 * w, 8), dtype=torch.float16, device=DEV)
+        ops.conv3x3(x16, pc, res1=f32, beta1=1.0, out16=o16, up2=True, rows=mode)
+        outs.append(o16.float())
+    assert rel_err(outs[0], outs[1])[0] < 2e-3 and rel_err(outs[0], outs[1])[1] < 2e-4
+    p3 = ops.PackedConv((torch.randn(3, 64, 3, 3, generator=g) / 24).to(DEV), (torch.randn(3, generator=g) * 0.1).to(DEV))
+    imgs = []
+    for mode in ('force', False):
+        o = torch.full((n, 3, h, w), float('nan'), device=DEV)
+        ops.conv3x3(x16, p3, out_nchw=o, rows=mode)
+        imgs.append(o)
+    assert not torch.isnan(imgs[0]).any()
+    assert rel_err(imgs[0], imgs[1])[0] < 1e-5
