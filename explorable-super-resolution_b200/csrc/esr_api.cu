@@ -16,6 +16,7 @@
 #include "aux_kernels.cuh"
 #include "conv3x3_tc.cuh"
 #include "conv3x3_rows.cuh"
+#include "conv3x3_wgrad.cuh"
 
 namespace {
 
@@ -170,6 +171,34 @@ int launch_conv(const void* kern, int grid, uint32_t smem_bytes, void* stream, v
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
+}
+
+struct WgradPlan {
+  int gyp, nbn, cpb, n_blocks, mt, rb;
+  uint32_t slot_bytes, gstage_bytes, smem_bytes;
+};
+// tiling of the weight-gradient kernel for (cin_planes, cout); returns false when it does not fit
+bool wgrad_plan(int cp, int cout, WgradPlan* w) {
+  if (cp < 1 || cp > 32 || cout < 1) return false;
+  w->gyp = (cout + 7) / 8;
+  w->mt = (3 * cp + 15) / 16;
+  if (cout <= 8) w->nbn = 16;
+  else if (cout >= 64 && w->mt * 192 <= 512) w->nbn = 64;
+  else w->nbn = 32;
+  if (w->mt * 3 * w->nbn > 512) return false;
+  w->cpb = w->nbn / 8;
+  w->n_blocks = (w->gyp + w->cpb - 1) / w->cpb;
+  const uint32_t group = esr::kWgPW * 16u;
+  w->slot_bytes = (uint32_t)cp * group;
+  w->gstage_bytes = 3u * w->cpb * group;
+  int rb = esr::kWgMaxRing;
+  for (; rb >= 4; --rb) {
+    w->smem_bytes = esr::kSmemHeader + 128u + (uint32_t)(rb + 2) * w->slot_bytes + 16u * group + esr::kWgGStages * w->gstage_bytes;
+    if (w->smem_bytes <= kSmemMax) break;
+  }
+  if (rb < 4) return false;
+  w->rb = rb;
+  return true;
 }
 
 // the row-streaming kernel pays off when its 128-pixel strips are mostly real pixels
@@ -413,6 +442,72 @@ int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int le
                                                                                       transpose_flip, (uint16_t*)wpacked_rows, total);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout) {
+  WgradPlan w;
+  if (!wgrad_plan(cin_planes, cout, &w)) return 0;
+  return (size_t)num_sms() * w.mt * 128 * 3 * w.nbn * sizeof(float);
+}
+
+int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
+  if (!a || !a->x || !a->gy || !a->workspace) return fail(ESR_ERR_INVALID, "wgrad: null pointer");
+  if (!a->dw && !a->db) return fail(ESR_ERR_INVALID, "wgrad: no output requested");
+  if (a->n <= 0 || a->h <= 0 || a->w <= 0) return fail(ESR_ERR_INVALID, "wgrad: bad shape %dx%dx%d", a->n, a->h, a->w);
+  if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "wgrad: bad dtype");
+  if (((uintptr_t)a->x & 15) || ((uintptr_t)a->gy & 15)) return fail(ESR_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
+  if (a->lead < 0 || a->lead > a->cin) return fail(ESR_ERR_INVALID, "wgrad: bad lead %d", a->lead);
+  const int cp = esr_conv3x3_cin_planes(a->cin, a->lead);
+  if (a->x_plane_off + cp > a->x_planes_total) return fail(ESR_ERR_INVALID, "wgrad: input planes out of range");
+  WgradPlan w;
+  if (!wgrad_plan(cp, a->cout, &w)) return fail(ESR_ERR_INVALID, "wgrad: (cin %d, cout %d) does not fit the tensor-core tiling", a->cin, a->cout);
+  if (a->gy_plane_off + w.gyp > a->gy_planes_total) return fail(ESR_ERR_INVALID, "wgrad: gradient planes out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dw) {
+    esr::WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = a->n; p.h = a->h; p.w = a->w;
+    p.strips = (a->w + esr::kWgPW - 1) / esr::kWgPW;
+    p.units = (long long)a->n * p.strips * a->h;
+    p.n_blocks = w.n_blocks;
+    int ranges = num_sms() / w.n_blocks;
+    if (ranges < 1) return fail(ESR_ERR_INVALID, "wgrad: too many n-blocks (%d)", w.n_blocks);
+    if ((long long)ranges > p.units) ranges = (int)p.units;
+    p.ranges = ranges;
+    p.x = (const uint8_t*)a->x; p.x_pt = a->x_planes_total; p.x_po = a->x_plane_off; p.cp = cp;
+    p.gy = (const uint8_t*)a->gy; p.gy_pt = a->gy_planes_total; p.gy_po = a->gy_plane_off; p.gyp = w.gyp;
+    p.nbn = w.nbn; p.cpb = w.cpb; p.mt = w.mt; p.rb = w.rb;
+    p.slot_bytes = w.slot_bytes; p.gstage_bytes = w.gstage_bytes;
+    // D=f32, A/B = f16|bf16, both MN-major (bits 15, 16), N = 3*nbn, M = 128
+    p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | (1u << 15) | (1u << 16) |
+              ((uint32_t)((3 * w.nbn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int grid = ranges * w.n_blocks;
+    const size_t need = (size_t)grid * w.mt * 128 * 3 * w.nbn * sizeof(float);
+    if (a->workspace_bytes < need) return fail(ESR_ERR_INVALID, "wgrad: workspace of %zu bytes needed, %zu given", need, a->workspace_bytes);
+    p.part = a->workspace;
+    int rc = set_max_smem_once((const void*)esr::conv3x3_wgrad_kernel);
+    if (rc) return rc;
+    esr::conv3x3_wgrad_kernel<<<grid, esr::kWgThreads, w.smem_bytes, st>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    const int total = a->cout * a->cin * 9;
+    esr::wgrad_reduce_kernel<<<grid_for((size_t)total, 256), 256, 0, st>>>(a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin,
+                                                                        a->lead, a->scale, a->accumulate, a->dw);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (a->db) {
+    if (!a->accumulate) CUDA_TRY(cudaMemsetAsync(a->db, 0, sizeof(float) * a->cout, st));
+    const size_t hw = (size_t)a->h * a->w;
+    size_t chunks = ((size_t)a->n * hw + 255) / 256;
+    if (chunks > 148 * 4) chunks = 148 * 4;
+    dim3 grid((unsigned)chunks, (unsigned)w.gyp);
+    esr::bias_grad_kernel<<<grid, 256, 0, st>>>((const uint16_t*)a->gy, a->dtype, a->n, a->gy_planes_total, a->gy_plane_off, a->cout, hw,
+                                                a->scale, a->db);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   return ESR_OK;
 }
 

@@ -39,6 +39,18 @@ class ConvArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    """mirror of esr_conv3x3_wgrad_args"""
+    _fields_ = [
+        ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("dtype", C.c_int),
+        ("x", C.c_void_p), ("x_planes_total", C.c_int), ("x_plane_off", C.c_int),
+        ("gy", C.c_void_p), ("gy_planes_total", C.c_int), ("gy_plane_off", C.c_int),
+        ("cout", C.c_int), ("cin", C.c_int), ("lead", C.c_int),
+        ("dw", C.c_void_p), ("db", C.c_void_p), ("scale", C.c_float), ("accumulate", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     "esr_last_error": (C.c_char_p, []),
@@ -53,6 +65,8 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esr_conv3x3_rows_config": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "esr_conv3x3_wgrad_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "esr_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     "esr_pack_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "esr_unpack_planes16": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "esr_unpack_planes32": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),

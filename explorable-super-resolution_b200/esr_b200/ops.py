@@ -122,6 +122,43 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     L.check(L.load().esr_conv3x3_fwd(C.byref(a), _stream()))
 
 
+_wgrad_ws = {}
+
+
+def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, db=None, scale=1.0, accumulate=False):
+    """Weight / bias gradient of a 3x3 conv: x16 = the conv's input planes, gy16 = gradient of its (pre-activation)
+    output.  Returns (dw [cout,cin,3,3] fp32, db [cout] fp32); pass dw/db tensors to accumulate into them."""
+    require_cuda(x16, gy16, dw, db)
+    lib = L.load()
+    n, xpt, h, w, e = x16.shape
+    assert e == 8 and gy16.dtype == x16.dtype and tuple(gy16.shape[2:]) == (h, w, 8) and gy16.shape[0] == n
+    dev = x16.device
+    if dw is None:
+        dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=dev)
+        accumulate = False
+    if db is None:
+        db = torch.empty((cout,), dtype=torch.float32, device=dev)
+    assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3) and db.dtype == torch.float32
+    cp = int(lib.esr_conv3x3_cin_planes(cin, lead))
+    nbytes = int(lib.esr_conv3x3_wgrad_workspace(cp, cout))
+    if nbytes == 0:
+        raise L.EsrError('conv3x3_wgrad: (cin %d, cout %d) is not supported by the tensor-core tiling' % (cin, cout))
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _wgrad_ws[key] = ws
+    a = L.WgradArgs()
+    a.n, a.h, a.w, a.dtype = n, h, w, _TORCH2ESR[x16.dtype]
+    a.x, a.x_planes_total, a.x_plane_off = x16.data_ptr(), xpt, x_off
+    a.gy, a.gy_planes_total, a.gy_plane_off = gy16.data_ptr(), gy16.shape[1], gy_off
+    a.cout, a.cin, a.lead = cout, cin, lead
+    a.dw, a.db, a.scale, a.accumulate = dw.data_ptr(), db.data_ptr(), scale, int(accumulate)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    L.check(lib.esr_conv3x3_wgrad(C.byref(a), _stream()))
+    return dw, db
+
+
 def planes_for(c):
     return (c + 7) // 8
 

@@ -124,6 +124,31 @@ int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, i
 int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out);
 int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int lead, int dtype, int transpose_flip,
                                   int nbn, void* wpacked_rows, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Weight / bias gradient of the same convolution (what autograd computes for nn.Conv2d inside
+ * models/modules/block.py:129-146 when models/SRRaGAN_model.py:436-500 calls l_g_total.backward()):
+ *   dw[co][ci][ky][kx] (+)= scale * sum_{n,y,x} gy[n][co][y][x] * x[n][ci][y+ky-1][x+kx-1]     (OIHW fp32)
+ *   db[co]             (+)= scale * sum_{n,y,x} gy[n][co][y][x]
+ * x: the conv's input activations (16-bit planes, the buffers the forward pass wrote; latent channels in their own
+ * leading plane group as for esr_pack_conv3x3_weights), gy: gradient w.r.t. the conv output BEFORE the activation
+ * (16-bit planes).  K = pixels on the tensor cores, vertical taps merged into M, horizontal taps into N
+ * (csrc/conv3x3_wgrad.cuh).  `workspace` holds per-CTA partial sums (esr_conv3x3_wgrad_workspace bytes).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, h, w;
+  int dtype;                 /* esr_dtype of x and gy */
+  const void* x; int x_planes_total; int x_plane_off;
+  const void* gy; int gy_planes_total; int gy_plane_off;
+  int cout, cin, lead;       /* real channel counts of the weight tensor; `lead` latent input channels */
+  float* dw;                 /* [cout][cin][3][3] fp32 or NULL */
+  float* db;                 /* [cout] fp32 or NULL */
+  float scale;
+  int accumulate;            /* 1: add into dw/db (gradient accumulation), 0: overwrite */
+  float* workspace; size_t workspace_bytes;
+} esr_conv3x3_wgrad_args;
+size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout);
+int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream);
+
 /* planes consumed by a conv with `cin` input channels of which the first `lead` are latent */
 int esr_conv3x3_cin_planes(int cin, int lead);
 
