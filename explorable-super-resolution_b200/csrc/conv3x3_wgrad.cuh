@@ -326,4 +326,15 @@ __global__ void bias_grad_kernel(const uint16_t* __restrict__ gy, int dtype, int
   }
 }
 
+// out[c] += scale * sum_{n,y,x} src[n][c][y][x]  (NCHW fp32: bias gradient of the last conv straight from dL/dG, which
+// has not been rounded to 16 bits).  grid = (chunks, c, n)
+__global__ void sum_nchw_kernel(const float* __restrict__ src, int c, size_t hw, float scale, float* __restrict__ out) {
+  const float* p = src + ((size_t)blockIdx.z * c + blockIdx.y) * hw;
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += __ldg(p + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out + blockIdx.y, s * scale);
+}
+
 }  // namespace esr

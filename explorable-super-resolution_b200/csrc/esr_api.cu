@@ -511,6 +511,19 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
   return ESR_OK;
 }
 
+int esr_sum_nchw(const float* src, int n, int c, int h, int w, float scale, int accumulate, float* out, void* stream) {
+  if (!src || !out || n <= 0 || c <= 0) return fail(ESR_ERR_INVALID, "sum_nchw: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * c, st));
+  const size_t hw = (size_t)h * w;
+  size_t chunks = (hw + 1023) / 1024;
+  if (chunks > 64) chunks = 64;
+  esr::sum_nchw_kernel<<<dim3((unsigned)chunks, (unsigned)c, (unsigned)n), 256, 0, st>>>(src, c, hw, scale, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 int esr_pack_nchw(const float* src, int n, int c, int h, int w, int pad, int dtype, void* dst16, float* dst32,
                   int planes_total, int plane_off, void* stream) {
   if (!src || (!dst16 && !dst32)) return fail(ESR_ERR_INVALID, "pack_nchw: null pointer");

@@ -14,7 +14,7 @@ Data layout in HBM (all planar-8, see include/esr_b200.h):
   * LR_conv fuses the ShortcutBlock add and writes its output already nearest-x2 replicated; every upconv does the
     same for the next one, so the up-sampled tensor is written once and never re-read for resizing.
 
-Backward (input gradient: what Z_optimization.py:747 needs; weights frozen): every conv's dgrad is the same tcgen05
+Backward (input gradient: what Z_optimization.py:747 needs; plus weight gradients for training): every conv's dgrad is the same tcgen05
 kernel with transposed/rotated weights (`transpose_flip`), the dense-block gradient accumulates in one fp32 buffer
 (in-place `res2 == out32`), LeakyReLU derivatives come from the saved 16-bit activations (`mask16`), and the latent
 channels' gradient is accumulated by every launch into one plane (`lead_acc`).
@@ -212,12 +212,29 @@ class RRDBEngine:
         sv.B, sv.n, sv.h, sv.w, sv.h0, sv.w0, sv.pad, sv.cin = B, n, h, w, h0, w0, pad, cin
         return out, sv
 
-    # ---------------------------------------------------------------- backward (input gradient)
-    @torch.no_grad()
+    # ---------------------------------------------------------------- backward
     def backward_input(self, g_out, sv):
-        """g_out: dL/dG on the padded HR domain [N, out_nc, S*h, S*w].  Returns dL/dx with x's layout
-        [N, z*S^2 + 3, h0, w0] (latent part exact; the LR-image part is returned only when pad == 0)."""
+        return self.backward(g_out, sv, wgrad=False)[0]
+
+    @torch.no_grad()
+    def backward(self, g_out, sv, wgrad=False):
+        """g_out: dL/dG on the padded HR domain [N, out_nc, S*h, S*w].  Returns (dL/dx, param_grads): dL/dx with x's
+        layout [N, z*S^2 + 3, h0, w0] (latent part exact; the LR-image part is returned only when pad == 0) and, when
+        `wgrad`, a list of (dW [cout,cin,3,3], db [cout]) fp32 per conv in `_convs()` order (else None).
+
+        Weight gradients (training, models/SRRaGAN_model.py:436-500): every conv's wgrad launch pairs the activation
+        buffer its forward launch read (kept by `save=True`) with the 16-bit gradient of its pre-activation output,
+        which the dgrad chain produces anyway as the operand of the next transposed conv."""
         net = self.net
+        convs = self._convs()
+        leads = self._leads(convs)
+        grads = [None] * len(convs) if wgrad else None
+
+        def wg(idx, x16, gy16, gy_off=0, scale=1.0):
+            if wgrad:
+                cout, cin = int(convs[idx].weight.shape[0]), int(convs[idx].weight.shape[1])
+                grads[idx] = ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale)
+
         B, n, h, w, pad = sv.B, sv.n, sv.h, sv.w, sv.pad
         dev = g_out.device
         wt = self.packed_t()
@@ -228,8 +245,11 @@ class RRDBEngine:
         nb = len(net.model[1].sub) - 1
         n_up = len(net.up_factors())
         H, W = h * S, w * S
+        # gradient operands share the activations' format (tcgen05 kind::f16 traps on f16 x bf16): training runs the whole
+        # engine in bf16 because fp16 gradients underflow (a dense block's inner gradients sit 3-4 decades below the trunk's)
+        gdt = self.dtype
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        f16 = lambda *s: torch.zeros(s, dtype=self.dtype, device=dev)
+        f16 = lambda *s: torch.zeros(s, dtype=gdt, device=dev)
         gz_hr = f32(n, 1, H, W, 8) if z else None
         gz_lr = f32(n, 1, h, w, 8) if z else None
         lead = dict(lead_planes=zp, lead_acc=gz_hr) if z else {}
@@ -237,9 +257,14 @@ class RRDBEngine:
         idx_hr0 = idx_lr + 1 + n_up
 
         # HR_conv1^T, HR_conv0^T (LeakyReLU derivative of the conv below comes from its saved output)
-        g16, _ = ops.pack_nchw(g_out.float().contiguous(), dtype=self.dtype)
+        g_out = g_out.float().contiguous()
+        g16, _ = ops.pack_nchw(g_out, dtype=gdt)
+        wg(idx_hr0 + 1, B['hr_b'], g16)
+        if wgrad:   # the last conv's bias gradient from the unrounded dL/dG (a sum with heavy cancellation)
+            grads[idx_hr0 + 1] = (grads[idx_hr0 + 1][0], ops.sum_nchw(g_out))
         g_b = f16(n, nfp, H, W, 8)
         ops.conv3x3(g16, wt[idx_hr0 + 1], mask16=B['hr_b'], mask_off=zp, mask_slope=SLOPE, out16=g_b, **lead)
+        wg(idx_hr0, B['hr_a'], g_b)
         g_a = f16(n, nfp, H, W, 8)
         ops.conv3x3(g_b, wt[idx_hr0], mask16=B['hr_a'], mask_off=zp, mask_slope=SLOPE, out16=g_a, **lead)
         del g_b, g16
@@ -248,15 +273,17 @@ class RRDBEngine:
         g_t32 = None
         for k in range(n_up - 1, -1, -1):
             hk, wk = h * 2 ** (k + 1), w * 2 ** (k + 1)
+            wg(idx_lr + 1 + k, B['up'][k], cur)
             gu = f32(n, nfp, hk, wk, 8)
             ops.conv3x3(cur, wt[idx_lr + 1 + k], out32=gu)
             if k > 0:   # B['up'][k] is the (replicated) LeakyReLU output of upconv k-1
-                _, cur = ops.downsum2x(gu, act16_hi=B['up'][k], slope=SLOPE, dtype=self.dtype, want32=False)
+                _, cur = ops.downsum2x(gu, act16_hi=B['up'][k], slope=SLOPE, dtype=gdt, want32=False)
             else:       # B['up'][0] is LR_conv + fea, no activation
-                g_t32, cur = ops.downsum2x(gu, dtype=self.dtype)
+                g_t32, cur = ops.downsum2x(gu, dtype=gdt)
             del gu
         lead = dict(lead_planes=zp, lead_acc=gz_lr) if z else {}
         # LR_conv^T -> gradient w.r.t. the last RRDB's output
+        wg(idx_lr, self._dense(B, True, nb - 1, 3) if nb > 0 else self._dense(B, True, 0, 0), cur)
         go32, go16 = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
         ops.conv3x3(cur, wt[idx_lr], out32=go32, out16=go16, **lead)
         gS = f32(n, nfp + 4 * gcp, h, w, 8)
@@ -273,13 +300,17 @@ class RRDBEngine:
                 else:
                     gin16, a5 = gy16[j % 2], 0.2
                 # conv5^T: gS = alpha * conv5^T(g); x4's slice is final -> masked 16-bit copy
+                wg(base + 4, Sb, gin16, scale=a5)
                 ops.conv3x3(gin16, wt[base + 4], alpha=a5, out32=gS, mask16=Sb, mask_off=zp, mask_slope=SLOPE,
                             tail_first=nfp + 3 * gcp, out16=G16, **lead)
                 for i in (3, 2, 1):
+                    # the slice of x_{i+1} in G16 is final: gradient of conv_{i+1}'s pre-activation output
+                    wg(base + i, Sb, G16, gy_off=nfp + i * gcp)
                     # conv_{i+1}^T: consumes the masked gradient of x_{i+1}, accumulates into gS[0 : nfp+i*gcp) in place,
                     # finalises x_i's slice
                     ops.conv3x3(G16, wt[base + i], in_plane_off=nfp + i * gcp, cin_planes=gcp, res2=gS, beta2=1.0, out32=gS,
                                 mask16=Sb, mask_off=zp, mask_slope=SLOPE, tail_first=nfp + (i - 1) * gcp, out16=G16, **lead)
+                wg(base, Sb, G16, gy_off=nfp)
                 # conv1^T closes the block: g_x = acc + gS[x] + (gradient arriving at the block's output)
                 if j == 2:
                     ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=go32, beta3=0.2,
@@ -293,7 +324,8 @@ class RRDBEngine:
             go32, gi32 = gi32, go32
             go16, gi16 = gi16, go16
         # ShortcutBlock: the fea_conv output feeds the first RRDB and the skip
-        _, gf16 = ops.planes_add(go32, g_t32, dtype=self.dtype, want32=False)
+        _, gf16 = ops.planes_add(go32, g_t32, dtype=gdt, want32=False)
+        wg(0, B['in16'], gf16)
         g_img = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
         ops.conv3x3(gf16, wt[0], out_nchw=g_img, **lead)
         gx = torch.zeros((n, sv.cin, sv.h0, sv.w0), dtype=torch.float32, device=dev)
@@ -302,4 +334,4 @@ class RRDBEngine:
             gx[:, :sv.cin - 3] = gz.view(n, z * S * S, sv.h0, sv.w0)
         if pad == 0:
             gx[:, sv.cin - 3:] = g_img
-        return gx
+        return gx, grads

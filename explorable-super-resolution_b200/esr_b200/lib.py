@@ -67,6 +67,7 @@ SIGNATURES = {
     "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_conv3x3_wgrad_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "esr_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    "esr_sum_nchw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_pack_nchw": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "esr_unpack_planes16": (C.c_int, [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p, C.c_void_p]),
     "esr_unpack_planes32": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),

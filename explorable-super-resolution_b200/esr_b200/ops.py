@@ -80,7 +80,7 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor."""
     require_cuda(x16, res1, res2, res3, out16, out32, out_nchw, lead_acc, mask16)
     n, pt, h, w, e = x16.shape
-    assert e == 8 and x16.dtype == pc.dtype
+    assert e == 8 and x16.dtype == pc.dtype   # tcgen05 kind::f16 wants both operands in one format (f16 x bf16 traps)
     a = L.ConvArgs()
     a.n, a.h, a.w, a.dtype = n, h, w, pc.esr_dtype
     a.in_, a.in_planes_total, a.in_plane_off = x16.data_ptr(), pt, in_plane_off
@@ -89,7 +89,7 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     a.cout, a.cout_pad, a.kcp = pc.cout, pc.cout_pad, pc.kcp
     a.lrelu, a.slope, a.alpha = int(lrelu), slope, alpha
     if res1 is not None:
-        assert res1.dtype in (torch.float32, pc.dtype) and tuple(res1.shape[2:]) == (h, w, 8) and res1.shape[0] == n
+        assert res1.dtype in (torch.float32, x16.dtype) and tuple(res1.shape[2:]) == (h, w, 8) and res1.shape[0] == n
         a.res1, a.res1_planes_total, a.res1_plane_off, a.beta1 = res1.data_ptr(), res1.shape[1], res1_off, beta1
         a.res1_is16 = int(res1.dtype != torch.float32)
     if res2 is not None:
@@ -102,12 +102,12 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
         assert lead_acc is not None and lead_acc.dtype == torch.float32 and tuple(lead_acc.shape[2:]) == (h, w, 8)
         a.lead_planes, a.lead_acc, a.lead_planes_total = lead_planes, lead_acc.data_ptr(), lead_acc.shape[1]
     if mask16 is not None:
-        assert mask16.dtype == pc.dtype and tuple(mask16.shape[2:]) == (h, w, 8)
+        assert mask16.dtype in _TORCH2ESR and tuple(mask16.shape[2:]) == (h, w, 8)   # only the sign is read
         a.mask16, a.mask_planes_total, a.mask_plane_off, a.mask_slope = mask16.data_ptr(), mask16.shape[1], mask_off, mask_slope
     a.tail_first_plane = tail_first
     if out16 is not None:
         f = 2 if up2 else (pixel_shuffle if pixel_shuffle else 1)
-        assert out16.dtype == pc.dtype and tuple(out16.shape[2:]) == (f * h, f * w, 8) and out16.shape[0] == n
+        assert out16.dtype == x16.dtype and tuple(out16.shape[2:]) == (f * h, f * w, 8) and out16.shape[0] == n
         a.out16, a.out16_planes_total, a.out16_plane_off = out16.data_ptr(), out16.shape[1], out16_off
         a.out16_up2, a.out16_pixel_shuffle = int(up2), int(pixel_shuffle)
     if out32 is not None:
@@ -157,6 +157,15 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     L.check(lib.esr_conv3x3_wgrad(C.byref(a), _stream()))
     return dw, db
+
+
+def sum_nchw(src, scale=1.0):
+    """per-channel sum of an NCHW fp32 tensor -> [C] fp32"""
+    require_cuda(src)
+    n, c, h, w = src.shape
+    out = torch.empty((c,), dtype=torch.float32, device=src.device)
+    L.check(L.load().esr_sum_nchw(_ptr(src), n, c, h, w, scale, 0, _ptr(out), _stream()))
+    return out
 
 
 def planes_for(c):
@@ -245,7 +254,7 @@ def downsum2x(src32, act16_hi=None, slope=0.2, dtype=torch.float16, want32=True,
     d32 = torch.empty((n, pt, h, w, 8), dtype=torch.float32, device=src32.device) if want32 else None
     d16 = torch.empty((n, pt, h, w, 8), dtype=dtype, device=src32.device) if want16 else None
     if act16_hi is not None:
-        assert act16_hi.shape == src32.shape and act16_hi.dtype == dtype
+        assert act16_hi.shape == src32.shape and act16_hi.dtype in _TORCH2ESR   # only the sign is read
     L.check(L.load().esr_downsum2x_planes(_ptr(src32), n, pt, h, w, _ptr(act16_hi), slope, _TORCH2ESR[dtype], _ptr(d32), _ptr(d16),
                                           _stream()))
     return d32, d16

@@ -63,9 +63,11 @@ class RRDBNet(nn.Module):
     def up_factors(self):
         return [3] if self.upscale == 3 else [2] * self._n_upscale
 
-    def engine(self):
+    def engine(self, dtype=None):
+        """engine for `dtype` (default: self.compute_dtype, fp16).  Training (weight gradients) uses the bf16 engine:
+        fp16 gradients underflow, and the tensor cores want activations, weights and gradients in one format."""
         from esr_b200.engine import RRDBEngine
-        key = self.compute_dtype
+        key = self.compute_dtype if dtype is None else dtype
         if key not in self._engines:
             self._engines[key] = RRDBEngine(self, dtype=key)
         return self._engines[key]

@@ -149,6 +149,10 @@ typedef struct {
 size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout);
 int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream);
 
+/* out[c] (+)= scale * sum over n, y, x of src[n][c][y][x] (NCHW fp32): the bias gradient of the generator's last conv
+ * taken from dL/dG itself, before it is rounded to 16-bit planes */
+int esr_sum_nchw(const float* src, int n, int c, int h, int w, float scale, int accumulate, float* out, void* stream);
+
 /* planes consumed by a conv with `cin` input channels of which the first `lead` are latent */
 int esr_conv3x3_cin_planes(int cin, int lead);
 

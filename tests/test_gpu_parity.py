@@ -359,11 +359,3 @@ def test_rrdb_latent_input_gradient_matches_reference_autograd():
     (net(x) * torch.from_numpy(g['wt']).to(DEV)).sum().backward()
     emax, el2, cos, frac = _grad_report('bare rrdb latent', x.grad.cpu(), torch.from_numpy(g['gx']))
     assert cos > 0.999 and frac > 0.97 and el2 < 3e-2, (emax, el2, cos, frac)
-
-
-def test_wgrad_is_refused_loudly():
-    _ops()
-    g = golden('rrdb_plain_x4')
-    net = mirror_rrdb(g).to(DEV)       # parameters require grad by default
-    with pytest.raises(NotImplementedError):
-        net(torch.from_numpy(g['x']).to(DEV))
