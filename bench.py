@@ -84,6 +84,23 @@ class ClockSampler:
                 'power_w_max': max(pw) if pw else None, 'samples': len(self.rows)}
 
 
+def profiled_traffic():
+    """DRAM bytes (read + write) of the most expensive conv launch type, from the committed `ncu --set full` summary"""
+    import csv
+    path = os.path.join(REPO, 'profiles', 'r01b_ncu_full_conv3x3_rows_summary.csv')
+    try:
+        rows = {r[0]: r for r in csv.reader(open(path)) if r and not r[0].startswith('#')}
+        t = [float(v) for v in rows['gpu__time_duration.sum'][2:]]
+        k = t.index(max(t))
+        mult = lambda u: {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
+        rd, wr = rows['dram__bytes_read.sum'], rows['dram__bytes_write.sum']
+        return {'bytes': float(rd[2 + k]) * mult(rd[1]) + float(wr[2 + k]) * mult(wr[1]), 'kernel': rows['Kernel Name'][2 + k],
+                'launch_us': t[k], 'algorithmic_bytes': 16 * 256 * 256 * (192 + 64 + 64) * 2.0,
+                'source': 'profiles/r01b_ncu_full_conv3x3_rows_summary.csv (conv5 192->64 + 16-bit residual, 16x256x256)'}
+    except Exception:
+        return None
+
+
 def build_model(dev):
     """CEM_PyTorch(RRDBNet) exactly as models.networks.define_G builds it for training (kaiming x0.1 init, seed 0)."""
     import contextlib
@@ -173,6 +190,7 @@ def main():
     ap.add_argument('--impl', default='esr_b200')
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the extra generator-training-step measurement')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -274,10 +292,49 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
 
+    # generator training step at the same shape (fwd + CEM + L1 + bwd with weight gradients + Adam; bf16 engine), extra key
+    train = None
+    if not args.no_train:
+        try:
+            from esr_b200 import parallel
+            params = [p_ for n_, p_ in model.named_parameters() if 'Filter_OP' not in n_]
+            for p_ in params:
+                p_.requires_grad_(True)
+            opt_g = torch.optim.Adam(params, lr=1e-4)
+            hr_dev = torch.rand(B, 3, LR * SCALE, LR * SCALE, device=dev)
+
+            def step_train():
+                opt_g.zero_grad(set_to_none=True)
+                loss = (model(x_dev) - hr_dev).abs().mean()
+                loss.backward()
+                parallel.average_gradients(params)
+                opt_g.step()
+            for _ in range(2):
+                step_train()
+            barrier()
+            l0 = lib.launch_count()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                step_train()
+            g1.record()
+            barrier()
+            ms_train = g0.elapsed_time(g1) / 3
+            train = {'ms_per_step': ms_train, 'gpu_launches_per_step': (lib.launch_count() - l0) // 3, 'dtype': 'bf16 operands, f32 master weights',
+                     'step': 'forward + CEM + L1 loss + backward (dgrad + wgrad) + gradient all-reduce + Adam', 'steps': 3}
+            for p_ in params:
+                p_.requires_grad_(False)
+                p_.grad = None
+            assert lib.watchdog()[0] == 0, 'pipeline watchdog fired in the training step'
+        except Exception as e:  # the forward numbers above stay valid
+            train = {'error': repr(e)[:300]}
+
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, conv_ms], device=dev)
+        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, conv_ms = [float(v) for v in t]
+        ms, ms_e2e, conv_ms = [float(v) for v in t[:3]]
+        if train and 'ms_per_step' in train:
+            train['ms_per_step'] = float(t[3])
     mp_step = world * B * (LR * SCALE) ** 2 / 1e6
     if rank == 0:
         pk, pk_src = peaks()
@@ -295,9 +352,15 @@ def main():
             'e2e': {'value': mp_step / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': x_host.numel() * 4,
                     'd2h_bytes_per_step': y_host.numel() * 4},
             'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_rows_kernel + conv3x3_tc_kernel (%d conv launches/step)' % n_conv, 'achieved': achieved, 'peak': peak,
-                         'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': pk_src + ', sustained bf16',
+                         'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': (profiled_traffic() or {}).get('bytes'),
+                         'traffic_detail': profiled_traffic(), 'peak_source': pk_src + ', sustained bf16',
                          'kernel_ms_per_step': conv_ms, 'algorithmic_tflop_per_step': flops_step / 1e12},
         }
+        if train is not None:
+            if 'ms_per_step' in train:
+                train['value'] = mp_step / (train['ms_per_step'] * 1e-3)
+                train['unit'] = 'HR-MP/s (fwd+bwd)'
+            out['train'] = train
         if not args.no_cpu_baseline and world == 1:
             out['cpu_baseline'] = cpu_baseline()
         print(json.dumps(out), flush=True)

@@ -219,6 +219,9 @@ cem_up_add_kernel(const float* __restrict__ f, const float* __restrict__ g, int 
   const int ilo = max((ylo - phase + s - 1) / s, 0), ihi = min((yhi - phase) / s, hl - 1);
   const int jlo = max((xlo - phase + s - 1) / s, 0), jhi = min((xhi - phase) / s, wl - 1);
   const int ni = max(ihi - ilo + 1, 0), nj = max(jhi - jlo + 1, 0);
+  // tiles whose filter footprint stays inside the image need no replicate-pad clamping (the common case)
+  const bool interior_y = Y0 - r >= 0 && Y0 + kUpT - 1 + r <= hh - 1;
+  const bool interior_x = X0 - r >= 0 && X0 + kUpT - 1 + r <= wh - 1;
   const int maxn = (kUpT + len) / s + 2;
   float* ft = sm;                    // [maxn][maxn] LR window
   float* hb = sm + maxn * maxn;      // [maxn][kUpT]  horizontally filtered rows
@@ -238,11 +241,18 @@ cem_up_add_kernel(const float* __restrict__ f, const float* __restrict__ g, int 
       const int ii = e / kUpT, xx = e - ii * kUpT;
       const int X = X0 + xx;
       float a = 0.f;
-      for (int b = 0; b < len; ++b) {
-        const int xs = clampi(X + b - r, 0, wh - 1) - phase;
-        if (xs >= 0 && xs % s == 0) {
-          const int j = xs / s - jlo;
-          if (j >= 0 && j < nj) a = fmaf(__ldg(khr + b), ft[ii * maxn + j], a);
+      if (interior_x) {
+        // polyphase: only every s-th tap meets a non-zero sample of the zero-stuffed row; no clamping inside the image
+        const int b0 = (((phase + r - X) % s) + s) % s;
+        int j = (X + b0 - r - phase) / s - jlo;
+        for (int b = b0; b < len; b += s, ++j) a = fmaf(__ldg(khr + b), ft[ii * maxn + j], a);
+      } else {
+        for (int b = 0; b < len; ++b) {
+          const int xs = clampi(X + b - r, 0, wh - 1) - phase;
+          if (xs >= 0 && xs % s == 0) {
+            const int j = xs / s - jlo;
+            if (j >= 0 && j < nj) a = fmaf(__ldg(khr + b), ft[ii * maxn + j], a);
+          }
         }
       }
       hb[ii * kUpT + xx] = a;
@@ -252,11 +262,17 @@ cem_up_add_kernel(const float* __restrict__ f, const float* __restrict__ g, int 
     for (int k = 0; k < 4; ++k) {
       const int Y = Y0 + ty0 + 8 * k;
       float a2 = 0.f;
-      for (int a = 0; a < len; ++a) {
-        const int ys = clampi(Y + a - r, 0, hh - 1) - phase;
-        if (ys >= 0 && ys % s == 0) {
-          const int i = ys / s - ilo;
-          if (i >= 0 && i < ni) a2 = fmaf(__ldg(kvr + a), hb[i * kUpT + tx], a2);
+      if (interior_y) {
+        const int a0 = (((phase + r - Y) % s) + s) % s;
+        int i = (Y + a0 - r - phase) / s - ilo;
+        for (int a = a0; a < len; a += s, ++i) a2 = fmaf(__ldg(kvr + a), hb[i * kUpT + tx], a2);
+      } else {
+        for (int a = 0; a < len; ++a) {
+          const int ys = clampi(Y + a - r, 0, hh - 1) - phase;
+          if (ys >= 0 && ys % s == 0) {
+            const int i = ys / s - ilo;
+            if (i >= 0 && i < ni) a2 = fmaf(__ldg(kvr + a), hb[i * kUpT + tx], a2);
+          }
         }
       }
       acc[k] += a2;

@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), batch sharded by rank, replicated weights.
+
+The forward / test / Z-optimisation paths shard by sample with no data-path collective.  Training adds
+  * one all-reduce of the generator's gradients per optimizer step (`average_gradients`: flat fp32 buckets over NCCL /
+    NVLink; the generator's parameters are ordinary autograd inputs of the fused node, so DistributedDataParallel works
+    as well), and
+  * a 2-scalar all-reduce where the reference takes a mean over the GLOBAL batch after nn.DataParallel gathered the
+    discriminator outputs on GPU 0 (models/SRRaGAN_model.py:353-354,475-476): `global_mean`.
+Everything here is backend-agnostic torch.distributed (NCCL on the GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def rank():
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+
+
+def shard_batch(n, world_size=None, r=None):
+    """[start, stop) of the samples of a global batch of n owned by rank r (contiguous, sizes differ by at most 1)"""
+    world_size = world() if world_size is None else world_size
+    r = rank() if r is None else r
+    base, rem = divmod(n, world_size)
+    start = r * base + min(r, rem)
+    return start, start + base + (1 if r < rem else 0)
+
+
+def average_gradients(params, bucket_bytes=64 << 20, group=None):
+    """In-place average of .grad over all ranks, in flat buckets of about `bucket_bytes` (a 17 M-parameter generator is two
+    buckets: the all-reduce is latency-bound on NVLink).  Parameters without a gradient contribute zeros so
+    that every rank issues the same collectives.  Returns the number of all-reduce calls."""
+    params = [p for p in params if p.requires_grad]
+    if world() == 1 or not params:
+        return 0
+    calls, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal calls, bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world())
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+        calls += 1
+        bucket, size = [], 0
+
+    for p in params:
+        bucket.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return calls
+
+
+def global_mean(local_values, group=None):
+    """mean over the GLOBAL batch of per-sample values held rank by rank (unequal shard sizes allowed): one 2-scalar
+    all-reduce (sum, count)"""
+    s = torch.stack([local_values.sum().float(), torch.tensor(float(local_values.numel()), device=local_values.device)])
+    if world() > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return s[0] / s[1]

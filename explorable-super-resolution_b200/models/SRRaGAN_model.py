@@ -1,28 +1,37 @@
 """SRRaGANModel — orchestration layer with the reference's surface (models/SRRaGAN_model.py).
 
-Built in this round: construction for inference / latent exploration (CEM + generator + checkpoint loading),
-`feed_data`, `Prepare_Input`, `GetLatent`, `test`, `Output_Batch`, `get_current_visuals`, `save`/`load` — i.e. everything
-`test.py`, the GUI's `Feed_n_Run_model` and `Z_optimizer.optimize` call.  `optimize_parameters` (the GAN training step:
-discriminator, VGG features, weight gradients) raises NotImplementedError until those kernels exist."""
+Built: construction for inference / latent exploration (CEM + generator + checkpoint loading), `feed_data`,
+`Prepare_Input`, `GetLatent`, `test`, `Output_Batch`, `get_current_visuals`, `save`/`load` — everything `test.py`, the GUI's
+`Feed_n_Run_model` and `Z_optimizer.optimize` call — and the generator branch of the training step
+(`optimize_parameters` with pixel + range losses, gradient accumulation, Adam, MultiStepLR: models/SRRaGAN_model.py:280-519
+with `gan_weight` / `feature_weight` unset, i.e. the PSNR-oriented pre-training configuration).  Configurations that need the
+discriminator, the VGG feature extractor or the latent structure loss raise NotImplementedError at construction: those
+networks are not built yet and there is no PyTorch fallback."""
 import os
 import re
 from collections import OrderedDict
 
 import numpy as np
 import torch
+import torch.nn as nn
+from torch.optim import lr_scheduler
 
 import CEM.CEMnet as CEMnet
 import models.networks as networks
-from models.modules.loss import FilterLoss
+from models.modules.loss import FilterLoss, CreateRangeLoss
 from .base_model import BaseModel
 
 
 class SRRaGANModel(BaseModel):
     def __init__(self, opt, accumulation_steps_per_batch=1, init_Fnet=None, init_Dnet=None, **kwargs):
         super(SRRaGANModel, self).__init__(opt)
+        train_opt = opt['train'] if self.is_train else None
         if self.is_train:
-            raise NotImplementedError('esr_b200: the SRRaGAN training step (D, VGG features, wgrad) is not built yet; '
-                                      'use is_train=False (test / latent exploration)')
+            unbuilt = [k for k in ('gan_weight', 'feature_weight', 'latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
+            if unbuilt:
+                raise NotImplementedError('esr_b200: the training step is built for the pixel / range losses only; %s need the '
+                                          'discriminator / VGG feature extractor / structure loss (SURVEY 8a-12..15), not built yet'
+                                          % ', '.join(unbuilt))
         self.log_path = opt['path']['log'] if opt['path'] is not None else None
         self.latent_input_domain = opt['network_G']['latent_input_domain']
         self.latent_input = opt['network_G']['latent_input'] if opt['network_G']['latent_input'] != 'None' else None
@@ -50,8 +59,53 @@ class SRRaGANModel(BaseModel):
         opt['network_G']['scale'] = opt['network_G']['scale'] if opt['network_G']['scale'] is not None else opt['scale']
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
-        self.netG.eval()
-        self.Set_Require_Grad_Status(self.netG, False)
+        logs_2_keep = ['l_g_pix', 'l_g_range', 'psnr_val', 'LR_decrease']
+        self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
+        if not self.is_train:
+            self.netG.eval()
+            self.Set_Require_Grad_Status(self.netG, False)
+            self.load()
+            return
+        # ---- training state (models/SRRaGAN_model.py:68-203, generator branch)
+        self.max_accumulation_steps = accumulation_steps_per_batch
+        self.grad_accumulation_steps_G = train_opt['grad_accumulation_steps_G'] or 1
+        self.netG.train()
+        if train_opt['pixel_weight'] is not None:
+            l_pix_type = train_opt['pixel_criterion']
+            if l_pix_type == 'l1':
+                self.cri_pix = nn.L1Loss().to(self.device)
+            elif l_pix_type == 'l2':
+                self.cri_pix = nn.MSELoss().to(self.device)
+            else:
+                raise NotImplementedError('Loss type [{:s}] not recognized.'.format(l_pix_type))
+            self.l_pix_w = train_opt['pixel_weight']
+        else:
+            print('Remove pixel loss.')
+            self.cri_pix = None
+        if train_opt['range_weight'] is not None:
+            self.cri_range = CreateRangeLoss(opt['range'])
+            self.l_range_w = train_opt['range_weight']
+        else:
+            print('Remove range loss.')
+            self.cri_range = None
+        self.cri_gan, self.cri_fea, self.D_init_iters = None, None, 0
+        wd_G = train_opt['weight_decay_G'] if train_opt['weight_decay_G'] else 0
+        optim_params = []
+        for k, v in self.netG.named_parameters():
+            if v.requires_grad:
+                optim_params.append(v)
+            else:
+                print('WARNING: params [{:s}] will not optimize.'.format(k))
+        self.lr_G = train_opt['lr_G']
+        self.optimizer_G = torch.optim.Adam(optim_params, lr=self.lr_G, weight_decay=wd_G,
+                                            betas=(train_opt['beta1_G'], train_opt['beta2_G'] if train_opt['beta2_G'] is not None else 0.999))
+        self.optimizers.append(self.optimizer_G)
+        if train_opt['lr_scheme'] == 'MultiStepLR':
+            for optimizer in self.optimizers:
+                self.schedulers.append(lr_scheduler.MultiStepLR(optimizer, train_opt['lr_steps'], train_opt['lr_gamma']))
+        else:
+            raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
+        self.generator_step, self.generator_changed, self.generator_started_learning = False, True, False
         self.load()
 
     # ---- I/O of one batch -------------------------------------------------------------------------
@@ -98,7 +152,46 @@ class SRRaGANModel(BaseModel):
             self.var_ref = (data['ref'] if 'ref' in data else data['HR']).to(self.device)
 
     def optimize_parameters(self):
-        raise NotImplementedError('esr_b200: SRRaGANModel.optimize_parameters is not built yet (SURVEY 8a-12..16)')
+        """Generator branch of models/SRRaGAN_model.py:280-519 (no discriminator): forward through CEM(G), crop the invalid
+        margins, pixel (+ range) loss scaled by the accumulation count, backward (dgrad + wgrad launches through the single
+        autograd node), Adam step on the last accumulation step.  Like the reference, the first gradient step is idle."""
+        self.gradient_step_num = self.step // self.max_accumulation_steps
+        first_acc = self.step % self.grad_accumulation_steps_G == 0
+        last_acc = self.step % self.grad_accumulation_steps_G == (self.grad_accumulation_steps_G - 1)
+        self.Set_Require_Grad_Status(self.netG, True)
+        if self.CEM_net is not None:
+            self.var_H, self.var_ref = self.CEM_net.HR_unpadder(self.var_H), self.CEM_net.HR_unpadder(self.var_ref)
+        static_Z = self.GetLatent() if self.latent_input is not None else None
+        self.Prepare_Input(LR_image=self.var_L, latent_input=static_Z)
+        self.fake_H = self.netG(self.model_input)
+        if self.CEM_net is not None:
+            self.fake_H = self.CEM_net.HR_unpadder(self.fake_H)
+        self.generator_step = self.gradient_step_num > 0   # one idle iteration first, to save the initial validation results
+        if self.generator_step:
+            self.generator_started_learning = True
+            if first_acc:
+                self.optimizer_G.zero_grad()
+                self.l_g_pix_grad_step, self.l_g_range_grad_step = [], []
+            l_g_total = 0
+            if self.cri_pix:
+                l_g_pix = self.cri_pix(self.fake_H, self.var_H)
+                l_g_total = l_g_total + self.l_pix_w * l_g_pix / self.grad_accumulation_steps_G
+            if self.cri_range:
+                l_g_range = self.cri_range(self.fake_H)
+                l_g_total = l_g_total + self.l_range_w * l_g_range / self.grad_accumulation_steps_G
+            l_g_total.backward()
+            if self.cri_pix:
+                self.l_g_pix_grad_step.append(l_g_pix.item())
+            if self.cri_range:
+                self.l_g_range_grad_step.append(l_g_range.item())
+            if last_acc:
+                self.optimizer_G.step()
+                self.generator_changed = True
+                if self.cri_pix:
+                    self.log_dict['l_g_pix'].append((self.gradient_step_num, np.mean(self.l_g_pix_grad_step)))
+                if self.cri_range:
+                    self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
+        self.step += 1
 
     def test(self, prevent_grads_calc=True, **kwargs):
         self.netG.eval()
@@ -123,7 +216,7 @@ class SRRaGANModel(BaseModel):
         return out
 
     def get_current_log(self):
-        return {}
+        return OrderedDict((k, v[-1][1]) for k, v in self.log_dict.items() if len(v) > 0)
 
     # ---- checkpoints --------------------------------------------------------------------------------
     def load(self, max_step=None, resume_train=None):

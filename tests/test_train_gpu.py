@@ -80,3 +80,50 @@ def test_sgd_step_reduces_l1_loss_and_accumulates():
     with torch.no_grad():
         loss1 = (net(x) - hr).abs().mean()
     assert loss1.item() < loss0.item(), (loss0.item(), loss1.item())
+
+
+def _train_opt(tmp_path, **train_over):
+    class ND(dict):
+        def __missing__(self, k):
+            return None
+    train = ND(pixel_weight=1.0, pixel_criterion='l1', range_weight=0.1, lr_G=2e-4, beta1_G=0.9, weight_decay_G=0,
+               lr_scheme='MultiStepLR', lr_steps=[1000], lr_gamma=0.5, grad_accumulation_steps_G=2, grad_accumulation_steps_D=2)
+    train.update(train_over)
+    return ND(model='srragan', scale=4, gpu_ids=[0], is_train=True, range=[0, 1], train=train,
+              datasets=ND(train=ND(patch_size=128, batch_size=2)),
+              path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, log=str(tmp_path)),
+              network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None,
+                           norm_type=None, mode='CNA', nf=32, nb=1, in_nc=3, out_nc=3, gc=32, scale=4))
+
+
+def test_srragan_model_generator_training_step(tmp_path):
+    """create_model(is_train) -> feed_data -> optimize_parameters, the calls train.py:69-116 makes: pixel + range loss,
+    two accumulation steps per Adam step, first gradient step idle (as in the reference); the L1 loss goes down."""
+    from esr_b200 import ops
+    from models import create_model
+    ops.device_check()
+    torch.manual_seed(5)
+    model = create_model(_train_opt(tmp_path), accumulation_steps_per_batch=2)
+    assert model.netG.module.pre_pad is False
+    lr = torch.rand(2, 3, 32, 32)
+    hr = torch.nn.functional.interpolate(lr, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    w0 = [p.detach().clone() for p in model.netG.parameters() if p.requires_grad]
+    for it in range(14):
+        model.feed_data({'LR': lr, 'HR': hr})
+        model.optimize_parameters()
+        if it == 1:   # gradient step 0 is idle
+            assert all(torch.equal(a, p.detach()) for a, p in zip(w0, [p for p in model.netG.parameters() if p.requires_grad]))
+    log = model.log_dict['l_g_pix']
+    assert len(log) == 6 and log[-1][1] < log[0][1], log
+    assert model.fake_H.shape == (2, 3, 128 - 80, 128 - 80)        # HR_unpadder crops the invalid margins (SRRaGAN_model.py:333)
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(w0, [p for p in model.netG.parameters() if p.requires_grad]))
+    model.update_learning_rate(3)
+    assert model.get_current_learning_rate() == 2e-4
+
+
+def test_srragan_model_refuses_unbuilt_losses(tmp_path):
+    from models import create_model
+    with pytest.raises(NotImplementedError):
+        create_model(_train_opt(tmp_path, gan_weight=5e-3))
+    with pytest.raises(NotImplementedError):
+        create_model(_train_opt(tmp_path, feature_weight=1.0))
