@@ -21,8 +21,9 @@
 
 namespace esr {
 
-constexpr int kWgThreads = 256;       // warp 0 producer, warp 1 MMA issuer, warps 4..7 TMEM zero-fill + final read-out
-constexpr int kWgPW = 64;             // pixels of a strip (4 K steps of 16 pixels per row)
+constexpr int kWgThreads = 256;       // warp 0 producer, warps 1..3 MMA issuers, warps 4..7 TMEM zero-fill + final read-out
+constexpr int kWgIssuers = 3;
+constexpr int kWgPW = 32;             // pixels of a strip = one TMA box row (2 K steps of 16 pixels)
 constexpr int kWgMaxRing = 8;
 constexpr int kWgGStages = 3;
 
@@ -40,6 +41,15 @@ struct WgradParams {
   float* part;                                 // [cta][mt][128][3*nbn] fp32 partial gradients
 };
 
+// position in a ring of `n` buffers with its mbarrier phase bit (no integer division in the per-row loops)
+struct WgRing {
+  int j;
+  uint32_t ph;
+  __device__ __forceinline__ void inc(int n) {
+    if (++j == n) { j = 0; ph ^= 1u; }
+  }
+};
+
 __device__ __forceinline__ bool wg_next_segment(const WgradParams& p, long long& u, long long u1, int& img, int& x0, int& ya,
                                                 int& yb) {
   if (u >= u1) return false;
@@ -53,7 +63,8 @@ __device__ __forceinline__ bool wg_next_segment(const WgradParams& p, long long&
   return true;
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   // header: x row full[8] | x row empty[8] | gy full[4] | gy empty[4] | done | zeroed | tmem pointer
@@ -76,13 +87,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.rb; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_xempty + 8 * s, 1);
+      mbar_init(bar_xempty + 8 * s, kWgIssuers);
     }
     for (int s = 0; s < kWgGStages; ++s) {
       mbar_init(bar_gfull + 8 * s, 1);
-      mbar_init(bar_gempty + 8 * s, 1);
+      mbar_init(bar_gempty + 8 * s, kWgIssuers);
     }
-    mbar_init(bar_done, 1);
+    mbar_init(bar_done, kWgIssuers);
     mbar_init(bar_zero, 4);
     fence_barrier_init();
   }
@@ -98,141 +109,96 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
   const int nblk = (int)blockIdx.x % p.n_blocks;
   const int rid = (int)blockIdx.x / p.n_blocks;
   const long long u0 = p.units * rid / p.ranges, u1 = p.units * (rid + 1) / p.ranges;
-  const size_t hw = (size_t)p.h * p.w;
-  const size_t plane16 = hw * 16;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
-    // x rows: one lane per plane (cp <= 32 planes); gy rows: one lane per (kx, plane) copy (3 * cpb <= 24)
-    int xi = 0;            // x rows loaded so far (ring index = xi % rb)
-    int gi = 0;            // gy rows loaded so far
-    long long u = u0;
-    int img, x0, ya, yb;
-    while (wg_next_segment(p, u, u1, img, x0, ya, yb)) {
-      const int valid = p.w - x0 < kWgPW ? p.w - x0 : kWgPW;   // x positions of this strip that exist
-      const uint8_t* xcol = p.x + (((size_t)img * p.x_pt + p.x_po) * hw + x0) * 16;
-      const uint8_t* gcol = p.gy + (((size_t)img * p.gy_pt + p.gy_po + nblk * p.cpb) * hw) * 16;
-      int seg_x = 0, seg_g = 0;
-      // gy copy handled by this lane: kx = lane / cpb, plane = lane % cpb; copy[k] = gy[row][x0 + k - kx + 1]
-      const int kx = lane / p.cpb, gpl = lane - kx * p.cpb;
-      const int gpl_src = nblk * p.cpb + gpl < p.gyp ? gpl : p.gyp - 1 - nblk * p.cpb;   // pad planes re-load the last real one
-      int gs = x0 + 1 - kx, gd = 0;                       // source pixel, destination pixel
-      if (gs < 0) { gd = -gs; gs = 0; }
-      int gcnt = kWgPW - gd;
-      if (gs + gcnt > p.w) gcnt = p.w - gs;
-      if (gcnt < 0) gcnt = 0;
-      for (int row = ya - 1; row <= yb; ++row) {
-        // ---- x row `row` (zeros outside the image)
-        {
-          const int j = xi % p.rb;
-          mbar_wait(bar_xempty + 8 * j, (uint32_t)(((xi / p.rb) & 1) ^ 1), 1u);
-          const uint32_t dst = xring + (uint32_t)j * p.slot_bytes;
-          const bool dup = j < 2;                         // ring slots 0,1 are mirrored behind the last slot
-          const uint32_t dst2 = xring + (uint32_t)(p.rb + j) * p.slot_bytes;
-          const bool real = row >= 0 && row < p.h;
-          if (!real) {
-            // zero row: all 32 lanes clear cp * kWgPW 16-byte pixels
-            for (uint32_t o = lane * 16u; o < p.slot_bytes; o += 512u) {
-              st_shared_zero16(dst + o);
-              if (dup) st_shared_zero16(dst2 + o);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xfull + 8 * j);
-          } else {
-            if (valid < kWgPW && seg_x < p.rb + 2) {
-              // pixels beyond the image edge are never written by this segment's copies: clear them once per slot
-              if (lane < p.cp) {
-                for (int k = valid; k < kWgPW; ++k) {
-                  st_shared_zero16(dst + lane * group_bytes + k * 16);
-                  if (dup) st_shared_zero16(dst2 + lane * group_bytes + k * 16);
-                }
-                fence_proxy_async();
-              }
-              __syncwarp();
-            }
-            if (lane == 0) mbar_expect_tx(bar_xfull + 8 * j, (uint32_t)p.cp * valid * 16u * (dup ? 2u : 1u));
-            __syncwarp();
-            if (lane < p.cp) {
-              const uint8_t* src = xcol + (size_t)lane * plane16 + (size_t)row * p.w * 16;
-              bulk_load(dst + lane * group_bytes, src, (uint32_t)valid * 16u, bar_xfull + 8 * j);
-              if (dup) bulk_load(dst2 + lane * group_bytes, src, (uint32_t)valid * 16u, bar_xfull + 8 * j);
-            }
+    // One TMA tensor load per activation row (box = 32 pixels x cp planes, landing as [plane][pixel] = consecutive M
+    // groups) and three per gradient row (the kx-shifted copies); rows / pixels outside the image are zero-filled by the
+    // TMA unit, which is exactly the convolution's zero padding.
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmG);
+      WgRing xr = {0, 0u};   // next x row slot
+      WgRing gr = {0, 0u};   // next gy stage
+      long long u = u0;
+      int img, x0, ya, yb;
+      while (wg_next_segment(p, u, u1, img, x0, ya, yb)) {
+        for (int row = ya - 1; row <= yb; ++row) {
+          {
+            const int j = xr.j;
+            mbar_wait(bar_xempty + 8 * j, xr.ph ^ 1u, 1u);
+            const bool dup = j < 2;                         // ring slots 0,1 are mirrored behind the last slot
+            mbar_expect_tx(bar_xfull + 8 * j, p.slot_bytes * (dup ? 2u : 1u));
+            tma_load_4d(xring + (uint32_t)j * p.slot_bytes, &tmX, bar_xfull + 8 * j, x0 * 8, row, p.x_po, img);
+            if (dup) tma_load_4d(xring + (uint32_t)(p.rb + j) * p.slot_bytes, &tmX, bar_xfull + 8 * j, x0 * 8, row, p.x_po, img);
+            xr.inc(p.rb);
           }
-          ++xi;
-          ++seg_x;
-        }
-        // ---- gy row `row` (output rows of the segment only)
-        if (row >= ya && row < yb) {
-          const int s = gi % kWgGStages;
-          mbar_wait(bar_gempty + 8 * s, (uint32_t)(((gi / kWgGStages) & 1) ^ 1), 2u);
-          const uint32_t dst = gst0 + (uint32_t)s * p.gstage_bytes + lane * group_bytes;
-          const bool mine = lane < 3 * p.cpb;
-          if (seg_g < kWgGStages) {
-            if (mine) {
-              for (int k = 0; k < gd; ++k) st_shared_zero16(dst + k * 16);
-              for (int k = gd + gcnt; k < kWgPW; ++k) st_shared_zero16(dst + k * 16);
-              fence_proxy_async();
-            }
-            __syncwarp();
+          if (row >= ya && row < yb) {
+            const int s = gr.j;
+            mbar_wait(bar_gempty + 8 * s, gr.ph ^ 1u, 2u);
+            const uint32_t dst = gst0 + (uint32_t)s * p.gstage_bytes;
+            mbar_expect_tx(bar_gfull + 8 * s, p.gstage_bytes);
+            // copy kx holds gy[row][x0 + k - kx + 1] at pixel k
+            for (int kx = 0; kx < 3; ++kx)
+              tma_load_4d(dst + (uint32_t)(kx * p.cpb) * group_bytes, &tmG, bar_gfull + 8 * s, (x0 + 1 - kx) * 8, row,
+                          p.gy_po + nblk * p.cpb, img);
+            gr.inc(kWgGStages);
           }
-          // every lane's byte count differs by at most one pixel: lane 0 posts the total
-          uint32_t tot = mine ? (uint32_t)gcnt * 16u : 0u;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-          if (lane == 0) mbar_expect_tx(bar_gfull + 8 * s, tot);
-          __syncwarp();
-          if (mine && gcnt > 0)
-            bulk_load(dst + gd * 16, gcol + (size_t)gpl_src * plane16 + ((size_t)row * p.w + gs) * 16, (uint32_t)gcnt * 16u,
-                      bar_gfull + 8 * s);
-          ++gi;
-          ++seg_g;
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
+  } else if (warp <= kWgIssuers) {
+    // ------------------------------------------------------------------ MMA issuers (one thread per warp).  The K steps
+    // of the launch are dealt round-robin to the issuers; every MMA accumulates into zero-initialised TMEM, so their
+    // order is irrelevant, and every buffer is released when all issuers have committed it.
+    const int iw = warp - 1;
     if (elect_one()) {
+      int kmod = 0;
       if (u0 < u1) mbar_wait(bar_zero, 0u, 6u);
       tc_fence_after();
       const uint64_t adesc_t = make_smem_desc(0u, 128u, group_bytes);   // MN-major: LBO = K-block (8 px) stride, SBO = group stride
       const uint64_t bdesc_t = make_smem_desc(0u, 128u, group_bytes);
-      int xi = 0, gi = 0;
+      WgRing cur = {0, 0u}, gr = {0, 0u};
+      const uint64_t mstep = (uint64_t)((16u * group_bytes) >> 4);
       long long u = u0;
       int img, x0, ya, yb;
       while (wg_next_segment(p, u, u1, img, x0, ya, yb)) {
         const int valid = p.w - x0 < kWgPW ? p.w - x0 : kWgPW;
         const int ksteps = (valid + 15) >> 4;
-        // rows ya-1, ya are the first two ring rows of this segment
+        // window of output row r = x rows r-1, r, r+1 = three consecutive ring rows p0, p1, p2
+        WgRing p0 = cur, p1 = cur, p2;
+        p1.inc(p.rb);
+        p2 = p1;
+        p2.inc(p.rb);
+        mbar_wait(bar_xfull + 8 * p0.j, p0.ph, 3u);
+        mbar_wait(bar_xfull + 8 * p1.j, p1.ph, 3u);
         for (int r = ya; r < yb; ++r) {
-          // window = x rows r-1, r, r+1 = ring indices xi, xi+1, xi+2
-          if (r == ya) {
-            mbar_wait(bar_xfull + 8 * (xi % p.rb), (uint32_t)((xi / p.rb) & 1), 3u);
-            mbar_wait(bar_xfull + 8 * ((xi + 1) % p.rb), (uint32_t)(((xi + 1) / p.rb) & 1), 3u);
-          }
-          mbar_wait(bar_xfull + 8 * ((xi + 2) % p.rb), (uint32_t)(((xi + 2) / p.rb) & 1), 3u);
-          const int s = gi % kWgGStages;
-          mbar_wait(bar_gfull + 8 * s, (uint32_t)((gi / kWgGStages) & 1), 4u);
+          mbar_wait(bar_xfull + 8 * p2.j, p2.ph, 3u);
+          mbar_wait(bar_gfull + 8 * gr.j, gr.ph, 4u);
           tc_fence_after();
-          const uint32_t a0 = xring + (uint32_t)(xi % p.rb) * p.slot_bytes;
-          const uint32_t b0 = gst0 + (uint32_t)s * p.gstage_bytes;
+          const uint64_t ad0 = adesc_t + (uint64_t)((xring + (uint32_t)p0.j * p.slot_bytes) >> 4);
+          const uint64_t bd0 = bdesc_t + (uint64_t)((gst0 + (uint32_t)gr.j * p.gstage_bytes) >> 4);
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t bd = bdesc_t + (uint64_t)((b0 + ks * 256u) >> 4);
-            for (int m = 0; m < p.mt; ++m) {
-              const uint64_t ad = adesc_t + (uint64_t)((a0 + (uint32_t)m * 16u * group_bytes + ks * 256u) >> 4);
-              umma_f16(tmem_base + (uint32_t)(m * N3), ad, bd, p.idesc, 1u);
+            if (kmod == iw) {
+              const uint64_t bd = bd0 + (uint64_t)(ks * 16);
+              uint64_t ad = ad0 + (uint64_t)(ks * 16);
+              uint32_t d = tmem_base;
+              for (int m = 0; m < p.mt; ++m, ad += mstep, d += (uint32_t)N3) umma_f16(d, ad, bd, p.idesc, 1u);
             }
+            if (++kmod == kWgIssuers) kmod = 0;
           }
-          umma_commit(bar_gempty + 8 * s);
-          umma_commit(bar_xempty + 8 * (xi % p.rb));          // row r-1 is not needed again
+          umma_commit(bar_gempty + 8 * gr.j);
+          umma_commit(bar_xempty + 8 * p0.j);                 // row r-1 is not needed again
           if (r == yb - 1) {                                   // ... and neither are the last two rows of the segment
-            umma_commit(bar_xempty + 8 * ((xi + 1) % p.rb));
-            umma_commit(bar_xempty + 8 * ((xi + 2) % p.rb));
+            umma_commit(bar_xempty + 8 * p1.j);
+            umma_commit(bar_xempty + 8 * p2.j);
           }
-          ++xi;
-          ++gi;
+          p0 = p1;
+          p1 = p2;
+          p2.inc(p.rb);
+          gr.inc(kWgGStages);
         }
-        xi += 2;
+        cur = p2;
       }
       umma_commit(bar_done);
     }
@@ -247,7 +213,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_zero);
-    mbar_wait(bar_done, 0u, 7u);
+    // the read-out warps have nothing to do until the whole range is accumulated: sleep between polls
+    while (!mbar_try_wait(bar_done, 0u)) __nanosleep(2000);
     tc_fence_after();
     float* out = p.part + (((size_t)blockIdx.x * p.mt) * 128 + wq * 32 + lane) * N3;
     for (int m = 0; m < p.mt; ++m) {
@@ -272,30 +239,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv3x3_wgrad_kernel(const __gr
   }
 }
 
-// dW[co][ci][ky][kx] (+)= scale * sum over CTAs of the partial accumulators.  One thread per weight.
+// dW[co][ci][ky][kx] (+)= scale * sum over CTAs of the partial accumulators.  One thread per accumulator element in the
+// partials' own memory order (coalesced reads of every CTA's block), scattered store into the OIHW gradient.
+// grid = (ceil(mt*128*N3 / 256), n_blocks)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int ranges, int n_blocks, int mt, int nbn, int cp, int cout, int cin,
                                     int lead, float scale, int accumulate, float* __restrict__ dw) {
-  const int total = cout * cin * 9;
   const int lead_pad = (lead + 7) / 8 * 8;
   const int N3 = 3 * nbn;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    int r = idx;
-    const int kx = r % 3; r /= 3;
-    const int ky = r % 3; r /= 3;
-    const int ci = r % cin;
-    const int co = r / cin;
-    const int pc = ci < lead ? ci : ci - lead + lead_pad;       // channel position in plane space
-    const int G = ky * cp + (pc >> 3);                            // (row, plane) group
-    const int m = G >> 4, L = ((G & 15) << 3) + (pc & 7);
-    const int nblk = co / nbn, col = kx * nbn + (co - nblk * nbn);
-    float acc = 0.f;
-    for (int rg = 0; rg < ranges; ++rg) {
-      const size_t cta = (size_t)rg * n_blocks + nblk;
-      acc += part[((cta * mt + m) * 128 + L) * N3 + col];
-    }
-    acc *= scale;
-    dw[idx] = accumulate ? dw[idx] + acc : acc;
-  }
+  const int per_cta = mt * 128 * N3;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per_cta) return;
+  const int nblk = blockIdx.y;
+  const int col = e % N3, L = (e / N3) % 128, m = e / (N3 * 128);
+  const int G = (m << 4) + (L >> 3);
+  const int ky = G / cp, plane = G - ky * cp;
+  const int pc = plane * 8 + (L & 7);
+  const int ci = pc < lead_pad ? (pc < lead ? pc : -1) : pc - lead_pad + lead;
+  const int kx = col / nbn, co = nblk * nbn + (col - kx * nbn);
+  if (ky >= 3 || ci < 0 || ci >= cin || co >= cout) return;
+  float acc = 0.f;
+  const float* src = part + (size_t)nblk * per_cta + e;
+  for (int rg = 0; rg < ranges; ++rg) acc += __ldg(src + (size_t)rg * n_blocks * per_cta);
+  acc *= scale;
+  float* dst = dw + (((size_t)co * cin + ci) * 3 + ky) * 3 + kx;
+  *dst = accumulate ? *dst + acc : acc;
 }
 
 // db[co] (+)= scale * sum_{n,y,x} gy[n][co][y][x]   (16-bit planes in, fp32 out).  grid = (chunks, planes)
@@ -317,12 +284,19 @@ __global__ void bias_grad_kernel(const uint16_t* __restrict__ gy, int dtype, int
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
   }
+  // block-level sum first: same-address atomics from every warp of a large grid serialise in L2
+  __shared__ float red[8][8];
+  const int wid = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int co = plane * 8 + k;
-      if (co < cout) atomicAdd(db + co, s[k] * scale);
-    }
+    for (int k = 0; k < 8; ++k) red[wid][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) t += red[w8][threadIdx.x];
+    const int co = plane * 8 + threadIdx.x;
+    if (co < cout) atomicAdd(db + co, t * scale);
   }
 }
 

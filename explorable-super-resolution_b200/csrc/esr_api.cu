@@ -488,12 +488,31 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     p.part = a->workspace;
     int rc = set_max_smem_once((const void*)esr::conv3x3_wgrad_kernel);
     if (rc) return rc;
-    esr::conv3x3_wgrad_kernel<<<grid, esr::kWgThreads, w.smem_bytes, st>>>(p);
+    // tensor maps over the planar-8 buffers: dims (8ch*W, H, planes, N); box = (8*32 elements, 1 row, planes of the operand, 1)
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    CUtensorMap tmx, tmg;
+    {
+      cuuint64_t gdim[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->x_planes_total, (cuuint64_t)a->n};
+      cuuint64_t gstr[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->x_planes_total};
+      cuuint32_t box[4] = {(cuuint32_t)esr::kWgPW * 8, 1, (cuuint32_t)cp, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult cr = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed with CUresult %d", (int)cr);
+      cuuint64_t gdim2[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->gy_planes_total, (cuuint64_t)a->n};
+      cuuint64_t gstr2[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->gy_planes_total};
+      cuuint32_t box2[4] = {(cuuint32_t)esr::kWgPW * 8, 1, (cuuint32_t)w.cpb, 1};
+      cr = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->gy), gdim2, gstr2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(gy) failed with CUresult %d", (int)cr);
+    }
+    esr::conv3x3_wgrad_kernel<<<grid, esr::kWgThreads, w.smem_bytes, st>>>(tmx, tmg, p);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    const int total = a->cout * a->cin * 9;
-    esr::wgrad_reduce_kernel<<<grid_for((size_t)total, 256), 256, 0, st>>>(a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin,
-                                                                        a->lead, a->scale, a->accumulate, a->dw);
+    const int per_cta = w.mt * 128 * 3 * w.nbn;
+    esr::wgrad_reduce_kernel<<<dim3((unsigned)((per_cta + 255) / 256), (unsigned)w.n_blocks), 256, 0, st>>>(
+        a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin, a->lead, a->scale, a->accumulate, a->dw);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -501,7 +520,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     if (!a->accumulate) CUDA_TRY(cudaMemsetAsync(a->db, 0, sizeof(float) * a->cout, st));
     const size_t hw = (size_t)a->h * a->w;
     size_t chunks = ((size_t)a->n * hw + 255) / 256;
-    if (chunks > 148 * 4) chunks = 148 * 4;
+    if (chunks > 148) chunks = 148;
     dim3 grid((unsigned)chunks, (unsigned)w.gyp);
     esr::bias_grad_kernel<<<grid, 256, 0, st>>>((const uint16_t*)a->gy, a->dtype, a->n, a->gy_planes_total, a->gy_plane_off, a->cout, hw,
                                                 a->scale, a->db);
