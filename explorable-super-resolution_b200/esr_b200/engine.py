@@ -76,12 +76,55 @@ class RRDBEngine:
         return self._packed
 
     def packed_t(self):
-        """dgrad operands: I/O swapped, taps rotated by 180 degrees, no bias"""
+        """dgrad operands of the convs OUTSIDE the dense blocks: I/O swapped, taps rotated by 180 degrees, no bias
+        (the dense blocks use `packed_bwd_dense`)"""
         convs = self._check_version()
         if self._packed_t is None:
-            self._packed_t = [ops.PackedConv(c.weight, None, dtype=self.dtype, lead=l, transpose_flip=True)
-                              for c, l in zip(convs, self._leads(convs))]
+            nb = len(self.net.model[1].sub) - 1
+            inside = lambda i: 1 <= i <= 15 * nb
+            self._packed_t = [None if inside(i) else ops.PackedConv(c.weight, None, dtype=self.dtype, lead=l, transpose_flip=True)
+                              for i, (c, l) in enumerate(zip(convs, self._leads(convs)))]
         return self._packed_t
+
+    def packed_bwd_dense(self):
+        """Backward of a dense block as a dense block.  With g_i the gradient of conv_i's pre-activation output
+        (block.py:230-235: x_i = lrelu(conv_i(cat(x, x_1..x_{i-1})))),
+
+            g_i = lrelu'(x_i) * sum_{j>i} conv_j^T(g_j)[slice x_i]        i = 4..1
+            g_x =               sum_{j>=1} conv_j^T(g_j)[slice x (and z)]
+
+        i.e. every gradient slice is ONE 3x3 conv over the concatenation [g_5 | g_4 | ... | g_{i+1}] with the combined
+        weight  Wc_i[c, (j, o), ky, kx] = W_j[o, col_i(c), 2-ky, 2-kx]: the same growing-prefix structure as the forward
+        (no fp32 partial-gradient buffer, FLOPs identical).  The block's output scale (0.2, or 0.04 for the third block of
+        an RRDB) is folded into the W_5 rows.  Returns [block][i] -> PackedConv, i = 0 (g_x [+ latent rows in front, padded
+        to one plane]) .. 4, blocks in forward order.  Built with a handful of batched tensor ops over all blocks."""
+        convs = self._check_version()
+        if getattr(self, '_packed_bd', None) is not None and self._packed_bd_version == self._packed_version:
+            return self._packed_bd
+        net = self.net
+        z, nf, gc = net.z_lead, net.nf, net.gc
+        nb = len(net.model[1].sub) - 1
+        R = 3 * nb
+        with torch.no_grad():
+            W = [torch.stack([convs[1 + r * 5 + jj].weight.detach().float() for r in range(R)]) for jj in range(5)]  # [R, cout_j, cin_j, 3, 3]
+            a5 = torch.tensor([0.04 if r % 3 == 2 else 0.2 for r in range(R)], device=W[0].device).view(R, 1, 1, 1, 1)
+            W[4] = W[4] * a5
+            tr = lambda t: t.permute(0, 2, 1, 3, 4).flip(3, 4)    # [R, o, c] -> [R, c, o], taps rotated by 180 degrees
+            out = [[None] * 5 for _ in range(R)]
+            for i in range(5):
+                if i == 0:
+                    cols = slice(0, z + nf)
+                else:
+                    cols = slice(z + nf + (i - 1) * gc, z + nf + i * gc)
+                parts = [tr(W[jj][:, :, cols]) for jj in range(4, i - 1 if i > 0 else -1, -1) if jj >= i]   # convs j = 5 .. i+1 (0-based jj >= i)
+                wc = torch.cat(parts, dim=2)
+                if i == 0 and z:
+                    wc = torch.cat([wc[:, :z], torch.zeros((R, 8 - z) + tuple(wc.shape[2:]), device=wc.device), wc[:, z:]], dim=1)
+                wc = wc.contiguous()
+                for r in range(R):
+                    out[r][i] = ops.PackedConv(wc[r], None, dtype=self.dtype)
+        self._packed_bd, self._packed_bd_version = out, self._packed_version
+        return out
 
     # ---------------------------------------------------------------- buffers
     def buffers(self, n, h, w, dev, save):
@@ -284,45 +327,36 @@ class RRDBEngine:
         lead = dict(lead_planes=zp, lead_acc=gz_lr) if z else {}
         # LR_conv^T -> gradient w.r.t. the last RRDB's output
         wg(idx_lr, self._dense(B, True, nb - 1, 3) if nb > 0 else self._dense(B, True, 0, 0), cur)
-        go32, go16 = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
-        ops.conv3x3(cur, wt[idx_lr], out32=go32, out16=go16, **lead)
-        gS = f32(n, nfp + 4 * gcp, h, w, 8)
-        G16 = f16(n, nfp + 4 * gcp, h, w, 8)
+        # dense blocks, in reverse.  Gd[t % 2] = [g_5 | g_4 | g_3 | g_2 | g_1] of block t; a block's closing launch writes the
+        # next block's g_5 (the gradient arriving at that block's output) straight into the other buffer.
+        wbd = self.packed_bwd_dense() if nb > 0 else None
+        Gd = [f16(n, nfp + 4 * gcp, h, w, 8) for _ in range(2)]
+        go32 = f32(n, nfp, h, w, 8)
+        ops.conv3x3(cur, wt[idx_lr], out32=go32, out16=Gd[0], **lead)
         gy32 = [f32(n, nfp, h, w, 8) for _ in range(2)]
-        gy16 = [f16(n, nfp, h, w, 8) for _ in range(2)]
-        gi32, gi16 = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
+        gi32 = f32(n, nfp, h, w, 8)
+        t = 0
         for k in range(nb - 1, -1, -1):
             for j in (2, 1, 0):
                 Sb = self._dense(B, True, k, j)
-                base = 1 + (3 * k + j) * 5
+                r = 3 * k + j
+                base = 1 + r * 5
+                G, Gn = Gd[t % 2], Gd[(t + 1) % 2]
+                wg(base + 4, Sb, G, scale=0.04 if j == 2 else 0.2)          # conv5: its output gradient is scale * g_5
+                for i in (4, 3, 2, 1):
+                    off = nfp + (4 - i) * gcp
+                    ops.conv3x3(G, wbd[r][i], cin_planes=off, mask16=Sb, mask_off=zp + nfp + (i - 1) * gcp, mask_slope=SLOPE,
+                                out16=G, out16_off=off)
+                    wg(base + i - 1, Sb, G, gy_off=off)
+                # closing launch: g_x (+ the latent rows) = conv over all five gradients + what arrives at the block's output
                 if j == 2:
-                    gin16, a5 = go16, 0.04
-                else:
-                    gin16, a5 = gy16[j % 2], 0.2
-                # conv5^T: gS = alpha * conv5^T(g); x4's slice is final -> masked 16-bit copy
-                wg(base + 4, Sb, gin16, scale=a5)
-                ops.conv3x3(gin16, wt[base + 4], alpha=a5, out32=gS, mask16=Sb, mask_off=zp, mask_slope=SLOPE,
-                            tail_first=nfp + 3 * gcp, out16=G16, **lead)
-                for i in (3, 2, 1):
-                    # the slice of x_{i+1} in G16 is final: gradient of conv_{i+1}'s pre-activation output
-                    wg(base + i, Sb, G16, gy_off=nfp + i * gcp)
-                    # conv_{i+1}^T: consumes the masked gradient of x_{i+1}, accumulates into gS[0 : nfp+i*gcp) in place,
-                    # finalises x_i's slice
-                    ops.conv3x3(G16, wt[base + i], in_plane_off=nfp + i * gcp, cin_planes=gcp, res2=gS, beta2=1.0, out32=gS,
-                                mask16=Sb, mask_off=zp, mask_slope=SLOPE, tail_first=nfp + (i - 1) * gcp, out16=G16, **lead)
-                wg(base, Sb, G16, gy_off=nfp)
-                # conv1^T closes the block: g_x = acc + gS[x] + (gradient arriving at the block's output)
-                if j == 2:
-                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=go32, beta3=0.2,
-                                out32=gy32[1], out16=gy16[1], **lead)
+                    ops.conv3x3(G, wbd[r][0], res3=go32, beta3=0.2, out32=gy32[1], out16=Gn, **lead)
                 elif j == 1:
-                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=gy32[1], beta3=1.0,
-                                out32=gy32[0], out16=gy16[0], **lead)
+                    ops.conv3x3(G, wbd[r][0], res3=gy32[1], beta3=1.0, out32=gy32[0], out16=Gn, **lead)
                 else:   # ... plus the RRDB skip connection
-                    ops.conv3x3(G16, wt[base], in_plane_off=nfp, cin_planes=gcp, res2=gS, beta2=1.0, res3=gy32[0], beta3=1.0,
-                                res1=go32, beta1=1.0, out32=gi32, out16=gi16, **lead)
+                    ops.conv3x3(G, wbd[r][0], res3=gy32[0], beta3=1.0, res1=go32, beta1=1.0, out32=gi32, out16=Gn, **lead)
+                t += 1
             go32, gi32 = gi32, go32
-            go16, gi16 = gi16, go16
         # ShortcutBlock: the fea_conv output feeds the first RRDB and the skip
         _, gf16 = ops.planes_add(go32, g_t32, dtype=gdt, want32=False)
         wg(0, B['in16'], gf16)

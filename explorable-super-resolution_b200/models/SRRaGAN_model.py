@@ -155,6 +155,8 @@ class SRRaGANModel(BaseModel):
         """Generator branch of models/SRRaGAN_model.py:280-519 (no discriminator): forward through CEM(G), crop the invalid
         margins, pixel (+ range) loss scaled by the accumulation count, backward (dgrad + wgrad launches through the single
         autograd node), Adam step on the last accumulation step.  Like the reference, the first gradient step is idle."""
+        if not self.is_train:
+            raise NotImplementedError('optimize_parameters needs a model built with is_train=True (no optimizer / losses exist)')
         self.gradient_step_num = self.step // self.max_accumulation_steps
         first_acc = self.step % self.grad_accumulation_steps_G == 0
         last_acc = self.step % self.grad_accumulation_steps_G == (self.grad_accumulation_steps_G - 1)
