@@ -461,4 +461,97 @@ __global__ void latent_grad_lr_kernel(const float* __restrict__ gz_lr, int n, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VGG feature extractor helpers (models/modules/architecture.py:658-724)
+// ------------------------------------------------------------------------------------------------
+
+// NCHW fp32 -> 16-bit planes with a per-channel affine map v*scale[c] + shift[c]: the ImageNet input normalisation
+// (x - mean) / std of VGGFeatureExtractor.forward (:719-720).  One thread per (n, plane, y, x).
+__global__ void pack_nchw_affine_kernel(const float* __restrict__ src, int n, int c, int h, int w, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, int dtype, uint16_t* __restrict__ dst16, int planes_total,
+                                        int plane_off, int planes) {
+  const size_t total = (size_t)n * planes * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int y = r % h; r /= h;
+    const int g = r % planes; r /= planes;
+    const int img = (int)r;
+    uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = g * 8 + k;
+      const float v = ch < c ? fmaf(__ldg(src + (((size_t)img * c + ch) * h + y) * w + x), __ldg(scale + ch), __ldg(shift + ch)) : 0.f;
+      pk[k >> 1] |= (uint32_t)to16(v, dtype) << ((k & 1) * 16);
+    }
+    *reinterpret_cast<uint4*>(dst16 + ((((size_t)img * planes_total + plane_off + g) * h + y) * w + x) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// 2x2 / stride 2 max pooling of 16-bit planes (nn.MaxPool2d(2, 2) inside torchvision's vgg19.features).
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ src, size_t nplanes, int h, int w, int dtype, uint4* __restrict__ dst) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = nplanes * ho * wo;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % wo; r /= wo;
+    const int y = r % ho; r /= ho;
+    const uint4* sp = src + (r * h + 2 * y) * w + 2 * x;
+    const uint4 q[4] = {__ldg(sp), __ldg(sp + 1), __ldg(sp + w), __ldg(sp + w + 1)};
+    uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint16_t best_bits = 0;
+      float best = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t wq = (k >> 1) == 0 ? q[t].x : ((k >> 1) == 1 ? q[t].y : ((k >> 1) == 2 ? q[t].z : q[t].w));
+        const uint16_t bits = (uint16_t)((wq >> ((k & 1) * 16)) & 0xFFFFu);
+        const float v = from16(bits, dtype);
+        if (t == 0 || v > best) { best = v; best_bits = bits; }
+      }
+      pk[k >> 1] |= (uint32_t)best_bits << ((k & 1) * 16);
+    }
+    dst[idx] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Backward of the pooling (+ the ReLU in front of it): the gradient of a pooled pixel goes to the FIRST maximum of its window
+// in row-major order (what torch's max_pool2d backward does) if that activation is positive, zeros elsewhere.
+// gout: 16-bit planes [nplanes][h/2][w/2], act: the pooling's input (post-ReLU) [nplanes][h][w]; gin like act.
+__global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ gout, const uint4* __restrict__ act, size_t nplanes, int h, int w, int dtype,
+                                      uint4* __restrict__ gin) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = nplanes * ho * wo;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % wo; r /= wo;
+    const int y = r % ho; r /= ho;
+    const size_t base = (r * h + 2 * y) * w + 2 * x;
+    const uint4 q[4] = {__ldg(act + base), __ldg(act + base + 1), __ldg(act + base + w), __ldg(act + base + w + 1)};
+    const uint4 g = __ldg(gout + idx);
+    uint32_t o[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int arg = 0;
+      float best = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t wq = (k >> 1) == 0 ? q[t].x : ((k >> 1) == 1 ? q[t].y : ((k >> 1) == 2 ? q[t].z : q[t].w));
+        const float v = from16((uint16_t)((wq >> ((k & 1) * 16)) & 0xFFFFu), dtype);
+        if (t == 0 || v > best) { best = v; arg = t; }
+      }
+      const uint32_t gw = (k >> 1) == 0 ? g.x : ((k >> 1) == 1 ? g.y : ((k >> 1) == 2 ? g.z : g.w));
+      const uint32_t gb = best > 0.f ? ((gw >> ((k & 1) * 16)) & 0xFFFFu) : 0u;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (t == arg) o[t][k >> 1] |= gb << ((k & 1) * 16);
+    }
+    gin[base] = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    gin[base + 1] = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
+    gin[base + w] = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
+    gin[base + w + 1] = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
+  }
+}
+
 }  // namespace esr

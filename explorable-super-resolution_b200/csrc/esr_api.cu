@@ -556,6 +556,40 @@ int esr_pack_nchw(const float* src, int n, int c, int h, int w, int pad, int dty
   return ESR_OK;
 }
 
+int esr_pack_nchw_affine(const float* src, int n, int c, int h, int w, const float* scale, const float* shift, int dtype, void* dst16,
+                         int planes_total, int plane_off, void* stream) {
+  if (!src || !scale || !shift || !dst16) return fail(ESR_ERR_INVALID, "pack_nchw_affine: null pointer");
+  const int planes = (c + 7) / 8;
+  if (plane_off + planes > planes_total) return fail(ESR_ERR_INVALID, "pack_nchw_affine: planes out of range");
+  const size_t total = (size_t)n * planes * h * w;
+  esr::pack_nchw_affine_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, scale, shift, dtype, (uint16_t*)dst16,
+                                                                                     planes_total, plane_off, planes);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_maxpool2x2_planes16(const void* src, int dtype, int n, int planes, int h, int w, void* dst, void* stream) {
+  if (!src || !dst) return fail(ESR_ERR_INVALID, "maxpool2x2: null pointer");
+  if ((h & 1) || (w & 1)) return fail(ESR_ERR_INVALID, "maxpool2x2: odd size %dx%d", h, w);
+  const size_t total = (size_t)n * planes * (h / 2) * (w / 2);
+  esr::maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (size_t)n * planes, h, w, dtype, (uint4*)dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_maxpool2x2_bwd_planes16(const void* gout, const void* act, int dtype, int n, int planes, int h, int w, void* gin, void* stream) {
+  if (!gout || !act || !gin) return fail(ESR_ERR_INVALID, "maxpool2x2_bwd: null pointer");
+  if ((h & 1) || (w & 1)) return fail(ESR_ERR_INVALID, "maxpool2x2_bwd: odd size %dx%d", h, w);
+  const size_t total = (size_t)n * planes * (h / 2) * (w / 2);
+  esr::maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)gout, (const uint4*)act, (size_t)n * planes, h, w,
+                                                                                   dtype, (uint4*)gin);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 int esr_unpack_planes16(const void* src16, int dtype, int n, int c, int h, int w, int planes_total, int plane_off,
                         float* dst, void* stream) {
   if (!src16 || !dst) return fail(ESR_ERR_INVALID, "unpack16: null pointer");

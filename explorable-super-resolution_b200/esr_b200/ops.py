@@ -191,6 +191,35 @@ def pack_nchw(src, *, pad=0, dtype=torch.float16, dst16=None, dst32=None, plane_
     return dst16, dst32
 
 
+def pack_nchw_affine(src, scale, shift, dtype=torch.float16):
+    """NCHW fp32 -> 16-bit planes of src * scale[c] + shift[c] (input normalisation of the VGG feature extractor)"""
+    require_cuda(src, scale, shift)
+    src = src.float().contiguous()
+    n, c, h, w = src.shape
+    dst = torch.empty((n, planes_for(c), h, w, 8), dtype=dtype, device=src.device)
+    L.check(L.load().esr_pack_nchw_affine(_ptr(src), n, c, h, w, _ptr(scale), _ptr(shift), _TORCH2ESR[dtype], _ptr(dst), dst.shape[1], 0,
+                                          _stream()))
+    return dst
+
+
+def maxpool2x2(src16):
+    require_cuda(src16)
+    n, pt, h, w, _ = src16.shape
+    dst = torch.empty((n, pt, h // 2, w // 2, 8), dtype=src16.dtype, device=src16.device)
+    L.check(L.load().esr_maxpool2x2_planes16(_ptr(src16), _TORCH2ESR[src16.dtype], n, pt, h, w, _ptr(dst), _stream()))
+    return dst
+
+
+def maxpool2x2_bwd(gout16, act16):
+    """gradient w.r.t. the pre-activation that fed ReLU -> MaxPool2d(2,2); act16 = the pooling's (post-ReLU) input"""
+    require_cuda(gout16, act16)
+    n, pt, h, w, _ = act16.shape
+    assert gout16.dtype == act16.dtype and tuple(gout16.shape) == (n, pt, h // 2, w // 2, 8)
+    gin = torch.empty_like(act16)
+    L.check(L.load().esr_maxpool2x2_bwd_planes16(_ptr(gout16), _ptr(act16), _TORCH2ESR[act16.dtype], n, pt, h, w, _ptr(gin), _stream()))
+    return gin
+
+
 def unpack_planes(src, c, plane_off=0):
     """planar-8 -> NCHW fp32 (first c channels starting at plane_off)."""
     require_cuda(src)

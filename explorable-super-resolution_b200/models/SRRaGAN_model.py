@@ -3,10 +3,9 @@
 Built: construction for inference / latent exploration (CEM + generator + checkpoint loading), `feed_data`,
 `Prepare_Input`, `GetLatent`, `test`, `Output_Batch`, `get_current_visuals`, `save`/`load` — everything `test.py`, the GUI's
 `Feed_n_Run_model` and `Z_optimizer.optimize` call — and the generator branch of the training step
-(`optimize_parameters` with pixel + range losses, gradient accumulation, Adam, MultiStepLR: models/SRRaGAN_model.py:280-519
-with `gan_weight` / `feature_weight` unset, i.e. the PSNR-oriented pre-training configuration).  Configurations that need the
-discriminator, the VGG feature extractor or the latent structure loss raise NotImplementedError at construction: those
-networks are not built yet and there is no PyTorch fallback."""
+(`optimize_parameters` with pixel + VGG-feature + range losses, gradient accumulation, Adam, MultiStepLR:
+models/SRRaGAN_model.py:280-519 with `gan_weight` unset).  Configurations that need the discriminator or the latent
+structure loss raise NotImplementedError at construction: those are not built yet and there is no PyTorch fallback."""
 import os
 import re
 from collections import OrderedDict
@@ -27,10 +26,10 @@ class SRRaGANModel(BaseModel):
         super(SRRaGANModel, self).__init__(opt)
         train_opt = opt['train'] if self.is_train else None
         if self.is_train:
-            unbuilt = [k for k in ('gan_weight', 'feature_weight', 'latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
+            unbuilt = [k for k in ('gan_weight', 'latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
             if unbuilt:
-                raise NotImplementedError('esr_b200: the training step is built for the pixel / range losses only; %s need the '
-                                          'discriminator / VGG feature extractor / structure loss (SURVEY 8a-12..15), not built yet'
+                raise NotImplementedError('esr_b200: the training step is built for the pixel / feature / range losses; %s need the '
+                                          'discriminator / structure loss (SURVEY 8a-12, 14, 15), not built yet'
                                           % ', '.join(unbuilt))
         self.log_path = opt['path']['log'] if opt['path'] is not None else None
         self.latent_input_domain = opt['network_G']['latent_input_domain']
@@ -59,7 +58,7 @@ class SRRaGANModel(BaseModel):
         opt['network_G']['scale'] = opt['network_G']['scale'] if opt['network_G']['scale'] is not None else opt['scale']
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
-        logs_2_keep = ['l_g_pix', 'l_g_range', 'psnr_val', 'LR_decrease']
+        logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'psnr_val', 'LR_decrease']
         self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
         if not self.is_train:
             self.netG.eval()
@@ -88,7 +87,20 @@ class SRRaGANModel(BaseModel):
         else:
             print('Remove range loss.')
             self.cri_range = None
-        self.cri_gan, self.cri_fea, self.D_init_iters = None, None, 0
+        if train_opt['feature_weight'] is not None:   # G feature loss (SRRaGAN_model.py:124-138)
+            l_fea_type = train_opt['feature_criterion']
+            if l_fea_type == 'l1':
+                self.cri_fea = nn.L1Loss().to(self.device)
+            elif l_fea_type == 'l2':
+                self.cri_fea = nn.MSELoss().to(self.device)
+            else:
+                raise NotImplementedError('Loss type [{:s}] not recognized.'.format(l_fea_type))
+            self.l_fea_w = train_opt['feature_weight']
+            self.netF = networks.define_F(opt, use_bn=False, **({'state_dict': kwargs['netF_state_dict']} if 'netF_state_dict' in kwargs else {})).to(self.device)
+        else:
+            print('Remove feature loss.')
+            self.cri_fea = None
+        self.cri_gan, self.D_init_iters = None, 0
         wd_G = train_opt['weight_decay_G'] if train_opt['weight_decay_G'] else 0
         optim_params = []
         for k, v in self.netG.named_parameters():
@@ -173,15 +185,22 @@ class SRRaGANModel(BaseModel):
             self.generator_started_learning = True
             if first_acc:
                 self.optimizer_G.zero_grad()
-                self.l_g_pix_grad_step, self.l_g_range_grad_step = [], []
+                self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step = [], [], []
             l_g_total = 0
             if self.cri_pix:
                 l_g_pix = self.cri_pix(self.fake_H, self.var_H)
                 l_g_total = l_g_total + self.l_pix_w * l_g_pix / self.grad_accumulation_steps_G
+            if self.cri_fea:   # perceptual loss: VGG features of the real image (no graph) and of the generated one
+                real_fea = self.netF(self.var_H).detach()
+                fake_fea = self.netF(self.fake_H)
+                l_g_fea = self.cri_fea(fake_fea, real_fea)
+                l_g_total = l_g_total + self.l_fea_w * l_g_fea / self.grad_accumulation_steps_G
             if self.cri_range:
                 l_g_range = self.cri_range(self.fake_H)
                 l_g_total = l_g_total + self.l_range_w * l_g_range / self.grad_accumulation_steps_G
             l_g_total.backward()
+            if self.cri_fea:
+                self.l_g_fea_grad_step.append(l_g_fea.item())
             if self.cri_pix:
                 self.l_g_pix_grad_step.append(l_g_pix.item())
             if self.cri_range:
@@ -191,6 +210,8 @@ class SRRaGANModel(BaseModel):
                 self.generator_changed = True
                 if self.cri_pix:
                     self.log_dict['l_g_pix'].append((self.gradient_step_num, np.mean(self.l_g_pix_grad_step)))
+                if self.cri_fea:
+                    self.log_dict['l_g_fea'].append((self.gradient_step_num, np.mean(self.l_g_fea_grad_step)))
                 if self.cri_range:
                     self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
         self.step += 1

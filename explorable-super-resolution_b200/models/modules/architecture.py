@@ -80,3 +80,52 @@ class RRDBNet(nn.Module):
             from esr_b200.autograd import rrdb_forward_with_grad
             return rrdb_forward_with_grad(self, x, pad)
         return self.engine().forward(x, pad=pad)
+
+
+class VGGFeatureExtractor(nn.Module):
+    """Perceptual-loss feature extractor with the reference's constructor and state-dict keys
+    (models/modules/architecture.py:658-724): torchvision's vgg19().features[:feature_layer + 1] behind the ImageNet
+    input normalisation, frozen.  Runs on esr_b200.vgg.VGGEngine (fused conv launches + max-pool kernels).
+    torchvision's pretrained weights cannot be downloaded here: pass `state_dict` (torchvision key layout
+    `features.N.weight`, optionally prefixed `module.`), or load one later; otherwise the weights are torchvision's
+    own initialisation (kaiming-normal fan_out), which is what `arch_config='untrained'` asks for in the reference."""
+
+    def __init__(self, feature_layer=34, use_bn=False, use_input_norm=True, device=torch.device('cpu'), state_dict=None, arch='vgg19',
+                 arch_config='', **kwargs):
+        super(VGGFeatureExtractor, self).__init__()
+        if use_bn or arch != 'vgg19' or arch_config.replace('untrained_', '').replace('untrained', '') != '':
+            raise NotImplementedError('esr_b200 VGGFeatureExtractor: only plain vgg19 (no batch norm, no modified architecture) is built')
+        from esr_b200.vgg import vgg19_layers
+        self.feature_layer = feature_layer
+        mods = []
+        for kind, idx, cin, cout in vgg19_layers(feature_layer):
+            mods.append(nn.Conv2d(cin, cout, 3, padding=1) if kind == 'conv' else (nn.ReLU(inplace=True) if kind == 'relu' else nn.MaxPool2d(2, 2)))
+        self.features = nn.Sequential(*mods)
+        for m in self.features.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+                nn.init.constant_(m.bias, 0)
+        if state_dict is not None:
+            state_dict = dict(zip([key.replace('module.', '') for key in state_dict.keys()], [value for value in state_dict.values()]))
+            self.load_state_dict({k: v for k, v in state_dict.items() if k in self.state_dict()}, strict=False)
+        elif 'untrained' not in arch_config:
+            print('WARNING: pretrained VGG19 weights are not available offline; VGGFeatureExtractor starts from torchvision\'s random '
+                  'initialisation until a state_dict is loaded.')
+        self.use_input_norm = use_input_norm
+        if self.use_input_norm:
+            self.register_buffer('mean', torch.Tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1).to(device))
+            self.register_buffer('std', torch.Tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1).to(device))
+        for k, v in self.features.named_parameters():
+            v.requires_grad = False
+        self.compute_dtype = torch.float16    # backward uses loss scaling (esr_b200.vgg): fp16's 10-bit mantissa, bf16's range not needed
+        self._engines = {}
+
+    def engine(self):
+        from esr_b200.vgg import VGGEngine
+        if self.compute_dtype not in self._engines:
+            self._engines[self.compute_dtype] = VGGEngine(self, dtype=self.compute_dtype)
+        return self._engines[self.compute_dtype]
+
+    def forward(self, x):
+        from esr_b200.vgg import vgg_forward
+        return vgg_forward(self, x)

@@ -100,4 +100,16 @@ def define_D(opt, CEM=None):
 
 
 def define_F(opt, use_bn=False, **kwargs):
-    raise NotImplementedError('esr_b200: VGGFeatureExtractor (SURVEY 8a-13) is not built yet in this round')
+    """models/networks.py:185-202: VGG19-54 before ReLU (feature_layer 34), input normalisation on, eval mode"""
+    gpu_ids = opt['gpu_ids']
+    device = torch.device('cuda' if gpu_ids else 'cpu')
+    feature_layer = 49 if use_bn else 34
+    if 'arch' in kwargs.keys() and 'vgg' in kwargs['arch']:
+        if len(kwargs['arch']) > len('vgg11_'):
+            feature_layer = int(kwargs['arch'][len('vgg11_'):])
+        kwargs['arch'] = kwargs['arch'][:len('vgg11')]
+    netF = arch.VGGFeatureExtractor(feature_layer=feature_layer, use_bn=use_bn, use_input_norm=True, device=device, **kwargs)
+    if gpu_ids:
+        netF = SingleDeviceDataParallel(netF.to(device))
+    netF.eval()  # No need to train
+    return netF

@@ -170,6 +170,19 @@ int esr_unpack_planes32(const float* src32, int n, int c, int h, int w,
                         int planes_total, int plane_off, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * VGG feature extractor (models/modules/architecture.py:658-724, the perceptual loss of SRRaGAN_model.py:448-451).
+ * Its 3x3 convolutions + ReLU are esr_conv3x3_fwd launches (LeakyReLU with slope 0); these are the remaining pieces:
+ *   pack_nchw_affine : (x - mean) / std input normalisation (:719-720) fused into the layout conversion, dst = v*scale[c]+shift[c]
+ *   maxpool2x2       : nn.MaxPool2d(2, 2) of torchvision's vgg19.features on 16-bit planes
+ *   maxpool2x2_bwd   : its backward fused with the preceding ReLU's (first maximum in row-major order, as torch)
+ * ---------------------------------------------------------------------------------------------- */
+int esr_pack_nchw_affine(const float* src, int n, int c, int h, int w, const float* scale, const float* shift, int dtype,
+                         void* dst16, int planes_total, int plane_off, void* stream);
+int esr_maxpool2x2_planes16(const void* src, int dtype, int n, int planes, int h, int w, void* dst, void* stream);
+int esr_maxpool2x2_bwd_planes16(const void* gout, const void* act, int dtype, int n, int planes, int h, int w, void* gin,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Consistency-Enforcing Module (CEM/CEMnet.py:254-311).  Filters are the separable factors of the
  * reference's numpy-designed kernels (CEMnet.py:22-33,186-206): ds_kernel = outer(kd_v, kd_h) and
  * inv_hTh = outer(ki_v, ki_h), computed on the host by the Python layer.  Every filter is passed as

@@ -126,4 +126,24 @@ def test_srragan_model_refuses_unbuilt_losses(tmp_path):
     with pytest.raises(NotImplementedError):
         create_model(_train_opt(tmp_path, gan_weight=5e-3))
     with pytest.raises(NotImplementedError):
-        create_model(_train_opt(tmp_path, feature_weight=1.0))
+        create_model(_train_opt(tmp_path, latent_weight=1.0))
+
+
+def test_srragan_model_perceptual_training_step(tmp_path):
+    """pixel + VGG-feature loss (SRRaGAN_model.py:434-451): real features detached, fake features carry the gradient
+    through the frozen extractor into the generator"""
+    from esr_b200 import ops
+    from models import create_model
+    ops.device_check()
+    torch.manual_seed(6)
+    model = create_model(_train_opt(tmp_path, feature_weight=1.0, feature_criterion='l1', grad_accumulation_steps_G=1, range_weight=None),
+                         accumulation_steps_per_batch=1)
+    assert all(not p.requires_grad for p in model.netF.parameters())
+    lr = torch.rand(2, 3, 36, 36)                      # 144 - 80 = 64: divisible by 16 for the four poolings
+    hr = torch.nn.functional.interpolate(lr, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    for it in range(8):
+        model.feed_data({'LR': lr, 'HR': hr})
+        model.optimize_parameters()
+    fea = model.log_dict['l_g_fea']
+    assert len(fea) == 7 and all(torch.isfinite(torch.tensor(v)) for _, v in fea)
+    assert fea[-1][1] < fea[0][1], fea
