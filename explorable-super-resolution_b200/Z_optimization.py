@@ -13,6 +13,8 @@ Adversarial, desired_SVD and digit objectives are SURVEY §8(f)-1 and raise NotI
 import time
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -42,9 +44,9 @@ class Optimizable_Z(torch.nn.Module):
     def forward(self):
         if self.Z_range is not None:
             big = torch.finfo(self.Z.dtype).max
-            self.Z.data = torch.clamp(self.Z.data, -big, big)
-        if self.mask is not None:
-            self.Z.data = self.mask * self.Z.data + (1 - self.mask) * self.initial_pre_tanh_Z
+            self.Z.data.clamp_(-big, big)     # in place (same values as the reference's re-assignment): the storage must stay
+        if self.mask is not None:             # put for the CUDA-graph replay of the iteration
+            self.Z.data.copy_(self.mask * self.Z.data + (1 - self.mask) * self.initial_pre_tanh_Z)
         return self.Z_range * torch.tanh(self.Z) if self.Z_range is not None else self.Z
 
     def PreTanhZ(self):
@@ -161,9 +163,12 @@ class Z_optimizer():
                 self.rmse_weight = data['rmse_weight']
             elif 'random' in objective:
                 self.STD_PRESERVING_WEIGHT = 1e3
-            self.optimizer = torch.optim.Adam(self.Z_model.parameters(), lr=initial_LR)
+            # capturable: the whole iteration (generator forward, backward to Z, Adam) can then be replayed as one CUDA graph
+            self.optimizer = torch.optim.Adam(self.Z_model.parameters(), lr=initial_LR, capturable=torch.cuda.is_available())
+            self._own_optimizer = True
         else:
             self.optimizer = existing_optimizer
+            self._own_optimizer = False
         self.LR = initial_LR
         self.scheduler = None
         self.loggers = loggers
@@ -193,8 +198,74 @@ class Z_optimizer():
             for i, p in enumerate(self.model.netG.parameters()):
                 p.requires_grad = self.original_requires_grad_status[i]
 
+    GRAPH_WARMUP_ITERS = 3
+
+    def _iteration(self, keep_pre_tanh):
+        """device work of one iteration of Z_optimization.py:663-754: Z -> generator (+CEM) with graph -> objective -> backward to
+        Z -> Adam step.  Returns (per-image loss values, scalar loss, copy of the pre-tanh Z the loss belongs to); no host reads."""
+        self.optimizer.zero_grad()
+        self.data['Z'] = self.Z_model()
+        pre_tanh = 1 * self.Z_model.PreTanhZ() if keep_pre_tanh else None
+        self.model.feed_data(self.data, need_GT=False)
+        self.model.test(prevent_grads_calc=False)
+        self.output_image = self.model.Output_Batch(within_0_1=True)
+        if self.model_training:
+            self.output_image = self.HR_unpadder(self.output_image)
+        if 'random' in self.objective:
+            dom = self.output_image
+            Z_loss = torch.min((dom.unsqueeze(0) - dom.unsqueeze(1)).abs() +
+                               torch.eye(dom.size(0), device=dom.device).unsqueeze(2).unsqueeze(3).unsqueeze(4), dim=0)[0]
+            if 'limited' in self.objective:
+                Z_loss = Z_loss - self.rmse_weight * (dom - self.initial_image).abs()
+            if self.Z_mask is not None:
+                Z_loss = Z_loss * self.image_mask
+            Z_loss = -1 * Z_loss.mean(dim=(1, 2, 3))
+        elif 'l1' in self.objective:
+            Z_loss = self.loss(self.output_image.to(self.device), self.desired_im.to(self.device))
+        elif 'STD' in self.objective and 'TV' not in self.objective:
+            Z_loss = self.Masked_STD(first_image_only=False)
+            if any(p in self.objective for p in ['increase', 'decrease']):
+                Z_loss = (Z_loss - self.desired_STD) ** 2
+            Z_loss = Z_loss.mean(0)
+        elif 'TV' in self.objective:
+            Z_loss = (self.STD_PRESERVING_WEIGHT * (self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean(0) + \
+                TV_Loss(self.output_image * self.image_mask)
+        if 'max' in self.objective:
+            Z_loss = -1 * Z_loss
+        Z_loss_items = Z_loss.detach()
+        Z_loss = Z_loss.mean()
+        if self.non_local_Z_optimization:
+            Z_loss = Z_loss + self.constraining_loss_weight * self.constraining_loss(self.output_image.to(self.device))
+        Z_loss.backward()
+        self.optimizer.step()
+        return Z_loss_items, Z_loss.detach(), pre_tanh
+
+    def _capture_iteration(self, keep_pre_tanh):
+        """One iteration is ~800 kernel launches of a few microseconds each at GUI region sizes: launch-bound.  After a few
+        eager iterations the iteration is captured once into a CUDA graph and replayed (same launches, same order, same
+        numerics).  Any capture problem falls back to eager iterations."""
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._side_stream):
+                static = self._iteration(keep_pre_tanh)
+            # the capture itself executes nothing: the first replay performs this iteration
+            return g, static
+        except Exception as e:  # pragma: no cover - depends on driver / allocator state
+            print('Z_optimizer: CUDA graph capture failed (%s); continuing with eager iterations.' % repr(e)[:200])
+            self._graph_ok = False
+            torch.cuda.synchronize()
+            return None, None
+
     def optimize(self):
         USE_MIN_LOSS_Z = not self.model_training
+        graph, static = None, None
+        self._graph_ok = (self._own_optimizer and torch.cuda.is_available() and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0'
+                          and not self.model_training and self.loggers is None
+                          and (self.max_iters < 0 or self.max_iters >= self.GRAPH_WARMUP_ITERS + 4))
+        if self._graph_ok:
+            self._side_stream = torch.cuda.Stream()
+            self._side_stream.wait_stream(torch.cuda.current_stream())
         self.Manage_Model_Grad_Requirements(verify_disabled=True)
         self.loss_values, per_iter_pre_tanh_Z = [], []
         if self.random_Z_inits and self.cur_iter == 0:
@@ -209,50 +280,30 @@ class Z_optimizer():
                     break
                 if (self.loss_values[self.max_iters] - self.loss_values[-1]) / np.abs(self.loss_values[self.max_iters]) < 1e-2 * self.LR:
                     break
-            self.optimizer.zero_grad()
-            self.data['Z'] = self.Z_model()
+            if graph is None and self._graph_ok and len(self.loss_values) == self.GRAPH_WARMUP_ITERS:
+                graph, static = self._capture_iteration(USE_MIN_LOSS_Z)
+            if graph is not None:
+                graph.replay()
+                Z_loss_items, Z_loss, pre_tanh = static
+            elif self._graph_ok:
+                # warm-up iterations run on the stream the capture will use: autograd's AccumulateGrad node of Z must not have
+                # been created on another stream (torch invalidates the capture otherwise)
+                with torch.cuda.stream(self._side_stream):
+                    Z_loss_items, Z_loss, pre_tanh = self._iteration(USE_MIN_LOSS_Z)
+                torch.cuda.current_stream().wait_stream(self._side_stream)
+            else:
+                Z_loss_items, Z_loss, pre_tanh = self._iteration(USE_MIN_LOSS_Z)
             if USE_MIN_LOSS_Z:
-                per_iter_pre_tanh_Z.append(1 * self.Z_model.PreTanhZ())
-            self.model.feed_data(self.data, need_GT=False)
-            self.model.test(prevent_grads_calc=False)
-            self.output_image = self.model.Output_Batch(within_0_1=True)
-            if self.model_training:
-                self.output_image = self.HR_unpadder(self.output_image)
-            if 'random' in self.objective:
-                dom = self.output_image
-                Z_loss = torch.min((dom.unsqueeze(0) - dom.unsqueeze(1)).abs() +
-                                   torch.eye(dom.size(0), device=dom.device).unsqueeze(2).unsqueeze(3).unsqueeze(4), dim=0)[0]
-                if 'limited' in self.objective:
-                    Z_loss = Z_loss - self.rmse_weight * (dom - self.initial_image).abs()
-                if self.Z_mask is not None:
-                    Z_loss = Z_loss * self.image_mask
-                Z_loss = -1 * Z_loss.mean(dim=(1, 2, 3))
-            elif 'l1' in self.objective:
-                Z_loss = self.loss(self.output_image.to(self.device), self.desired_im.to(self.device))
-            elif 'STD' in self.objective and 'TV' not in self.objective:
-                Z_loss = self.Masked_STD(first_image_only=False)
-                if any(p in self.objective for p in ['increase', 'decrease']):
-                    Z_loss = (Z_loss - self.desired_STD) ** 2
-                Z_loss = Z_loss.mean(0)
-            elif 'TV' in self.objective:
-                Z_loss = (self.STD_PRESERVING_WEIGHT * (self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean(0) + \
-                    TV_Loss(self.output_image * self.image_mask)
-            if 'max' in self.objective:
-                Z_loss = -1 * Z_loss
+                per_iter_pre_tanh_Z.append(pre_tanh.clone() if graph is not None else pre_tanh)
             cur_LR = self.optimizer.param_groups[0]['lr']
             if self.loggers is not None:
                 for logger_num, logger in enumerate(self.loggers):
-                    cur_value = Z_loss[logger_num].mean().item() if Z_loss.dim() > 0 else Z_loss.mean().item()
+                    cur_value = Z_loss_items[logger_num].mean().item() if Z_loss_items.dim() > 0 else Z_loss_items.mean().item()
                     logger.print_format_results('val', {'epoch': 0, 'iters': z_iter, 'time': time.time(), 'model': '', 'lr': cur_LR,
                                                         'Z_loss': cur_value}, dont_print=True)
             if not self.model_training:
-                self.latest_Z_loss_values = [val.mean().item() for val in Z_loss] if Z_loss.dim() > 0 else [Z_loss.item()]
-            Z_loss = Z_loss.mean()
-            if self.non_local_Z_optimization:
-                Z_loss = Z_loss + self.constraining_loss_weight * self.constraining_loss(self.output_image.to(self.device))
-            Z_loss.backward()
+                self.latest_Z_loss_values = [val.mean().item() for val in Z_loss_items] if Z_loss_items.dim() > 0 else [Z_loss_items.item()]
             self.loss_values.append(Z_loss.item())
-            self.optimizer.step()
             z_iter += 1
         if USE_MIN_LOSS_Z:
             if np.min(self.loss_values) != self.loss_values[-1]:

@@ -243,7 +243,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // partials' own memory order (coalesced reads of every CTA's block), scattered store into the OIHW gradient.
 // grid = (ceil(mt*128*N3 / 256), n_blocks)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int ranges, int n_blocks, int mt, int nbn, int cp, int cout, int cin,
-                                    int lead, float scale, int accumulate, float* __restrict__ dw) {
+                                    int lead, float scale, int accumulate, float* __restrict__ dw, int cin_total, int cin_off) {
   const int lead_pad = (lead + 7) / 8 * 8;
   const int N3 = 3 * nbn;
   const int per_cta = mt * 128 * N3;
@@ -261,7 +261,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int ranges, 
   const float* src = part + (size_t)nblk * per_cta + e;
   for (int rg = 0; rg < ranges; ++rg) acc += __ldg(src + (size_t)rg * n_blocks * per_cta);
   acc *= scale;
-  float* dst = dw + (((size_t)co * cin + ci) * 3 + ky) * 3 + kx;
+  float* dst = dw + (((size_t)co * cin_total + cin_off + ci) * 3 + ky) * 3 + kx;
   *dst = accumulate ? *dst + acc : acc;
 }
 

@@ -458,6 +458,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
   if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "wgrad: bad dtype");
   if (((uintptr_t)a->x & 15) || ((uintptr_t)a->gy & 15)) return fail(ESR_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
   if (a->lead < 0 || a->lead > a->cin) return fail(ESR_ERR_INVALID, "wgrad: bad lead %d", a->lead);
+  if (a->cin_total > 0 && (a->cin_off < 0 || a->cin_off + a->cin > a->cin_total)) return fail(ESR_ERR_INVALID, "wgrad: bad input-channel slice");
   const int cp = esr_conv3x3_cin_planes(a->cin, a->lead);
   if (a->x_plane_off + cp > a->x_planes_total) return fail(ESR_ERR_INVALID, "wgrad: input planes out of range");
   WgradPlan w;
@@ -512,7 +513,8 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     CUDA_TRY(cudaGetLastError());
     const int per_cta = w.mt * 128 * 3 * w.nbn;
     esr::wgrad_reduce_kernel<<<dim3((unsigned)((per_cta + 255) / 256), (unsigned)w.n_blocks), 256, 0, st>>>(
-        a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin, a->lead, a->scale, a->accumulate, a->dw);
+        a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin, a->lead, a->scale, a->accumulate, a->dw,
+        a->cin_total > 0 ? a->cin_total : a->cin, a->cin_off);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
   }

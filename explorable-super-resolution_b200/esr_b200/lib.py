@@ -47,7 +47,7 @@ class WgradArgs(C.Structure):
         ("gy", C.c_void_p), ("gy_planes_total", C.c_int), ("gy_plane_off", C.c_int),
         ("cout", C.c_int), ("cin", C.c_int), ("lead", C.c_int),
         ("dw", C.c_void_p), ("db", C.c_void_p), ("scale", C.c_float), ("accumulate", C.c_int),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("cin_total", C.c_int), ("cin_off", C.c_int),
     ]
 
 

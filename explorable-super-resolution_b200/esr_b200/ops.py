@@ -139,23 +139,33 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
     if db is None:
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
     assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3) and db.dtype == torch.float32
-    cp = int(lib.esr_conv3x3_cin_planes(cin, lead))
-    nbytes = int(lib.esr_conv3x3_wgrad_workspace(cp, cout))
-    if nbytes == 0:
-        raise L.EsrError('conv3x3_wgrad: (cin %d, cout %d) is not supported by the tensor-core tiling' % (cin, cout))
+    # wide convs are covered in input-channel slices of at most 208 channels (5 M chunks of (row, plane) groups)
+    cp_all = int(lib.esr_conv3x3_cin_planes(cin, lead))
+    if cp_all <= 26:
+        slices = [(0, cin, lead, x_off)]
+    else:
+        if lead:
+            raise L.EsrError('conv3x3_wgrad: latent lead channels with more than 208 input channels are not supported')
+        slices = [(c0, min(192, cin - c0), 0, x_off + c0 // 8) for c0 in range(0, cin, 192)]
     key = (str(dev), torch.cuda.current_stream().cuda_stream)
-    ws = _wgrad_ws.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _wgrad_ws[key] = ws
-    a = L.WgradArgs()
-    a.n, a.h, a.w, a.dtype = n, h, w, _TORCH2ESR[x16.dtype]
-    a.x, a.x_planes_total, a.x_plane_off = x16.data_ptr(), xpt, x_off
-    a.gy, a.gy_planes_total, a.gy_plane_off = gy16.data_ptr(), gy16.shape[1], gy_off
-    a.cout, a.cin, a.lead = cout, cin, lead
-    a.dw, a.db, a.scale, a.accumulate = dw.data_ptr(), db.data_ptr(), scale, int(accumulate)
-    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
-    L.check(lib.esr_conv3x3_wgrad(C.byref(a), _stream()))
+    for si, (c0, cs, ld, xo) in enumerate(slices):
+        cp = int(lib.esr_conv3x3_cin_planes(cs, ld))
+        nbytes = int(lib.esr_conv3x3_wgrad_workspace(cp, cout))
+        if nbytes == 0:
+            raise L.EsrError('conv3x3_wgrad: (cin %d, cout %d) is not supported by the tensor-core tiling' % (cs, cout))
+        ws = _wgrad_ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _wgrad_ws[key] = ws
+        a = L.WgradArgs()
+        a.n, a.h, a.w, a.dtype = n, h, w, _TORCH2ESR[x16.dtype]
+        a.x, a.x_planes_total, a.x_plane_off = x16.data_ptr(), xpt, xo
+        a.gy, a.gy_planes_total, a.gy_plane_off = gy16.data_ptr(), gy16.shape[1], gy_off
+        a.cout, a.cin, a.lead = cout, cs, ld
+        a.cin_total, a.cin_off = cin, c0
+        a.dw, a.db, a.scale, a.accumulate = dw.data_ptr(), (db.data_ptr() if si == 0 else None), scale, int(accumulate)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(lib.esr_conv3x3_wgrad(C.byref(a), _stream()))
     return dw, db
 
 

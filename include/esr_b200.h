@@ -145,6 +145,10 @@ typedef struct {
   float scale;
   int accumulate;            /* 1: add into dw/db (gradient accumulation), 0: overwrite */
   float* workspace; size_t workspace_bytes;
+  /* input-channel slicing for wide convs (3*cin/8 groups must fit 5 M chunks, i.e. cin <= 208 per launch): this launch covers
+   * the `cin` channels starting at `cin_off` of a weight tensor with `cin_total` input channels (0 = cin); x_plane_off
+   * points at the first plane of the slice */
+  int cin_total, cin_off;
 } esr_conv3x3_wgrad_args;
 size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout);
 int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream);

@@ -29,6 +29,8 @@ def _watchdog():
     (1, 3, 64, 25, 64, 0, torch.float16),
     (1, 67, 32, 20, 84, 3, torch.float16),     # latent channels in their own plane group
     (1, 64, 256, 16, 64, 0, torch.float16),    # 8 n-blocks
+    (1, 256, 128, 20, 64, 0, torch.float16),   # wide conv: two input-channel slices
+    (1, 512, 512, 8, 8, 0, torch.float16),     # VGG-size conv: three slices, 16 n-blocks
 ])
 def test_wgrad_matches_autograd(n, cin, cout, h, w, lead, dtype):
     from esr_b200 import ops

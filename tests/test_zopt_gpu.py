@@ -118,3 +118,32 @@ def test_z_optimizer_other_objectives_run(tmp_path):
         assert Z.shape == (bs, 3, 64, 48) and torch.isfinite(Z).all() and len(zo.loss_values) >= 1
     with pytest.raises(NotImplementedError):
         Z_optimizer(objective='hist', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
+
+
+def test_z_optimizer_graph_replay_matches_eager(tmp_path, monkeypatch):
+    """the CUDA-graph replay of the iteration (launch-bound at GUI region sizes) is the same computation as the eager loop: same
+    loss curve and latent map up to the rounding of Adam's capturable (tensor-valued step) arithmetic"""
+    from esr_b200 import ops
+    ops.device_check()
+    from Z_optimization import Z_optimizer
+    model, g = _model(tmp_path)
+    gen = torch.Generator().manual_seed(9)
+    x_lr = torch.rand(2, 3, 16, 12, generator=gen).cuda()
+    desired = torch.rand(1, 3, 64, 48, generator=gen).cuda()
+    runs = []
+    for flag in ('1', '0'):
+        monkeypatch.setenv('ESR_ZOPT_GRAPH', flag)
+        data = {'LR': x_lr, 'desired': desired}
+        model.feed_data({'LR': x_lr, 'Z': 0}, need_GT=False)
+        model.test()
+        zo = Z_optimizer(objective='l1', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=12, data=data, initial_LR=0.1, batch_size=2)
+        Z = zo.optimize()
+        runs.append((list(zo.loss_values), Z.clone(), zo._graph_ok))
+    assert runs[0][2] is True and runs[1][2] is False          # the first run really replayed a graph
+    assert len(runs[0][0]) == len(runs[1][0])
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-3, atol=1e-6), (runs[0][0], runs[1][0])
+    assert runs[0][0][-1] < runs[0][0][3] < runs[0][0][0]          # the replayed iterations keep optimising
+    # Adam turns every near-zero gradient component into a +-lr move, so single latent pixels may differ (see the oracle test)
+    close = ((runs[0][1] - runs[1][1]).abs() < 0.02).float().mean().item()
+    cos = torch.nn.functional.cosine_similarity(runs[0][1].flatten(), runs[1][1].flatten(), dim=0).item()
+    assert close > 0.9 and cos > 0.98, (close, cos)
