@@ -118,7 +118,7 @@ def build_model(dev):
     return net.to(dev), cem
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out_fd):
     """oracle port on the host cores; each step = 1 image of the C2 workload (256x256 -> 1024x1024)."""
     if rank != 0:
         return
@@ -150,12 +150,12 @@ def run_reference(args, rank, world):
     mp = (LR * SCALE) ** 2 / 1e6
     val = mp / dt
     sample = '1 of %d images per step (1x3x%dx%d -> %dx%d), fp32, torch CPU, %d threads' % (BATCH, LR, LR, LR * SCALE, LR * SCALE, cores)
-    print(json.dumps({
+    _emit(out_fd, {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'C2: RRDBNet nb=23 nf=64 x4 + CEM forward, batch 16 of 256x256 LR per GPU (reference arm: 1-image sample per step)'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
 
 
 def cpu_baseline():
@@ -182,7 +182,20 @@ def cpu_baseline():
             'sample': '1x3x128x128 LR crop (1/64 of a step), %d reps, fp32 torch CPU oracle, %d threads' % (reps, cores)}
 
 
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL prints its version at init) are sent to stderr instead"""
+    sys.stdout.flush()
+    fd = os.dup(1)
+    os.dup2(2, 1)
+    return fd
+
+
+def _emit(fd, obj):
+    os.write(fd, (json.dumps(obj) + '\n').encode())
+
+
 def main():
+    out_fd = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -196,7 +209,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out_fd)
         return
 
     import torch
@@ -363,7 +376,7 @@ def main():
             out['train'] = train
         if not args.no_cpu_baseline and world == 1:
             out['cpu_baseline'] = cpu_baseline()
-        print(json.dumps(out), flush=True)
+        _emit(out_fd, out)
     if world > 1:
         dist.destroy_process_group()
 
