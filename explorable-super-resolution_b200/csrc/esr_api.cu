@@ -201,11 +201,13 @@ bool wgrad_plan(int cp, int cout, WgradPlan* w) {
   return true;
 }
 
-// the row-streaming kernel pays off when its 128-pixel strips are mostly real pixels
+// The row-streaming kernel is used when its 128-pixel strips are mostly real pixels.  (Forward-type launches win 1.5-2x per
+// launch even at 41 % lane fill - tools/small_conv_time.py - but the generic backward epilogue with many n-blocks does not,
+// so the small-image dispatch stays with the tile kernel for now.)  ESR_ROWS=0 forces the tile kernel, ESR_ROWS=2 the row kernel.
 bool rows_shape_ok(int w) {
-  static const bool enabled = [] { const char* e = getenv("ESR_ROWS"); return !(e && e[0] == '0'); }();
+  static const int mode = [] { const char* e = getenv("ESR_ROWS"); return e ? atoi(e) : 1; }();   // 0 never, 1 by width, 2 always
   const int strips = (w + 127) / 128;
-  return enabled && w * 100 >= strips * 128 * 80;
+  return mode == 2 || (mode == 1 && w * 100 >= strips * 128 * 80);
 }
 
 }  // namespace

