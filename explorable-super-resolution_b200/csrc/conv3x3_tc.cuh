@@ -288,6 +288,7 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
 //   kMode 1: out16 = lrelu(acc + bias) [+ beta1*res1(fp32)]  plain or nearest-x2 replicated store   (growth convs, HR convs,
 //            LR_conv + ShortcutBlock add)
 //   kMode 2: v = alpha*(acc + bias) + beta1*res1(16-bit) [+ beta2*res2(fp32)] -> out16 [+ out32]   (conv5 of a dense block)
+//   kMode 4: out16 = acc * (act > 0 ? 1 : mask_slope)   no bias                (gradient slices of the dense-block backward)
 template <int NBN, int kMode>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid, int nblk) {
   const size_t hw = (size_t)p.h * p.w;
@@ -304,8 +305,18 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
     const bool has2 = (kMode == 2 && p.res2 != nullptr) || (kMode == 1 && p.res1 != nullptr);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
-      bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+      if (kMode == 4) {
+        bb[g][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bb[g][1] = bb[g][0];
+      } else {
+        bb[g][0] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8));
+        bb[g][1] = __ldg(reinterpret_cast<const float4*>(p.bias + chu + g * 8 + 4));
+      }
+    }
+    if (kMode == 4 && valid) {   // saved activation of the slice: only its sign is used
+      const uint16_t* mk = p.mask16 + (((size_t)img * p.mask_pt + p.mask_po + gu) * hw + pix) * 8;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) q1[g] = __ldg(reinterpret_cast<const uint4*>(mk + (size_t)g * hw * 8));
     }
     if (kMode == 1 && has2 && valid) {   // fp32 residual (the ShortcutBlock's skip) rides in the f2 registers
       const float* r2 = reinterpret_cast<const float*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu) * hw + pix) * 8;
@@ -339,7 +350,12 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
         v[2] = __uint_as_float(rg[2]) + bb[g][0].z; v[3] = __uint_as_float(rg[3]) + bb[g][0].w;
         v[4] = __uint_as_float(rg[4]) + bb[g][1].x; v[5] = __uint_as_float(rg[5]) + bb[g][1].y;
         v[6] = __uint_as_float(rg[6]) + bb[g][1].z; v[7] = __uint_as_float(rg[7]) + bb[g][1].w;
-        if (kMode == 1) {
+        if (kMode == 4) {
+          float a[8];
+          unpack8(q1[g], p.dtype, a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
+        } else if (kMode == 1) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
           if (has2) {

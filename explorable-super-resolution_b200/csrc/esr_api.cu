@@ -119,7 +119,7 @@ int rows_nbn_for(int cin_planes, int cout) {
 }
 
 typedef void (*RowsKernelFn)(const esr::ConvParams);
-// epi: 0 generic epilogue, 1 / 2 the specialised forward epilogues (conv_epilogue_fast)
+// epi: 0 generic epilogue, 1 / 2 / 4 the specialised epilogues (conv_epilogue_fast), 3 the NCHW image store
 RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
   if (bwd) {
     switch (nbn) {
@@ -129,15 +129,16 @@ RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
     }
     return nullptr;
   }
-  switch (nbn * 4 + epi) {
-    case 16 * 4 + 0: return esr::conv3x3_rows_kernel<16, false, 0>;
-    case 16 * 4 + 3: return esr::conv3x3_rows_kernel<16, false, 3>;
-    case 32 * 4 + 0: return esr::conv3x3_rows_kernel<32, false, 0>;
-    case 32 * 4 + 1: return esr::conv3x3_rows_kernel<32, false, 1>;
-    case 32 * 4 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
-    case 64 * 4 + 0: return esr::conv3x3_rows_kernel<64, false, 0>;
-    case 64 * 4 + 1: return esr::conv3x3_rows_kernel<64, false, 1>;
-    case 64 * 4 + 2: return esr::conv3x3_rows_kernel<64, false, 2>;
+  switch (nbn * 8 + epi) {
+    case 16 * 8 + 0: return esr::conv3x3_rows_kernel<16, false, 0>;
+    case 16 * 8 + 3: return esr::conv3x3_rows_kernel<16, false, 3>;
+    case 32 * 8 + 0: return esr::conv3x3_rows_kernel<32, false, 0>;
+    case 32 * 8 + 1: return esr::conv3x3_rows_kernel<32, false, 1>;
+    case 32 * 8 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
+    case 32 * 8 + 4: return esr::conv3x3_rows_kernel<32, false, 4>;
+    case 64 * 8 + 0: return esr::conv3x3_rows_kernel<64, false, 0>;
+    case 64 * 8 + 1: return esr::conv3x3_rows_kernel<64, false, 1>;
+    case 64 * 8 + 2: return esr::conv3x3_rows_kernel<64, false, 2>;
   }
   return nullptr;
 }
@@ -362,7 +363,10 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
       else if (p.res1 && p.res1_is16 && !p.lrelu && !p.out16_up2) epi = 2;
     }
     if (!bwd && nbn == 16 && p.out_nchw && p.out_nchw_c <= 8 && !p.out16 && !p.out32 && !p.res1 && !p.res2 && !p.res3) epi = 3;
-    RowsKernelFn rk = select_rows_kernel(nbn, bwd, epi);
+    // gradient slice of the dense-block backward: mask * acc -> 16-bit planes, nothing else
+    const bool mask_only = bwd && nbn == 32 && a->cout % 32 == 0 && p.mask16 && p.out16 && !p.lead_planes && !p.res1 && !p.res2 && !p.res3 &&
+                           !p.out32 && !p.out_nchw && !p.out16_up2 && !p.out16_ps && p.tail_first == 0 && p.alpha == 1.0f && !p.lrelu;
+    RowsKernelFn rk = mask_only ? select_rows_kernel(32, false, 4) : select_rows_kernel(nbn, bwd, epi);
     if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
     p.nb_n = nbn;
     p.n_blocks = (a->cout + nbn - 1) / nbn;

@@ -165,3 +165,21 @@ def test_rows_fast_epilogue_shortcut_add_and_image_store():
         imgs.append(o)
     assert not torch.isnan(imgs[0]).any()
     assert rel_err(imgs[0], imgs[1])[0] < 1e-5
+
+
+def test_rows_mask_only_epilogue_equals_generic():
+    """gradient-slice launches of the dense-block backward (acc * LeakyReLU'(saved activation) -> 16-bit planes): the
+    specialised epilogue against the generic one of the tile kernel"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(51)
+    n, cin, cout, h, w = 2, 96, 32, 41, 256
+    x16, _ = ops.pack_nchw(torch.randn(n, cin, h, w, generator=g).to(DEV))
+    act16, _ = ops.pack_nchw(torch.randn(n, cout, h, w, generator=g).to(DEV))
+    pc = ops.PackedConv((torch.randn(cout, cin, 3, 3, generator=g) / 30).to(DEV), None)
+    outs = []
+    for mode in ('force', False):
+        o16 = torch.zeros((n, 6, h, w, 8), dtype=torch.float16, device=DEV)
+        ops.conv3x3(x16, pc, mask16=act16, mask_slope=0.2, out16=o16, out16_off=1, rows=mode)
+        outs.append(o16.float())
+    assert float(outs[0][:, 0].abs().max()) == 0.0 and float(outs[0][:, 5].abs().max()) == 0.0
+    assert rel_err(outs[0], outs[1])[0] < 2e-3 and rel_err(outs[0], outs[1])[1] < 2e-4
