@@ -23,7 +23,9 @@ namespace esr {
 
 constexpr int kWgThreads = 256;       // warp 0 producer, warps 1..3 MMA issuers, warps 4..7 TMEM zero-fill + final read-out
 constexpr int kWgIssuers = 3;
-constexpr int kWgPW = 32;             // pixels of a strip = one TMA box row (2 K steps of 16 pixels)
+constexpr int kWgBox = 32;            // pixels of one TMA box row (2 K steps of 16 pixels)
+constexpr int kWgNB = 2;              // boxes per strip row: the per-row bookkeeping is amortised over 4 K steps
+constexpr int kWgPW = kWgBox * kWgNB; // pixels of a strip
 constexpr int kWgMaxRing = 8;
 constexpr int kWgGStages = 3;
 
@@ -36,7 +38,8 @@ struct WgradParams {
   int nbn, cpb;                                // channels / planes of one n-block
   int mt;                                      // M chunks of 16 (row, plane) groups
   int rb;                                      // ring rows (+2 duplicate slots)
-  uint32_t slot_bytes, gstage_bytes;
+  uint32_t slot_bytes, gstage_bytes;           // per 32-pixel box: cp * 512 and 3 * cpb * 512
+  uint32_t ring_bytes;                         // one box ring: (rb + 2) slots + slack
   uint32_t idesc;
   float* part;                                 // [cta][mt][128][3*nbn] fp32 partial gradients
 };
@@ -76,8 +79,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t bar_zero = smem_base + 200;
   const uint32_t tmem_slot = smem_base + 208;
   const uint32_t xring = smem_base + kSmemHeader;
-  const uint32_t group_bytes = kWgPW * 16u;                               // one plane of one row
-  const uint32_t gst0 = xring + (uint32_t)(p.rb + 2) * p.slot_bytes + 16u * group_bytes;   // + slack for the last M chunk
+  const uint32_t group_bytes = kWgBox * 16u;                              // one plane of one box row
+  // x: kWgNB rings [box][row slot][plane][32 px] (rows of one box are consecutive M groups); gy stages [box][kx][plane][32 px]
+  const uint32_t gst0 = xring + kWgNB * p.ring_bytes;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -128,20 +132,26 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const int j = xr.j;
             mbar_wait(bar_xempty + 8 * j, xr.ph ^ 1u, 1u);
             const bool dup = j < 2;                         // ring slots 0,1 are mirrored behind the last slot
-            mbar_expect_tx(bar_xfull + 8 * j, p.slot_bytes * (dup ? 2u : 1u));
-            tma_load_4d(xring + (uint32_t)j * p.slot_bytes, &tmX, bar_xfull + 8 * j, x0 * 8, row, p.x_po, img);
-            if (dup) tma_load_4d(xring + (uint32_t)(p.rb + j) * p.slot_bytes, &tmX, bar_xfull + 8 * j, x0 * 8, row, p.x_po, img);
+            mbar_expect_tx(bar_xfull + 8 * j, kWgNB * p.slot_bytes * (dup ? 2u : 1u));
+#pragma unroll
+            for (int b = 0; b < kWgNB; ++b) {
+              const uint32_t ring = xring + b * p.ring_bytes;
+              tma_load_4d(ring + (uint32_t)j * p.slot_bytes, &tmX, bar_xfull + 8 * j, (x0 + b * kWgBox) * 8, row, p.x_po, img);
+              if (dup) tma_load_4d(ring + (uint32_t)(p.rb + j) * p.slot_bytes, &tmX, bar_xfull + 8 * j, (x0 + b * kWgBox) * 8, row, p.x_po, img);
+            }
             xr.inc(p.rb);
           }
           if (row >= ya && row < yb) {
             const int s = gr.j;
             mbar_wait(bar_gempty + 8 * s, gr.ph ^ 1u, 2u);
-            const uint32_t dst = gst0 + (uint32_t)s * p.gstage_bytes;
-            mbar_expect_tx(bar_gfull + 8 * s, p.gstage_bytes);
+            const uint32_t dst = gst0 + (uint32_t)s * kWgNB * p.gstage_bytes;
+            mbar_expect_tx(bar_gfull + 8 * s, kWgNB * p.gstage_bytes);
             // copy kx holds gy[row][x0 + k - kx + 1] at pixel k
-            for (int kx = 0; kx < 3; ++kx)
-              tma_load_4d(dst + (uint32_t)(kx * p.cpb) * group_bytes, &tmG, bar_gfull + 8 * s, (x0 + 1 - kx) * 8, row,
-                          p.gy_po + nblk * p.cpb, img);
+#pragma unroll
+            for (int b = 0; b < kWgNB; ++b)
+              for (int kx = 0; kx < 3; ++kx)
+                tma_load_4d(dst + b * p.gstage_bytes + (uint32_t)(kx * p.cpb) * group_bytes, &tmG, bar_gfull + 8 * s,
+                            (x0 + b * kWgBox + 1 - kx) * 8, row, p.gy_po + nblk * p.cpb, img);
             gr.inc(kWgGStages);
           }
         }
@@ -177,11 +187,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           mbar_wait(bar_gfull + 8 * gr.j, gr.ph, 4u);
           tc_fence_after();
           const uint64_t ad0 = adesc_t + (uint64_t)((xring + (uint32_t)p0.j * p.slot_bytes) >> 4);
-          const uint64_t bd0 = bdesc_t + (uint64_t)((gst0 + (uint32_t)gr.j * p.gstage_bytes) >> 4);
+          const uint64_t bd0 = bdesc_t + (uint64_t)((gst0 + (uint32_t)gr.j * kWgNB * p.gstage_bytes) >> 4);
           for (int ks = 0; ks < ksteps; ++ks) {
             if (kmod == iw) {
-              const uint64_t bd = bd0 + (uint64_t)(ks * 16);
-              uint64_t ad = ad0 + (uint64_t)(ks * 16);
+              // K step ks = 16 pixels: box ks / 2, half ks % 2 of its 32 pixels
+              const uint64_t bd = bd0 + (uint64_t)((ks >> 1) * (p.gstage_bytes >> 4) + (ks & 1) * 16);
+              uint64_t ad = ad0 + (uint64_t)((ks >> 1) * (p.ring_bytes >> 4) + (ks & 1) * 16);
               uint32_t d = tmem_base;
               for (int m = 0; m < p.mt; ++m, ad += mstep, d += (uint32_t)N3) umma_f16(d, ad, bd, p.idesc, 1u);
             }

@@ -176,7 +176,7 @@ int launch_conv(const void* kern, int grid, uint32_t smem_bytes, void* stream, v
 
 struct WgradPlan {
   int gyp, nbn, cpb, n_blocks, mt, rb;
-  uint32_t slot_bytes, gstage_bytes, smem_bytes;
+  uint32_t slot_bytes, gstage_bytes, ring_bytes, smem_bytes;
 };
 // tiling of the weight-gradient kernel for (cin_planes, cout); returns false when it does not fit
 bool wgrad_plan(int cp, int cout, WgradPlan* w) {
@@ -189,12 +189,13 @@ bool wgrad_plan(int cp, int cout, WgradPlan* w) {
   if (w->mt * 3 * w->nbn > 512) return false;
   w->cpb = w->nbn / 8;
   w->n_blocks = (w->gyp + w->cpb - 1) / w->cpb;
-  const uint32_t group = esr::kWgPW * 16u;
+  const uint32_t group = esr::kWgBox * 16u;
   w->slot_bytes = (uint32_t)cp * group;
   w->gstage_bytes = 3u * w->cpb * group;
   int rb = esr::kWgMaxRing;
   for (; rb >= 4; --rb) {
-    w->smem_bytes = esr::kSmemHeader + 128u + (uint32_t)(rb + 2) * w->slot_bytes + 16u * group + esr::kWgGStages * w->gstage_bytes;
+    w->ring_bytes = (uint32_t)(rb + 2) * w->slot_bytes + 16u * group;   // + slack for the last M chunk
+    w->smem_bytes = esr::kSmemHeader + 128u + esr::kWgNB * (w->ring_bytes + esr::kWgGStages * w->gstage_bytes);
     if (w->smem_bytes <= kSmemMax) break;
   }
   if (rb < 4) return false;
@@ -485,7 +486,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     p.x = (const uint8_t*)a->x; p.x_pt = a->x_planes_total; p.x_po = a->x_plane_off; p.cp = cp;
     p.gy = (const uint8_t*)a->gy; p.gy_pt = a->gy_planes_total; p.gy_po = a->gy_plane_off; p.gyp = w.gyp;
     p.nbn = w.nbn; p.cpb = w.cpb; p.mt = w.mt; p.rb = w.rb;
-    p.slot_bytes = w.slot_bytes; p.gstage_bytes = w.gstage_bytes;
+    p.slot_bytes = w.slot_bytes; p.gstage_bytes = w.gstage_bytes; p.ring_bytes = w.ring_bytes;
     // D=f32, A/B = f16|bf16, both MN-major (bits 15, 16), N = 3*nbn, M = 128
     p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | (1u << 15) | (1u << 16) |
               ((uint32_t)((3 * w.nbn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -502,14 +503,14 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     {
       cuuint64_t gdim[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->x_planes_total, (cuuint64_t)a->n};
       cuuint64_t gstr[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->x_planes_total};
-      cuuint32_t box[4] = {(cuuint32_t)esr::kWgPW * 8, 1, (cuuint32_t)cp, 1};
+      cuuint32_t box[4] = {(cuuint32_t)esr::kWgBox * 8, 1, (cuuint32_t)cp, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult cr = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed with CUresult %d", (int)cr);
       cuuint64_t gdim2[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->gy_planes_total, (cuuint64_t)a->n};
       cuuint64_t gstr2[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->gy_planes_total};
-      cuuint32_t box2[4] = {(cuuint32_t)esr::kWgPW * 8, 1, (cuuint32_t)w.cpb, 1};
+      cuuint32_t box2[4] = {(cuuint32_t)esr::kWgBox * 8, 1, (cuuint32_t)w.cpb, 1};
       cr = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->gy), gdim2, gstr2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(gy) failed with CUresult %d", (int)cr);
