@@ -30,6 +30,28 @@ def _param_version(mods):
     return tuple((m.weight._version, m.bias._version, m.weight.data_ptr()) for m in mods)
 
 
+def combine_dense_backward_weights(W, a5, z, nf, gc):
+    """Weights of the dense-block backward written as a dense block (see RRDBEngine.packed_bwd_dense).
+
+    W[jj]: [R, cout_j, cin_j, 3, 3] weights of conv_{jj+1} of R dense blocks (block.py:196-242; input channels
+    [z latent | nf | gc*(jj)]), a5: [R] output scale of each block.  Returns a list over i = 0..4 of [R, rows_i, K_i, 3, 3]
+    tensors: the conv that maps the concatenated gradients [g_5 | g_4 | ... | g_{i+1}] (K_i channels) to the gradient of
+    slice i (i = 0: [z rows padded to 8 | nf rows], i >= 1: the gc rows of x_i), taps rotated by 180 degrees, the block scale
+    folded into the g_5 columns.  Pure tensor re-layout (no arithmetic except the scale): tested on CPU against autograd."""
+    R = W[0].shape[0]
+    tr = lambda t: t.permute(0, 2, 1, 3, 4).flip(3, 4)    # [R, o, c] -> [R, c, o], taps rotated by 180 degrees
+    W = list(W)
+    W[4] = W[4] * a5.view(R, 1, 1, 1, 1)
+    out = []
+    for i in range(5):
+        cols = slice(0, z + nf) if i == 0 else slice(z + nf + (i - 1) * gc, z + nf + i * gc)
+        wc = torch.cat([tr(W[jj][:, :, cols]) for jj in range(4, i - 1 if i > 0 else -1, -1)], dim=2)   # convs 5 .. i+1
+        if i == 0 and z:
+            wc = torch.cat([wc[:, :z], torch.zeros((R, 8 - z) + tuple(wc.shape[2:]), device=wc.device, dtype=wc.dtype), wc[:, z:]], dim=1)
+        out.append(wc.contiguous())
+    return out
+
+
 class _Saved:
     """activations kept by a forward pass that a backward pass will use"""
     pass
@@ -107,22 +129,9 @@ class RRDBEngine:
         R = 3 * nb
         with torch.no_grad():
             W = [torch.stack([convs[1 + r * 5 + jj].weight.detach().float() for r in range(R)]) for jj in range(5)]  # [R, cout_j, cin_j, 3, 3]
-            a5 = torch.tensor([0.04 if r % 3 == 2 else 0.2 for r in range(R)], device=W[0].device).view(R, 1, 1, 1, 1)
-            W[4] = W[4] * a5
-            tr = lambda t: t.permute(0, 2, 1, 3, 4).flip(3, 4)    # [R, o, c] -> [R, c, o], taps rotated by 180 degrees
-            out = [[None] * 5 for _ in range(R)]
-            for i in range(5):
-                if i == 0:
-                    cols = slice(0, z + nf)
-                else:
-                    cols = slice(z + nf + (i - 1) * gc, z + nf + i * gc)
-                parts = [tr(W[jj][:, :, cols]) for jj in range(4, i - 1 if i > 0 else -1, -1) if jj >= i]   # convs j = 5 .. i+1 (0-based jj >= i)
-                wc = torch.cat(parts, dim=2)
-                if i == 0 and z:
-                    wc = torch.cat([wc[:, :z], torch.zeros((R, 8 - z) + tuple(wc.shape[2:]), device=wc.device), wc[:, z:]], dim=1)
-                wc = wc.contiguous()
-                for r in range(R):
-                    out[r][i] = ops.PackedConv(wc[r], None, dtype=self.dtype)
+            a5 = torch.tensor([0.04 if r % 3 == 2 else 0.2 for r in range(R)], device=W[0].device)
+            combined = combine_dense_backward_weights(W, a5, z, nf, gc)
+            out = [[ops.PackedConv(combined[i][r], None, dtype=self.dtype) for i in range(5)] for r in range(R)]
         self._packed_bd, self._packed_bd_version = out, self._packed_version
         return out
 
