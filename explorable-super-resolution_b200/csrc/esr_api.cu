@@ -203,13 +203,14 @@ bool wgrad_plan(int cp, int cout, WgradPlan* w) {
   return true;
 }
 
-// The row-streaming kernel is used when its 128-pixel strips are mostly real pixels.  (Forward-type launches win 1.5-2x per
-// launch even at 41 % lane fill - tools/small_conv_time.py - but the generic backward epilogue with many n-blocks does not,
-// so the small-image dispatch stays with the tile kernel for now.)  ESR_ROWS=0 forces the tile kernel, ESR_ROWS=2 the row kernel.
-bool rows_shape_ok(int w) {
-  static const int mode = [] { const char* e = getenv("ESR_ROWS"); return e ? atoi(e) : 1; }();   // 0 never, 1 by width, 2 always
+// The row-streaming kernel is used when its 128-pixel strips are mostly real pixels, and for forward-type launches on any image
+// at least 32 pixels wide: they win 1.5-2x per launch even at 41 % lane fill (resident weights, no per-tile pipeline refill;
+// tools/small_conv_time.py), while the generic backward epilogue with many n-blocks does not.  ESR_ROWS=0 forces the tile kernel, ESR_ROWS=2 the row kernel.
+bool rows_shape_ok(int w, bool bwd) {
+  static const int mode = [] { const char* e = getenv("ESR_ROWS"); return e ? atoi(e) : 1; }();   // 0 never, 1 by shape, 2 always
   const int strips = (w + 127) / 128;
-  return mode == 2 || (mode == 1 && w * 100 >= strips * 128 * 80);
+  if (mode != 1) return mode == 2;
+  return w * 100 >= strips * 128 * 80 || (!bwd && w >= 32);
 }
 
 }  // namespace
@@ -353,7 +354,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c;
 
   const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
-  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w))) {
+  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w, bwd))) {
     // ---- row-streaming kernel (conv3x3_rows.cuh)
     const int nbn = a->rows_nbn;
     if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "conv3x3: rows_nbn must be 16, 32 or 64");
