@@ -300,10 +300,12 @@ def main():
     # (2) the same K steps again with a CUDA-event pair around every conv launch (the dominant kernel's duration for
     #     the roofline; kept out of (1) because the event records serialise the programmatic dependent launches)
     record['on'] = True
+    ops.PLAN_REPLAY = False      # one host call per conv, so that each launch can sit between its own event pair
     barrier()
     for _ in range(args.steps):
         step_resident()
     barrier()
+    ops.PLAN_REPLAY = True
     record['on'] = False
     conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / args.steps
     n_conv = len(conv_events) // args.steps

@@ -425,6 +425,18 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   return launch_conv((const void*)kern, grid, smem_bytes, stream, kargs);
 }
 
+int esr_conv3x3_fwd_batch(const esr_conv3x3_args* args, int count, void* stream, int* failed_index) {
+  if (!args || count < 0) return fail(ESR_ERR_INVALID, "conv3x3 batch: bad arguments");
+  for (int i = 0; i < count; ++i) {
+    const int rc = esr_conv3x3_fwd(args + i, stream);
+    if (rc != ESR_OK) {
+      if (failed_index) *failed_index = i;
+      return rc;
+    }
+  }
+  return ESR_OK;
+}
+
 int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out) {
   const int nbn = rows_nbn_for(cin_planes, cout);
   if (nbn_out) *nbn_out = nbn;

@@ -65,6 +65,7 @@ class RRDBEngine:
         self._packed_t = None
         self._packed_version = None
         self._bufs = {}
+        self._plans = {}
 
     # ---------------------------------------------------------------- weights
     def _convs(self):
@@ -173,6 +174,60 @@ class RRDBEngine:
         a, b_ = (0, 1) if k % 2 == 0 else (1, 0)
         return B['D'][(a, b_, 2, b_)[j]]
 
+    def _conv_sequence(self, B, pk, save, out, plan):
+        """every conv launch of one forward pass, in order (recorded into `plan` when given, launched otherwise)"""
+        net = self.net
+        z = net.z_lead
+        zp = 1 if z else 0
+        nfp, gcp = net.nf // 8, net.gc // 8
+        T, F = B['T'], B['F']
+        nb = len(net.model[1].sub) - 1
+        conv = (lambda *a, **k: ops.conv3x3(*a, plan=plan, **k)) if plan is not None else ops.conv3x3
+        it = iter(pk)
+        # fea_conv: no activation; fp32 copy kept for the ShortcutBlock add
+        conv(B['in16'], next(it), out16=self._dense(B, save, 0, 0), out16_off=zp, out32=F)
+        for k in range(nb):
+            src_T = F if k == 0 else T[k % 2]
+            dst_T = T[(k + 1) % 2]
+            for j in range(3):
+                Di, Do = self._dense(B, save, k, j), self._dense(B, save, k, j + 1)
+                for i in range(4):
+                    conv(Di, next(it), cin_planes=zp + nfp + i * gcp, lrelu=True, slope=SLOPE,
+                                out16=Di, out16_off=zp + nfp + i * gcp)
+                if j < 2:   # x5*0.2 + x, residual from the 16-bit copy of x in the block's own buffer
+                    conv(Di, next(it), alpha=0.2, res1=Di, res1_off=zp, beta1=1.0, out16=Do, out16_off=zp)
+                else:       # ... and the RRDB residual from the fp32 trunk
+                    conv(Di, next(it), alpha=0.04, res1=Di, res1_off=zp, beta1=0.2, res2=src_T, beta2=1.0,
+                                out16=Do, out16_off=zp, out32=dst_T)
+        Dlast = self._dense(B, save, nb - 1, 3) if nb > 0 else self._dense(B, save, 0, 0)
+        ups = B['up']
+        factors = net.up_factors()
+        if any(r != 2 for r in factors):
+            raise NotImplementedError('esr_b200: only x2 up-sampling stages are built (scale 2/4/8)')
+        if net.upsample_mode == 'upconv':
+            # LR_conv + ShortcutBlock add, stored nearest-x2 replicated for the first upconv (block.py:299-300)
+            conv(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=ups[0], up2=True)
+            for k in range(len(factors)):
+                if k < len(factors) - 1:
+                    conv(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=ups[k + 1], up2=True)
+                else:  # the last upconv feeds HR_conv0, which sees the HR latent in plane 0 of hr_a
+                    conv(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=B['hr_a'], out16_off=zp)
+        else:
+            if save:
+                raise NotImplementedError('esr_b200: backward through the pixelshuffle upsampler is not built')
+            # pixelshuffle_block (block.py:278-291): conv(nf -> 4nf) -> PixelShuffle(2) -> act; the shuffle is the
+            # store addressing of the conv epilogue, the (elementwise) activation is applied before it
+            tmp = B['D'][2] if Dlast is not B['D'][2] else B['D'][0]
+            conv(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=tmp, out16_off=zp)
+            src, src_off = tmp, zp
+            for k in range(len(factors)):
+                dst, dst_off = (ups[k], 0) if k < len(factors) - 1 else (B['hr_a'], zp)
+                conv(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, slope=SLOPE, out16=dst, out16_off=dst_off,
+                            pixel_shuffle=2)
+                src, src_off = dst, dst_off
+        conv(B['hr_a'], next(it), lrelu=True, slope=SLOPE, out16=B['hr_b'], out16_off=zp)
+        conv(B['hr_b'], next(it), out_nchw=out)
+
     # ---------------------------------------------------------------- forward
     @torch.no_grad()
     def forward(self, x, pad=0, save=False):
@@ -213,51 +268,24 @@ class RRDBEngine:
         else:
             ops.pack_nchw(x, pad=pad, dst16=B['in16'], plane_off=0)
 
-        it = iter(pk)
-        # fea_conv: no activation; fp32 copy kept for the ShortcutBlock add
-        ops.conv3x3(B['in16'], next(it), out16=self._dense(B, save, 0, 0), out16_off=zp, out32=F)
-        for k in range(nb):
-            src_T = F if k == 0 else T[k % 2]
-            dst_T = T[(k + 1) % 2]
-            for j in range(3):
-                Di, Do = self._dense(B, save, k, j), self._dense(B, save, k, j + 1)
-                for i in range(4):
-                    ops.conv3x3(Di, next(it), cin_planes=zp + nfp + i * gcp, lrelu=True, slope=SLOPE,
-                                out16=Di, out16_off=zp + nfp + i * gcp)
-                if j < 2:   # x5*0.2 + x, residual from the 16-bit copy of x in the block's own buffer
-                    ops.conv3x3(Di, next(it), alpha=0.2, res1=Di, res1_off=zp, beta1=1.0, out16=Do, out16_off=zp)
-                else:       # ... and the RRDB residual from the fp32 trunk
-                    ops.conv3x3(Di, next(it), alpha=0.04, res1=Di, res1_off=zp, beta1=0.2, res2=src_T, beta2=1.0,
-                                out16=Do, out16_off=zp, out32=dst_T)
-        Dlast = self._dense(B, save, nb - 1, 3) if nb > 0 else self._dense(B, save, 0, 0)
-        ups = B['up']
-        factors = net.up_factors()
-        if any(r != 2 for r in factors):
-            raise NotImplementedError('esr_b200: only x2 up-sampling stages are built (scale 2/4/8)')
-        if net.upsample_mode == 'upconv':
-            # LR_conv + ShortcutBlock add, stored nearest-x2 replicated for the first upconv (block.py:299-300)
-            ops.conv3x3(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=ups[0], up2=True)
-            for k in range(len(factors)):
-                if k < len(factors) - 1:
-                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=ups[k + 1], up2=True)
-                else:  # the last upconv feeds HR_conv0, which sees the HR latent in plane 0 of hr_a
-                    ops.conv3x3(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=B['hr_a'], out16_off=zp)
-        else:
-            if save:
-                raise NotImplementedError('esr_b200: backward through the pixelshuffle upsampler is not built')
-            # pixelshuffle_block (block.py:278-291): conv(nf -> 4nf) -> PixelShuffle(2) -> act; the shuffle is the
-            # store addressing of the conv epilogue, the (elementwise) activation is applied before it
-            tmp = B['D'][2] if Dlast is not B['D'][2] else B['D'][0]
-            ops.conv3x3(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=tmp, out16_off=zp)
-            src, src_off = tmp, zp
-            for k in range(len(factors)):
-                dst, dst_off = (ups[k], 0) if k < len(factors) - 1 else (B['hr_a'], zp)
-                ops.conv3x3(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, slope=SLOPE, out16=dst, out16_off=dst_off,
-                            pixel_shuffle=2)
-                src, src_off = dst, dst_off
-        ops.conv3x3(B['hr_a'], next(it), lrelu=True, slope=SLOPE, out16=B['hr_b'], out16_off=zp)
         out = torch.empty((n, net.out_nc, h * S, w * S), dtype=torch.float32, device=dev)
-        ops.conv3x3(B['hr_b'], next(it), out_nchw=out)
+        if ops.PLAN_REPLAY:
+            # the ~350 launches have fixed arguments (cached buffers, packed weights): replay the recorded structs with one
+            # host call; only the output image is new
+            key = (n, h, w, str(dev), bool(save))
+            plan = self._plans.get(key)
+            if plan is None or plan.version != self._packed_version or plan.bufs is not B or plan.pk is not pk:
+                rec = []
+                self._conv_sequence(B, pk, save, out, rec)
+                plan = ops.LaunchPlan(rec)
+                plan.version, plan.bufs, plan.pk = self._packed_version, B, pk
+                if len(self._plans) >= 2:
+                    self._plans.pop(next(iter(self._plans)))
+                self._plans[key] = plan
+            plan.array[plan.n - 1].out_nchw = out.data_ptr()
+            plan.run()
+        else:
+            self._conv_sequence(B, pk, save, out, None)
         if not save:
             return out
         sv = _Saved()

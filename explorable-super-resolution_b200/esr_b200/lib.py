@@ -59,6 +59,7 @@ SIGNATURES = {
     "esr_device_check": (C.c_int, []),
     "esr_debug_watchdog": (C.c_int, [C.POINTER(C.c_uint), C.c_int]),
     "esr_conv3x3_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "esr_conv3x3_fwd_batch": (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "esr_conv3x3_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
     "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

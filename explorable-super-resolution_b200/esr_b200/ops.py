@@ -11,6 +11,9 @@ from . import lib as L
 
 _TORCH2ESR = {torch.float16: L.ESR_F16, torch.bfloat16: L.ESR_BF16}
 
+# engines replay recorded launch sequences (LaunchPlan) when True; False launches every conv through its own host call
+PLAN_REPLAY = True
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -76,8 +79,9 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
             res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0, res3=None, res3_off=0, beta3=1.0,
             out16=None, out16_off=0, up2=False, pixel_shuffle=0, out32=None, out32_off=0,
             out_nchw=None, lead_planes=0, lead_acc=None, mask16=None, mask_off=0, mask_slope=0.2, tail_first=0,
-            tile_p=0, tile_mt=0, rows=True):
-    """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor."""
+            tile_p=0, tile_mt=0, rows=True, plan=None):
+    """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor.  With `plan` (a list) the filled argument struct is
+    appended instead of launched: `LaunchPlan` replays such a recording with one host call."""
     require_cuda(x16, res1, res2, res3, out16, out32, out_nchw, lead_acc, mask16)
     n, pt, h, w, e = x16.shape
     assert e == 8 and x16.dtype == pc.dtype   # tcgen05 kind::f16 wants both operands in one format (f16 x bf16 traps)
@@ -119,7 +123,26 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     a.tile_p, a.tile_mt = tile_p, tile_mt
     if pc.wrows is not None and rows:   # rows: True = library decides by width, 'force' = always, False = tile kernel
         a.wpacked_rows, a.rows_nbn, a.rows_mode = pc.wrows.data_ptr(), pc.rows_nbn, (1 if rows == 'force' else 0)
+    if plan is not None:
+        plan.append(a)
+        return
     L.check(L.load().esr_conv3x3_fwd(C.byref(a), _stream()))
+
+
+class LaunchPlan:
+    """A recorded sequence of conv launches with fixed arguments (cached activation buffers, packed weights) replayed by ONE
+    host call (esr_conv3x3_fwd_batch).  The caller keeps every tensor the structs point at alive and drops the plan when any
+    of them is re-allocated."""
+
+    def __init__(self, recorded):
+        self.n = len(recorded)
+        self.array = (L.ConvArgs * self.n)(*recorded)
+        self._failed = C.c_int(-1)
+
+    def run(self):
+        rc = L.load().esr_conv3x3_fwd_batch(self.array, self.n, _stream(), C.byref(self._failed))
+        if rc != 0:
+            raise L.EsrError('esr_b200 error %d in planned launch %d: %s' % (rc, self._failed.value, L.load().esr_last_error().decode()))
 
 
 _wgrad_ws = {}

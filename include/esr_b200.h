@@ -104,6 +104,11 @@ typedef struct {
 } esr_conv3x3_args;
 
 int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream);
+/* `count` launches in order on one stream from one host call: a generator forward is ~350 fused convs with fixed arguments
+ * (cached buffers, packed weights), so the host side replays a recorded argument array instead of rebuilding every struct
+ * (the per-call host work, not the GPU, bounds single-image inference).  Stops at the first failure and returns its status;
+ * *failed_index (may be NULL) receives its position. */
+int esr_conv3x3_fwd_batch(const esr_conv3x3_args* args, int count, void* stream, int* failed_index);
 
 /* bytes of the packed weight image for (cin_planes, cout) with chunk size kcp */
 size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out);
