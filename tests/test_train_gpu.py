@@ -136,16 +136,16 @@ def test_srragan_model_perceptual_training_step(tmp_path):
     from models import create_model
     ops.device_check()
     torch.manual_seed(6)
-    model = create_model(_train_opt(tmp_path, feature_weight=1.0, feature_criterion='l1', grad_accumulation_steps_G=1, range_weight=None),
-                         accumulation_steps_per_batch=1)
+    model = create_model(_train_opt(tmp_path, feature_weight=1.0, feature_criterion='l1', grad_accumulation_steps_G=1, range_weight=None,
+                                    lr_G=1e-3), accumulation_steps_per_batch=1)
     assert all(not p.requires_grad for p in model.netF.parameters())
     lr = torch.rand(2, 3, 36, 36)                      # 144 - 80 = 64: divisible by 16 for the four poolings
     hr = torch.nn.functional.interpolate(lr, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
-    for it in range(8):
+    for it in range(16):
         model.feed_data({'LR': lr, 'HR': hr})
         model.optimize_parameters()
     fea, pix = model.log_dict['l_g_fea'], model.log_dict['l_g_pix']
-    assert len(fea) == 7 and all(torch.isfinite(torch.tensor(v)) for _, v in fea)
-    # seven Adam steps on a random extractor: the weighted objective goes down (either term may wobble on its own)
-    total = lambda k: fea[k][1] + 1.0 * pix[k][1]
-    assert min(total(k) for k in range(3, 7)) < total(0), (fea, pix)
+    assert len(fea) == 15 and all(torch.isfinite(torch.tensor(v)) for _, v in fea)
+    # fifteen Adam steps (lr 1e-3) on a random extractor: the weighted objective goes down (single steps may wobble: bf16)
+    total = [fea[k][1] + 1.0 * pix[k][1] for k in range(15)]
+    assert sum(total[-3:]) / 3 < total[0], total
