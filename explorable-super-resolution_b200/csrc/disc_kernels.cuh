@@ -1,0 +1,325 @@
+// Discriminator_VGG_128 helper kernels (models/modules/architecture.py:446-508): BatchNorm2d with batch statistics fused
+// with LeakyReLU on planar-8 tensors, space-to-depth addressing for the 4x4 stride-2 convolutions (which run as 3x3
+// convolutions over the 2x2 space-to-depth image), and the two fully connected layers.  All HBM-bound, read-once/write-once.
+#pragma once
+#include "aux_kernels.cuh"
+
+namespace esr {
+
+constexpr int kBnMaxChunks = 64;   // partial sums per plane (workspace = planes * kBnMaxChunks * 16 floats)
+
+// offset (in floats) of channel group g of pixel (img, y, x) in a gradient tensor.
+//   layout 0: fp32 planes [n][P][h][w][8]
+//   layout 1: fp32 planes of the space-to-depth image [n][4P][h/2][w/2][8], plane (py*2+px)*P + g, py = y&1, px = x&1
+//             (what the transposed 3x3 conv of a 4x4 stride-2 conv produces)
+//   layout 2: NCHW fp32 [n][C][h][w] (returns the offset of channel g*8; channel stride = h*w)
+__device__ __forceinline__ size_t grad_offset(int layout, int img, int g, int y, int x, int P, int h, int w, int C) {
+  if (layout == 0) return ((((size_t)img * P + g) * h + y) * w + x) * 8;
+  if (layout == 1) {
+    const int h2 = h >> 1, w2 = w >> 1;
+    const int pl = ((y & 1) * 2 + (x & 1)) * P + g;
+    return ((((size_t)img * 4 * P + pl) * h2 + (y >> 1)) * w2 + (x >> 1)) * 8;
+  }
+  return (((size_t)img * C + g * 8) * h + y) * w + x;
+}
+
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__device__ __forceinline__ void load_grad8(const float* g, int layout, int img, int gi, int y, int x, int P, int h, int w, int C, float* v) {
+  const size_t o = grad_offset(layout, img, gi, y, x, P, h, w, C);
+  if (layout == 2) {
+    const size_t hw = (size_t)h * w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (gi * 8 + k < C) ? __ldg(g + o + k * hw) : 0.f;
+  } else {
+    load8(g + o, v);
+  }
+}
+
+// block-level sum of 16 per-thread values -> part[0..15] (thread 0..15 write)
+__device__ __forceinline__ void block_sum16(float* acc, float* part) {
+  __shared__ float sm[8][16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sm[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[wv][threadIdx.x];
+    part[threadIdx.x] = s;
+  }
+}
+
+// ---- forward ---------------------------------------------------------------------------------------------------------------------
+// per-(plane, chunk) partial sums of y and y^2 over (n, h, w).  grid (chunks, P), 256 threads.
+__global__ void bn_partial_kernel(const float* __restrict__ y, int n, int P, int hw, float* __restrict__ part, int chunks) {
+  const int g = blockIdx.y, chunk = blockIdx.x;
+  const size_t M = (size_t)n * hw;
+  const size_t per = (M + chunks - 1) / chunks;
+  const size_t m0 = (size_t)chunk * per, m1 = m0 + per < M ? m0 + per : M;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (size_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+    const size_t img = m / hw, pix = m - img * hw;
+    float v[8];
+    load8(y + ((img * P + g) * hw + pix) * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[k] += v[k]; acc[8 + k] = fmaf(v[k], v[k], acc[8 + k]); }
+  }
+  block_sum16(acc, part + ((size_t)g * chunks + chunk) * 16);
+}
+
+// one thread per channel: batch mean / biased variance (double combine of the partials), the affine the apply kernel uses
+// (scale = gamma * invstd, shift = beta - mean * scale) and the running-statistics update of nn.BatchNorm2d
+// (momentum 0.1, unbiased variance).  train == 0: statistics come from running_mean / running_var.
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int chunks, int C, double M, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int train, float* running_mean,
+                                   float* running_var, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean, var;
+  if (train) {
+    double s = 0.0, q = 0.0;
+    const float* pp = part + (size_t)(c >> 3) * chunks * 16 + (c & 7);
+    for (int k = 0; k < chunks; ++k) { s += pp[k * 16]; q += pp[k * 16 + 8]; }
+    mean = s / M;
+    var = q / M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    if (running_var) running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * var * (M > 1.0 ? M / (M - 1.0) : 1.0));
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = (double)gamma[c] * invstd;
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)invstd;
+  scale[c] = (float)sc;
+  shift[c] = (float)((double)beta[c] - mean * sc);
+}
+
+// out = LeakyReLU(y * scale[c] + shift[c]) -> 16-bit planes (plain, or space-to-depth for a following 4x4 stride-2 conv)
+// and / or NCHW fp32 (the classifier's input).  One thread per (img, plane, y, x).
+__global__ void bn_lrelu_apply_kernel(const float* __restrict__ y32, const float* __restrict__ scale, const float* __restrict__ shift,
+                                      float slope, int n, int P, int h, int w, int C, int dtype, uint16_t* __restrict__ dst16, int s2d,
+                                      float* __restrict__ dst_nchw) {
+  const size_t total = (size_t)n * P * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int yy = r % h; r /= h;
+    const int g = r % P; r /= P;
+    const int img = (int)r;
+    float v[8], sc[8], sh[8];
+    load8(y32 + idx * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      sc[k] = c < C ? __ldg(scale + c) : 0.f;
+      sh[k] = c < C ? __ldg(shift + c) : 0.f;
+      float t = fmaf(v[k], sc[k], sh[k]);
+      v[k] = t > 0.f ? t : t * slope;
+    }
+    if (dst16) {
+      uint4 pk;
+      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
+      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
+      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
+      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
+      const size_t o = grad_offset(s2d ? 1 : 0, img, g, yy, x, P, h, w, C);
+      *reinterpret_cast<uint4*>(dst16 + o) = pk;
+    }
+    if (dst_nchw) {
+      const size_t hw = (size_t)h * w;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        if (c < C) dst_nchw[((size_t)img * C + c) * hw + (size_t)yy * w + x] = v[k];
+      }
+    }
+  }
+}
+
+// 16-bit planes -> space-to-depth 16-bit planes (for a 4x4 stride-2 conv whose input was produced by another path)
+__global__ void s2d_planes16_kernel(const uint4* __restrict__ src, int n, int P, int h, int w, uint4* __restrict__ dst) {
+  const size_t total = (size_t)n * P * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int yy = r % h; r /= h;
+    const int g = r % P; r /= P;
+    dst[grad_offset(1, (int)r, g, yy, x, P, h, w, 0) >> 3] = __ldg(src + idx);
+  }
+}
+
+// ---- backward --------------------------------------------------------------------------------------------------------------------
+// gb = g * lrelu'(y*scale+shift); partial sums of gb and gb * xhat (xhat = (y - mean) * invstd) per (plane, chunk)
+__global__ void bn_bwd_partial_kernel(const float* __restrict__ g, int layout, const float* __restrict__ y32, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      float slope, int n, int P, int h, int w, int C, float* __restrict__ part, int chunks) {
+  const int gi = blockIdx.y, chunk = blockIdx.x;
+  const size_t hw = (size_t)h * w, M = (size_t)n * hw;
+  const size_t per = (M + chunks - 1) / chunks;
+  const size_t m0 = (size_t)chunk * per, m1 = m0 + per < M ? m0 + per : M;
+  float sc[8], sh[8], mu[8], is[8], acc[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = gi * 8 + k;
+    sc[k] = c < C ? scale[c] : 0.f; sh[k] = c < C ? shift[c] : 0.f; mu[k] = c < C ? mean[c] : 0.f; is[k] = c < C ? invstd[c] : 0.f;
+    acc[k] = 0.f; acc[8 + k] = 0.f;
+  }
+  for (size_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+    const int img = (int)(m / hw);
+    const int pix = (int)(m - (size_t)img * hw);
+    const int yy = pix / w, x = pix - yy * w;
+    float v[8], gv[8];
+    load8(y32 + (((size_t)img * P + gi) * hw + pix) * 8, v);
+    load_grad8(g, layout, img, gi, yy, x, P, h, w, C, gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gb = fmaf(v[k], sc[k], sh[k]) > 0.f ? gv[k] : gv[k] * slope;
+      acc[k] += gb;
+      acc[8 + k] = fmaf(gb, (v[k] - mu[k]) * is[k], acc[8 + k]);
+    }
+  }
+  block_sum16(acc, part + ((size_t)gi * chunks + chunk) * 16);
+}
+
+// dbeta = sum gb, dgamma = sum gb*xhat (gscale undoes a loss scale); c1 = dbeta / M, c2 = dgamma / M for the apply pass
+// (zeros when the layer normalised with running statistics)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int chunks, int C, double M, int train, float gscale, int accumulate,
+                                       float* dgamma, float* dbeta, float* __restrict__ c1, float* __restrict__ c2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  const float* pp = part + (size_t)(c >> 3) * chunks * 16 + (c & 7);
+  for (int k = 0; k < chunks; ++k) { s += pp[k * 16]; q += pp[k * 16 + 8]; }
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)(s * gscale);
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)(q * gscale);
+  c1[c] = train ? (float)(s / M) : 0.f;
+  c2[c] = train ? (float)(q / M) : 0.f;
+}
+
+// gy = scale * (gb - c1 - xhat * c2) -> 16-bit planes: the gradient of the conv's output, operand of its dgrad / wgrad launches.
+// Layers without normalisation pass scale = 1, shift = 0, mean = 0, invstd = 1, c1 = c2 = 0.
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int layout, const float* __restrict__ y32, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ c1, const float* __restrict__ c2, float slope, int n, int P, int h, int w, int C,
+                                    int dtype, uint16_t* __restrict__ gy16) {
+  const size_t total = (size_t)n * P * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int yy = r % h; r /= h;
+    const int gi = r % P; r /= P;
+    const int img = (int)r;
+    float v[8], gv[8], o[8];
+    load8(y32 + idx * 8, v);
+    load_grad8(g, layout, img, gi, yy, x, P, h, w, C, gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = gi * 8 + k;
+      if (c < C) {
+        const float sc = __ldg(scale + c);
+        const float gb = fmaf(v[k], sc, __ldg(shift + c)) > 0.f ? gv[k] : gv[k] * slope;
+        const float xh = (v[k] - __ldg(mean + c)) * __ldg(invstd + c);
+        o[k] = sc * (gb - __ldg(c1 + c) - xh * __ldg(c2 + c));
+      } else {
+        o[k] = 0.f;
+      }
+    }
+    uint4 pk;
+    pk.x = (uint32_t)to16(o[0], dtype) | ((uint32_t)to16(o[1], dtype) << 16);
+    pk.y = (uint32_t)to16(o[2], dtype) | ((uint32_t)to16(o[3], dtype) << 16);
+    pk.z = (uint32_t)to16(o[4], dtype) | ((uint32_t)to16(o[5], dtype) << 16);
+    pk.w = (uint32_t)to16(o[6], dtype) | ((uint32_t)to16(o[7], dtype) << 16);
+    *reinterpret_cast<uint4*>(gy16 + idx * 8) = pk;
+  }
+}
+
+// ---- fully connected layers (fp32; 8192 -> 100 -> 1 at the reference's sizes: a few MFLOP, weight-read bound) ---------------------
+// out[b][j] = act(bias[j] + sum_k x[b][k] * W[j][k]); one block per output feature, batch in groups of 8
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, int B, int K, int J,
+                                  int lrelu, float slope, float* __restrict__ out) {
+  __shared__ float sm[8][8];
+  const int j = blockIdx.x;
+  const float* wr = W + (size_t)j * K;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (b0 + i < B) acc[i] = fmaf(wv, __ldg(x + (size_t)(b0 + i) * K + k), acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();   // sm reuse across batch groups
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && b0 + threadIdx.x < B) {
+      float s = bias ? bias[j] : 0.f;
+      for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[wv][threadIdx.x];
+      if (lrelu) s = s > 0.f ? s : s * slope;
+      out[(size_t)(b0 + threadIdx.x) * J + j] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ float masked_grad(const float* g, const float* act, float slope, int b, int j, int J) {
+  const float v = g[(size_t)b * J + j];
+  return (act && !(act[(size_t)b * J + j] > 0.f)) ? v * slope : v;
+}
+
+// gx[b][k] = sum_j g'[b][j] * W[j][k], g' = g masked by the layer's own LeakyReLU (act = its output, NULL = linear)
+__global__ void linear_bwd_input_kernel(const float* __restrict__ g, const float* __restrict__ act, float slope, const float* __restrict__ W,
+                                        int B, int K, int J, float* __restrict__ gx) {
+  const size_t total = (size_t)B * K;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / K), k = (int)(idx - (size_t)b * K);
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(masked_grad(g, act, slope, b, j, J), __ldg(W + (size_t)j * K + k), acc);
+    gx[idx] = acc;
+  }
+}
+
+// dW[j][k] (+)= gscale * sum_b g'[b][j] * x[b][k];  db[j] (+)= gscale * sum_b g'[b][j]
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict__ act, float slope, const float* __restrict__ x,
+                                         int B, int K, int J, float gscale, int accumulate, float* dW, float* db) {
+  const size_t total = (size_t)J * K;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / K), k = (int)(idx - (size_t)j * K);
+    float acc = 0.f, accb = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float gm = masked_grad(g, act, slope, b, j, J);
+      acc = fmaf(gm, __ldg(x + (size_t)b * K + k), acc);
+      accb += gm;
+    }
+    if (dW) dW[idx] = (accumulate ? dW[idx] : 0.f) + gscale * acc;
+    if (db && k == 0) db[j] = (accumulate ? db[j] : 0.f) + gscale * accb;
+  }
+}
+
+}  // namespace esr

@@ -17,6 +17,7 @@
 #include "conv3x3_tc.cuh"
 #include "conv3x3_rows.cuh"
 #include "conv3x3_wgrad.cuh"
+#include "disc_kernels.cuh"
 
 namespace {
 
@@ -769,6 +770,122 @@ int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl,
                                                                                rank, crop, out_hr);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+// ---- discriminator: BatchNorm2d (batch statistics) + LeakyReLU, space-to-depth, fully connected layers ----------------------------
+static int bn_chunks(size_t m) {
+  size_t c = (m + 1023) / 1024;
+  if (c < 1) c = 1;
+  if (c > (size_t)esr::kBnMaxChunks) c = esr::kBnMaxChunks;
+  return (int)c;
+}
+
+size_t esr_bn_workspace_bytes(int planes) { return planes > 0 ? (size_t)planes * esr::kBnMaxChunks * 16 * sizeof(float) : 0; }
+
+int esr_bn_stats(const float* y32, int n, int planes, int h, int w, int c, const float* gamma, const float* beta, float eps,
+                 float momentum, int train, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                 float* scale, float* shift, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!y32 || !gamma || !beta || !save_mean || !save_invstd || !scale || !shift) return fail(ESR_ERR_INVALID, "bn_stats: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_stats: bad shape");
+  if (!train && (!running_mean || !running_var)) return fail(ESR_ERR_INVALID, "bn_stats: eval mode needs running statistics");
+  const size_t m = (size_t)n * h * w;
+  const int chunks = bn_chunks(m);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (train) {
+    if (!workspace || workspace_bytes < esr_bn_workspace_bytes(planes)) return fail(ESR_ERR_INVALID, "bn_stats: workspace too small");
+    esr::bn_partial_kernel<<<dim3((unsigned)chunks, (unsigned)planes), 256, 0, st>>>(y32, n, planes, h * w, workspace, chunks);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  esr::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(workspace, chunks, c, (double)m, gamma, beta, eps, momentum, train, running_mean,
+                                                          running_var, save_mean, save_invstd, scale, shift);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_bn_lrelu_fwd(const float* y32, int n, int planes, int h, int w, int c, const float* scale, const float* shift, float slope,
+                     int dtype, void* dst16, int space_to_depth, float* dst_nchw, void* stream) {
+  if (!y32 || !scale || !shift || (!dst16 && !dst_nchw)) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: bad shape");
+  if (dtype != ESR_F16 && dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: bad dtype");
+  if (space_to_depth && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: space-to-depth needs an even size, got %dx%d", h, w);
+  const size_t total = (size_t)n * planes * h * w;
+  esr::bn_lrelu_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y32, scale, shift, slope, n, planes, h, w, c, dtype,
+                                                                                  (uint16_t*)dst16, space_to_depth, dst_nchw);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_space_to_depth_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream) {
+  if (!src || !dst) return fail(ESR_ERR_INVALID, "space_to_depth: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1)) return fail(ESR_ERR_INVALID, "space_to_depth: bad shape %dx%d", h, w);
+  const size_t total = (size_t)n * planes * h * w;
+  esr::s2d_planes16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, n, planes, h, w, (uint4*)dst);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_bn_lrelu_bwd(const float* g, int g_layout, const float* y32, int n, int planes, int h, int w, int c, const float* scale,
+                     const float* shift, const float* save_mean, const float* save_invstd, float slope, int has_bn, int train, float gscale,
+                     int accumulate, float* dgamma, float* dbeta, float* c1, float* c2, int dtype, void* gy16, float* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!g || !y32 || !scale || !shift || !save_mean || !save_invstd || !c1 || !c2 || !gy16) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad shape");
+  if (g_layout < 0 || g_layout > 2) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad gradient layout %d", g_layout);
+  if (g_layout == 1 && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: space-to-depth gradient needs an even size");
+  if (dtype != ESR_F16 && dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)n * h * w;
+  if (has_bn) {
+    if (!workspace || workspace_bytes < esr_bn_workspace_bytes(planes)) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: workspace too small");
+    const int chunks = bn_chunks(m);
+    esr::bn_bwd_partial_kernel<<<dim3((unsigned)chunks, (unsigned)planes), 256, 0, st>>>(g, g_layout, y32, scale, shift, save_mean, save_invstd,
+                                                                                        slope, n, planes, h, w, c, workspace, chunks);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    esr::bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(workspace, chunks, c, (double)m, train, gscale, accumulate, dgamma, dbeta, c1, c2);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  const size_t total = (size_t)n * planes * h * w;
+  esr::bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(g, g_layout, y32, scale, shift, save_mean, save_invstd, c1, c2, slope, n, planes,
+                                                                h, w, c, dtype, (uint16_t*)gy16);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_linear_fwd(const float* x, const float* weight, const float* bias, int batch, int in_features, int out_features, int lrelu,
+                   float slope, float* out, void* stream) {
+  if (!x || !weight || !out) return fail(ESR_ERR_INVALID, "linear_fwd: null pointer");
+  if (batch <= 0 || in_features <= 0 || out_features <= 0) return fail(ESR_ERR_INVALID, "linear_fwd: bad shape");
+  esr::linear_fwd_kernel<<<out_features, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, batch, in_features, out_features, lrelu, slope, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_linear_bwd(const float* g, const float* act, float slope, const float* x, const float* weight, int batch, int in_features,
+                   int out_features, float gscale, int accumulate, float* gx, float* dweight, float* dbias, void* stream) {
+  if (!g || !x || !weight) return fail(ESR_ERR_INVALID, "linear_bwd: null pointer");
+  if (batch <= 0 || in_features <= 0 || out_features <= 0) return fail(ESR_ERR_INVALID, "linear_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gx) {
+    esr::linear_bwd_input_kernel<<<grid_for((size_t)batch * in_features, 256), 256, 0, st>>>(g, act, slope, weight, batch, in_features,
+                                                                                            out_features, gx);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (dweight || dbias) {
+    esr::linear_bwd_weight_kernel<<<grid_for((size_t)out_features * in_features, 256), 256, 0, st>>>(g, act, slope, x, batch, in_features,
+                                                                                                    out_features, gscale, accumulate, dweight, dbias);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   return ESR_OK;
 }
 

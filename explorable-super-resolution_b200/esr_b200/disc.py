@@ -1,0 +1,228 @@
+"""Discriminator_VGG_128 engine (models/modules/architecture.py:446-508): the critic of the SRRaGAN training step
+(models/SRRaGAN_model.py:342-395 D step, :466-477 generator-side GAN term).
+
+Every convolution is a tensor-core launch of the generator's conv kernels: 3x3 convs directly, 4x4 stride-2 convs as 3x3 convs
+over the 2x2 space-to-depth image with re-indexed weights (`k4s2_to_3x3`) - the producer's BatchNorm/LeakyReLU kernel stores
+straight into the space-to-depth layout, the transposed launch returns the gradient in it and the BatchNorm backward reads it
+there, so the re-arrangement never exists as a pass of its own.  BatchNorm2d uses batch statistics in training mode (per
+process, like each replica of the reference's nn.DataParallel) and updates the running statistics in place.  The classifier
+(Linear 512*4*4 -> 100 -> 1) runs in fp32.  Backward: input gradient (generator's GAN term) and / or parameter gradients
+(D step), fp32 master gradients in the reference's parameter shapes.  No PyTorch/cuDNN fallback."""
+import torch
+
+from . import ops
+
+SLOPE = 0.2
+
+
+def k4s2_to_3x3(w):
+    """[O, C, 4, 4] stride-2 pad-1 kernel -> [O, 4C, 3, 3] stride-1 pad-1 kernel over the space-to-depth image
+    S[(py*2+px)*C + c][Y][X] = x[c][2Y+py][2X+px]:  W'[o, (py,px,c), ty, tx] = W[o, c, 2ty+py-1, 2tx+px-1] (zero outside 0..3)"""
+    o, c = w.shape[0], w.shape[1]
+    out = w.new_zeros((o, 2, 2, c, 3, 3))
+    for ty in range(3):
+        for py in range(2):
+            ky = 2 * ty + py - 1
+            if not 0 <= ky <= 3:
+                continue
+            for tx in range(3):
+                for px in range(2):
+                    kx = 2 * tx + px - 1
+                    if 0 <= kx <= 3:
+                        out[:, py, px, :, ty, tx] = w[:, :, ky, kx]
+    return out.reshape(o, 4 * c, 3, 3)
+
+
+def k3x3_to_k4s2(w3):
+    """inverse gather of `k4s2_to_3x3` (used on weight gradients): [O, 4C, 3, 3] -> [O, C, 4, 4]"""
+    o, c4 = w3.shape[0], w3.shape[1]
+    c = c4 // 4
+    w6 = w3.reshape(o, 2, 2, c, 3, 3)
+    out = w3.new_empty((o, c, 4, 4))
+    for ky in range(4):
+        ty, py = (ky + 1) // 2, (ky + 1) % 2
+        for kx in range(4):
+            tx, px = (kx + 1) // 2, (kx + 1) % 2
+            out[:, :, ky, kx] = w6[:, py, px, :, ty, tx]
+    return out
+
+
+class _Layer:
+    __slots__ = ('conv', 'bn', 'k4', 'cin', 'cout')
+
+
+class DiscEngine:
+    def __init__(self, module, dtype=torch.bfloat16):
+        self.m = module
+        self.dtype = dtype
+        self.layers = []
+        mods = list(module.features.children())
+        i = 0
+        while i < len(mods):
+            conv = mods[i]
+            assert isinstance(conv, torch.nn.Conv2d)
+            L = _Layer()
+            L.conv, L.bn = conv, None
+            L.k4 = tuple(conv.kernel_size) == (4, 4)
+            if L.k4:
+                assert tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (1, 1)
+            else:
+                assert tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)
+            L.cin, L.cout = conv.in_channels, conv.out_channels
+            i += 1
+            if i < len(mods) and isinstance(mods[i], torch.nn.BatchNorm2d):
+                L.bn = mods[i]
+                i += 1
+            assert isinstance(mods[i], torch.nn.LeakyReLU) and abs(mods[i].negative_slope - SLOPE) < 1e-12
+            i += 1
+            if L.k4 and L.cin % 8:
+                raise NotImplementedError('esr_b200 discriminator: stride-2 convs need a multiple of 8 input channels')
+            self.layers.append(L)
+        self.fc1, self.fc2 = module.classifier[0], module.classifier[2]
+        self._ver = None
+        self._pk = self._pkt = None
+        self._const = {}
+
+    # ---- parameters ----------------------------------------------------------------------------------------------------------
+    def params(self):
+        """every parameter in module.parameters() order"""
+        return list(self.m.parameters())
+
+    def _packed(self):
+        ver = tuple((L.conv.weight._version, L.conv.weight.data_ptr(), L.conv.bias._version) for L in self.layers)
+        if ver != self._ver:
+            self._pk, self._pkt = [], []
+            for L in self.layers:
+                w = L.conv.weight.detach().float()
+                if L.k4:
+                    w = k4s2_to_3x3(w)
+                self._pk.append(ops.PackedConv(w, L.conv.bias, dtype=self.dtype))
+                self._pkt.append(ops.PackedConv(w, None, dtype=self.dtype, transpose_flip=True))
+            self._ver = ver
+        return self._pk, self._pkt
+
+    def _identity_affine(self, c, dev):
+        key = (c, str(dev))
+        if key not in self._const:
+            one, zero = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+            self._const[key] = (zero, one, one, zero)     # mean, invstd, scale, shift
+        return self._const[key]
+
+    # ---- forward -------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, save=False):
+        x = x.float().contiguous()
+        ops.require_cuda(x)
+        n, c, h, w = x.shape
+        if c != self.layers[0].cin:
+            raise ops.L.EsrError('Discriminator_VGG_128 expects %d-channel images' % self.layers[0].cin)
+        pk, _ = self._packed()
+        dev = x.device
+        train = self.m.training
+        cur, _ = ops.pack_nchw(x, dtype=self.dtype)
+        saved = []
+        feat = None
+        for li, L in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            nn_, pin, hh, ww, _ = cur.shape          # for a stride-2 conv `cur` already is the space-to-depth image
+            y32 = torch.empty((n, ops.planes_for(L.cout), hh, ww, 8), dtype=torch.float32, device=dev)
+            ops.conv3x3(cur, pk[li], out32=y32)
+            if L.bn is not None:
+                bn = L.bn
+                use_batch = train or bn.running_mean is None
+                if train and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                mean, invstd, scale, shift = ops.bn_stats(y32, L.cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom, use_batch,
+                                                          bn.running_mean, bn.running_var)
+            else:
+                use_batch = False
+                mean, invstd, scale, shift = self._identity_affine(L.cout, dev)
+            nxt_k4 = (not last) and self.layers[li + 1].k4
+            if nxt_k4 and (hh % 2 or ww % 2):
+                raise ops.L.EsrError('Discriminator_VGG_128: image size must be even in front of every stride-2 conv')
+            out16, out_nchw = ops.bn_lrelu_fwd(y32, L.cout, scale, shift, SLOPE, self.dtype, space_to_depth=nxt_k4, want16=not last,
+                                               want_nchw=last)
+            if save:
+                saved.append((cur, y32, mean, invstd, scale, shift, use_batch))
+            if last:
+                feat = out_nchw
+            else:
+                cur = out16
+        flat = feat.reshape(n, -1)
+        if flat.shape[1] != self.fc1.in_features:
+            raise ops.L.EsrError('Discriminator_VGG_128: classifier expects %d features, the image gives %d (input_patch_size mismatch)'
+                                 % (self.fc1.in_features, flat.shape[1]))
+        h1 = ops.linear_fwd(flat, self.fc1.weight.detach(), self.fc1.bias.detach(), lrelu=True, slope=SLOPE)
+        out = ops.linear_fwd(h1, self.fc2.weight.detach(), self.fc2.bias.detach())
+        if save:
+            return out, (saved, feat, h1, (h, w))
+        return out
+
+    # ---- backward ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def backward(self, g_out, sv, want_input=True, want_params=True):
+        """g_out: dL/dlogits [N,1] -> (dL/dx [N,C,H,W] | None, [gradient per parameter in module.parameters() order] | None)"""
+        saved, feat, h1, (H, W) = sv
+        _, pkt = self._packed()
+        n = feat.shape[0]
+        dev = feat.device
+        g_out = g_out.float().contiguous()
+        grads = {}
+        g_h1, dw2, db2 = ops.linear_bwd(g_out, None, h1, self.fc2.weight.detach(), want_w=want_params)
+        flat = feat.reshape(n, -1)
+        g_flat, dw1, db1 = ops.linear_bwd(g_h1, h1, flat, self.fc1.weight.detach(), slope=SLOPE, want_w=want_params)
+        if want_params:
+            grads[id(self.fc1.weight)], grads[id(self.fc1.bias)] = dw1, db1
+            grads[id(self.fc2.weight)], grads[id(self.fc2.bias)] = dw2, db2
+        g, layout = g_flat.reshape(feat.shape), 2
+        gx = None
+        for li in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[li]
+            cur, y32, mean, invstd, scale, shift, use_batch = saved[li]
+            dgamma = dbeta = None
+            if L.bn is not None and want_params:
+                dgamma = torch.empty(L.cout, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(L.cout, dtype=torch.float32, device=dev)
+            gy16 = ops.bn_lrelu_bwd(g, layout, y32, L.cout, scale, shift, mean, invstd, SLOPE, self.dtype, has_bn=L.bn is not None,
+                                    train=use_batch, dgamma=dgamma, dbeta=dbeta)
+            if want_params:
+                if L.bn is not None:
+                    grads[id(L.bn.weight)], grads[id(L.bn.bias)] = dgamma, dbeta
+                cin3 = 4 * L.cin if L.k4 else L.cin
+                dw, db = ops.conv3x3_wgrad(cur, gy16, L.cout, cin3)
+                grads[id(L.conv.weight)] = k3x3_to_k4s2(dw) if L.k4 else dw
+                grads[id(L.conv.bias)] = db
+            if li == 0:
+                if want_input:
+                    gx = torch.zeros((n, L.cin, H, W), dtype=torch.float32, device=dev)
+                    ops.conv3x3(gy16, pkt[0], out_nchw=gx)
+                break
+            g = torch.empty((n, cur.shape[1], cur.shape[2], cur.shape[3], 8), dtype=torch.float32, device=dev)
+            ops.conv3x3(gy16, pkt[li], out32=g)
+            layout = 1 if L.k4 else 0
+        plist = [grads.get(id(p)) for p in self.params()] if want_params else None
+        return gx, plist
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, *params):
+        out, sv = eng.forward(x, save=True)
+        ctx.eng, ctx.sv, ctx.n_params = eng, sv, len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        want_params = any(ctx.needs_input_grad[2:])
+        gx, plist = ctx.eng.backward(g, ctx.sv, want_input=ctx.needs_input_grad[0], want_params=want_params)
+        pg = tuple((plist[k] if (want_params and ctx.needs_input_grad[2 + k]) else None) for k in range(ctx.n_params))
+        return (gx, None) + pg
+
+
+def disc_forward(module, x):
+    eng = module.engine()
+    params = eng.params()
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        return _DiscFn.apply(x, eng, *params)
+    return eng.forward(x)

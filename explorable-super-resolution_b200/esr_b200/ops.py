@@ -364,3 +364,93 @@ def latent_grad(gz_hr, gz_lr, n, c, hh, wh, s, pad_hr):
     dst = torch.empty((n, c, hh, wh), dtype=torch.float32, device=dev)
     L.check(L.load().esr_latent_grad(_ptr(gz_hr), _ptr(gz_lr), n, c, hh, wh, s, pad_hr, _ptr(dst), _stream()))
     return dst
+
+
+# ---- discriminator pieces (BatchNorm2d + LeakyReLU on planes, space-to-depth, fully connected layers) ----------------------------
+_bn_ws = {}
+
+
+def _bn_workspace(dev, planes):
+    nbytes = int(L.load().esr_bn_workspace_bytes(planes))
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    ws = _bn_ws.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        _bn_ws[key] = ws
+    return ws
+
+
+def bn_stats(y32, c, gamma, beta, eps, momentum, train, running_mean, running_var):
+    """batch (train) or running (eval) statistics of fp32 planes -> (save_mean, save_invstd, scale, shift), each [c] fp32;
+    train=True also updates running_mean / running_var in place like nn.BatchNorm2d"""
+    require_cuda(y32, gamma, beta, running_mean, running_var)
+    n, p, h, w, _ = y32.shape
+    assert y32.dtype == torch.float32
+    out = torch.empty((4, c), dtype=torch.float32, device=y32.device)
+    ws = _bn_workspace(y32.device, p)
+    L.check(L.load().esr_bn_stats(_ptr(y32), n, p, h, w, c, _ptr(gamma), _ptr(beta), eps, momentum, int(train), _ptr(running_mean),
+                                  _ptr(running_var), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _ptr(ws), ws.numel() * 4, _stream()))
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_lrelu_fwd(y32, c, scale, shift, slope, dtype, space_to_depth=False, want16=True, want_nchw=False):
+    """LeakyReLU(y * scale[c] + shift[c]) -> (16-bit planes [plain | space-to-depth], NCHW fp32)"""
+    require_cuda(y32, scale, shift)
+    n, p, h, w, _ = y32.shape
+    d16 = None
+    if want16:
+        shape = (n, 4 * p, h // 2, w // 2, 8) if space_to_depth else (n, p, h, w, 8)
+        d16 = torch.empty(shape, dtype=dtype, device=y32.device)
+    dn = torch.empty((n, c, h, w), dtype=torch.float32, device=y32.device) if want_nchw else None
+    L.check(L.load().esr_bn_lrelu_fwd(_ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), slope, _TORCH2ESR[dtype], _ptr(d16),
+                                      int(space_to_depth), _ptr(dn), _stream()))
+    return d16, dn
+
+
+def space_to_depth(src16):
+    require_cuda(src16)
+    n, p, h, w, _ = src16.shape
+    dst = torch.empty((n, 4 * p, h // 2, w // 2, 8), dtype=src16.dtype, device=src16.device)
+    L.check(L.load().esr_space_to_depth_planes16(_ptr(src16), n, p, h, w, _ptr(dst), _stream()))
+    return dst
+
+
+def bn_lrelu_bwd(g, g_layout, y32, c, scale, shift, mean, invstd, slope, dtype, *, has_bn, train=True, gscale=1.0, dgamma=None, dbeta=None,
+                 accumulate=False, scratch=None):
+    """gradient of the conv output y from the gradient g of LeakyReLU(BN(y)) -> gy16 planes; fills dgamma / dbeta when given.
+    g_layout 0: fp32 planes like y, 1: fp32 planes of the space-to-depth image, 2: NCHW fp32."""
+    require_cuda(g, y32, scale, shift, mean, invstd, dgamma, dbeta)
+    n, p, h, w, _ = y32.shape
+    assert g.dtype == torch.float32 and g.numel() == (n * c * h * w if g_layout == 2 else y32.numel())
+    gy16 = torch.empty((n, p, h, w, 8), dtype=dtype, device=y32.device)
+    if scratch is None:
+        scratch = torch.zeros((2, c), dtype=torch.float32, device=y32.device)
+    ws = _bn_workspace(y32.device, p) if has_bn else None
+    L.check(L.load().esr_bn_lrelu_bwd(_ptr(g), g_layout, _ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), slope,
+                                      int(has_bn), int(train), gscale, int(accumulate), _ptr(dgamma), _ptr(dbeta), _ptr(scratch[0]),
+                                      _ptr(scratch[1]), _TORCH2ESR[dtype], _ptr(gy16), _ptr(ws), (ws.numel() * 4 if ws is not None else 0),
+                                      _stream()))
+    return gy16
+
+
+def linear_fwd(x, weight, bias, lrelu=False, slope=0.2):
+    require_cuda(x, weight, bias)
+    b, k = x.shape
+    j = weight.shape[0]
+    assert x.dtype == weight.dtype == torch.float32 and weight.shape[1] == k
+    out = torch.empty((b, j), dtype=torch.float32, device=x.device)
+    L.check(L.load().esr_linear_fwd(_ptr(x), _ptr(weight), _ptr(bias), b, k, j, int(lrelu), slope, _ptr(out), _stream()))
+    return out
+
+
+def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1.0):
+    """-> (gx [B,K] | None, dW [J,K] | None, db [J] | None); act = the layer's LeakyReLU output (None for a linear layer)"""
+    require_cuda(g, act, x, weight)
+    b, k = x.shape
+    j = weight.shape[0]
+    assert g.dtype == torch.float32 and tuple(g.shape) == (b, j)
+    gx = torch.empty((b, k), dtype=torch.float32, device=x.device) if want_gx else None
+    dw = torch.empty((j, k), dtype=torch.float32, device=x.device) if want_w else None
+    db = torch.empty((j,), dtype=torch.float32, device=x.device) if want_w else None
+    L.check(L.load().esr_linear_bwd(_ptr(g), _ptr(act), slope, _ptr(x), _ptr(weight), b, k, j, gscale, 0, _ptr(gx), _ptr(dw), _ptr(db), _stream()))
+    return gx, dw, db

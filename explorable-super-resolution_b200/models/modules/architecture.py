@@ -129,3 +129,46 @@ class VGGFeatureExtractor(nn.Module):
     def forward(self, x):
         from esr_b200.vgg import vgg_forward
         return vgg_forward(self, x)
+
+
+class Discriminator_VGG_128(nn.Module):
+    """VGG-style critic with the reference's constructor, module tree and state-dict keys (`features.{0,2,3,5,6,...}`,
+    `classifier.{0,2}`; models/modules/architecture.py:446-508): conv0 3x3 (no norm) then alternating 4x4 stride-2 / 3x3
+    convs up to 8*base_nf channels, each Conv -> BatchNorm2d -> LeakyReLU(0.2), then Linear(8*base_nf*s*s -> 100) -> LeakyReLU
+    -> Linear(100 -> 1).  Runs on esr_b200.disc.DiscEngine (tensor-core conv launches, BatchNorm / Linear kernels).  The
+    truncated (`nb` < 10) and patch-discriminator (`num_2_strides` < 5) variants are not built."""
+
+    def __init__(self, in_nc, base_nf, norm_type='batch', act_type='leakyrelu', mode='CNA', input_patch_size=128, num_2_strides=5, nb=10):
+        super(Discriminator_VGG_128, self).__init__()
+        assert num_2_strides <= 5, 'Can be modified by adding more stridable layers, if needed.'
+        nb = 10 if nb is None else nb
+        if num_2_strides != 5 or nb < 10:
+            raise NotImplementedError('esr_b200 Discriminator_VGG_128: only the full 10-layer, 5-stride network with the FC classifier is built')
+        if norm_type != 'batch' or act_type != 'leakyrelu' or mode != 'CNA':
+            raise NotImplementedError('esr_b200 Discriminator_VGG_128: only batch norm + leakyrelu(0.2) in CNA order is built')
+        self.num_2_strides = 5
+        size = 1 * input_patch_size
+        chans = [(in_nc, base_nf, 3), (base_nf, base_nf, 4), (base_nf, base_nf * 2, 3), (base_nf * 2, base_nf * 2, 4),
+                 (base_nf * 2, base_nf * 4, 3), (base_nf * 4, base_nf * 4, 4), (base_nf * 4, base_nf * 8, 3), (base_nf * 8, base_nf * 8, 4),
+                 (base_nf * 8, base_nf * 8, 3), (base_nf * 8, base_nf * 8, 4)]
+        blocks = []
+        for k, (ci, co, ks) in enumerate(chans):
+            blocks.append(B.conv_block(ci, co, kernel_size=ks, stride=2 if ks == 4 else 1, norm_type=None if k == 0 else norm_type,
+                                       act_type=act_type, mode=mode))
+            if ks == 4:
+                size = math.ceil((size - 1) / 2)
+        self.features = B.sequential(*blocks)
+        self.last_FC_layers = True
+        self.classifier = nn.Sequential(nn.Linear(base_nf * 8 * int(size) ** 2, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
+        self.compute_dtype = torch.bfloat16   # training precision of the step (BASELINE config 3); fp16 is a switch for inference use
+        self._engines = {}
+
+    def engine(self):
+        from esr_b200.disc import DiscEngine
+        if self.compute_dtype not in self._engines:
+            self._engines[self.compute_dtype] = DiscEngine(self, dtype=self.compute_dtype)
+        return self._engines[self.compute_dtype]
+
+    def forward(self, x):
+        from esr_b200.disc import disc_forward
+        return disc_forward(self, x)

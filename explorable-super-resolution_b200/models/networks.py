@@ -95,8 +95,30 @@ def define_G(opt, CEM=None, num_latent_channels=None, **kwargs):
     return netG
 
 
-def define_D(opt, CEM=None):
-    raise NotImplementedError('esr_b200: Discriminator_VGG_128 (SURVEY 8a-12) is not built yet in this round')
+def define_D(opt, CEM=None, **kwargs):
+    """models/networks.py:125-182: the critic sees HR patches with the CEM's invalid margins cropped; kaiming init (scale 1)"""
+    gpu_ids = opt['gpu_ids']
+    opt_net = opt['network_D']
+    which_model = opt_net['which_model_D']
+    input_patch_size = opt['datasets']['train']['patch_size']
+    in_nc = opt_net['in_nc']
+    assert not ((opt_net['pre_clipping'] or opt_net['decomposed_input']) and which_model != 'PatchGAN'), 'Unsupported yet'
+    if CEM is not None:
+        input_patch_size -= 2 * CEM.invalidity_margins_HR
+    if which_model == 'discriminator_vgg_128':
+        kw = {}
+        if 'num_2_strides' in opt_net and opt_net['num_2_strides'] is not None:
+            kw['num_2_strides'] = opt_net['num_2_strides']
+        netD = arch.Discriminator_VGG_128(in_nc=in_nc, base_nf=opt_net['nf'], nb=opt_net['n_layers'], norm_type=opt_net['norm_type'],
+                                          mode=opt_net['mode'], act_type=opt_net['act_type'], input_patch_size=input_patch_size, **kw)
+    else:
+        raise NotImplementedError('Discriminator model [{:s}] not recognized (esr_b200 builds discriminator_vgg_128 only)'.format(which_model))
+    init_weights(netD, init_type='kaiming', scale=1)
+    if torch.cuda.is_available():
+        netD = netD.cuda()
+    if gpu_ids:
+        netD = SingleDeviceDataParallel(netD)
+    return netD
 
 
 def define_F(opt, use_bn=False, **kwargs):

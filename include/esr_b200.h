@@ -246,6 +246,40 @@ int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, in
 /* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Discriminator_VGG_128 (models/modules/architecture.py:446-508; D step SRRaGAN_model.py:342-395, G-side GAN term :466-477).
+ * Its 3x3 convolutions are esr_conv3x3_fwd launches; a 4x4 stride-2 pad-1 convolution (block.py:129-146 with kernel_size=4,
+ * stride=2) is the 3x3 convolution of the 2x2 space-to-depth image with re-indexed weights
+ *     W'[o][(py*2+px)*C + c][ty][tx] = W[o][c][2*ty+py-1][2*tx+px-1]   (zero where the 4x4 index falls outside 0..3),
+ * so forward, input-gradient and weight-gradient launches are the same tensor-core kernels.  The remaining pieces:
+ *   esr_bn_stats      nn.BatchNorm2d batch statistics of the conv output (fp32 planes) -> save_mean / save_invstd, the affine
+ *                     scale = gamma*invstd, shift = beta - mean*scale, and the running-statistics update (unbiased variance);
+ *                     train = 0 takes the statistics from running_mean / running_var instead (module.eval()).
+ *   esr_bn_lrelu_fwd  LeakyReLU(y*scale[c] + shift[c]) -> 16-bit planes, plain or space-to-depth ([n][4*planes][h/2][w/2][8],
+ *                     plane (py*2+px)*planes + g) for a following stride-2 conv, and / or NCHW fp32 (classifier input, :505).
+ *   esr_bn_lrelu_bwd  gradient of the conv output from the gradient `g` of the activation: dgamma / dbeta (scaled by gscale,
+ *                     optional accumulate), c1 = dbeta/M, c2 = dgamma/M scratch, gy16 = scale*(g*lrelu' - c1 - xhat*c2).
+ *                     g_layout: 0 fp32 planes, 1 fp32 planes of the space-to-depth image (output of a stride-2 conv's
+ *                     transposed launch), 2 NCHW fp32.  has_bn = 0: activation only (scale=1, shift=0, mean=0, invstd=1,
+ *                     c1=c2=0 arrays supplied by the caller; no reductions run).
+ *   esr_linear_fwd / esr_linear_bwd  nn.Linear (+ LeakyReLU) in fp32; bwd masks g with the layer's own activation `act`.
+ * ---------------------------------------------------------------------------------------------- */
+size_t esr_bn_workspace_bytes(int planes);
+int esr_bn_stats(const float* y32, int n, int planes, int h, int w, int c, const float* gamma, const float* beta, float eps,
+                 float momentum, int train, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                 float* scale, float* shift, float* workspace, size_t workspace_bytes, void* stream);
+int esr_bn_lrelu_fwd(const float* y32, int n, int planes, int h, int w, int c, const float* scale, const float* shift, float slope,
+                     int dtype, void* dst16, int space_to_depth, float* dst_nchw, void* stream);
+int esr_space_to_depth_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
+int esr_bn_lrelu_bwd(const float* g, int g_layout, const float* y32, int n, int planes, int h, int w, int c, const float* scale,
+                     const float* shift, const float* save_mean, const float* save_invstd, float slope, int has_bn, int train,
+                     float gscale, int accumulate, float* dgamma, float* dbeta, float* c1, float* c2, int dtype, void* gy16,
+                     float* workspace, size_t workspace_bytes, void* stream);
+int esr_linear_fwd(const float* x, const float* weight, const float* bias, int batch, int in_features, int out_features, int lrelu,
+                   float slope, float* out, void* stream);
+int esr_linear_bwd(const float* g, const float* act, float slope, const float* x, const float* weight, int batch, int in_features,
+                   int out_features, float gscale, int accumulate, float* gx, float* dweight, float* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,3 +180,41 @@ def z_optimize_l1(sd, ds_kernel, inv_hTh, s, pre, margin_lr, nf, nb, z, x_lr, de
     best = int(np.argmin(losses))
     final = zp.detach() if losses[best] == losses[-1] else iterates[best]
     return losses if losses[best] == losses[-1] else losses[:best + 1], Z_range * torch.tanh(final)
+
+
+# ---- discriminator and GAN losses (training step) ---------------------------------------------------------------------------------
+def discriminator_vgg128_forward(x, sd, training=True, eps=1e-5, momentum=0.1, update_running=False):
+    """Discriminator_VGG_128.forward (models/modules/architecture.py:446-508): conv0 3x3 + LeakyReLU (no norm), then nine
+    conv_block(CNA) = Conv2d (4x4 stride 2 pad 1 / 3x3 stride 1 pad 1, bias) -> BatchNorm2d(affine) -> LeakyReLU(0.2)
+    (block.py:129-146), flatten (:505), Linear -> LeakyReLU(0.2) -> Linear (:493).  Module indices in `features`: conv0 at 0,
+    layer k >= 1 has its conv at 3k-1 and its norm at 3k.  training=True normalises with batch statistics (biased variance);
+    update_running=True also applies nn.BatchNorm2d's running-statistics update to the tensors in `sd` (in place)."""
+    y = F.leaky_relu(F.conv2d(x, sd['features.0.weight'], sd['features.0.bias'], stride=1, padding=1), LRELU_SLOPE)
+    k = 1
+    while 'features.%d.weight' % (3 * k - 1) in sd:
+        w = sd['features.%d.weight' % (3 * k - 1)]
+        y = F.conv2d(y, w, sd['features.%d.bias' % (3 * k - 1)], stride=2 if w.shape[-1] == 4 else 1, padding=1)
+        p = 'features.%d.' % (3 * k)
+        rm, rv = sd[p + 'running_mean'], sd[p + 'running_var']
+        if training and not update_running:
+            rm, rv = rm.clone(), rv.clone()
+        y = F.leaky_relu(F.batch_norm(y, rm, rv, sd[p + 'weight'], sd[p + 'bias'], training, momentum, eps), LRELU_SLOPE)
+        k += 1
+    y = y.reshape(y.shape[0], -1)
+    y = F.leaky_relu(F.linear(y, sd['classifier.0.weight'], sd['classifier.0.bias']), LRELU_SLOPE)
+    return F.linear(y, sd['classifier.2.weight'], sd['classifier.2.bias'])
+
+
+def gan_loss_vanilla(logits, target_is_real):
+    """GANLoss('vanilla') = BCEWithLogitsLoss against constant 1 / 0 labels (models/modules/loss.py:212-246)"""
+    return F.binary_cross_entropy_with_logits(logits, torch.full_like(logits, 1.0 if target_is_real else 0.0))
+
+
+def relativistic_d_loss(pred_real, pred_fake):
+    """discriminator step (models/SRRaGAN_model.py:353-354,360): (BCE(real - mean(fake), 1) + BCE(fake - mean(real), 0)) / 2"""
+    return (gan_loss_vanilla(pred_real - pred_fake.mean(), True) + gan_loss_vanilla(pred_fake - pred_real.mean(), False)) / 2
+
+
+def relativistic_g_loss(pred_real, pred_fake):
+    """generator's GAN term (models/SRRaGAN_model.py:475-476), before the gan_weight factor; pred_real is detached there"""
+    return (gan_loss_vanilla(pred_real - pred_fake.mean(), False) + gan_loss_vanilla(pred_fake - pred_real.mean(), True)) / 2
