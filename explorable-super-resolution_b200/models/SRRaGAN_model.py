@@ -2,10 +2,12 @@
 
 Built: construction for inference / latent exploration (CEM + generator + checkpoint loading), `feed_data`,
 `Prepare_Input`, `GetLatent`, `test`, `Output_Batch`, `get_current_visuals`, `save`/`load` — everything `test.py`, the GUI's
-`Feed_n_Run_model` and `Z_optimizer.optimize` call — and the generator branch of the training step
-(`optimize_parameters` with pixel + VGG-feature + range losses, gradient accumulation, Adam, MultiStepLR:
-models/SRRaGAN_model.py:280-519 with `gan_weight` unset).  Configurations that need the discriminator or the latent
-structure loss raise NotImplementedError at construction: those are not built yet and there is no PyTorch fallback."""
+`Feed_n_Run_model` and `Z_optimizer.optimize` call — and the training step (`optimize_parameters`,
+models/SRRaGAN_model.py:280-519): discriminator step (Discriminator_VGG_128, vanilla / lsgan / wgan losses, relativistic by
+default) and generator step (pixel + VGG-feature + range + GAN losses), gradient accumulation for both, Adam, MultiStepLR,
+D_update_ratio / D_init_iters scheduling.  Configurations that need WGAN-GP's double backward, the decomposed-output
+critic, D verification or the latent structure loss raise NotImplementedError at construction: those are not built and
+there is no PyTorch fallback."""
 import os
 import re
 from collections import OrderedDict
@@ -17,7 +19,8 @@ from torch.optim import lr_scheduler
 
 import CEM.CEMnet as CEMnet
 import models.networks as networks
-from models.modules.loss import FilterLoss, CreateRangeLoss
+from esr_b200 import parallel
+from models.modules.loss import FilterLoss, CreateRangeLoss, GANLoss
 from .base_model import BaseModel
 
 
@@ -26,11 +29,17 @@ class SRRaGANModel(BaseModel):
         super(SRRaGANModel, self).__init__(opt)
         train_opt = opt['train'] if self.is_train else None
         if self.is_train:
-            unbuilt = [k for k in ('gan_weight', 'latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
+            unbuilt = [k for k in ('latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
+            if train_opt['gan_weight'] is not None:
+                if train_opt['gan_type'] == 'wgan-gp':
+                    unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
+                if train_opt['D_verification'] is not None or isinstance(train_opt['D_update_ratio'], list):
+                    unbuilt.append('D_verification / automatic D_update_ratio controller')
+                if opt['network_D']['decomposed_input'] or train_opt['hinge_threshold'] is not None:
+                    unbuilt.append('decomposed_input / hinge_threshold')
             if unbuilt:
-                raise NotImplementedError('esr_b200: the training step is built for the pixel / feature / range losses; %s need the '
-                                          'discriminator / structure loss (SURVEY 8a-12, 14, 15), not built yet'
-                                          % ', '.join(unbuilt))
+                raise NotImplementedError('esr_b200: the training step is built for the pixel / feature / range / GAN losses; %s are '
+                                          'not built' % ', '.join(unbuilt))
         self.log_path = opt['path']['log'] if opt['path'] is not None else None
         self.latent_input_domain = opt['network_G']['latent_input_domain']
         self.latent_input = opt['network_G']['latent_input'] if opt['network_G']['latent_input'] != 'None' else None
@@ -58,7 +67,8 @@ class SRRaGANModel(BaseModel):
         opt['network_G']['scale'] = opt['network_G']['scale'] if opt['network_G']['scale'] is not None else opt['scale']
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
-        logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'psnr_val', 'LR_decrease']
+        logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'l_d_real_fake', 'D_real', 'D_fake', 'D_logits_diff',
+                       'Correctly_distinguished', 'psnr_val', 'LR_decrease']
         self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
         if not self.is_train:
             self.netG.eval()
@@ -68,7 +78,15 @@ class SRRaGANModel(BaseModel):
         # ---- training state (models/SRRaGAN_model.py:68-203, generator branch)
         self.max_accumulation_steps = accumulation_steps_per_batch
         self.grad_accumulation_steps_G = train_opt['grad_accumulation_steps_G'] or 1
+        self.grad_accumulation_steps_D = train_opt['grad_accumulation_steps_D'] or 1
         self.netG.train()
+        self.l_gan_w = train_opt['gan_weight']
+        self.D_exists = self.l_gan_w is not None
+        self.D_verified, self.verified_D_saved = True, True          # D_verification is None (SRRaGAN_model.py:74)
+        if self.D_exists:
+            self.relativistic_D = opt['network_D']['relativistic'] is None or bool(opt['network_D']['relativistic'])
+            self.netD = networks.define_D(opt, CEM=self.CEM_net).to(self.device)
+            self.netD.train()
         if train_opt['pixel_weight'] is not None:
             l_pix_type = train_opt['pixel_criterion']
             if l_pix_type == 'l1':
@@ -100,7 +118,13 @@ class SRRaGANModel(BaseModel):
         else:
             print('Remove feature loss.')
             self.cri_fea = None
-        self.cri_gan, self.D_init_iters = None, 0
+        if self.D_exists:   # GD gan loss (SRRaGAN_model.py:150-159)
+            self.cri_gan = GANLoss(train_opt['gan_type'], 1.0, 0.0).to(self.device)
+            self.global_D_update_ratio = train_opt['D_update_ratio'] if train_opt['D_update_ratio'] is not None else 1
+            self.D_init_iters = train_opt['D_init_iters'] if train_opt['D_init_iters'] else 0
+        else:
+            print('Remove GAN loss')
+            self.cri_gan, self.D_init_iters, self.global_D_update_ratio = None, 0, 1
         wd_G = train_opt['weight_decay_G'] if train_opt['weight_decay_G'] else 0
         optim_params = []
         for k, v in self.netG.named_parameters():
@@ -112,6 +136,13 @@ class SRRaGANModel(BaseModel):
         self.optimizer_G = torch.optim.Adam(optim_params, lr=self.lr_G, weight_decay=wd_G,
                                             betas=(train_opt['beta1_G'], train_opt['beta2_G'] if train_opt['beta2_G'] is not None else 0.999))
         self.optimizers.append(self.optimizer_G)
+        self.optimizer_D = None
+        if self.D_exists:
+            wd_D = train_opt['weight_decay_D'] if train_opt['weight_decay_D'] else 0
+            self.lr_D = train_opt['lr_D']
+            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=self.lr_D, weight_decay=wd_D,
+                                                betas=(train_opt['beta1_D'], train_opt['beta2_D'] if train_opt['beta2_D'] is not None else 0.999))
+            self.optimizers.append(self.optimizer_D)
         if train_opt['lr_scheme'] == 'MultiStepLR':
             for optimizer in self.optimizers:
                 self.schedulers.append(lr_scheduler.MultiStepLR(optimizer, train_opt['lr_steps'], train_opt['lr_gamma']))
@@ -163,49 +194,128 @@ class SRRaGANModel(BaseModel):
             self.var_H = data['HR'].to(self.device)
             self.var_ref = (data['ref'] if 'ref' in data else data['HR']).to(self.device)
 
+    @staticmethod
+    def _batch_mean(t):
+        """mean over the GLOBAL batch: the reference takes it after nn.DataParallel gathered the critic's outputs
+        (SRRaGAN_model.py:353-354,475-476); with one process per GPU that is a 2-scalar all-reduce"""
+        if parallel.world() == 1:
+            return torch.mean(t)
+        tot = parallel.global_mean(t.detach()) * 1.0
+        n_glob = t.numel() * parallel.world()
+        return tot + (t.sum() - t.detach().sum()) / n_glob
+
     def optimize_parameters(self):
-        """Generator branch of models/SRRaGAN_model.py:280-519 (no discriminator): forward through CEM(G), crop the invalid
-        margins, pixel (+ range) loss scaled by the accumulation count, backward (dgrad + wgrad launches through the single
-        autograd node), Adam step on the last accumulation step.  Like the reference, the first gradient step is idle."""
+        """models/SRRaGAN_model.py:280-519: forward through CEM(G) and crop the invalid margins; discriminator step
+        (critic on the real patch and on the detached fake one, relativistic average loss, Adam on the last accumulation step);
+        generator step (pixel + feature + range + GAN terms scaled by the accumulation count, one backward through the critic,
+        the VGG extractor, the CEM projection and the generator: dgrad + wgrad launches behind single autograd nodes)."""
         if not self.is_train:
             raise NotImplementedError('optimize_parameters needs a model built with is_train=True (no optimizer / losses exist)')
         self.gradient_step_num = self.step // self.max_accumulation_steps
         first_acc = self.step % self.grad_accumulation_steps_G == 0
         last_acc = self.step % self.grad_accumulation_steps_G == (self.grad_accumulation_steps_G - 1)
-        self.Set_Require_Grad_Status(self.netG, True)
+        first_acc_D = self.step % self.grad_accumulation_steps_D == 0
+        last_acc_D = self.step % self.grad_accumulation_steps_D == (self.grad_accumulation_steps_D - 1)
+        acc_G, acc_D = self.grad_accumulation_steps_G, self.grad_accumulation_steps_D
+        if self.D_exists:
+            if first_acc:
+                self.generator_step = self.gradient_step_num > self.D_init_iters
+                if self.generator_step:
+                    self.generator_step = self.gradient_step_num % max([1, self.global_D_update_ratio]) == 0
+                    # when D's batch is larger than G's, G steps on the last D accumulation steps only (:292-293)
+                    self.generator_step = self.generator_step and self.step % acc_D >= acc_D - acc_G
+            if first_acc_D:
+                self.discriminator_step = self.gradient_step_num >= -self.D_init_iters
+                if self.discriminator_step:
+                    self.discriminator_step = self.gradient_step_num % max([1, np.ceil(1 / self.global_D_update_ratio)]) == 0
+        # G forward: its graph is only kept when a generator step follows
+        self.Set_Require_Grad_Status(self.netG, bool(not self.D_exists or self.generator_step))
         if self.CEM_net is not None:
             self.var_H, self.var_ref = self.CEM_net.HR_unpadder(self.var_H), self.CEM_net.HR_unpadder(self.var_ref)
         static_Z = self.GetLatent() if self.latent_input is not None else None
         self.Prepare_Input(LR_image=self.var_L, latent_input=static_Z)
-        self.fake_H = self.netG(self.model_input)
+        if self.D_exists and not self.generator_step:
+            with torch.no_grad():
+                self.fake_H = self.netG(self.model_input)
+        else:
+            self.fake_H = self.netG(self.model_input)
         if self.CEM_net is not None:
             self.fake_H = self.CEM_net.HR_unpadder(self.fake_H)
-        self.generator_step = self.gradient_step_num > 0   # one idle iteration first, to save the initial validation results
+        if not self.D_exists:
+            self.generator_step = self.gradient_step_num > 0   # one idle iteration first, to save the initial validation results
+        elif self.discriminator_step:
+            # ---- D step (:340-414)
+            self.Set_Require_Grad_Status(self.netD, True)
+            if first_acc_D:
+                self.optimizer_D.zero_grad()
+                self.l_d_real_grad_step, self.l_d_fake_grad_step, self.D_real_grad_step, self.D_fake_grad_step = [], [], [], []
+                self.D_logits_diff_grad_step = []
+            pred_d_real = self.netD(self.var_ref)
+            pred_d_fake = self.netD(self.fake_H.detach())   # detach to avoid BP to G
+            if self.relativistic_D:
+                l_d_real = self.cri_gan(pred_d_real - self._batch_mean(pred_d_fake), True)
+                l_d_fake = self.cri_gan(pred_d_fake - self._batch_mean(pred_d_real), False)
+            else:
+                l_d_real = 2 * self.cri_gan(pred_d_real, True)
+                l_d_fake = 2 * self.cri_gan(pred_d_fake, False)
+            l_d_total = (l_d_real + l_d_fake) / 2 / acc_D
+            l_d_total.backward()
+            self.l_d_real_grad_step.append(l_d_real.item())
+            self.l_d_fake_grad_step.append(l_d_fake.item())
+            self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
+            self.D_fake_grad_step.append(torch.mean(pred_d_fake.detach()).item())
+            self.D_logits_diff_grad_step.append(list(torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).cpu().numpy()))
+            if last_acc_D:
+                parallel.average_gradients(self.netD.parameters())
+                self.optimizer_D.step()
+                self.log_dict['l_d_real'].append((self.gradient_step_num, np.mean(self.l_d_real_grad_step)))
+                self.log_dict['l_d_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step)))
+                self.log_dict['l_d_real_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step) + np.mean(self.l_d_real_grad_step)))
+                self.log_dict['D_real'].append((self.gradient_step_num, np.mean(self.D_real_grad_step)))
+                self.log_dict['D_fake'].append((self.gradient_step_num, np.mean(self.D_fake_grad_step)))
+                self.log_dict['D_logits_diff'].append((self.gradient_step_num, np.mean(self.D_logits_diff_grad_step)))
+                self.log_dict['Correctly_distinguished'].append((self.gradient_step_num, np.mean([v0 > 0 for v1 in self.D_logits_diff_grad_step for v0 in v1])))
         if self.generator_step:
+            # ---- G step (:417-519)
             self.generator_started_learning = True
+            if self.D_exists:
+                self.Set_Require_Grad_Status(self.netD, False)
+            self.Set_Require_Grad_Status(self.netG, True)
             if first_acc:
                 self.optimizer_G.zero_grad()
-                self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step = [], [], []
+                self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step, self.l_g_gan_grad_step = [], [], [], []
             l_g_total = 0
             if self.cri_pix:
                 l_g_pix = self.cri_pix(self.fake_H, self.var_H)
-                l_g_total = l_g_total + self.l_pix_w * l_g_pix / self.grad_accumulation_steps_G
+                l_g_total = l_g_total + self.l_pix_w * l_g_pix / acc_G
             if self.cri_fea:   # perceptual loss: VGG features of the real image (no graph) and of the generated one
                 real_fea = self.netF(self.var_H).detach()
                 fake_fea = self.netF(self.fake_H)
                 l_g_fea = self.cri_fea(fake_fea, real_fea)
-                l_g_total = l_g_total + self.l_fea_w * l_g_fea / self.grad_accumulation_steps_G
+                l_g_total = l_g_total + self.l_fea_w * l_g_fea / acc_G
             if self.cri_range:
                 l_g_range = self.cri_range(self.fake_H)
-                l_g_total = l_g_total + self.l_range_w * l_g_range / self.grad_accumulation_steps_G
+                l_g_total = l_g_total + self.l_range_w * l_g_range / acc_G
+            if self.D_exists:   # G gan loss (:466-479)
+                pred_g_fake = self.netD(self.fake_H)
+                if self.relativistic_D:
+                    pred_d_real = self.netD(self.var_ref).detach()
+                    l_g_gan = self.l_gan_w * (self.cri_gan(pred_d_real - self._batch_mean(pred_g_fake), False) +
+                                              self.cri_gan(pred_g_fake - self._batch_mean(pred_d_real), True)) / 2 / acc_G
+                else:
+                    l_g_gan = self.l_gan_w * self.cri_gan(pred_g_fake, True) / acc_G
+                l_g_total = l_g_total + l_g_gan
             l_g_total.backward()
             if self.cri_fea:
                 self.l_g_fea_grad_step.append(l_g_fea.item())
             if self.cri_pix:
                 self.l_g_pix_grad_step.append(l_g_pix.item())
+            if self.cri_gan:
+                self.l_g_gan_grad_step.append(l_g_gan.item())
             if self.cri_range:
                 self.l_g_range_grad_step.append(l_g_range.item())
             if last_acc:
+                parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad])
                 self.optimizer_G.step()
                 self.generator_changed = True
                 if self.cri_pix:
@@ -214,6 +324,8 @@ class SRRaGANModel(BaseModel):
                     self.log_dict['l_g_fea'].append((self.gradient_step_num, np.mean(self.l_g_fea_grad_step)))
                 if self.cri_range:
                     self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
+                if self.cri_gan:
+                    self.log_dict['l_g_gan'].append((self.gradient_step_num, np.mean(self.l_g_gan_grad_step)))
         self.step += 1
 
     def test(self, prevent_grads_calc=True, **kwargs):
@@ -255,9 +367,19 @@ class SRRaGANModel(BaseModel):
             print('Testing model for G [{:s}] ...'.format(os.path.join(models_dir, name)))
             self.load_network(os.path.join(models_dir, name), self.netG)
             self.gradient_step_num = step_of(name)
+            d_path = os.path.join(models_dir, name.replace('_G.pth', '_D.pth'))
+            if self.D_exists and os.path.exists(d_path):
+                print('Loading also model for D [{:s}] ...'.format(d_path))
+                self.load_network(d_path, self.netD, optimizer=self.optimizer_D)
         elif path is not None and path['pretrained_model_G'] is not None:
             print('loading model for G [{:s}] ...'.format(path['pretrained_model_G']))
             self.load_network(path['pretrained_model_G'], self.netG)
+        if self.D_exists and not own and path is not None and path['pretrained_model_D'] is not None:
+            print('loading model for D [{:s}] ...'.format(path['pretrained_model_D']))
+            self.load_network(path['pretrained_model_D'], self.netD, optimizer=self.optimizer_D)
 
     def save(self, iter_label):
-        return self.save_network(self.save_dir, self.netG, 'G', iter_label, self.optimizer_G)
+        saving_path = self.save_network(self.save_dir, self.netG, 'G', iter_label, self.optimizer_G)
+        if self.D_exists:
+            self.save_network(self.save_dir, self.netD, 'D', iter_label, self.optimizer_D)
+        return saving_path
