@@ -1,6 +1,9 @@
 """Timings of the other BASELINE.json configurations on one B200 (bench.py itself measures configs[1]):
   C1  RRDBNet nf32 nb4 x4, 1x3x128x128 forward (+ parity against the reference's golden crop)
   C3g generator side of the SRRaGAN train step: CEM(RRDB nf64 nb23), per-GPU batch 4 of 52x52 LR, pixel + VGG-feature loss, Adam
+  C3  the full SRRaGAN train step of that configuration: D step (Discriminator_VGG_128 on 128x128 crops, relativistic loss, Adam) +
+      G step (pixel + VGG-feature + relativistic GAN loss through the frozen critic, Adam)
+  D   Discriminator_VGG_128 alone, forward + backward (parameter gradients), batches of 4 and 32 crops of 128x128
   C4  Z_optimizer, objective l1, 100 iterations over 8 regions of 64x64 LR (padded to 84x84), latent model
   C5  RRDBNet nf128 nb23 x8, 1x3x128x128 -> 1024x1024 forward and forward+backward (L1)
 Prints one JSON line per configuration."""
@@ -75,6 +78,53 @@ if 'C3g' in which:
     print(json.dumps({'config': 'C3 generator side (pixel + VGG feature loss, no discriminator), batch 4 of 52x52 LR', 'ms_per_step': ms,
                       'HR_MP_per_s': 4 * 208 * 208 / 1e6 / (ms * 1e-3), 'launches': nl, 'l_g_pix': model.log_dict['l_g_pix'][-1][1]}), flush=True)
     del model
+
+if 'C3' in which:
+    from models import create_model
+    train = ND(pixel_weight=1e-2, pixel_criterion='l1', feature_weight=1.0, feature_criterion='l1', gan_type='vanilla', gan_weight=5e-3,
+               lr_G=1e-4, beta1_G=0.9, weight_decay_G=0, lr_D=1e-4, beta1_D=0.9, weight_decay_D=0, D_update_ratio=1, D_init_iters=0,
+               lr_scheme='MultiStepLR', lr_steps=[100000], lr_gamma=0.5, grad_accumulation_steps_G=1, grad_accumulation_steps_D=1)
+    opt = ND(model='srragan', scale=4, gpu_ids=[0], is_train=True, range=[0, 1], train=train, datasets=ND(train=ND(patch_size=208, batch_size=4)),
+             path=ND(models='/tmp/esr_c3/models', pretrained_model_G=None, log='/tmp/esr_c3'),
+             network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None,
+                          norm_type=None, mode='CNA', nf=64, nb=23, in_nc=3, out_nc=3, gc=32, scale=4),
+             network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=64, in_nc=3))
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = create_model(opt)
+    lr_img, hr_img = torch.rand(4, 3, 52, 52), torch.rand(4, 3, 208, 208)
+
+    def step():
+        model.feed_data({'LR': lr_img, 'HR': hr_img})
+        model.optimize_parameters()
+    ms, nl = timed(step, warm=3, reps=5)
+    print(json.dumps({'config': 'C3 full SRRaGAN step (D step + G step with pixel + VGG feature + relativistic GAN loss), batch 4 of 52x52 LR',
+                      'ms_per_step': ms, 'HR_MP_per_s': 4 * 208 * 208 / 1e6 / (ms * 1e-3), 'launches': nl,
+                      'l_d_real_fake': model.log_dict['l_d_real_fake'][-1][1], 'l_g_gan': model.log_dict['l_g_gan'][-1][1],
+                      'D_logits_diff': model.log_dict['D_logits_diff'][-1][1]}), flush=True)
+    del model
+
+if 'D' in which:
+    import models.networks as networks
+    torch.manual_seed(0)
+    netD = arch.Discriminator_VGG_128(3, 64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        networks.init_weights(netD, 'kaiming', scale=1)
+    netD = netD.to(dev).train()
+    optD = torch.optim.Adam(netD.parameters(), lr=1e-4)
+    for bsz in (4, 32):
+        img = torch.rand(bsz, 3, 128, 128, device=dev)
+        with torch.no_grad():
+            ms_f, nl_f = timed(lambda: netD(img), warm=3, reps=10)
+
+        def dstep():
+            optD.zero_grad(set_to_none=True)
+            netD(img).mean().backward()
+            optD.step()
+        ms_t, nl_t = timed(dstep, warm=3, reps=10)
+        gf = 4.454 * bsz   # GFLOP forward, algorithmic (the space-to-depth form of the stride-2 convs executes more)
+        print(json.dumps({'config': 'Discriminator_VGG_128 nf64, %d crops of 128x128' % bsz, 'fwd_ms': ms_f, 'fwd_TFLOPs_algorithmic': gf / ms_f,
+                          'train_ms': ms_t, 'train_TFLOPs_algorithmic': 3 * gf / ms_t, 'launches_fwd': nl_f, 'launches_train': nl_t}), flush=True)
+    del netD
 
 if 'C4' in which:
     from models import create_model
