@@ -35,7 +35,7 @@ class SRRaGANModel(BaseModel):
                     unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
                 if train_opt['D_verification'] is not None or isinstance(train_opt['D_update_ratio'], list):
                     unbuilt.append('D_verification / automatic D_update_ratio controller')
-                if opt['network_D']['decomposed_input'] or train_opt['hinge_threshold'] is not None:
+                if (opt['network_D'] or {}).get('decomposed_input') or train_opt['hinge_threshold'] is not None:
                     unbuilt.append('decomposed_input / hinge_threshold')
             if unbuilt:
                 raise NotImplementedError('esr_b200: the training step is built for the pixel / feature / range / GAN losses; %s are '

@@ -38,7 +38,7 @@ def d2s_nchw(x):
 
 class PackedConv:
     def __init__(self, weight, bias, dtype=torch.float32, lead=0, transpose_flip=False, **kw):
-        self.w = weight.detach().to(dtype)
+        self.w = weight.detach().to(dtype).float()     # operand rounding of the tensor-core image, fp32 accumulation
         self.b = None if (bias is None or transpose_flip) else bias.detach().float()
         self.t = transpose_flip
         self.dtype = dtype
@@ -46,7 +46,7 @@ class PackedConv:
 
 def conv3x3(x16, pc, *, out32=None, out_nchw=None, **kw):
     assert not kw, kw
-    x = from_planes(x16).to(pc.dtype)
+    x = from_planes(x16).float()
     if pc.t:
         y = F.conv_transpose2d(x[:, :pc.w.shape[0]], pc.w, padding=1)
     else:

@@ -93,7 +93,8 @@ def _train_opt(tmp_path, **train_over):
               datasets=ND(train=ND(patch_size=128, batch_size=2)),
               path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, log=str(tmp_path)),
               network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None,
-                           norm_type=None, mode='CNA', nf=32, nb=1, in_nc=3, out_nc=3, gc=32, scale=4))
+                           norm_type=None, mode='CNA', nf=32, nb=1, in_nc=3, out_nc=3, gc=32, scale=4),
+              network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=16, in_nc=3))
 
 
 def test_srragan_model_generator_training_step(tmp_path):

@@ -1,9 +1,7 @@
 """Discriminator_VGG_128 on the B200, through the C-ABI: the BatchNorm / space-to-depth / Linear kernels against torch stand-ins
 (tests/disc_emul.py) on identical operands, the whole critic against the unmodified reference's golden fixture
 (oracle/make_golden_disc.py) and against the oracle at the reference's size (base_nf 64), and the GAN branch of
-SRRaGANModel.optimize_parameters.  Tolerances: fp16 operands (10-bit mantissa, activations re-rounded after each of the ten
-BatchNorm-renormalised stages; measured 5.5e-3 of the logit range on the 8-channel fixture) hold logits to 1e-2; training runs in
-bf16 (8-bit mantissa, ten conv stages each way): logits 5e-2, gradients by cosine >= 0.99 / rel-L2 <= 0.1."""
+SRRaGANModel.optimize_parameters.  Tolerances are stated at the tests."""
 import numpy as np
 import pytest
 import torch
@@ -112,48 +110,71 @@ def _mirror(g, dtype):
     return net.to(DEV)
 
 
-@pytest.mark.parametrize('dtype,tol_out,tol_l2,min_cos', [(torch.float16, 1e-2, 3e-2, 0.999), (torch.bfloat16, 5e-2, 1e-1, 0.99)])
-def test_discriminator_matches_reference_golden(dtype, tol_out, tol_l2, min_cos):
+def _run(net, g, gscale):
+    """logits, image gradient and parameter gradients of loss = sum(logits * wt) on the fixture's batch"""
+    dev = next(net.parameters()).device
+    x = torch.from_numpy(g['x'].astype(np.float32)).to(dev).requires_grad_(True)
+    out = net(x)
+    (out * (gscale * torch.from_numpy(g['wt']).to(dev))).sum().backward()
+    grads = {name: p.grad.detach().cpu() / gscale for name, p in net.named_parameters()}
+    return out.detach().cpu(), x.grad.detach().cpu() / gscale, grads, {k: v.detach().cpu().clone() for k, v in net.state_dict().items() if 'running' in k}
+
+
+# vs the unmodified reference (fp32): logits, gradient rel-L2, gradient cosine; vs the same arithmetic with operands rounded on the host
+@pytest.mark.parametrize('dtype,tol_out,tol_l2,min_cos,tol_same', [(torch.float16, 1e-2, 8e-2, 0.995, 1.5e-2), (torch.bfloat16, 5e-2, 0.3, 0.95, 6e-2)])
+def test_discriminator_matches_reference_golden(monkeypatch, dtype, tol_out, tol_l2, min_cos, tol_same):
+    """Two references.  (1) The unmodified reference's fp32 outputs / gradients (golden fixture).  This random-initialised,
+    batch-normalised 10-stage critic on a 4-image batch amplifies a relative perturbation about 100x (fp32 stand-ins reproduce
+    the fixture to 1e-6; rounding only the conv operands to fp16 / bf16 on the host moves the gradients by 5e-2 / 1.8e-1 -
+    tools/disc_parity.py), so the fp32 comparison is held to operand-precision bounds.  (2) The same algebra with
+    the same operand rounding done by torch on the host (tests/disc_emul.py): the CUDA path must agree with THAT much more
+    closely than with fp32 - it differs only by accumulation order and rounding ties."""
     from esr_b200 import ops
+    import models.modules.architecture as arch
     ops.device_check()
     g = golden('disc_vgg128_nf8')
+    gscale = 64.0 if dtype == torch.float16 else 1.0   # fp16 gradients of a 1e-3-size loss would underflow; the chain is linear in it
+    with monkeypatch.context() as mp:
+        E.install(mp)
+        emul = arch.Discriminator_VGG_128(in_nc=3, base_nf=int(g['cfg'][0]), input_patch_size=128)
+        emul.load_state_dict(_sd(g), strict=True)
+        emul.compute_dtype = dtype
+        emul.train()
+        e_out, e_gx, e_grads, _ = _run(emul, g, gscale)
     net = _mirror(g, dtype)
     net.train()
-    x = torch.from_numpy(g['x'].astype(np.float32)).to(DEV).requires_grad_(True)
-    out = net(x)
-    ref_out = torch.from_numpy(g['out'])
+    out, gx, grads, running = _run(net, g, gscale)
+    cos = lambda a, b: F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+    ref_out, ref_gx = torch.from_numpy(g['out']), torch.from_numpy(g['gx'])
     assert out.shape == (4, 1)
-    assert rel_err(out.detach().cpu(), ref_out)[0] < tol_out, (out.detach().cpu().flatten(), ref_out.flatten())
+    assert rel_err(out, ref_out)[0] < tol_out, (out.flatten(), ref_out.flatten())
+    assert rel_err(out, e_out)[0] < tol_same / 4, (out.flatten(), e_out.flatten())
     for k in g.files:
         if k.startswith('r:'):
-            assert rel_err(net.state_dict()[k[2:]].cpu(), torch.from_numpy(g[k]))[0] < tol_out, k
-    # fp16 gradients of a 1e-3-size loss would underflow: the chain is linear in the upstream gradient, scale it
-    gscale = 64.0 if dtype == torch.float16 else 1.0
-    (out * (gscale * torch.from_numpy(g['wt']).to(DEV))).sum().backward()
-    cos = lambda a, b: F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
-    gx, rgx = x.grad.cpu() / gscale, torch.from_numpy(g['gx'])
-    assert cos(gx, rgx) > min_cos and rel_err(gx, rgx)[1] < tol_l2, (cos(gx, rgx), rel_err(gx, rgx))
-    params = dict(net.named_parameters())
-    bad, worst = [], (0.0, '')
+            assert rel_err(running[k[2:]], torch.from_numpy(g[k]))[0] < tol_out, k
+    assert cos(gx, ref_gx) > min_cos and rel_err(gx, ref_gx)[1] < tol_l2, (cos(gx, ref_gx), rel_err(gx, ref_gx))
+    assert rel_err(gx, e_gx)[1] < tol_same, rel_err(gx, e_gx)
+    bad, worst, worst_same = [], (0.0, ''), (0.0, '')
     for k in g.files:
         if not k.startswith('g:'):
             continue
         name = k[2:]
-        # a conv bias in front of a batch norm has an analytically zero gradient (round-off noise on both sides)
-        if name.endswith('.bias') and params[name[:-5] + '.weight'].dim() == 4 and name != 'features.0.bias':
+        # a conv bias in front of a batch norm has an analytically zero gradient (round-off noise on every side)
+        if name.endswith('.bias') and grads[name[:-5] + '.weight'].dim() == 4 and name != 'features.0.bias':
             continue
-        a, b = params[name].grad.cpu() / gscale, torch.from_numpy(g[k])
-        el2, c = rel_err(a, b)[1], cos(a, b)
-        worst = max(worst, (el2, name))
-        if not (el2 < tol_l2 and c > min_cos):
-            bad.append((name, round(el2, 4), round(c, 5)))
+        a, b = grads[name], torch.from_numpy(g[k])
+        el2, c, same = rel_err(a, b)[1], cos(a, b), rel_err(a, e_grads[name])[1]
+        worst, worst_same = max(worst, (el2, name)), max(worst_same, (same, name))
+        if not (el2 < tol_l2 and c > min_cos and same < tol_same):
+            bad.append((name, round(el2, 4), round(c, 5), round(same, 5)))
     assert not bad, bad
-    print('worst discriminator gradient (%s): %s rel-L2 %.2e' % (dtype, worst[1], worst[0]))
+    print('discriminator gradients (%s): worst vs reference fp32 %s rel-L2 %.2e; worst vs host arithmetic with the same operand rounding %s %.2e'
+          % (dtype, worst[1], worst[0], worst_same[1], worst_same[0]))
     # eval mode: running statistics
     net.eval()
     with torch.no_grad():
         net.load_state_dict({**_sd(g), **{k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('r:')}}, strict=True)
-        out_eval = net(x.detach())
+        out_eval = net(torch.from_numpy(g['x'].astype(np.float32)).to(DEV))
     assert rel_err(out_eval.cpu(), torch.from_numpy(g['out_eval']))[0] < tol_out
 
 

@@ -99,8 +99,8 @@ if 'C3' in which:
     ms, nl = timed(step, warm=3, reps=5)
     print(json.dumps({'config': 'C3 full SRRaGAN step (D step + G step with pixel + VGG feature + relativistic GAN loss), batch 4 of 52x52 LR',
                       'ms_per_step': ms, 'HR_MP_per_s': 4 * 208 * 208 / 1e6 / (ms * 1e-3), 'launches': nl,
-                      'l_d_real_fake': model.log_dict['l_d_real_fake'][-1][1], 'l_g_gan': model.log_dict['l_g_gan'][-1][1],
-                      'D_logits_diff': model.log_dict['D_logits_diff'][-1][1]}), flush=True)
+                      'l_d_real_fake': float(model.log_dict['l_d_real_fake'][-1][1]), 'l_g_gan': float(model.log_dict['l_g_gan'][-1][1]),
+                      'D_logits_diff': float(model.log_dict['D_logits_diff'][-1][1])}), flush=True)
     del model
 
 if 'D' in which:
