@@ -15,36 +15,47 @@ from . import ops
 SLOPE = 0.2
 
 
+_K4_INDEX = {}
+
+
+def _k4_index(c, dev):
+    """gather tables of the re-indexing for `c` input channels: (src [4c*9] into a flattened [c*16] kernel, valid [4c*9],
+    inverse [c*16] into a flattened [4c*9] kernel)"""
+    key = (c, str(dev))
+    if key not in _K4_INDEX:
+        src = torch.zeros((2, 2, c, 3, 3), dtype=torch.long)
+        valid = torch.zeros((2, 2, c, 3, 3), dtype=torch.float32)
+        inv = torch.zeros((c, 4, 4), dtype=torch.long)
+        ch = torch.arange(c)
+        for ty in range(3):
+            for py in range(2):
+                ky = 2 * ty + py - 1
+                if not 0 <= ky <= 3:
+                    continue
+                for tx in range(3):
+                    for px in range(2):
+                        kx = 2 * tx + px - 1
+                        if 0 <= kx <= 3:
+                            src[py, px, :, ty, tx] = ch * 16 + ky * 4 + kx
+                            valid[py, px, :, ty, tx] = 1.0
+                            inv[:, ky, kx] = (((py * 2 + px) * c + ch) * 3 + ty) * 3 + tx
+        _K4_INDEX[key] = (src.reshape(-1).to(dev), valid.reshape(-1).to(dev), inv.reshape(-1).to(dev))
+    return _K4_INDEX[key]
+
+
 def k4s2_to_3x3(w):
     """[O, C, 4, 4] stride-2 pad-1 kernel -> [O, 4C, 3, 3] stride-1 pad-1 kernel over the space-to-depth image
     S[(py*2+px)*C + c][Y][X] = x[c][2Y+py][2X+px]:  W'[o, (py,px,c), ty, tx] = W[o, c, 2ty+py-1, 2tx+px-1] (zero outside 0..3)"""
     o, c = w.shape[0], w.shape[1]
-    out = w.new_zeros((o, 2, 2, c, 3, 3))
-    for ty in range(3):
-        for py in range(2):
-            ky = 2 * ty + py - 1
-            if not 0 <= ky <= 3:
-                continue
-            for tx in range(3):
-                for px in range(2):
-                    kx = 2 * tx + px - 1
-                    if 0 <= kx <= 3:
-                        out[:, py, px, :, ty, tx] = w[:, :, ky, kx]
-    return out.reshape(o, 4 * c, 3, 3)
+    src, valid, _ = _k4_index(c, w.device)
+    return (w.reshape(o, c * 16)[:, src] * valid.to(w.dtype)).reshape(o, 4 * c, 3, 3)
 
 
 def k3x3_to_k4s2(w3):
     """inverse gather of `k4s2_to_3x3` (used on weight gradients): [O, 4C, 3, 3] -> [O, C, 4, 4]"""
-    o, c4 = w3.shape[0], w3.shape[1]
-    c = c4 // 4
-    w6 = w3.reshape(o, 2, 2, c, 3, 3)
-    out = w3.new_empty((o, c, 4, 4))
-    for ky in range(4):
-        ty, py = (ky + 1) // 2, (ky + 1) % 2
-        for kx in range(4):
-            tx, px = (kx + 1) // 2, (kx + 1) % 2
-            out[:, :, ky, kx] = w6[:, py, px, :, ty, tx]
-    return out
+    o, c = w3.shape[0], w3.shape[1] // 4
+    _, _, inv = _k4_index(c, w3.device)
+    return w3.reshape(o, 4 * c * 9)[:, inv].reshape(o, c, 4, 4)
 
 
 class _Layer:
