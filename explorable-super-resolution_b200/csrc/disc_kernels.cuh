@@ -322,4 +322,79 @@ __global__ void linear_bwd_weight_kernel(const float* __restrict__ g, const floa
   }
 }
 
+// ---- structure-tensor statistics of the latent-control loss (models/modules/loss.py:51-62,133-147: FilterLoss with
+// 'structure_tensor' latent channels) -------------------------------------------------------------------------------------------------
+// dx = x[i][j+1] - x[i][j], dy = x[i+1][j] - x[i][j] (the reference's 2x2 depth-wise filters, no padding); per image the
+// sums over channels and the (h-1) x (w-1) valid positions of dx^2, dy^2, dx*dy.  HBM-bound: the image is read once.
+constexpr int kStChunks = 32;
+
+__global__ void structure_tensor_partial_kernel(const float* __restrict__ img, int c, int h, int w, float* __restrict__ part) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const size_t per_c = (size_t)(h - 1) * (w - 1), total = per_c * c;
+  const size_t per = (total + kStChunks - 1) / kStChunks;
+  const size_t t0 = (size_t)chunk * per, t1 = t0 + per < total ? t0 + per : total;
+  const float* base = img + (size_t)n * c * h * w;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (size_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    const size_t ch = t / per_c, r = t - ch * per_c;
+    const int i = (int)(r / (w - 1)), j = (int)(r - (size_t)i * (w - 1));
+    const float* p = base + (ch * h + i) * w + j;
+    const float v = __ldg(p), dx = __ldg(p + 1) - v, dy = __ldg(p + w) - v;
+    a0 = fmaf(dx, dx, a0); a1 = fmaf(dy, dy, a1); a2 = fmaf(dx, dy, a2);
+  }
+  __shared__ float sm[8][3];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm[warp][0] = a0; sm[warp][1] = a1; sm[warp][2] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) s += sm[wv][threadIdx.x];
+    part[((size_t)n * kStChunks + chunk) * 3 + threadIdx.x] = s;
+  }
+}
+
+// out[n][k] = mean over channels and valid positions (double combine of the partials)
+__global__ void structure_tensor_finalize_kernel(const float* __restrict__ part, int n, double inv_count, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 3) return;
+  const int img = t / 3, k = t - img * 3;
+  double s = 0.0;
+  for (int ch = 0; ch < kStChunks; ++ch) s += part[((size_t)img * kStChunks + ch) * 3 + k];
+  out[t] = (float)(s * inv_count);
+}
+
+// gradient of sum_k g[n][k] * mean_k with respect to the image: with px = (2 g0 dx + g2 dy)/N, py = (2 g1 dy + g2 dx)/N on the
+// valid positions, grad x[i][j] = -px(i,j) - py(i,j) + px(i,j-1) + py(i-1,j).  One thread per pixel (gather form, no atomics).
+__global__ void structure_tensor_bwd_kernel(const float* __restrict__ img, const float* __restrict__ g, int n, int c, int h, int w, float inv_count,
+                                            float* __restrict__ grad) {
+  const size_t total = (size_t)n * c * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int j = r % w; r /= w;
+    const int i = r % h; r /= h;
+    const int im = (int)(r / c);
+    const float g0 = 2.f * __ldg(g + im * 3) * inv_count, g1 = 2.f * __ldg(g + im * 3 + 1) * inv_count, g2 = __ldg(g + im * 3 + 2) * inv_count;
+    const float* p = img + idx;
+    const float v = __ldg(p);
+    float acc = 0.f;
+    if (i < h - 1 && j < w - 1) {
+      const float dx = __ldg(p + 1) - v, dy = __ldg(p + w) - v;
+      acc -= fmaf(g0, dx, g2 * dy) + fmaf(g1, dy, g2 * dx);
+    }
+    if (j > 0 && i < h - 1) {     // position (i, j-1): this pixel is its right neighbour
+      const float u = __ldg(p - 1), dx = v - u, dy = __ldg(p + w - 1) - u;
+      acc += fmaf(g0, dx, g2 * dy);
+    }
+    if (i > 0 && j < w - 1) {     // position (i-1, j): this pixel is its lower neighbour
+      const float u = __ldg(p - w), dx = __ldg(p - w + 1) - u, dy = v - u;
+      acc += fmaf(g1, dy, g2 * dx);
+    }
+    grad[idx] = acc;
+  }
+}
+
 }  // namespace esr

@@ -889,4 +889,32 @@ int esr_linear_bwd(const float* g, const float* act, float slope, const float* x
   return ESR_OK;
 }
 
+size_t esr_structure_tensor_workspace_bytes(int n) { return n > 0 ? (size_t)n * esr::kStChunks * 3 * sizeof(float) : 0; }
+
+int esr_structure_tensor_fwd(const float* img, int n, int c, int h, int w, float* out, float* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!img || !out || !workspace) return fail(ESR_ERR_INVALID, "structure_tensor_fwd: null pointer");
+  if (n <= 0 || c <= 0 || h < 2 || w < 2) return fail(ESR_ERR_INVALID, "structure_tensor_fwd: bad shape %dx%dx%dx%d", n, c, h, w);
+  if (workspace_bytes < esr_structure_tensor_workspace_bytes(n)) return fail(ESR_ERR_INVALID, "structure_tensor_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  esr::structure_tensor_partial_kernel<<<dim3(esr::kStChunks, (unsigned)n), 256, 0, st>>>(img, c, h, w, workspace);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  esr::structure_tensor_finalize_kernel<<<(n * 3 + 127) / 128, 128, 0, st>>>(workspace, n, 1.0 / ((double)c * (h - 1) * (w - 1)), out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_structure_tensor_bwd(const float* img, const float* g, int n, int c, int h, int w, float* grad_img, void* stream) {
+  if (!img || !g || !grad_img) return fail(ESR_ERR_INVALID, "structure_tensor_bwd: null pointer");
+  if (n <= 0 || c <= 0 || h < 2 || w < 2) return fail(ESR_ERR_INVALID, "structure_tensor_bwd: bad shape %dx%dx%dx%d", n, c, h, w);
+  const size_t total = (size_t)n * c * h * w;
+  esr::structure_tensor_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, g, n, c, h, w,
+                                                                                       (float)(1.0 / ((double)c * (h - 1) * (w - 1))), grad_img);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 }  // extern "C"

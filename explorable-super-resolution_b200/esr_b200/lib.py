@@ -99,6 +99,9 @@ SIGNATURES = {
     "esr_linear_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_float, C.c_void_p, C.c_void_p]),
     "esr_linear_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_float, C.c_int] +
                        [C.c_void_p] * 4),
+    "esr_structure_tensor_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "esr_structure_tensor_fwd": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "esr_structure_tensor_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
 }
 
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -454,3 +454,24 @@ def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1
     db = torch.empty((j,), dtype=torch.float32, device=x.device) if want_w else None
     L.check(L.load().esr_linear_bwd(_ptr(g), _ptr(act), slope, _ptr(x), _ptr(weight), b, k, j, gscale, 0, _ptr(gx), _ptr(dw), _ptr(db), _stream()))
     return gx, dw, db
+
+
+# ---- structure-tensor statistics of the latent-control loss ----------------------------------------------------------------------
+def structure_tensor(img):
+    """[N,C,H,W] fp32 -> [N,3] per-image means of (dx^2, dy^2, dx*dy) of the 2x2 finite differences"""
+    require_cuda(img)
+    n, c, h, w = img.shape
+    assert img.dtype == torch.float32
+    out = torch.empty((n, 3), dtype=torch.float32, device=img.device)
+    ws = torch.empty(int(L.load().esr_structure_tensor_workspace_bytes(n)) // 4, dtype=torch.float32, device=img.device)
+    L.check(L.load().esr_structure_tensor_fwd(_ptr(img), n, c, h, w, _ptr(out), _ptr(ws), ws.numel() * 4, _stream()))
+    return out
+
+
+def structure_tensor_bwd(img, g):
+    require_cuda(img, g)
+    n, c, h, w = img.shape
+    assert g.dtype == torch.float32 and tuple(g.shape) == (n, 3)
+    grad = torch.empty_like(img)
+    L.check(L.load().esr_structure_tensor_bwd(_ptr(img), _ptr(g), n, c, h, w, _ptr(grad), _stream()))
+    return grad

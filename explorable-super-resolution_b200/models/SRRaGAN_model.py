@@ -4,9 +4,9 @@ Built: construction for inference / latent exploration (CEM + generator + checkp
 `Prepare_Input`, `GetLatent`, `test`, `Output_Batch`, `get_current_visuals`, `save`/`load` — everything `test.py`, the GUI's
 `Feed_n_Run_model` and `Z_optimizer.optimize` call — and the training step (`optimize_parameters`,
 models/SRRaGAN_model.py:280-519): discriminator step (Discriminator_VGG_128, vanilla / lsgan / wgan losses, relativistic by
-default) and generator step (pixel + VGG-feature + range + GAN losses), gradient accumulation for both, Adam, MultiStepLR,
+default) and generator step (pixel + VGG-feature + range + GAN + latent-control losses), gradient accumulation for both, Adam, MultiStepLR,
 D_update_ratio / D_init_iters scheduling.  Configurations that need WGAN-GP's double backward, the decomposed-output
-critic, D verification or the latent structure loss raise NotImplementedError at construction: those are not built and
+critic, D verification, the optimised-Z reference loss or non-structure-tensor latent descriptors raise NotImplementedError at construction: those are not built and
 there is no PyTorch fallback."""
 import os
 import re
@@ -24,12 +24,20 @@ from models.modules.loss import FilterLoss, CreateRangeLoss, GANLoss
 from .base_model import BaseModel
 
 
+def SVD_2_LatentZ(SVD_values, max_lambda=1):
+    """utils/util.py:285-291: (lambda0, lambda1, theta) -> (sum Ix^2, sum Iy^2, sum Ix*Iy) mapped to a symmetric range"""
+    l0, l1, th = SVD_values[:, 0, ...], SVD_values[:, 1, ...], SVD_values[:, -1, ...]
+    return torch.stack([2 * max_lambda * (l1 * (torch.sin(th) ** 2) + l0 * (torch.cos(th) ** 2)) - max_lambda,
+                        2 * max_lambda * (l0 * (torch.sin(th) ** 2) + l1 * (torch.cos(th) ** 2)) - max_lambda,
+                        2 * (l0 - l1) * torch.sin(th) * torch.cos(th)], 1)
+
+
 class SRRaGANModel(BaseModel):
     def __init__(self, opt, accumulation_steps_per_batch=1, init_Fnet=None, init_Dnet=None, **kwargs):
         super(SRRaGANModel, self).__init__(opt)
         train_opt = opt['train'] if self.is_train else None
         if self.is_train:
-            unbuilt = [k for k in ('latent_weight', 'optimalZ_loss_weight') if train_opt[k] is not None]
+            unbuilt = [k for k in ('optimalZ_loss_weight',) if train_opt[k] is not None]
             if train_opt['gan_weight'] is not None:
                 if train_opt['gan_type'] == 'wgan-gp':
                     unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
@@ -45,10 +53,16 @@ class SRRaGANModel(BaseModel):
         self.latent_input = opt['network_G']['latent_input'] if opt['network_G']['latent_input'] != 'None' else None
         if self.latent_input is not None:
             self.Z_size_factor = opt['scale'] if 'HR' in opt['network_G']['latent_input_domain'] else 1
-            assert isinstance(opt['network_G']['latent_channels'], int)
         self.cri_latent = None
         self.optimalZ_loss_type = None
         self.num_latent_channels = FilterLoss(latent_channels=opt['network_G']['latent_channels']).num_channels
+        if self.latent_input is not None and self.is_train:   # latent-control loss L_struct (SRRaGAN_model.py:37-40)
+            self.l_latent_w = train_opt['latent_weight']
+            if self.l_latent_w is not None:
+                self.cri_latent = FilterLoss(latent_channels=opt['network_G']['latent_channels'])
+                if not self.cri_latent.built:
+                    raise NotImplementedError('esr_b200: latent_weight needs a structure-tensor latent descriptor (got %r)'
+                                              % (opt['network_G']['latent_channels'],))
         self.CEM_net = None
         self.CEM_arch = opt['network_G']['CEM_arch']
         self.step = 0
@@ -68,7 +82,7 @@ class SRRaGANModel(BaseModel):
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
         logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'l_d_real_fake', 'D_real', 'D_fake', 'D_logits_diff',
-                       'Correctly_distinguished', 'psnr_val', 'LR_decrease']
+                       'Correctly_distinguished', 'psnr_val', 'LR_decrease'] + ['l_g_latent_%d' % i for i in range(self.num_latent_channels)]
         self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
         if not self.is_train:
             self.netG.eval()
@@ -179,7 +193,16 @@ class SRRaGANModel(BaseModel):
             if 'Z' in data.keys():
                 cur_Z = data['Z']
             else:
-                cur_Z = 2 * torch.rand([self.var_L.size(0), self.num_latent_channels] + hr_size).type(self.var_L.type()) - 1
+                if self.cri_latent is not None:    # spatially uniform codes while the latent-control loss trains (:251-253)
+                    cur_Z = torch.rand([self.var_L.size(0), self.num_latent_channels, 1, 1])
+                else:
+                    cur_Z = torch.rand([self.var_L.size(0), self.num_latent_channels] + hr_size).type(self.var_L.type())
+                if self.opt['network_G']['latent_channels'] in ['SVD_structure_tensor', 'SVDinNormedOut_structure_tensor']:
+                    cur_Z[:, -1, ...] = 2 * np.pi * cur_Z[:, -1, ...]   # (lambda0, lambda1, theta) -> structure tensor values (:256-259)
+                    self.SVD = {'theta': cur_Z[:, -1, ...], 'lambda0_ratio': 1 * cur_Z[:, 0, ...], 'lambda1_ratio': 1 * cur_Z[:, 1, ...]}
+                    cur_Z = SVD_2_LatentZ(cur_Z).detach()
+                else:
+                    cur_Z = 2 * cur_Z - 1
             if isinstance(cur_Z, (int, float)) or (not torch.is_tensor(cur_Z) and (np.ndim(cur_Z) < 4 or np.shape(cur_Z)[2] == 1)):
                 cur_Z = cur_Z * np.ones([1, self.num_latent_channels] + hr_size)
             elif torch.is_tensor(cur_Z) and cur_Z.dim() == 4 and cur_Z.size(2) == 1:
@@ -284,6 +307,7 @@ class SRRaGANModel(BaseModel):
             if first_acc:
                 self.optimizer_G.zero_grad()
                 self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step, self.l_g_gan_grad_step = [], [], [], []
+                self.l_g_latent_grad_step = []
             l_g_total = 0
             if self.cri_pix:
                 l_g_pix = self.cri_pix(self.fake_H, self.var_H)
@@ -296,6 +320,10 @@ class SRRaGANModel(BaseModel):
             if self.cri_range:
                 l_g_range = self.cri_range(self.fake_H)
                 l_g_total = l_g_total + self.l_range_w * l_g_range / acc_G
+            if self.cri_latent:   # latent-control loss (:455-461)
+                l_g_latent = self.cri_latent({'SR': self.fake_H, 'HR': self.var_H, 'Z': static_Z}).mean(0)
+                l_g_total = l_g_total + self.l_latent_w * l_g_latent.mean() / acc_G
+                self.l_g_latent_grad_step.append([v.item() for v in l_g_latent])
             if self.D_exists:   # G gan loss (:466-479)
                 pred_g_fake = self.netD(self.fake_H)
                 if self.relativistic_D:
@@ -326,6 +354,9 @@ class SRRaGANModel(BaseModel):
                     self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
                 if self.cri_gan:
                     self.log_dict['l_g_gan'].append((self.gradient_step_num, np.mean(self.l_g_gan_grad_step)))
+                if self.cri_latent:
+                    for ch in range(self.num_latent_channels):
+                        self.log_dict['l_g_latent_%d' % ch].append((self.gradient_step_num, np.mean([v[ch] for v in self.l_g_latent_grad_step])))
         self.step += 1
 
     def test(self, prevent_grads_calc=True, **kwargs):

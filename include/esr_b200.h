@@ -280,6 +280,18 @@ int esr_linear_fwd(const float* x, const float* weight, const float* bias, int b
 int esr_linear_bwd(const float* g, const float* act, float slope, const float* x, const float* weight, int batch, int in_features,
                    int out_features, float gscale, int accumulate, float* gx, float* dweight, float* dbias, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Latent-control loss L_struct (models/modules/loss.py:27-209, FilterLoss with structure-tensor latent channels; used at
+ * SRRaGAN_model.py:455-460).  The reference applies two 2x2 depth-wise finite-difference filters (:51-62), squares /
+ * multiplies their outputs and averages per image (:140-147).  One pass here:
+ *   out[n] = (mean dx^2, mean dy^2, mean dx*dy),  dx = x[i][j+1]-x[i][j], dy = x[i+1][j]-x[i][j], over c x (h-1) x (w-1)
+ *   bwd: gradient of sum_k g[n][k]*out[n][k] with respect to the image (NCHW fp32, same shape).
+ * ---------------------------------------------------------------------------------------------- */
+size_t esr_structure_tensor_workspace_bytes(int n);
+int esr_structure_tensor_fwd(const float* img, int n, int c, int h, int w, float* out, float* workspace, size_t workspace_bytes,
+                             void* stream);
+int esr_structure_tensor_bwd(const float* img, const float* g, int n, int c, int h, int w, float* grad_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,3 +218,31 @@ def relativistic_d_loss(pred_real, pred_fake):
 def relativistic_g_loss(pred_real, pred_fake):
     """generator's GAN term (models/SRRaGAN_model.py:475-476), before the gan_weight factor; pred_real is detached there"""
     return (gan_loss_vanilla(pred_real - pred_fake.mean(), False) + gan_loss_vanilla(pred_fake - pred_real.mean(), True)) / 2
+
+
+# ---- latent-control loss L_struct -------------------------------------------------------------------------------------------------
+def structure_tensor_means(img):
+    """per-image means of (Ix^2, Iy^2, Ix*Iy) with the 2x2 depth-wise filters [[-1,1],[0,0]] and [[-1,0],[1,0]] applied without
+    padding (models/modules/loss.py:51-62, 140-147): Ix = x[i][j+1]-x[i][j], Iy = x[i+1][j]-x[i][j] on the (H-1)x(W-1) grid"""
+    ix = (img[:, :, :, 1:] - img[:, :, :, :-1])[:, :, :-1, :]
+    iy = (img[:, :, 1:, :] - img[:, :, :-1, :])[:, :, :, :-1]
+    return torch.stack([(ix ** 2).mean(dim=(1, 2, 3)), (iy ** 2).mean(dim=(1, 2, 3)), (ix * iy).mean(dim=(1, 2, 3))], 1)
+
+
+def filter_loss_structure_tensor(sr, hr, z, history, latent_channels='SVDinNormedOut_structure_tensor', noise_std=1 / 255):
+    """FilterLoss.forward in model-training mode for the structure-tensor descriptors (loss.py:133-178,208): measured values
+    normalised by the ground truth's structure tensor, targets = spatial mean of Z mapped onto the running 5-95 percentile
+    range of everything measured so far (`history`: one list per channel, extended in place); returns |measured - target| [B,3]"""
+    cur_z = z.mean(dim=(2, 3))
+    d_sr, d_hr = structure_tensor_means(sr), structure_tensor_means(hr)
+    if latent_channels == 'SVDinNormedOut_structure_tensor':
+        norm = torch.sqrt(d_hr[:, 0]) * torch.sqrt(d_hr[:, 1])
+        measured = [d_sr[:, i] / (norm + noise_std) for i in range(3)]
+    else:
+        measured = [d_sr[:, i] / (d_hr[:, i] + torch.sign(d_sr[:, i]) * noise_std) if i < 2 else d_sr[:, i] for i in range(3)]
+    target = []
+    for i in range(3):
+        history[i] += [v.item() for v in measured[i]]
+        ub, lb = np.percentile(history[i], 95), np.percentile(history[i], 5)
+        target.append(cur_z[:, i] / 2 * (ub - lb) + np.mean([ub, lb]))
+    return (torch.stack(measured, 1) - torch.stack(target, 1)).abs()
