@@ -362,12 +362,62 @@ def main():
         except Exception as e:  # the forward numbers above stay valid
             train = {'error': repr(e)[:300]}
 
+    # full SRRaGAN step at the per-GPU shape of BASELINE config 3 (batch 4 of 52x52 LR, 208x208 HR patches, 128x128 critic crops):
+    # D step (Discriminator_VGG_128, relativistic loss, Adam) + G step (pixel + VGG-feature + relativistic GAN loss, Adam), through
+    # create_model / feed_data (host tensors) / optimize_parameters, gradients all-reduced over the ranks.  Extra key.
+    gan = None
+    if not args.no_train:
+        try:
+            import contextlib, io
+            from models import create_model
+
+            class ND(dict):
+                def __missing__(self, k):
+                    return None
+            tr = ND(pixel_weight=1e-2, pixel_criterion='l1', feature_weight=1.0, feature_criterion='l1', gan_type='vanilla', gan_weight=5e-3,
+                    lr_G=1e-4, beta1_G=0.9, weight_decay_G=0, lr_D=1e-4, beta1_D=0.9, weight_decay_D=0, D_update_ratio=1, D_init_iters=0,
+                    lr_scheme='MultiStepLR', lr_steps=[100000], lr_gamma=0.5, grad_accumulation_steps_G=1, grad_accumulation_steps_D=1)
+            o3 = ND(model='srragan', scale=4, gpu_ids=[local], is_train=True, range=[0, 1], train=tr, datasets=ND(train=ND(patch_size=208, batch_size=4)),
+                    path=ND(models='/tmp/esr_bench_c3/models', pretrained_model_G=None, log='/tmp/esr_bench_c3'),
+                    network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None,
+                                 norm_type=None, mode='CNA', nf=NF, nb=NB, in_nc=3, out_nc=3, gc=32, scale=4),
+                    network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=64, in_nc=3))
+            with contextlib.redirect_stdout(io.StringIO()):
+                m3 = create_model(o3)
+            lr3, hr3 = torch.rand(4, 3, 52, 52, generator=gen), torch.rand(4, 3, 208, 208, generator=gen)
+
+            def step_gan():
+                m3.feed_data({'LR': lr3, 'HR': hr3})
+                m3.optimize_parameters()
+            for _ in range(3):
+                step_gan()
+            barrier()
+            l0 = lib.launch_count()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                step_gan()
+            g1.record()
+            barrier()
+            ms_gan = g0.elapsed_time(g1) / 5
+            gan = {'ms_per_step': ms_gan, 'gpu_launches_per_step': (lib.launch_count() - l0) // 5, 'steps': 5,
+                   'config': 'C3 per-GPU shape: batch 4 of 52x52 LR -> 208x208, critic on 128x128 crops, bf16 operands, f32 master weights',
+                   'step': 'D step + G step (pixel + VGG-feature + relativistic GAN loss) + gradient all-reduces + two Adam steps',
+                   'l_d_real_fake': float(m3.log_dict['l_d_real_fake'][-1][1]), 'l_g_gan': float(m3.log_dict['l_g_gan'][-1][1])}
+            del m3
+            assert lib.watchdog()[0] == 0, 'pipeline watchdog fired in the GAN step'
+        except Exception as e:
+            gan = {'error': repr(e)[:300]}
+
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0], device=dev)
+        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0,
+                          gan['ms_per_step'] if gan and 'ms_per_step' in gan else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e, conv_ms = [float(v) for v in t[:3]]
         if train and 'ms_per_step' in train:
             train['ms_per_step'] = float(t[3])
+        if gan and 'ms_per_step' in gan:
+            gan['ms_per_step'] = float(t[4])
     mp_step = world * B * (LR * SCALE) ** 2 / 1e6
     if rank == 0:
         pk, pk_src = peaks()
@@ -394,6 +444,11 @@ def main():
                 train['value'] = mp_step / (train['ms_per_step'] * 1e-3)
                 train['unit'] = 'HR-MP/s (fwd+bwd)'
             out['train'] = train
+        if gan is not None:
+            if 'ms_per_step' in gan:
+                gan['value'] = world * 4 * 208 * 208 / 1e6 / (gan['ms_per_step'] * 1e-3)
+                gan['unit'] = 'HR-MP/s (fwd+bwd, D+G)'
+            out['gan_step'] = gan
         if not args.no_cpu_baseline and world == 1:
             out['cpu_baseline'] = cpu_baseline()
         _emit(out_fd, out)
