@@ -72,3 +72,28 @@ def global_mean(local_values, group=None):
     if world() > 1:
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
     return s[0] / s[1]
+
+
+class _GlobalMeanFn(torch.autograd.Function):
+    """differentiable mean over the global batch.  Forward: one 2-scalar all-reduce.  Backward: every rank's loss depends on
+    the mean, so the gradient reaching it is summed over the ranks (one scalar all-reduce) before it is spread over the local
+    values; with rank-mean losses and averaged parameter gradients this reproduces the single-process gradient exactly."""
+
+    @staticmethod
+    def forward(ctx, t):
+        s = torch.stack([t.sum().float(), torch.tensor(float(t.numel()), device=t.device)])
+        if world() > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ctx.n, ctx.shape = float(s[1]), t.shape
+        return s[0] / s[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.clone().float()
+        if world() > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return (g / ctx.n).expand(ctx.shape)
+
+
+def global_mean_autograd(local_values):
+    return _GlobalMeanFn.apply(local_values)

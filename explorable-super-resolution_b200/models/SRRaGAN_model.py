@@ -223,9 +223,7 @@ class SRRaGANModel(BaseModel):
         (SRRaGAN_model.py:353-354,475-476); with one process per GPU that is a 2-scalar all-reduce"""
         if parallel.world() == 1:
             return torch.mean(t)
-        tot = parallel.global_mean(t.detach()) * 1.0
-        n_glob = t.numel() * parallel.world()
-        return tot + (t.sum() - t.detach().sum()) / n_glob
+        return parallel.global_mean_autograd(t)
 
     def optimize_parameters(self):
         """models/SRRaGAN_model.py:280-519: forward through CEM(G) and crop the invalid margins; discriminator step

@@ -32,7 +32,23 @@ def _worker(rank, world, port, q):
     vals = torch.arange(7.0)
     s, e = parallel.shard_batch(7)
     gm = float(parallel.global_mean(vals[s:e]))
-    q.put((rank, err, calls, gm, (a, b), (s, e)))
+    # relativistic critic loss (SRRaGAN_model.py:353-354): means over the GLOBAL batch, differentiable across ranks
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    critic = torch.nn.Linear(12, 1)
+    real, fake = torch.randn(6, 12, generator=torch.Generator().manual_seed(2)), torch.randn(6, 12, generator=torch.Generator().manual_seed(3))
+
+    def rel_loss(pr, pf, mean):
+        return (F.binary_cross_entropy_with_logits(pr - mean(pf), torch.ones_like(pr)) +
+                F.binary_cross_entropy_with_logits(pf - mean(pr), torch.zeros_like(pf))) / 2
+    rel_loss(critic(real[a:b]), critic(fake[a:b]), parallel.global_mean_autograd).backward()
+    parallel.average_gradients(list(critic.parameters()))
+    got_c = [p.grad.clone() for p in critic.parameters()]
+    ref_c = torch.nn.Linear(12, 1)
+    ref_c.load_state_dict(critic.state_dict())
+    rel_loss(ref_c(real), ref_c(fake), torch.mean).backward()
+    err_rel = max(float((g - p.grad).abs().max()) for g, p in zip(got_c, ref_c.parameters()))
+    q.put((rank, max(err, err_rel), calls, gm, (a, b), (s, e)))
     dist.barrier()
     dist.destroy_process_group()
 
