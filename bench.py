@@ -329,6 +329,7 @@ def main():
     train = None
     if not args.no_train:
         try:
+            print('[bench] train leg', file=sys.stderr, flush=True)
             from esr_b200 import parallel
             params = [p_ for n_, p_ in model.named_parameters() if 'Filter_OP' not in n_]
             for p_ in params:
@@ -362,12 +363,22 @@ def main():
         except Exception as e:  # the forward numbers above stay valid
             train = {'error': repr(e)[:300]}
 
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, conv_ms = [float(v) for v in t[:3]]
+        if train and 'ms_per_step' in train:
+            train['ms_per_step'] = float(t[3])
+    # everything the JSON line needs from the device is now in host floats; the CPU baseline and the extra GAN-step leg run after
+    cpu_base = cpu_baseline() if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
     # full SRRaGAN step at the per-GPU shape of BASELINE config 3 (batch 4 of 52x52 LR, 208x208 HR patches, 128x128 critic crops):
     # D step (Discriminator_VGG_128, relativistic loss, Adam) + G step (pixel + VGG-feature + relativistic GAN loss, Adam), through
     # create_model / feed_data (host tensors) / optimize_parameters, gradients all-reduced over the ranks.  Extra key.
     gan = None
     if not args.no_train:
         try:
+            torch.cuda.synchronize()       # an asynchronous fault of an earlier leg surfaces here, not inside this one
+            print('[bench] gan_step leg', file=sys.stderr, flush=True)
             import contextlib, io
             from models import create_model
 
@@ -400,6 +411,10 @@ def main():
             g1.record()
             barrier()
             ms_gan = g0.elapsed_time(g1) / 5
+            if world > 1:
+                tg = torch.tensor([ms_gan], device=dev)
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+                ms_gan = float(tg[0])
             gan = {'ms_per_step': ms_gan, 'gpu_launches_per_step': (lib.launch_count() - l0) // 5, 'steps': 5,
                    'config': 'C3 per-GPU shape: batch 4 of 52x52 LR -> 208x208, critic on 128x128 crops, bf16 operands, f32 master weights',
                    'step': 'D step + G step (pixel + VGG-feature + relativistic GAN loss) + gradient all-reduces + two Adam steps',
@@ -409,15 +424,6 @@ def main():
         except Exception as e:
             gan = {'error': repr(e)[:300]}
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0,
-                          gan['ms_per_step'] if gan and 'ms_per_step' in gan else 0.0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, conv_ms = [float(v) for v in t[:3]]
-        if train and 'ms_per_step' in train:
-            train['ms_per_step'] = float(t[3])
-        if gan and 'ms_per_step' in gan:
-            gan['ms_per_step'] = float(t[4])
     mp_step = world * B * (LR * SCALE) ** 2 / 1e6
     if rank == 0:
         pk, pk_src = peaks()
@@ -449,8 +455,8 @@ def main():
                 gan['value'] = world * 4 * 208 * 208 / 1e6 / (gan['ms_per_step'] * 1e-3)
                 gan['unit'] = 'HR-MP/s (fwd+bwd, D+G)'
             out['gan_step'] = gan
-        if not args.no_cpu_baseline and world == 1:
-            out['cpu_baseline'] = cpu_baseline()
+        if cpu_base is not None:
+            out['cpu_baseline'] = cpu_base
         _emit(out_fd, out)
     if world > 1:
         dist.destroy_process_group()
