@@ -466,6 +466,23 @@ int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int le
   return ESR_OK;
 }
 
+int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* stream, int* failed_index) {
+  if (!items || count < 0) return fail(ESR_ERR_INVALID, "pack batch: bad arguments");
+  for (int i = 0; i < count; ++i) {
+    const esr_pack_item* it = items + i;
+    int rc = esr_pack_conv3x3_weights(it->w_oihw, it->cout, it->cin, it->lead, it->kcp, it->dtype, it->transpose_flip, it->wpacked,
+                                      it->bias_out, it->bias_in, stream);
+    if (rc == ESR_OK && it->wpacked_rows)
+      rc = esr_pack_conv3x3_weights_rows(it->w_oihw, it->cout, it->cin, it->lead, it->dtype, it->transpose_flip, it->rows_nbn,
+                                         it->wpacked_rows, stream);
+    if (rc != ESR_OK) {
+      if (failed_index) *failed_index = i;
+      return rc;
+    }
+  }
+  return ESR_OK;
+}
+
 size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout) {
   WgradPlan w;
   if (!wgrad_plan(cin_planes, cout, &w)) return 0;

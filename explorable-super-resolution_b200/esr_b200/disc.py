@@ -102,13 +102,16 @@ class DiscEngine:
     def _packed(self):
         ver = tuple((L.conv.weight._version, L.conv.weight.data_ptr(), L.conv.bias._version) for L in self.layers)
         if ver != self._ver:
-            self._pk, self._pkt = [], []
-            for L in self.layers:
-                w = L.conv.weight.detach().float()
-                if L.k4:
-                    w = k4s2_to_3x3(w)
-                self._pk.append(ops.PackedConv(w, L.conv.bias, dtype=self.dtype))
-                self._pkt.append(ops.PackedConv(w, None, dtype=self.dtype, transpose_flip=True))
+            q = []
+            ws = [k4s2_to_3x3(L.conv.weight.detach().float()) if L.k4 else L.conv.weight.detach().float() for L in self.layers]
+            if self._pk is None or self._pk[0].wpacked.device != ws[0].device:
+                self._pk = [ops.PackedConv(w, L.conv.bias, dtype=self.dtype, queue=q) for w, L in zip(ws, self.layers)]
+                self._pkt = [ops.PackedConv(w, None, dtype=self.dtype, transpose_flip=True, queue=q) for w in ws]
+            else:       # after an optimizer step: same buffers, every conv re-packed by one host call
+                for pc, pct, w, L in zip(self._pk, self._pkt, ws, self.layers):
+                    pc.repack(w, L.conv.bias, q)
+                    pct.repack(w, None, q)
+            ops.run_pack_queue(q)
             self._ver = ver
         return self._pk, self._pkt
 

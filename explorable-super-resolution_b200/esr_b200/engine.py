@@ -64,6 +64,8 @@ class RRDBEngine:
         self._packed = None
         self._packed_t = None
         self._packed_version = None
+        self._packed_bd = None
+        self._stale = {'p': False, 't': False, 'bd': False}
         self._bufs = {}
         self._plans = {}
 
@@ -89,24 +91,47 @@ class RRDBEngine:
         convs = self._convs()
         ver = _param_version(convs)
         if ver != self._packed_version:
-            self._packed, self._packed_t, self._packed_version = None, None, ver
+            # the packed buffers persist (recorded launch plans keep pointing at them): they are refreshed in place, every conv
+            # of the network in one host call, the next time they are asked for
+            self._packed_version = ver
+            self._stale = {'p': True, 't': True, 'bd': True}
         return convs
+
+    def _refresh(self, kind, existing, build, sources):
+        """existing packed objects (flat list, None entries allowed) refreshed in place from `sources` [(weight, bias)], or built
+        by `build(queue)` the first time / after the parameters moved to another device"""
+        q = []
+        flat = [pc for pc in (existing or []) if pc is not None]
+        dev = next(w for w, _ in sources if w is not None).device
+        if not flat or flat[0].wpacked.device != dev:
+            existing = build(q)
+        elif self._stale[kind]:
+            for pc, (w, b) in zip(existing, sources):
+                if pc is not None:
+                    pc.repack(w, b, q)
+        ops.run_pack_queue(q)
+        self._stale[kind] = False
+        return existing
 
     def packed(self):
         convs = self._check_version()
-        if self._packed is None:
-            self._packed = [ops.PackedConv(c.weight, c.bias, dtype=self.dtype, lead=l) for c, l in zip(convs, self._leads(convs))]
+        leads = self._leads(convs)
+        self._packed = self._refresh('p', self._packed,
+                                     lambda q: [ops.PackedConv(c.weight, c.bias, dtype=self.dtype, lead=l, queue=q) for c, l in zip(convs, leads)],
+                                     [(c.weight, c.bias) for c in convs])
         return self._packed
 
     def packed_t(self):
         """dgrad operands of the convs OUTSIDE the dense blocks: I/O swapped, taps rotated by 180 degrees, no bias
         (the dense blocks use `packed_bwd_dense`)"""
         convs = self._check_version()
-        if self._packed_t is None:
-            nb = len(self.net.model[1].sub) - 1
-            inside = lambda i: 1 <= i <= 15 * nb
-            self._packed_t = [None if inside(i) else ops.PackedConv(c.weight, None, dtype=self.dtype, lead=l, transpose_flip=True)
-                              for i, (c, l) in enumerate(zip(convs, self._leads(convs)))]
+        leads = self._leads(convs)
+        nb = len(self.net.model[1].sub) - 1
+        inside = lambda i: 1 <= i <= 15 * nb
+        self._packed_t = self._refresh('t', self._packed_t,
+                                       lambda q: [None if inside(i) else ops.PackedConv(c.weight, None, dtype=self.dtype, lead=l, transpose_flip=True, queue=q)
+                                                  for i, (c, l) in enumerate(zip(convs, leads))],
+                                       [(c.weight, None) for c in convs])
         return self._packed_t
 
     def packed_bwd_dense(self):
@@ -122,7 +147,7 @@ class RRDBEngine:
         an RRDB) is folded into the W_5 rows.  Returns [block][i] -> PackedConv, i = 0 (g_x [+ latent rows in front, padded
         to one plane]) .. 4, blocks in forward order.  Built with a handful of batched tensor ops over all blocks."""
         convs = self._check_version()
-        if getattr(self, '_packed_bd', None) is not None and self._packed_bd_version == self._packed_version:
+        if self._packed_bd is not None and not self._stale['bd'] and self._packed_bd[0][0].wpacked.device == convs[0].weight.device:
             return self._packed_bd
         net = self.net
         z, nf, gc = net.z_lead, net.nf, net.gc
@@ -132,8 +157,12 @@ class RRDBEngine:
             W = [torch.stack([convs[1 + r * 5 + jj].weight.detach().float() for r in range(R)]) for jj in range(5)]  # [R, cout_j, cin_j, 3, 3]
             a5 = torch.tensor([0.04 if r % 3 == 2 else 0.2 for r in range(R)], device=W[0].device)
             combined = combine_dense_backward_weights(W, a5, z, nf, gc)
-            out = [[ops.PackedConv(combined[i][r], None, dtype=self.dtype) for i in range(5)] for r in range(R)]
-        self._packed_bd, self._packed_bd_version = out, self._packed_version
+            flat_old = [pc for row in self._packed_bd for pc in row] if self._packed_bd is not None else None
+            flat = self._refresh('bd', flat_old,
+                                 lambda q: [ops.PackedConv(combined[i][r], None, dtype=self.dtype, queue=q) for r in range(R) for i in range(5)],
+                                 [(combined[i][r], None) for r in range(R) for i in range(5)])
+            out = [flat[r * 5:(r + 1) * 5] for r in range(R)]
+        self._packed_bd = out
         return out
 
     # ---------------------------------------------------------------- buffers
@@ -274,11 +303,11 @@ class RRDBEngine:
             # host call; only the output image is new
             key = (n, h, w, str(dev), bool(save))
             plan = self._plans.get(key)
-            if plan is None or plan.version != self._packed_version or plan.bufs is not B or plan.pk is not pk:
+            if plan is None or plan.bufs is not B or plan.pk is not pk:   # weights are re-packed in place: the plan survives
                 rec = []
                 self._conv_sequence(B, pk, save, out, rec)
                 plan = ops.LaunchPlan(rec)
-                plan.version, plan.bufs, plan.pk = self._packed_version, B, pk
+                plan.bufs, plan.pk = B, pk
                 if len(self._plans) >= 2:
                     self._plans.pop(next(iter(self._plans)))
                 self._plans[key] = plan

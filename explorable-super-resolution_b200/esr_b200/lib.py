@@ -51,6 +51,13 @@ class WgradArgs(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    """mirror of esr_pack_item"""
+    _fields_ = [("w", C.c_void_p), ("cout", C.c_int), ("cin", C.c_int), ("lead", C.c_int), ("kcp", C.c_int), ("dtype", C.c_int),
+                ("transpose_flip", C.c_int), ("wpacked", C.c_void_p), ("bias_out", C.c_void_p), ("bias_in", C.c_void_p),
+                ("wpacked_rows", C.c_void_p), ("rows_nbn", C.c_int)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     "esr_last_error": (C.c_char_p, []),
@@ -64,6 +71,7 @@ SIGNATURES = {
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
     "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_pack_conv3x3_weights_batch": (C.c_int, [C.POINTER(PackItem), C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "esr_conv3x3_rows_config": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_conv3x3_wgrad_workspace": (C.c_size_t, [C.c_int, C.c_int]),

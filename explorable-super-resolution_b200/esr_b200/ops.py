@@ -35,44 +35,85 @@ def device_check():
     L.check(L.load().esr_device_check())
 
 
-class PackedConv:
-    """Tensor-core image of one 3x3 conv's weights (+ padded fp32 bias).  `lead` = latent channels in front."""
+_cfg_cache = {}
 
-    def __init__(self, weight, bias, dtype=torch.float16, lead=0, transpose_flip=False, kcp=None, rows=True):
+
+def _pack_config(cin_planes, cout, kcp, want_rows):
+    """(packed bytes, cout_pad, row-image n-block, row-image bytes) - pure functions of the shape, memoised"""
+    key = (cin_planes, cout, kcp, want_rows)
+    if key not in _cfg_cache:
         lib = L.load()
+        cp = C.c_int(0)
+        nbytes = int(lib.esr_conv3x3_packed_bytes(cin_planes, cout, kcp, C.byref(cp)))
+        nbn, nb = C.c_int(0), C.c_size_t(0)
+        ok = want_rows and lib.esr_conv3x3_rows_config(cin_planes, cout, C.byref(nbn), C.byref(nb)) == 0
+        _cfg_cache[key] = (nbytes, cp.value, nbn.value if ok else 0, nb.value if ok else 0)
+    return _cfg_cache[key]
+
+
+def run_pack_queue(queue):
+    """launch every queued weight re-packing with ONE host call (esr_pack_conv3x3_weights_batch)"""
+    if not queue:
+        return
+    arr = (L.PackItem * len(queue))(*[q[0] for q in queue])
+    failed = C.c_int(-1)
+    rc = L.load().esr_pack_conv3x3_weights_batch(arr, len(queue), _stream(), C.byref(failed))
+    if rc != 0:
+        raise L.EsrError('esr_b200 error %d packing conv %d: %s' % (rc, failed.value, L.load().esr_last_error().decode()))
+    del queue[:]
+
+
+class PackedConv:
+    """Tensor-core image of one 3x3 conv's weights (+ padded fp32 bias).  `lead` = latent channels in front.  The buffers are
+    allocated once; `repack` refreshes them in place after an optimizer step (recorded launch arguments stay valid).  With
+    `queue` (a list) the packing launches are deferred to `run_pack_queue`."""
+
+    def __init__(self, weight, bias, dtype=torch.float16, lead=0, transpose_flip=False, kcp=None, rows=True, queue=None):
         require_cuda(weight, bias)
-        weight = weight.detach().float().contiguous()
         cout, cin = int(weight.shape[0]), int(weight.shape[1])
         assert tuple(weight.shape[2:]) == (3, 3), "only 3x3 kernels"
         self.dtype = dtype
         self.esr_dtype = _TORCH2ESR[dtype]
         self.lead = lead
+        self.transpose_flip = bool(transpose_flip)
+        self._w_shape = (cout, cin, 3, 3)
+        lead_planes = (lead + 7) // 8 + (cin - lead + 7) // 8     # esr_conv3x3_cin_planes
         if transpose_flip:
             # dgrad: outputs are the forward inputs in plane space ([latent plane | rest]), inputs the forward outputs
-            self.cout, self.cin = int(lib.esr_conv3x3_cin_planes(cin, lead)) * 8, cout
+            self.cout, self.cin = lead_planes * 8, cout
             self.cin_planes = (cout + 7) // 8
         else:
             self.cout, self.cin = cout, cin
-            self.cin_planes = int(lib.esr_conv3x3_cin_planes(cin, lead))
+            self.cin_planes = lead_planes
         if kcp is None:
             kcp = 4 if self.cin_planes >= 4 else 2
         self.kcp = kcp
-        cp = C.c_int(0)
-        nbytes = int(lib.esr_conv3x3_packed_bytes(self.cin_planes, self.cout, kcp, C.byref(cp)))
-        self.cout_pad = cp.value
+        nbytes, self.cout_pad, self.rows_nbn, rows_bytes = _pack_config(self.cin_planes, self.cout, kcp, bool(rows))
         self.wpacked = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
         self.bias = torch.empty(self.cout_pad, dtype=torch.float32, device=weight.device)
-        b = bias.detach().float().contiguous() if (bias is not None and not transpose_flip) else None
-        L.check(lib.esr_pack_conv3x3_weights(_ptr(weight), cout, cin, lead, kcp, self.esr_dtype, int(transpose_flip),
-                                             _ptr(self.wpacked), _ptr(self.bias), _ptr(b), _stream()))
         # second image for the row-streaming kernel (used for images wide enough for 128-pixel strips)
-        nbn, nb = C.c_int(0), C.c_size_t(0)
-        self.wrows, self.rows_nbn = None, 0
-        if rows and lib.esr_conv3x3_rows_config(self.cin_planes, self.cout, C.byref(nbn), C.byref(nb)) == 0:
-            self.rows_nbn = nbn.value
-            self.wrows = torch.empty(nb.value, dtype=torch.uint8, device=weight.device)
-            L.check(lib.esr_pack_conv3x3_weights_rows(_ptr(weight), cout, cin, lead, self.esr_dtype, int(transpose_flip),
-                                                      self.rows_nbn, _ptr(self.wrows), _stream()))
+        self.wrows = torch.empty(rows_bytes, dtype=torch.uint8, device=weight.device) if self.rows_nbn else None
+        self._enqueue(weight, bias, queue)
+
+    def _enqueue(self, weight, bias, queue):
+        weight = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if (bias is not None and not self.transpose_flip) else None
+        it = L.PackItem()
+        it.w, it.cout, it.cin, it.lead, it.kcp = weight.data_ptr(), self._w_shape[0], self._w_shape[1], self.lead, self.kcp
+        it.dtype, it.transpose_flip = self.esr_dtype, int(self.transpose_flip)
+        it.wpacked, it.bias_out, it.bias_in = self.wpacked.data_ptr(), self.bias.data_ptr(), (b.data_ptr() if b is not None else None)
+        it.wpacked_rows, it.rows_nbn = (self.wrows.data_ptr() if self.wrows is not None else None), self.rows_nbn
+        entry = (it, weight, b)          # the fp32 sources stay referenced until the launches are issued
+        if queue is None:
+            run_pack_queue([entry])
+        else:
+            queue.append(entry)
+
+    def repack(self, weight, bias, queue=None):
+        """refresh the packed images in place from new weight values (same shape, same device)"""
+        require_cuda(weight, bias)
+        assert tuple(weight.shape) == self._w_shape and weight.device == self.wpacked.device
+        self._enqueue(weight, bias, queue)
 
 
 def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2, alpha=1.0,
@@ -146,6 +187,18 @@ class LaunchPlan:
 
 
 _wgrad_ws = {}
+_wgrad_ws_size = {}
+
+
+def _cin_planes(cin, lead):
+    return (lead + 7) // 8 + (cin - lead + 7) // 8     # esr_conv3x3_cin_planes
+
+
+def _wgrad_ws_bytes(cp, cout):
+    key = (cp, cout)
+    if key not in _wgrad_ws_size:
+        _wgrad_ws_size[key] = int(L.load().esr_conv3x3_wgrad_workspace(cp, cout))
+    return _wgrad_ws_size[key]
 
 
 def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, db=None, scale=1.0, accumulate=False):
@@ -163,7 +216,7 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
     assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3) and db.dtype == torch.float32
     # wide convs are covered in input-channel slices of at most 208 channels (5 M chunks of (row, plane) groups)
-    cp_all = int(lib.esr_conv3x3_cin_planes(cin, lead))
+    cp_all = _cin_planes(cin, lead)
     if cp_all <= 26:
         slices = [(0, cin, lead, x_off)]
     else:
@@ -172,8 +225,8 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
         slices = [(c0, min(192, cin - c0), 0, x_off + c0 // 8) for c0 in range(0, cin, 192)]
     key = (str(dev), torch.cuda.current_stream().cuda_stream)
     for si, (c0, cs, ld, xo) in enumerate(slices):
-        cp = int(lib.esr_conv3x3_cin_planes(cs, ld))
-        nbytes = int(lib.esr_conv3x3_wgrad_workspace(cp, cout))
+        cp = _cin_planes(cs, ld)
+        nbytes = _wgrad_ws_bytes(cp, cout)
         if nbytes == 0:
             raise L.EsrError('conv3x3_wgrad: (cin %d, cout %d) is not supported by the tensor-core tiling' % (cs, cout))
         ws = _wgrad_ws.get(key)

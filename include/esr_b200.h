@@ -246,6 +246,16 @@ int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, in
 /* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
 
+/* Re-packing after an optimizer step: every conv of a network in ONE host call (the same two kernels per item as
+ * esr_pack_conv3x3_weights / esr_pack_conv3x3_weights_rows; wpacked_rows == NULL skips the row-kernel image).  The packed
+ * buffers are caller-owned and can be re-used in place across steps, so recorded launch arguments stay valid. */
+typedef struct {
+  const float* w_oihw; int cout, cin, lead, kcp, dtype, transpose_flip;
+  void* wpacked; float* bias_out; const float* bias_in;
+  void* wpacked_rows; int rows_nbn;
+} esr_pack_item;
+int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* stream, int* failed_index);
+
 /* ------------------------------------------------------------------------------------------------
  * Discriminator_VGG_128 (models/modules/architecture.py:446-508; D step SRRaGAN_model.py:342-395, G-side GAN term :466-477).
  * Its 3x3 convolutions are esr_conv3x3_fwd launches; a 4x4 stride-2 pad-1 convolution (block.py:129-146 with kernel_size=4,

@@ -38,10 +38,14 @@ def d2s_nchw(x):
 
 class PackedConv:
     def __init__(self, weight, bias, dtype=torch.float32, lead=0, transpose_flip=False, **kw):
-        self.w = weight.detach().to(dtype).float()     # operand rounding of the tensor-core image, fp32 accumulation
-        self.b = None if (bias is None or transpose_flip) else bias.detach().float()
         self.t = transpose_flip
         self.dtype = dtype
+        self.wpacked = weight          # only its .device is looked at
+        self.repack(weight, bias)
+
+    def repack(self, weight, bias, queue=None):
+        self.w = weight.detach().to(self.dtype).float()     # operand rounding of the tensor-core image, fp32 accumulation
+        self.b = None if (bias is None or self.t) else bias.detach().float()
 
 
 def conv3x3(x16, pc, *, out32=None, out_nchw=None, **kw):
@@ -138,6 +142,7 @@ def conv3x3_wgrad(x16, gy16, cout, cin, **kw):
 
 def install(monkeypatch):
     from esr_b200 import ops
+    monkeypatch.setattr(ops, 'run_pack_queue', lambda q: None)
     for name in ('PackedConv', 'conv3x3', 'pack_nchw', 'bn_stats', 'bn_lrelu_fwd', 'bn_lrelu_bwd', 'linear_fwd', 'linear_bwd', 'conv3x3_wgrad'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'require_cuda', lambda *a: None)
