@@ -308,37 +308,65 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
 // ---------------------------------------------------------------------------------------------
 // weight packing for the row kernel: OIHW fp32 -> [n_block][chunk][dx][plane-in-chunk (4)][ky*NBN + co][8 cin] 16-bit
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_rows_kernel(const float* __restrict__ w, int cout, int cin, int lead, int nb_n, int nchunks, int dtype,
-                                         int transpose_flip, uint16_t* __restrict__ dst, size_t total) {
+__device__ __forceinline__ uint16_t pack_weights_rows_elem(const float* __restrict__ w, int cout, int cin, int lead, int nb_n, int nchunks, int dtype,
+                                                           int transpose_flip, size_t idx) {
   const int lc_out = transpose_flip ? cin : cout;
   const int lc_in = transpose_flip ? cout : cin;
   const int lead_pad = (lead + 7) / 8 * 8;
   const int n3 = 3 * nb_n;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    size_t r = idx;
-    const int ci8 = r % 8; r /= 8;
-    const int nn = r % n3; r /= n3;
-    const int j = r % kRowsKch; r /= kRowsKch;
-    const int dx = r % 3; r /= 3;
-    const int c = r % nchunks; r /= nchunks;
-    const int nb = (int)r;
-    const int ky = nn / nb_n;
-    int o = nb * nb_n + (nn - ky * nb_n);
-    int i = (c * kRowsKch + j) * 8 + ci8;
-    if (!transpose_flip) {
-      if (i < lead_pad) i = i < lead ? i : -1;
-      else i = i - lead_pad + lead;
+  size_t r = idx;
+  const int ci8 = r % 8; r /= 8;
+  const int nn = r % n3; r /= n3;
+  const int j = r % kRowsKch; r /= kRowsKch;
+  const int dx = r % 3; r /= 3;
+  const int c = r % nchunks; r /= nchunks;
+  const int nb = (int)r;
+  const int ky = nn / nb_n;
+  int o = nb * nb_n + (nn - ky * nb_n);
+  int i = (c * kRowsKch + j) * 8 + ci8;
+  if (!transpose_flip) {
+    if (i < lead_pad) i = i < lead ? i : -1;
+    else i = i - lead_pad + lead;
+  } else {
+    if (o < lead_pad) o = o < lead ? o : -1;
+    else o = o - lead_pad + lead;
+  }
+  float val = 0.f;
+  if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
+    if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + dx];
+    else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - dx)];
+  }
+  return (uint16_t)(pack2(val, 0.f, dtype) & 0xFFFFu);
+}
+
+__global__ void pack_weights_rows_kernel(const float* __restrict__ w, int cout, int cin, int lead, int nb_n, int nchunks, int dtype,
+                                         int transpose_flip, uint16_t* __restrict__ dst, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    dst[idx] = pack_weights_rows_elem(w, cout, cin, lead, nb_n, nchunks, dtype, transpose_flip, idx);
+}
+
+// Every conv of a network re-packed by ONE launch (after an optimizer step): blockIdx.y = conv, the job table lives in device
+// memory.  Per job: the tile-kernel image, the row-kernel image (optional) and the zero-padded fp32 bias.
+struct PackJob {
+  const float* w; int cout, cin, lead, kcp, nb_n, nchunks, dtype, transpose_flip;
+  uint16_t* dst; unsigned long long total;
+  int rows_nb_n, rows_nchunks; uint16_t* rows_dst; unsigned long long rows_total;
+  float* bias_out; const float* bias_in; int cout_pad, bias_n;
+};
+
+__global__ void pack_weights_batch_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob jb = jobs[blockIdx.y];
+  const size_t all = (size_t)jb.total + (size_t)jb.rows_total + (size_t)jb.cout_pad;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < all; idx += (size_t)gridDim.x * blockDim.x) {
+    if (idx < jb.total) {
+      jb.dst[idx] = pack_weights_elem(jb.w, jb.cout, jb.cin, jb.lead, jb.kcp, jb.nb_n, jb.nchunks, jb.dtype, jb.transpose_flip, idx);
+    } else if (idx < jb.total + jb.rows_total) {
+      const size_t k = idx - jb.total;
+      jb.rows_dst[k] = pack_weights_rows_elem(jb.w, jb.cout, jb.cin, jb.lead, jb.rows_nb_n, jb.rows_nchunks, jb.dtype, jb.transpose_flip, k);
     } else {
-      if (o < lead_pad) o = o < lead ? o : -1;
-      else o = o - lead_pad + lead;
+      const int k = (int)(idx - jb.total - jb.rows_total);
+      jb.bias_out[k] = (jb.bias_in && k < jb.bias_n) ? jb.bias_in[k] : 0.f;
     }
-    float val = 0.f;
-    if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
-      if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + dx];
-      else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - dx)];
-    }
-    const uint32_t pk = pack2(val, 0.f, dtype);
-    dst[idx] = (uint16_t)(pk & 0xFFFFu);
   }
 }
 

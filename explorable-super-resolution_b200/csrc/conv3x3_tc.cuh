@@ -592,41 +592,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // weight packing: OIHW fp32 -> [n_block][chunk][tap][plane-in-chunk][cout-in-block][8 cin] 16-bit
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int lead, int kcp, int nb_n, int n_blocks,
-                                    int nchunks, int dtype, int transpose_flip, uint16_t* __restrict__ dst,
-                                    size_t total) {
+// one element of the packed image (shared by the per-conv kernel and the batched one)
+__device__ __forceinline__ uint16_t pack_weights_elem(const float* __restrict__ w, int cout, int cin, int lead, int kcp, int nb_n, int nchunks,
+                                                      int dtype, int transpose_flip, size_t idx) {
   // logical conv: out channels = (transpose_flip ? cin : cout) of the source tensor
   const int lc_out = transpose_flip ? cin : cout;
   const int lc_in = transpose_flip ? cout : cin;
   const int lead_pad = (lead + 7) / 8 * 8;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    size_t r = idx;
-    const int ci8 = r % 8; r /= 8;
-    const int n = r % nb_n; r /= nb_n;
-    const int j = r % kcp; r /= kcp;
-    const int tap = r % 9; r /= 9;
-    const int c = r % nchunks; r /= nchunks;
-    const int nb = (int)r;
-    int o = nb * nb_n + n;
-    int i = (c * kcp + j) * 8 + ci8;
-    // channel position in plane space -> source channel: the `lead` latent channels sit in their own zero-padded
-    // plane group in front (forward: on the input side; transpose/dgrad: on the output side)
-    if (!transpose_flip) {
-      if (i < lead_pad) i = i < lead ? i : -1;
-      else i = i - lead_pad + lead;
-    } else {
-      if (o < lead_pad) o = o < lead ? o : -1;
-      else o = o - lead_pad + lead;
-    }
-    float val = 0.f;
-    if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
-      const int ky = tap / 3, kx = tap % 3;
-      if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + kx];
-      else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - kx)];
-    }
-    const uint32_t pk = pack2(val, 0.f, dtype);
-    dst[idx] = (uint16_t)(pk & 0xFFFFu);
+  size_t r = idx;
+  const int ci8 = r % 8; r /= 8;
+  const int n = r % nb_n; r /= nb_n;
+  const int j = r % kcp; r /= kcp;
+  const int tap = r % 9; r /= 9;
+  const int c = r % nchunks; r /= nchunks;
+  const int nb = (int)r;
+  int o = nb * nb_n + n;
+  int i = (c * kcp + j) * 8 + ci8;
+  // channel position in plane space -> source channel: the `lead` latent channels sit in their own zero-padded
+  // plane group in front (forward: on the input side; transpose/dgrad: on the output side)
+  if (!transpose_flip) {
+    if (i < lead_pad) i = i < lead ? i : -1;
+    else i = i - lead_pad + lead;
+  } else {
+    if (o < lead_pad) o = o < lead ? o : -1;
+    else o = o - lead_pad + lead;
   }
+  float val = 0.f;
+  if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
+    const int ky = tap / 3, kx = tap % 3;
+    if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + kx];
+    else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - kx)];
+  }
+  return (uint16_t)(pack2(val, 0.f, dtype) & 0xFFFFu);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int lead, int kcp, int nb_n, int n_blocks,
+                                    int nchunks, int dtype, int transpose_flip, uint16_t* __restrict__ dst,
+                                    size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    dst[idx] = pack_weights_elem(w, cout, cin, lead, kcp, nb_n, nchunks, dtype, transpose_flip, idx);
 }
 
 }  // namespace esr

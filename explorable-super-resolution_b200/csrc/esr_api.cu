@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <set>
+#include <vector>
 
 #include "aux_kernels.cuh"
 #include "conv3x3_tc.cuh"
@@ -466,19 +467,75 @@ int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int le
   return ESR_OK;
 }
 
-int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* stream, int* failed_index) {
+size_t esr_pack_batch_scratch_bytes(int count) { return count > 0 ? (size_t)count * sizeof(esr::PackJob) : 0; }
+
+int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* scratch, size_t scratch_bytes, void* stream,
+                                   int* failed_index) {
   if (!items || count < 0) return fail(ESR_ERR_INVALID, "pack batch: bad arguments");
+  if (count == 0) return ESR_OK;
+  static const bool fused = [] { const char* e = getenv("ESR_PACK_FUSED"); return !(e && e[0] == '0'); }();
+  if (!fused || !scratch || scratch_bytes < esr_pack_batch_scratch_bytes(count)) {
+    // one launch pair per conv (the path single convs use)
+    for (int i = 0; i < count; ++i) {
+      const esr_pack_item* it = items + i;
+      int rc = esr_pack_conv3x3_weights(it->w_oihw, it->cout, it->cin, it->lead, it->kcp, it->dtype, it->transpose_flip, it->wpacked,
+                                        it->bias_out, it->bias_in, stream);
+      if (rc == ESR_OK && it->wpacked_rows)
+        rc = esr_pack_conv3x3_weights_rows(it->w_oihw, it->cout, it->cin, it->lead, it->dtype, it->transpose_flip, it->rows_nbn,
+                                           it->wpacked_rows, stream);
+      if (rc != ESR_OK) {
+        if (failed_index) *failed_index = i;
+        return rc;
+      }
+    }
+    return ESR_OK;
+  }
+  // one launch for all of them: job table -> device scratch, blockIdx.y = conv
+  std::vector<esr::PackJob> jobs((size_t)count);
   for (int i = 0; i < count; ++i) {
     const esr_pack_item* it = items + i;
-    int rc = esr_pack_conv3x3_weights(it->w_oihw, it->cout, it->cin, it->lead, it->kcp, it->dtype, it->transpose_flip, it->wpacked,
-                                      it->bias_out, it->bias_in, stream);
-    if (rc == ESR_OK && it->wpacked_rows)
-      rc = esr_pack_conv3x3_weights_rows(it->w_oihw, it->cout, it->cin, it->lead, it->dtype, it->transpose_flip, it->rows_nbn,
-                                         it->wpacked_rows, stream);
-    if (rc != ESR_OK) {
-      if (failed_index) *failed_index = i;
-      return rc;
+    if (failed_index) *failed_index = i;
+    if (!it->w_oihw || !it->wpacked) return fail(ESR_ERR_INVALID, "pack batch: null pointer in item %d", i);
+    if (it->lead < 0 || it->lead > it->cin) return fail(ESR_ERR_INVALID, "pack batch: bad lead %d in item %d", it->lead, i);
+    if (it->kcp != 2 && it->kcp != 4) return fail(ESR_ERR_INVALID, "pack batch: kcp must be 2 or 4 (item %d)", i);
+    esr::PackJob& jb = jobs[(size_t)i];
+    memset(&jb, 0, sizeof(jb));
+    // same derivation as esr_pack_conv3x3_weights / esr_pack_conv3x3_weights_rows
+    const int lc_out = it->transpose_flip ? it->cin : it->cout;
+    const int lc_in = it->transpose_flip ? it->cout : it->cin;
+    const int lc_out_planespace = it->transpose_flip ? esr_conv3x3_cin_planes(it->cin, it->lead) * 8 : lc_out;
+    int cout_pad = 0;
+    const int nb_n = nblock_for(lc_out_planespace, &cout_pad);
+    const int n_blocks = cout_pad / nb_n;
+    const int cin_planes = it->transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(it->cin, it->lead);
+    const int nchunks = (cin_planes + it->kcp - 1) / it->kcp;
+    jb.w = it->w_oihw; jb.cout = it->cout; jb.cin = it->cin; jb.lead = it->lead; jb.kcp = it->kcp; jb.nb_n = nb_n; jb.nchunks = nchunks;
+    jb.dtype = it->dtype; jb.transpose_flip = it->transpose_flip;
+    jb.dst = (uint16_t*)it->wpacked;
+    jb.total = (unsigned long long)n_blocks * nchunks * 9 * it->kcp * nb_n * 8;
+    if (it->wpacked_rows) {
+      const int nbn = it->rows_nbn;
+      if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "pack batch: row n-block must be 16, 32 or 64 (item %d)", i);
+      const int rows_out = it->transpose_flip ? esr_conv3x3_cin_planes(it->cin, it->lead) * 8 : it->cout;
+      const int rows_chunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+      const int rows_blocks = (rows_out + nbn - 1) / nbn;
+      jb.rows_nb_n = nbn; jb.rows_nchunks = rows_chunks; jb.rows_dst = (uint16_t*)it->wpacked_rows;
+      jb.rows_total = (unsigned long long)rows_blocks * rows_chunks * 3 * esr::kRowsKch * 3 * nbn * 8;
     }
+    if (it->bias_out) {
+      jb.bias_out = it->bias_out; jb.cout_pad = cout_pad;
+      jb.bias_in = it->transpose_flip ? nullptr : it->bias_in;
+      jb.bias_n = it->cout;
+    }
+  }
+  if (failed_index) *failed_index = -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(scratch, jobs.data(), sizeof(esr::PackJob) * (size_t)count, cudaMemcpyHostToDevice, st));
+  for (int i0 = 0; i0 < count; i0 += 65535) {     // gridDim.y limit
+    const int n = count - i0 < 65535 ? count - i0 : 65535;
+    esr::pack_weights_batch_kernel<<<dim3(8, (unsigned)n), 256, 0, st>>>((const esr::PackJob*)scratch + i0);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
   }
   return ESR_OK;
 }

@@ -71,7 +71,8 @@ SIGNATURES = {
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
     "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "esr_pack_conv3x3_weights_batch": (C.c_int, [C.POINTER(PackItem), C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "esr_pack_batch_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "esr_pack_conv3x3_weights_batch": (C.c_int, [C.POINTER(PackItem), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]),
     "esr_conv3x3_rows_config": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_conv3x3_wgrad_workspace": (C.c_size_t, [C.c_int, C.c_int]),

@@ -36,6 +36,7 @@ def device_check():
 
 
 _cfg_cache = {}
+_pack_scratch = {}
 
 
 def _pack_config(cin_planes, cout, kcp, want_rows):
@@ -57,7 +58,15 @@ def run_pack_queue(queue):
         return
     arr = (L.PackItem * len(queue))(*[q[0] for q in queue])
     failed = C.c_int(-1)
-    rc = L.load().esr_pack_conv3x3_weights_batch(arr, len(queue), _stream(), C.byref(failed))
+    lib = L.load()
+    dev = queue[0][1].device
+    need = int(lib.esr_pack_batch_scratch_bytes(len(queue)))
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    scratch = _pack_scratch.get(key)
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        _pack_scratch[key] = scratch
+    rc = lib.esr_pack_conv3x3_weights_batch(arr, len(queue), _ptr(scratch), scratch.numel(), _stream(), C.byref(failed))
     if rc != 0:
         raise L.EsrError('esr_b200 error %d packing conv %d: %s' % (rc, failed.value, L.load().esr_last_error().decode()))
     del queue[:]

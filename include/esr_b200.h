@@ -254,7 +254,11 @@ typedef struct {
   void* wpacked; float* bias_out; const float* bias_in;
   void* wpacked_rows; int rows_nbn;
 } esr_pack_item;
-int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* stream, int* failed_index);
+size_t esr_pack_batch_scratch_bytes(int count);
+/* scratch: caller-owned device memory of esr_pack_batch_scratch_bytes(count) bytes for the job table of the single fused launch
+ * (NULL, or ESR_PACK_FUSED=0 in the environment: one launch pair per conv instead) */
+int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* scratch, size_t scratch_bytes, void* stream,
+                                   int* failed_index);
 
 /* ------------------------------------------------------------------------------------------------
  * Discriminator_VGG_128 (models/modules/architecture.py:446-508; D step SRRaGAN_model.py:342-395, G-side GAN term :466-477).
