@@ -104,21 +104,26 @@ def test_conv3x3_fused_epilogues():
 
 
 def test_upsample_and_pixel_shuffle_stores_are_bit_exact_permutations():
+    """The folded stores are pure index permutations of the plain store.  Two LAUNCHES of the same conv are compared, and the
+    row-streaming kernel's three MMA-issuer warps add their K chunks into one TMEM accumulator in arrival order, so the fp32
+    summation order is not fixed from launch to launch (last-bit differences, rarely a 16-bit rounding tie).  Small-integer
+    operands make every partial sum exact (|acc| <= 2*576+3 < 2^11), which isolates what this test is about: the indexing."""
     ops = _ops()
     g = torch.Generator().manual_seed(6)
     n, cin, h, w = 1, 64, 19, 33
-    x16, _ = ops.pack_nchw(torch.randn(n, cin, h, w, generator=g).to(DEV))
+    x16, _ = ops.pack_nchw(torch.randint(-2, 3, (n, cin, h, w), generator=g).float().to(DEV))
     # nearest x2 folded into the store == F.interpolate(nearest) of the plain result (block.py:299-300)
-    pc = ops.PackedConv((torch.randn(64, cin, 3, 3, generator=g) / 24).to(DEV), torch.zeros(64, device=DEV))
+    pc = ops.PackedConv(torch.randint(-1, 2, (64, cin, 3, 3), generator=g).float().to(DEV), torch.zeros(64, device=DEV))
     plain = torch.zeros((n, 8, h, w, 8), dtype=torch.float16, device=DEV)
     up = torch.zeros((n, 8, 2 * h, 2 * w, 8), dtype=torch.float16, device=DEV)
     ops.conv3x3(x16, pc, lrelu=True, out16=plain)
     ops.conv3x3(x16, pc, lrelu=True, out16=up, up2=True)
     a = ops.unpack_planes(plain, 64)
+    assert float(a.abs().max()) > 8                       # a real convolution result, not zeros
     assert torch.equal(ops.unpack_planes(up, 64), F.interpolate(a, scale_factor=2, mode='nearest'))
     assert torch.equal(ops.unpack_planes(ops.upsample2x(plain), 64), F.interpolate(a, scale_factor=2, mode='nearest'))
     # pixel shuffle folded into the store == nn.PixelShuffle of the plain result (block.py:287), 256 conv channels
-    pc4 = ops.PackedConv((torch.randn(256, cin, 3, 3, generator=g) / 24).to(DEV), torch.randn(256, generator=g).to(DEV))
+    pc4 = ops.PackedConv(torch.randint(-1, 2, (256, cin, 3, 3), generator=g).float().to(DEV), torch.randint(-3, 4, (256,), generator=g).float().to(DEV))
     plain4 = torch.zeros((n, 32, h, w, 8), dtype=torch.float16, device=DEV)
     shuf = torch.zeros((n, 8, 2 * h, 2 * w, 8), dtype=torch.float16, device=DEV)
     ops.conv3x3(x16, pc4, out16=plain4)
