@@ -384,26 +384,42 @@ class SRRaGANModel(BaseModel):
 
     # ---- checkpoints --------------------------------------------------------------------------------
     def load(self, max_step=None, resume_train=None):
+        """models/SRRaGAN_model.py:732-771.  Self-trained checkpoints (`<step>_G.pth` [+ `<step>_D.pth`] in path.models) are taken
+        when resuming training (`train.resume` / resume_train: optimizer states and the step counter come back too), when a
+        `max_step` is asked for, or when testing; otherwise the pretrained paths.  (With nothing to resume from, the reference
+        fails on an empty list; here the pretrained path is used.)"""
         path = self.opt['path']
         models_dir = path['models'] if path is not None else None
+        resume_training = resume_train if resume_train is not None else bool(self.is_train and self.opt['train']['resume'])
         own = [n for n in os.listdir(models_dir) if '_G.pth' in n] if (models_dir and os.path.isdir(models_dir)) else []
-        if own:
-            step_of = lambda n: int(re.search(r'(\d)+(?=_G.pth)', n).group(0))
-            own = sorted(own, key=step_of)
-            if max_step is not None:
-                own = [n for n in own if step_of(n) <= max_step]
+        step_of = lambda n: int(re.search(r'(\d)+(?=_G.pth)', n).group(0))
+        own = sorted(own, key=step_of)
+        if max_step is not None:
+            own = [n for n in own if step_of(n) <= max_step]
+        load_own = (max_step is not None or resume_training or not self.is_train) and len(own) > 0
+        if load_own:
             name = own[-1]
-            print('Testing model for G [{:s}] ...'.format(os.path.join(models_dir, name)))
-            self.load_network(os.path.join(models_dir, name), self.netG)
-            self.gradient_step_num = step_of(name)
-            d_path = os.path.join(models_dir, name.replace('_G.pth', '_D.pth'))
-            if self.D_exists and os.path.exists(d_path):
-                print('Loading also model for D [{:s}] ...'.format(d_path))
-                self.load_network(d_path, self.netD, optimizer=self.optimizer_D)
-        elif path is not None and path['pretrained_model_G'] is not None:
+            loaded_step = step_of(name)
+            d_path = os.path.join(models_dir, '%d_D.pth' % loaded_step)
+            if self.is_train:
+                self.step = (loaded_step + 1) * self.max_accumulation_steps
+                print('Resuming training with model for G [{:s}] ...'.format(os.path.join(models_dir, name)))
+                self.load_network(os.path.join(models_dir, name), self.netG, optimizer=self.optimizer_G)
+                if self.D_exists:
+                    print('Resuming training with model for D [{:s}] ...'.format(d_path))
+                    self.load_network(d_path, self.netD, optimizer=self.optimizer_D)
+            else:
+                print('Testing model for G [{:s}] ...'.format(os.path.join(models_dir, name)))
+                self.load_network(os.path.join(models_dir, name), self.netG)
+                if 'netD' in self.__dict__ and os.path.exists(d_path):   # when running from the GUI
+                    print('Loading also model for D [{:s}] ...'.format(d_path))
+                    self.load_network(d_path, self.netD)
+                self.gradient_step_num = loaded_step
+            return
+        if path is not None and path['pretrained_model_G'] is not None:
             print('loading model for G [{:s}] ...'.format(path['pretrained_model_G']))
             self.load_network(path['pretrained_model_G'], self.netG)
-        if self.D_exists and not own and path is not None and path['pretrained_model_D'] is not None:
+        if self.is_train and self.D_exists and path is not None and path['pretrained_model_D'] is not None:
             print('loading model for D [{:s}] ...'.format(path['pretrained_model_D']))
             self.load_network(path['pretrained_model_D'], self.netD, optimizer=self.optimizer_D)
 
