@@ -164,6 +164,15 @@ class SRRaGANModel(BaseModel):
             raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
         self.generator_step, self.generator_changed, self.generator_started_learning = False, True, False
         self.load()
+        # learning rates after loading (SRRaGAN_model.py:208-218): once the adversarial term is in use (D verified, the default
+        # without D_verification) the generator runs at the DISCRIMINATOR's learning rate
+        if self.D_exists:
+            for param_group in self.optimizer_D.param_groups:
+                param_group['lr'] = self.lr_D
+            if self.verified_D_saved:
+                self.lr_G = 1 * self.lr_D
+        for param_group in self.optimizer_G.param_groups:
+            param_group['lr'] = self.lr_G
 
     # ---- I/O of one batch -------------------------------------------------------------------------
     def Output_Batch(self, within_0_1):

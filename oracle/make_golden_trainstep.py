@@ -1,0 +1,127 @@
+"""Orchestration golden fixture: the UNMODIFIED reference `SRRaGANModel` (models/SRRaGAN_model.py) driven on CPU for several
+`feed_data` / `optimize_parameters` calls with small STAND-IN generator / critic modules injected through `networks.define_G` /
+`define_D` (so the fixture pins the training-step logic itself - D/G scheduling, loss weights, relativistic losses, gradient
+accumulation, Adam steps - independently of the network kernels).  Stores the data, the initial stand-in weights, every logged
+loss series and the final weights.  Build container only (`python oracle/make_golden_trainstep.py`); the fixture is committed."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+from make_golden import save  # noqa: E402
+
+PATCH, SCALE, BATCH = 32, 4, 4
+
+
+class ND(dict):
+    def __missing__(self, k):
+        return None
+
+
+class GStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.c2 = nn.Conv2d(8, 3, 3, padding=1)
+
+    def forward(self, x):
+        return self.c2(nn.functional.interpolate(nn.functional.leaky_relu(self.c1(x), 0.2), scale_factor=SCALE, mode='nearest'))
+
+
+class DiscriminatorStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.features = nn.Sequential(nn.Conv2d(3, 8, 4, stride=4), nn.LeakyReLU(0.2), nn.Conv2d(8, 8, 4, stride=4), nn.BatchNorm2d(8), nn.LeakyReLU(0.2))
+        self.classifier = nn.Linear(8 * (PATCH // 16) ** 2, 1)
+
+    def forward(self, x):
+        return self.classifier(self.features(x).flatten(1))
+
+
+def make_opt(tmp, variant):
+    train = ND(pixel_weight=1e-2, pixel_criterion='l1', gan_type='vanilla', gan_weight=5e-3, range_weight=0.5, lr_G=1e-3, beta1_G=0.9, weight_decay_G=0,
+               lr_D=2e-3, beta1_D=0.9, weight_decay_D=0, D_update_ratio=1, D_init_iters=0, lr_scheme='MultiStepLR', lr_steps=[1000], lr_gamma=0.5,
+               grad_accumulation_steps_G=1, grad_accumulation_steps_D=1, resume=0)
+    train.update(variant)
+    return ND(model='srragan', scale=SCALE, gpu_ids=None, is_train=True, range=[0, 1], train=train,
+              datasets=ND(train=ND(patch_size=PATCH, batch_size=BATCH)),
+              path=ND(models=os.path.join(tmp, 'models'), pretrained_model_G=None, pretrained_model_D=None, log=tmp, experiments_root=tmp),
+              network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='None', latent_input_domain='HR_downscaled', latent_channels=0,
+                           norm_type=None, mode='CNA', nf=8, nb=1, in_nc=3, out_nc=3, gc=32, scale=SCALE),
+              network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3))
+
+
+VARIANTS = {
+    'relativistic': dict(),
+    'accumulate': dict(grad_accumulation_steps_G=2, grad_accumulation_steps_D=2),
+    'plain_gan_ratio2': dict(D_update_ratio=2, _relativistic=0),
+    'lsgan': dict(gan_type='lsgan'),
+    'wgan_plain': dict(gan_type='wgan', _relativistic=0),
+    'init_iters': dict(D_init_iters=2),
+    'acc_d2_g1': dict(grad_accumulation_steps_D=2, grad_accumulation_steps_G=1),
+    'no_gan': dict(gan_weight=None),
+}
+N_CALLS = 8
+
+
+def run(model_cls, networks, tmp, variant_name, data):
+    variant = dict(VARIANTS[variant_name])
+    rel = variant.pop('_relativistic', None)
+    opt = make_opt(tmp, variant)
+    if rel is not None:
+        opt['network_D']['relativistic'] = rel
+
+    def define_G(opt, **kw):
+        torch.manual_seed(100)
+        return GStand()
+
+    def define_D(opt, **kw):
+        torch.manual_seed(200)
+        return DiscriminatorStand()
+    old = networks.define_G, networks.define_D
+    networks.define_G, networks.define_D = define_G, define_D
+    try:
+        acc = max(opt['train']['grad_accumulation_steps_G'], opt['train']['grad_accumulation_steps_D'])
+        model = model_cls(opt, accumulation_steps_per_batch=acc)
+    finally:
+        networks.define_G, networks.define_D = old
+    init = {'G0:' + k: v.detach().clone().numpy() for k, v in model.netG.state_dict().items()}
+    if model.D_exists:
+        init.update({'D0:' + k: v.detach().clone().numpy() for k, v in model.netD.state_dict().items()})
+    for it in range(N_CALLS):
+        model.feed_data({'LR': data['LR'][it].clone(), 'HR': data['HR'][it].clone()})
+        model.optimize_parameters()
+    logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
+            if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished')}
+    final = {'G1:' + k: v.detach().numpy() for k, v in model.netG.state_dict().items()}
+    if model.D_exists:
+        final.update({'D1:' + k: v.detach().numpy() for k, v in model.netD.state_dict().items()})
+    return init, logs, final
+
+
+def main():
+    import tempfile
+    import models.networks as networks
+    from models.SRRaGAN_model import SRRaGANModel
+    g = torch.Generator().manual_seed(31)
+    data = {'LR': torch.rand(N_CALLS, BATCH, 3, PATCH // SCALE, PATCH // SCALE, generator=g), 'HR': torch.rand(N_CALLS, BATCH, 3, PATCH, PATCH, generator=g)}
+    arrays = {'LR': data['LR'].numpy(), 'HR': data['HR'].numpy()}
+    for name in VARIANTS:
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, 'models'))
+            init, logs, final = run(SRRaGANModel, networks, tmp, name, data)
+        for d in (init, logs, final):
+            arrays.update({name + '/' + k: v for k, v in d.items()})
+        print(name, {k: v.shape for k, v in logs.items()})
+    save('trainstep_orchestration', **arrays)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,111 @@
+"""The training-step logic of SRRaGANModel.optimize_parameters against the UNMODIFIED reference (oracle/make_golden_trainstep.py):
+the same small stand-in generator / critic (plain torch modules, CPU) are injected through networks.define_G / define_D in both
+code bases, the same batches are fed, and every logged loss series and the final weights of both networks must agree - this
+pins the D/G scheduling (D_update_ratio, first idle generator step), the loss weighting, the relativistic / plain / lsgan
+losses, gradient accumulation and the Adam steps independently of the CUDA kernels."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from util import golden
+
+PATCH, SCALE, BATCH = 32, 4, 4
+
+
+class ND(dict):
+    def __missing__(self, k):
+        return None
+
+
+class GStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.c2 = nn.Conv2d(8, 3, 3, padding=1)
+
+    def forward(self, x):
+        return self.c2(nn.functional.interpolate(nn.functional.leaky_relu(self.c1(x), 0.2), scale_factor=SCALE, mode='nearest'))
+
+
+class DiscriminatorStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.features = nn.Sequential(nn.Conv2d(3, 8, 4, stride=4), nn.LeakyReLU(0.2), nn.Conv2d(8, 8, 4, stride=4), nn.BatchNorm2d(8), nn.LeakyReLU(0.2))
+        self.classifier = nn.Linear(8 * (PATCH // 16) ** 2, 1)
+
+    def forward(self, x):
+        return self.classifier(self.features(x).flatten(1))
+
+
+VARIANTS = {
+    'relativistic': dict(),
+    'accumulate': dict(grad_accumulation_steps_G=2, grad_accumulation_steps_D=2),
+    'plain_gan_ratio2': dict(D_update_ratio=2, _relativistic=0),
+    'lsgan': dict(gan_type='lsgan'),
+    'wgan_plain': dict(gan_type='wgan', _relativistic=0),
+    'init_iters': dict(D_init_iters=2),
+    'acc_d2_g1': dict(grad_accumulation_steps_D=2, grad_accumulation_steps_G=1),
+    'no_gan': dict(gan_weight=None),
+}
+
+
+def _opt(tmp_path, variant):
+    train = ND(pixel_weight=1e-2, pixel_criterion='l1', gan_type='vanilla', gan_weight=5e-3, range_weight=0.5, lr_G=1e-3, beta1_G=0.9, weight_decay_G=0,
+               lr_D=2e-3, beta1_D=0.9, weight_decay_D=0, D_update_ratio=1, D_init_iters=0, lr_scheme='MultiStepLR', lr_steps=[1000], lr_gamma=0.5,
+               grad_accumulation_steps_G=1, grad_accumulation_steps_D=1, resume=0)
+    train.update(variant)
+    return ND(model='srragan', scale=SCALE, gpu_ids=None, is_train=True, range=[0, 1], train=train,
+              datasets=ND(train=ND(patch_size=PATCH, batch_size=BATCH)),
+              path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, pretrained_model_D=None, log=str(tmp_path)),
+              network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='None', latent_input_domain='HR_downscaled', latent_channels=0,
+                           norm_type=None, mode='CNA', nf=8, nb=1, in_nc=3, out_nc=3, gc=32, scale=SCALE),
+              network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3))
+
+
+@pytest.mark.parametrize('name', list(VARIANTS))
+def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
+    if torch.cuda.is_available():
+        pytest.skip('CPU-suite test: the stand-in networks and the fixture live on the host')
+    import models.networks as networks
+    from models.SRRaGAN_model import SRRaGANModel
+    g = golden('trainstep_orchestration')
+    variant = dict(VARIANTS[name])
+    rel = variant.pop('_relativistic', None)
+    opt = _opt(tmp_path, variant)
+    if rel is not None:
+        opt['network_D']['relativistic'] = rel
+
+    def define_G(opt, **kw):
+        torch.manual_seed(100)
+        return GStand()
+
+    def define_D(opt, **kw):
+        torch.manual_seed(200)
+        return DiscriminatorStand()
+    monkeypatch.setattr(networks, 'define_G', define_G)
+    monkeypatch.setattr(networks, 'define_D', define_D)
+    acc = max(opt['train']['grad_accumulation_steps_G'], opt['train']['grad_accumulation_steps_D'])
+    model = SRRaGANModel(opt, accumulation_steps_per_batch=acc)
+    for k, v in model.netG.state_dict().items():
+        assert np.array_equal(v.numpy(), g['%s/G0:%s' % (name, k)]), k          # same starting point as the reference run
+    if model.D_exists:
+        for k, v in model.netD.state_dict().items():
+            assert np.array_equal(v.numpy(), g['%s/D0:%s' % (name, k)]), k
+    for it in range(g['LR'].shape[0]):
+        model.feed_data({'LR': torch.from_numpy(g['LR'][it]).clone(), 'HR': torch.from_numpy(g['HR'][it]).clone()})
+        model.optimize_parameters()
+    for key in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished'):
+        if '%s/log:%s' % (name, key) not in g.files:
+            assert len(model.log_dict.get(key, [])) == 0, key
+            continue
+        ref = g['%s/log:%s' % (name, key)]
+        own = np.array(model.log_dict[key], dtype=np.float64)
+        assert own.shape == ref.shape, (key, own.shape, ref.shape)
+        assert np.array_equal(own[:, 0], ref[:, 0]), key                         # logged at the same gradient steps
+        assert np.allclose(own[:, 1], ref[:, 1], rtol=1e-4, atol=1e-6), (key, own[:, 1], ref[:, 1])
+    for k, v in model.netG.state_dict().items():
+        assert np.allclose(v.numpy(), g['%s/G1:%s' % (name, k)], rtol=1e-4, atol=1e-6), k
+    if model.D_exists:
+        for k, v in model.netD.state_dict().items():
+            assert np.allclose(v.numpy(), g['%s/D1:%s' % (name, k)], rtol=1e-4, atol=1e-6), k
