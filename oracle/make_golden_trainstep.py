@@ -26,9 +26,9 @@ class ND(dict):
 
 
 class GStand(nn.Module):
-    def __init__(self):
+    def __init__(self, in_nc=3):
         super().__init__()
-        self.c1 = nn.Conv2d(3, 8, 3, padding=1)
+        self.c1 = nn.Conv2d(in_nc, 8, 3, padding=1)
         self.c2 = nn.Conv2d(8, 3, 3, padding=1)
 
     def forward(self, x):
@@ -36,7 +36,7 @@ class GStand(nn.Module):
 
 
 class DiscriminatorStand(nn.Module):
-    def __init__(self):
+    def __init__(self, PATCH=PATCH):
         super().__init__()
         self.features = nn.Sequential(nn.Conv2d(3, 8, 4, stride=4), nn.LeakyReLU(0.2), nn.Conv2d(8, 8, 4, stride=4), nn.BatchNorm2d(8), nn.LeakyReLU(0.2))
         self.classifier = nn.Linear(8 * (PATCH // 16) ** 2, 1)
@@ -45,15 +45,17 @@ class DiscriminatorStand(nn.Module):
         return self.classifier(self.features(x).flatten(1))
 
 
-def make_opt(tmp, variant):
+def make_opt(tmp, variant, latent=False):
     train = ND(pixel_weight=1e-2, pixel_criterion='l1', gan_type='vanilla', gan_weight=5e-3, range_weight=0.5, lr_G=1e-3, beta1_G=0.9, weight_decay_G=0,
                lr_D=2e-3, beta1_D=0.9, weight_decay_D=0, D_update_ratio=1, D_init_iters=0, lr_scheme='MultiStepLR', lr_steps=[1000], lr_gamma=0.5,
                grad_accumulation_steps_G=1, grad_accumulation_steps_D=1, resume=0)
     train.update(variant)
+    patch = 96 if latent else PATCH
     return ND(model='srragan', scale=SCALE, gpu_ids=None, is_train=True, range=[0, 1], train=train,
-              datasets=ND(train=ND(patch_size=PATCH, batch_size=BATCH)),
+              datasets=ND(train=ND(patch_size=patch, batch_size=BATCH)),
               path=ND(models=os.path.join(tmp, 'models'), pretrained_model_G=None, pretrained_model_D=None, log=tmp, experiments_root=tmp),
-              network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='None', latent_input_domain='HR_downscaled', latent_channels=0,
+              network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='all_layers' if latent else 'None', latent_input_domain='HR_downscaled',
+                           latent_channels='SVDinNormedOut_structure_tensor' if latent else 0,
                            norm_type=None, mode='CNA', nf=8, nb=1, in_nc=3, out_nc=3, gc=32, scale=SCALE),
               network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3))
 
@@ -67,6 +69,7 @@ VARIANTS = {
     'init_iters': dict(D_init_iters=2),
     'acc_d2_g1': dict(grad_accumulation_steps_D=2, grad_accumulation_steps_G=1),
     'no_gan': dict(gan_weight=None),
+    'latent': dict(latent_weight=1.0, _latent=1),
 }
 N_CALLS = 8
 
@@ -74,17 +77,19 @@ N_CALLS = 8
 def run(model_cls, networks, tmp, variant_name, data):
     variant = dict(VARIANTS[variant_name])
     rel = variant.pop('_relativistic', None)
-    opt = make_opt(tmp, variant)
+    latent = bool(variant.pop('_latent', 0))
+    opt = make_opt(tmp, variant, latent)
+    patch = opt['datasets']['train']['patch_size']
     if rel is not None:
         opt['network_D']['relativistic'] = rel
 
     def define_G(opt, **kw):
         torch.manual_seed(100)
-        return GStand()
+        return GStand(3 + 3 * SCALE ** 2 if latent else 3)
 
     def define_D(opt, **kw):
         torch.manual_seed(200)
-        return DiscriminatorStand()
+        return DiscriminatorStand(patch - 80 if latent else patch)
     old = networks.define_G, networks.define_D
     networks.define_G, networks.define_D = define_G, define_D
     try:
@@ -95,11 +100,14 @@ def run(model_cls, networks, tmp, variant_name, data):
     init = {'G0:' + k: v.detach().clone().numpy() for k, v in model.netG.state_dict().items()}
     if model.D_exists:
         init.update({'D0:' + k: v.detach().clone().numpy() for k, v in model.netD.state_dict().items()})
+    torch.manual_seed(5)      # feed_data draws the latent codes from the global generator
+    key = 'lat' if latent else ''
     for it in range(N_CALLS):
-        model.feed_data({'LR': data['LR'][it].clone(), 'HR': data['HR'][it].clone()})
+        model.feed_data({'LR': data[key + 'LR'][it].clone(), 'HR': data[key + 'HR'][it].clone()})
         model.optimize_parameters()
     logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
-            if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished')}
+            if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
+                                    'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2')}
     final = {'G1:' + k: v.detach().numpy() for k, v in model.netG.state_dict().items()}
     if model.D_exists:
         final.update({'D1:' + k: v.detach().numpy() for k, v in model.netD.state_dict().items()})
@@ -111,8 +119,10 @@ def main():
     import models.networks as networks
     from models.SRRaGAN_model import SRRaGANModel
     g = torch.Generator().manual_seed(31)
-    data = {'LR': torch.rand(N_CALLS, BATCH, 3, PATCH // SCALE, PATCH // SCALE, generator=g), 'HR': torch.rand(N_CALLS, BATCH, 3, PATCH, PATCH, generator=g)}
-    arrays = {'LR': data['LR'].numpy(), 'HR': data['HR'].numpy()}
+    q = lambda t: t.half().float()      # fp16-exact values: the fixture stores them in 16 bits
+    data = {'LR': q(torch.rand(N_CALLS, BATCH, 3, PATCH // SCALE, PATCH // SCALE, generator=g)), 'HR': q(torch.rand(N_CALLS, BATCH, 3, PATCH, PATCH, generator=g))}
+    data['latLR'], data['latHR'] = q(torch.rand(N_CALLS, 2, 3, 24, 24, generator=g)), q(torch.rand(N_CALLS, 2, 3, 96, 96, generator=g))
+    arrays = {k: v.numpy().astype(np.float16) for k, v in data.items()}
     for name in VARIANTS:
         with tempfile.TemporaryDirectory() as tmp:
             os.makedirs(os.path.join(tmp, 'models'))
