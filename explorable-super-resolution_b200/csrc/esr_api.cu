@@ -570,6 +570,11 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     int ranges = num_sms() / w.n_blocks;
     if (ranges < 1) return fail(ESR_ERR_INVALID, "wgrad: too many n-blocks (%d)", w.n_blocks);
     if ((long long)ranges > p.units) ranges = (int)p.units;
+    // small images: every CTA dumps a full partial (mt*128*3*nbn floats) whatever its share of rows, and the reduce reads all of
+    // them (profiles/r01c_launches_c3_step.csv: the reduce costs as much as the wgrad at ~1.4 rows per CTA).  ESR_WGRAD_MIN_ROWS=k
+    // gives every CTA at least k row units (default 1 = one range per SM as measured so far; to be tuned on the GPU).
+    static const int min_rows = [] { const char* e = getenv("ESR_WGRAD_MIN_ROWS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    if (min_rows > 1 && p.units / min_rows < ranges) ranges = (int)(p.units / min_rows > 0 ? p.units / min_rows : 1);
     p.ranges = ranges;
     p.x = (const uint8_t*)a->x; p.x_pt = a->x_planes_total; p.x_po = a->x_plane_off; p.cp = cp;
     p.gy = (const uint8_t*)a->gy; p.gy_pt = a->gy_planes_total; p.gy_po = a->gy_plane_off; p.gyp = w.gyp;
