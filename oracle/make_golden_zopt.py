@@ -49,7 +49,8 @@ def make_opt(tmp):
 # (the reference's plain 'l1' objective with an image mask references a variable that only the 'scribble' objectives define,
 #  Z_optimization.py:427 - it only runs in the training-time mode, where no mask exists: case 'l1' + training below)
 CASES = [('max_STD', {}, 1, 6, False), ('min_STD', {}, 1, 6, False), ('TV', {}, 1, 6, False), ('STD_increase', {'STD_increment': 0.01}, 1, 6, False),
-         ('STD_decrease', {'STD_increment': 0.02}, 1, 6, False), ('l1', {}, 2, 8, True)]
+         ('STD_decrease', {'STD_increment': 0.02}, 1, 6, False), ('l1', {}, 2, 8, True),
+         ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False)]
 
 
 def build_model(model_cls, networks, tmp):
@@ -89,14 +90,14 @@ def main():
         for idx, (objective, extra, bs, iters, training) in enumerate(CASES):
             data = {'LR': x_lr.expand(bs, -1, -1, -1).contiguous(), 'desired': desired, **extra}
             model.feed_data({'LR': data['LR'], 'Z': torch.zeros(bs, 3, SCALE * H, SCALE * W)}, need_GT=False)
-            if training:      # training-time use (SRRaGAN_model.py:108-112): no image mask, random initial Z drawn inside optimize()
+            if training is True:      # training-time use (SRRaGAN_model.py:108-112): no image mask, random initial Z drawn inside optimize()
                 model.__dict__.pop('fake_H', None)
             else:
                 model.test()
             torch.manual_seed(17 + idx)
             with contextlib.redirect_stdout(io.StringIO()):
                 zo = Zmod.Z_optimizer(objective=objective, Z_size=[SCALE * H, SCALE * W], model=model, Z_range=1.0, max_iters=iters, data=data,
-                                      initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training else None)
+                                      initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random')
                 Z = zo.optimize()
             arrays['%d:loss' % idx] = np.array([float(v) for v in zo.loss_values], dtype=np.float64)
             arrays['%d:Z' % idx] = Z.detach().cpu().numpy()

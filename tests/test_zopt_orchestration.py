@@ -31,7 +31,8 @@ class GStand(nn.Module):
 
 
 CASES = [('max_STD', {}, 1, 6, False), ('min_STD', {}, 1, 6, False), ('TV', {}, 1, 6, False), ('STD_increase', {'STD_increment': 0.01}, 1, 6, False),
-         ('STD_decrease', {'STD_increment': 0.02}, 1, 6, False), ('l1', {}, 2, 8, True)]
+         ('STD_decrease', {'STD_increment': 0.02}, 1, 6, False), ('l1', {}, 2, 8, True),
+         ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False)]
 
 
 def _opt(tmp_path):
@@ -63,14 +64,14 @@ def test_z_optimizer_loop_matches_reference(monkeypatch, tmp_path, idx):
     x_lr, desired = torch.from_numpy(g['x_lr']), torch.from_numpy(g['desired'])
     data = {'LR': x_lr.expand(bs, -1, -1, -1).contiguous(), 'desired': desired, **extra}
     model.feed_data({'LR': data['LR'], 'Z': torch.zeros(bs, 3, SCALE * H, SCALE * W)}, need_GT=False)
-    if training:
+    if training is True:
         model.__dict__.pop('fake_H', None)
     else:
         model.test()
     torch.manual_seed(17 + idx)
     with contextlib.redirect_stdout(io.StringIO()):
         zo = Zmod.Z_optimizer(objective=objective, Z_size=[SCALE * H, SCALE * W], model=model, Z_range=1.0, max_iters=iters, data=data,
-                              initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training else None)
+                              initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random')
         Z = zo.optimize()
     ref_loss = g['%d:loss' % idx]
     own_loss = np.array([float(v) for v in zo.loss_values])
