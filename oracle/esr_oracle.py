@@ -1,13 +1,17 @@
 """ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 CPU restatement (functional PyTorch fp32 on explicit state-dict tensors) of the reference's hot path:
-RRDBNet forward, the CEM projection, and the latent packing.  Only tests/, __graft_entry__.smoke() and
+RRDBNet forward, the CEM projection, the latent packing, the Z-optimisation l1 loop, Discriminator_VGG_128, the (relativistic)
+GAN losses and the structure-tensor latent-control loss.  Only tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs may import this file; the product path
 (explorable-super-resolution_b200/) never does and has no CPU fallback.
 
 Parity status: PINNED.  The reference has no tests or golden vectors of its own, so the pins are
-outputs of the unmodified reference executed in the build container by oracle/make_golden.py
-(tests/golden/*.npz); tests/test_oracle.py checks this file against every one of them.
+outputs of the unmodified reference executed in the build container by oracle/make_golden*.py
+(tests/golden/*.npz); tests/test_oracle.py, tests/test_discriminator_cpu.py and tests/test_filterloss_cpu.py check this file
+against every one of them.  The orchestration layers (SRRaGANModel.optimize_parameters, Z_optimizer.optimize, checkpoint
+loading) are pinned directly: oracle/make_golden_trainstep.py / _zopt.py / _ckpt.py run the reference's own classes on the CPU
+and tests/test_trainstep_orchestration.py / test_zopt_orchestration.py / test_checkpoint_compat.py hold the product's to them.
 
 Every function cites the reference lines it restates (paths relative to /root/reference/codes)."""
 import math
