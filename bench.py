@@ -128,7 +128,7 @@ def run_reference(args, rank, world, out_fd):
     from CEM.CEMnet import CEMnet, Get_CEM_Conf
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
+    torch.default_generator.manual_seed(0)     # CPU generator only: this leg must not depend on the device's health
     net = arch.RRDBNet(3, 3, NF, NB, upscale=SCALE, num_latent_channels=0)
     for p in net.parameters():
         if p.dim() > 1:
@@ -166,7 +166,7 @@ def cpu_baseline():
     from CEM.CEMnet import CEMnet, Get_CEM_Conf
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
+    torch.default_generator.manual_seed(0)     # CPU generator only: this leg must not depend on the device's health
     net = arch.RRDBNet(3, 3, NF, NB, upscale=SCALE, num_latent_channels=0)
     sd = {'generated_image_model.' + k: v.detach() * (0.1 if v.dim() > 1 else 0.0) for k, v in net.state_dict().items()}
     cem = CEMnet(Get_CEM_Conf(SCALE))
@@ -324,6 +324,10 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:      # max over ranks of the headline numbers, before any extra leg runs
+        t = torch.tensor([ms, ms_e2e, conv_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, conv_ms = [float(v) for v in t]
 
     # generator training step at the same shape (fwd + CEM + L1 + bwd with weight gradients + Adam; bf16 engine), extra key
     train = None
@@ -354,6 +358,10 @@ def main():
             g1.record()
             barrier()
             ms_train = g0.elapsed_time(g1) / 3
+            if world > 1:
+                tt = torch.tensor([ms_train], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms_train = float(tt[0])
             train = {'ms_per_step': ms_train, 'gpu_launches_per_step': (lib.launch_count() - l0) // 3, 'dtype': 'bf16 operands, f32 master weights',
                      'step': 'forward + CEM + L1 loss + backward (dgrad + wgrad) + gradient all-reduce + Adam', 'steps': 3}
             for p_ in params:
@@ -363,14 +371,13 @@ def main():
         except Exception as e:  # the forward numbers above stay valid
             train = {'error': repr(e)[:300]}
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e, conv_ms, train['ms_per_step'] if train and 'ms_per_step' in train else 0.0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, conv_ms = [float(v) for v in t[:3]]
-        if train and 'ms_per_step' in train:
-            train['ms_per_step'] = float(t[3])
-    # everything the JSON line needs from the device is now in host floats; the CPU baseline and the extra GAN-step leg run after
-    cpu_base = cpu_baseline() if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
+    # the CPU baseline and the extra GAN-step leg run after everything the JSON line needs from the device is in host floats
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        try:
+            cpu_base = cpu_baseline()
+        except Exception as e:
+            cpu_base = {'error': repr(e)[:300]}
     # full SRRaGAN step at the per-GPU shape of BASELINE config 3 (batch 4 of 52x52 LR, 208x208 HR patches, 128x128 critic crops):
     # D step (Discriminator_VGG_128, relativistic loss, Adam) + G step (pixel + VGG-feature + relativistic GAN loss, Adam), through
     # create_model / feed_data (host tensors) / optimize_parameters, gradients all-reduced over the ranks.  Extra key.
