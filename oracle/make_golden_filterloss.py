@@ -4,7 +4,6 @@ second call's mean with respect to the reconstructed image.  Build container onl
 import os
 import sys
 
-import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)

@@ -5,7 +5,6 @@ matched positionally, zero weights for the latent input channels IN FRONT of eve
 filters untouched."""
 import contextlib
 import io
-import os
 
 import numpy as np
 import pytest
