@@ -58,6 +58,47 @@ def Cubic_Kernel(sf):
     return np.outer(taps, taps)
 
 
+def Return_Filter_Energy_Distribution(filter):
+    """fraction of the filter's L2 norm left after peeling 0, 1, 2, ... frames off its border (imresize_CEM.py:177-179)"""
+    n = filter.shape[0]
+    norms = [np.sqrt(np.sum(filter ** 2))] + [np.sqrt(np.sum(filter[f:-f, f:-f] ** 2)) for f in range(1, int(np.ceil(n / 2)))]
+    return norms / norms[0]
+
+
+def Center_Mass(kernel, ds_factor):
+    """Zero-pads a square kernel so that its centre of mass sits at the centre, keeps it square, then crops equal frames holding
+    less than 1 % of its norm such that (size - 1 [+1 for even factors]) is a multiple of ds_factor; unit sum (imresize_CEM.py:135-175)."""
+    assert kernel.shape[0] == kernel.shape[1], 'Currently supporting only square kernels'
+    n = kernel.shape[0]
+    gx, gy = np.meshgrid(np.arange(n), np.arange(n))
+    cx, cy = float(convolve2d(gx, kernel, mode='valid')[0, 0]) + 1, float(convolve2d(gy, kernel, mode='valid')[0, 0]) + 1
+    x_pad, y_pad = 2 * (n / 2 - cx), 2 * (n / 2 - cy)
+    diff = np.round(np.abs(y_pad)) - np.round(np.abs(x_pad))
+    pads = {'x': [np.maximum(0, -x_pad), np.maximum(0, x_pad)], 'y': [np.maximum(0, -y_pad), np.maximum(0, y_pad)]}
+    rnd = lambda v: int(np.round(v))
+
+    def widen(pre, post, extra):      # split the padding the other axis needs, minding which side the rounding favoured
+        lean_right = np.round(post) - post - (np.round(pre) - pre)
+        pre, post = rnd(pre), rnd(post)
+        big, small = int(np.ceil(extra / 2)), int(np.floor(extra / 2))
+        return (pre + small, post + big) if lean_right > 0 else (pre + big, post + small)
+    if diff > 0:
+        pads['y'] = [rnd(pads['y'][0]), rnd(pads['y'][1])]
+        pads['x'] = list(widen(pads['x'][0], pads['x'][1], diff))
+    elif diff < 0:
+        pads['x'] = [rnd(pads['x'][0]), rnd(pads['x'][1])]
+        pads['y'] = list(widen(pads['y'][0], pads['y'][1], -diff))
+    kernel = np.pad(kernel, ((rnd(pads['y'][0]), rnd(pads['y'][1])), (rnd(pads['x'][0]), rnd(pads['x'][1]))), mode='constant')
+    assert kernel.shape[0] == kernel.shape[1], 'I caused the kernel to stop being a square...'
+    margins = np.argwhere(Return_Filter_Energy_Distribution(kernel) < 0.99)[0][0] * np.ones([2]).astype(np.int32)
+    side = 0
+    while np.mod(kernel.shape[0] - np.sum(margins) - 1 + np.mod(ds_factor + 1, 2), ds_factor) != 0:
+        margins[side] -= 1
+        side = (side + 1) % 2
+    kernel = kernel[margins[0]:-margins[1], margins[0]:-margins[1]]
+    return kernel / np.sum(kernel)
+
+
 def _default_kernel(sf, blur_sigma=None):
     k = Cubic_Kernel(sf)
     if blur_sigma is not None:
@@ -73,9 +114,8 @@ def imresize(im, scale_factor=None, output_shape=None, kernel=None, align_center
              use_zero_padding=False, antialiasing=True, kernel_shift_flag=False):
     """Same contract as the reference's imresize (imresize_CEM.py:8-87): integer up/down factors only,
     kernels cached per factor on the function object, edge (replicate) padding unless use_zero_padding."""
-    if isinstance(kernel, np.ndarray):
-        raise NotImplementedError('externally estimated (non-default) kernels are not wired yet (SURVEY 8f-4)')
-    assert kernel is None or any(w in kernel for w in ['cubic', 'blurry_cubic', 'reset_2_default'])
+    given = isinstance(kernel, np.ndarray)
+    assert kernel is None or given or any(w in kernel for w in ['cubic', 'blurry_cubic', 'reset_2_default'])
     cache = imresize.__dict__.setdefault('kernels', {})
     if scale_factor is None:
         scale_factor = [output_shape[0] / im.shape[0]]
@@ -88,7 +128,17 @@ def imresize(im, scale_factor=None, output_shape=None, kernel=None, align_center
     pre, post = calc_strides(im, f, align_center)
     pad_after = np.maximum(0, pre - post)
     pad_before = np.maximum(0, post - pre)
-    if str(s) not in cache or kernel == 'reset_2_default':
+    if given:
+        # an externally estimated DOWN-scaling kernel (KernelGAN, GUI.py:1594-1603; imresize_CEM.py:23-33): stored as the up-scaling
+        # kernel of this factor - rotated, re-centred on its centre of mass, cropped to 99 % of its energy - until 'reset_2_default'
+        if str(s) in cache:
+            print('Overriding previous kernel with given kernel...')
+        assert np.abs(1 - np.sum(kernel)) < np.finfo(np.float32).eps, 'Supplied non-default kernel does not sum to 1'
+        k = Center_Mass(np.rot90(kernel, 2), ds_factor=s) * s ** 2
+        assert k.shape[0] == k.shape[1], 'Only square kernels supported for now'
+        assert np.all(np.mod(k.shape + pad_after + pad_before - 1, s) == 0), 'Convolution-invalidated size should be an integer multiplication of sf_4_kernel'
+        cache[str(s)] = k
+    elif str(s) not in cache or kernel == 'reset_2_default':
         sigma = float(kernel[len('blurry_cubic_'):]) if (kernel is not None and 'blurry_cubic' in kernel) else None
         cache[str(s)] = _default_kernel(s, sigma)
     aa = np.pad(cache[str(s)], ((pad_before[0], pad_after[0]), (pad_before[1], pad_after[1])), mode='constant')

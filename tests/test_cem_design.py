@@ -45,3 +45,28 @@ def test_numpy_projection_utilities_run():
     assert out.shape == hr.shape
     from CEM.imresize_CEM import imresize
     assert np.abs(imresize(out, [1 / 4]) - lr)[3:-3, 3:-3].max() < 1e-4
+
+
+@pytest.mark.parametrize('tag,s', [('x4', 4), ('x2', 2)])
+def test_estimated_kernel_design_matches_reference(tag, s):
+    """CEMnet(upscale_kernel=ndarray) - the externally estimated (non-separable, off-centre) down-scaling kernel of the GUI's
+    KernelGAN route (GUI.py:1594-1603): centre-of-mass re-centring, energy cropping, hTh inversion with the 0.1 magnitude bound."""
+    from CEM.CEMnet import CEMnet, Get_CEM_Conf, _separable_terms
+    from CEM.imresize_CEM import imresize
+    g = golden('cem_estimated_kernel')
+    conf = Get_CEM_Conf(s)
+    conf.lower_magnitude_bound = 0.1
+    try:
+        cem = CEMnet(conf, upscale_kernel=g[tag + ':kernel'])
+        assert cem.ds_kernel.shape == g[tag + ':ds_kernel'].shape and np.abs(cem.ds_kernel - g[tag + ':ds_kernel']).max() < 1e-15
+        assert cem.inv_hTh.shape == g[tag + ':inv_hTh'].shape and np.abs(cem.inv_hTh - g[tag + ':inv_hTh']).max() < 1e-12
+        assert [cem.invalidity_margins_LR, cem.invalidity_margins_HR] == list(g[tag + ':margins'])
+        # the CUDA filters take separable terms: this kernel needs several and is still represented to fp32 accuracy
+        kv, kh = _separable_terms(cem.ds_kernel)
+        assert kv.shape[0] > 1
+        assert np.abs(kv.astype(np.float64).T @ kh.astype(np.float64) - cem.ds_kernel).max() < 1e-6 * np.abs(cem.ds_kernel).max()
+        # the given kernel stays in force for later calls with this factor until it is reset (imresize_CEM.py:24-33)
+        assert np.array_equal(CEMnet(conf).ds_kernel, cem.ds_kernel)
+    finally:
+        imresize(None, [s, s], return_upscale_kernel=True, kernel='reset_2_default')
+    assert np.array_equal(CEMnet(Get_CEM_Conf(s)).ds_kernel, golden('cem_x%d' % s)['ds_kernel'])
