@@ -61,3 +61,27 @@ def test_ops_fail_loudly_without_cuda():
         return
     with pytest.raises(lib.EsrError):
         ops.pack_nchw(torch.zeros(1, 3, 4, 4))
+
+
+def test_integration_stub_matches_binding():
+    """the ctypes stub shown to maintainers in INTEGRATION.md lists the same fields, in the same order, as the shipped binding"""
+    from esr_b200 import lib
+    txt = open(os.path.join(REPO, 'INTEGRATION.md')).read()
+    body = txt[txt.index('class ConvArgs(C.Structure):'):txt.index('lib.esr_conv3x3_fwd.argtypes')]
+    shown = re.findall(r'\("([a-z_0-9]+)", C\.c_[a-z_]+\)', body)
+    assert shown == [f[0] for f in lib.ConvArgs._fields_]
+
+
+def test_pack_item_struct_matches_header_order():
+    from esr_b200 import lib
+    txt = open(os.path.join(REPO, 'include', 'esr_b200.h')).read()
+    end = txt.index('} esr_pack_item;')
+    body = re.sub(r'/\*.*?\*/', '', txt[txt.rindex('typedef struct {', 0, end):end], flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.replace('typedef struct {', '').strip()
+        if not decl:
+            continue
+        for part in decl.split(','):
+            fields.append(re.findall(r'([A-Za-z_][A-Za-z0-9_]*)\s*$', part.strip())[0])
+    assert fields == ['w_oihw' if f[0] == 'w' else f[0] for f in lib.PackItem._fields_]
