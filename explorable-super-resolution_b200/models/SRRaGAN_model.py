@@ -32,6 +32,27 @@ def SVD_2_LatentZ(SVD_values, max_lambda=1):
                         2 * (l0 - l1) * torch.sin(th) * torch.cos(th)], 1)
 
 
+def _tensor2img(t, min_max=(0, 1)):
+    """utils/util.py:196-228 for one image, float output: [C,H,W] RGB tensor -> [H,W,C] BGR array clipped and scaled to [0,1]"""
+    img = t.squeeze().float().cpu().numpy()
+    if img.ndim == 3:
+        img = np.transpose(img[[2, 1, 0], :, :], (1, 2, 0))
+    img = (np.clip(img, min_max[0], min_max[1]) - min_max[0]) / (min_max[1] - min_max[0])
+    return img.astype(np.float32)
+
+
+def _psnr(img1, img2):
+    """utils/util.py:340-347, images in [0,255]"""
+    mse = np.mean((img1.astype(np.float64) - img2.astype(np.float64)) ** 2)
+    return float('inf') if mse == 0 else 20 * np.log10(255.0 / np.sqrt(mse))
+
+
+def _save_png(img, path):
+    import cv2                      # utils/util.py:231-232 (BGR array -> file)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    cv2.imwrite(path, img)
+
+
 class SRRaGANModel(BaseModel):
     def __init__(self, opt, accumulation_steps_per_batch=1, init_Fnet=None, init_Dnet=None, **kwargs):
         super(SRRaGANModel, self).__init__(opt)
@@ -389,7 +410,132 @@ class SRRaGANModel(BaseModel):
         return out
 
     def get_current_log(self):
-        return OrderedDict((k, v[-1][1]) for k, v in self.log_dict.items() if len(v) > 0)
+        out = OrderedDict()
+        for k, v in self.log_dict.items():
+            if len(v) > 0:
+                out[k] = v[-1][1] if (isinstance(v[-1], tuple) or len(v[-1]) > 1) else v[-1]
+        return out
+
+    # ---- what the reference's train.py calls around the step (validation, logs, loss-driven lr drop) ------------------------
+    def perform_validation(self, data_loader, cur_Z, print_rlt, first_eval, save_images):
+        """models/SRRaGAN_model.py:533-590: run every validation image through `test()`, PSNR against HR on [0,255] images, a collage of
+        centre crops per call (and of the HR images on the first one).  Image conversion / PSNR / PNG writing follow utils/util.py:196-232,340-347."""
+        psnrs, collage, gt_collage, sr_images = [], [], [], []
+        idx = 0
+        if save_images:
+            num = len(data_loader.dataset)
+            rows = int(np.floor(np.sqrt(num)))
+            while rows > 1 and np.round(num / rows) != num / rows:
+                rows -= 1
+            patch = min([min(im['HR'].shape[1:]) for im in data_loader.dataset]) - 2
+        for val_data in data_loader:
+            if save_images and idx % rows == 0:
+                collage.append([])
+                gt_collage.append([])
+            idx += 1
+            val_data['Z'] = cur_Z
+            self.feed_data(val_data)
+            self.test()
+            visuals = self.get_current_visuals()
+            sr_img, gt_img = 255 * _tensor2img(visuals['SR']), 255 * _tensor2img(visuals['HR'])
+            sr_images.append(sr_img)
+            psnrs.append(_psnr(sr_img, gt_img))
+            if save_images:
+                m = ((np.array(sr_img.shape[:2]) - patch) / 2).astype(np.int32)
+                collage[-1].append(np.clip(sr_img[m[0]:-m[0], m[1]:-m[1], ...], 0, 255).astype(np.uint8))
+                if first_eval:
+                    gt_collage[-1].append(np.clip(gt_img[m[0]:-m[0], m[1]:-m[1], ...], 0, 255).astype(np.uint8))
+        avg_psnr = 1 * np.mean(psnrs)
+        if save_images:
+            self.generator_changed = False
+            if 'im_collages' not in self.__dict__:
+                self.im_collages = []
+            self.im_collages.append(np.concatenate([np.concatenate(col, 0) for col in collage], 1))
+            name = '{:d}_{}PSNR{:.3f}.png'.format(self.gradient_step_num, ('Z' + str(cur_Z)) if self.opt['network_G']['latent_input'] else '', avg_psnr)
+            _save_png(self.im_collages[-1], os.path.join(self.opt['path']['val_images'], name))
+            if first_eval:
+                _save_png(np.concatenate([np.concatenate(col, 0) for col in gt_collage], 1), os.path.join(self.opt['path']['val_images'], 'GT_HR.png'))
+        print_rlt['psnr'] += avg_psnr
+        return sr_images
+
+    def update_learning_rate(self, cur_step=None):
+        """models/SRRaGAN_model.py:592-632 (returns "learning rate too low"): once enough discriminator steps are logged, the standard
+        deviation of the D loss over the last `steps_4_loss_std` steps is recorded; above `std_4_lr_drop` the run rolls back to the
+        checkpoint before that window and every optimizer's lr is multiplied by `lr_gamma`."""
+        tr = self.opt['train']
+        if not self.D_exists or tr['steps_4_loss_std'] is None:
+            return False
+        n = tr['steps_4_loss_std']
+        if len(self.log_dict['D_logits_diff']) >= n:
+            vals = [(v[1] + self.log_dict['l_d_fake'][i][1]) / 2 for i, v in enumerate(self.log_dict['l_d_real']) if v[0] >= cur_step - n]
+            self.log_dict.setdefault('D_loss_STD', []).append([self.gradient_step_num, np.std(vals)])
+            reduce_lr = (tr['std_4_lr_drop'] is not None) and self.log_dict['D_loss_STD'][-1][1] > tr['std_4_lr_drop']
+        else:
+            reduce_lr = False
+        if len(self.log_dict['D_logits_diff']) < 2 * n or self.log_dict['D_logits_diff'][0][0] > cur_step - n:   # not before a minimal number of steps
+            return False
+        if reduce_lr:
+            cur_LR = [o.param_groups[0]['lr'] for o in self.optimizers]
+            self.load(max_step=cur_step - n, resume_train=True)
+            for k, optimizer in enumerate(self.optimizers):
+                for group in optimizer.param_groups:
+                    group['lr'] = cur_LR[k] * tr['lr_gamma']
+                    if group['lr'] < 1e-8:
+                        return True
+            lrs = {'lr_G': self.optimizer_G.param_groups[0]['lr'], 'lr_D': self.optimizer_D.param_groups[0]['lr']}
+            print('LR(D) reduced to %.2e, LR(G) reduced to %.2e.' % (lrs['lr_D'], lrs['lr_G']))
+            np.savez(os.path.join(self.log_path, 'lr.npz'), step_num=cur_step, **lrs)
+            self.log_dict['LR_decrease'].append([self.step // self.max_accumulation_steps, lrs])
+        return False
+
+    def save_log(self):
+        """logs.npz in the reference's layout (:644-651): every log series plus D_verified / verified_D_saved / lr_G / lr_D"""
+        blob = dict(self.log_dict)
+        for attr in ('D_verified', 'verified_D_saved', 'lr_G', 'lr_D'):
+            if attr in self.__dict__:
+                blob[attr] = getattr(self, attr)
+        np.savez(os.path.join(self.log_path, 'logs.npz'), **{k: np.array(v, dtype=object) if k == 'LR_decrease' else v for k, v in blob.items()})
+        if self.cri_latent is not None and hasattr(self.cri_latent, 'collected_ratios'):
+            np.savez(os.path.join(self.log_path, 'collected_stats.npz'), *self.cri_latent.collected_ratios)
+
+    def load_log(self, max_step=None):
+        """(:653-675) the inverse of save_log, optionally truncated to gradient steps <= max_step (roll-back after an lr drop)"""
+        from collections import deque
+        loaded = np.load(os.path.join(self.log_path, 'logs.npz'), allow_pickle=True)
+        self.log_dict = OrderedDict((k, []) for k in self.log_dict.keys())
+        for key in loaded.files:
+            if key in ('D_verified', 'verified_D_saved', 'lr_G', 'lr_D'):
+                setattr(self, key, loaded[key])
+                continue
+            self.log_dict[key] = [tuple(v) for v in loaded[key]] if key == 'psnr_val' else list(loaded[key])
+            if max_step is not None:
+                self.log_dict[key] = [pair for pair in self.log_dict[key] if pair[0] <= max_step]
+        if self.cri_latent is not None and hasattr(self.cri_latent, 'collected_ratios'):
+            stats = np.load(os.path.join(self.log_path, 'collected_stats.npz'))
+            for i, f in enumerate(stats.files):
+                self.cri_latent.collected_ratios[i] = deque(stats[f], maxlen=self.cri_latent.collected_ratios[i].maxlen)
+
+    def display_log_figure(self):
+        """one PDF per logged series (models/base_model.py:211-274), written when matplotlib is installed; plotting is not part of the
+        accelerated path, a missing matplotlib only skips the figures"""
+        try:
+            import matplotlib
+            matplotlib.use('Agg')
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        for key, series in self.log_dict.items():
+            if key == 'LR_decrease' or len(series) == 0:
+                continue
+            steps, vals = np.array([v[0] for v in series]), np.array([float(v[1]) for v in series])
+            plt.figure(1)
+            plt.clf()
+            plt.plot(steps, vals)
+            for decrease in self.log_dict.get('LR_decrease', []):
+                plt.plot([decrease[0], decrease[0]], [vals.min(), vals.max()], 'k')
+            plt.xlabel('Steps')
+            plt.legend([key + ' (%.2e)' % vals.mean()], loc='best')
+            plt.savefig(os.path.join(self.log_path, 'logs_%s.pdf' % key))
 
     # ---- checkpoints --------------------------------------------------------------------------------
     def load(self, max_step=None, resume_train=None):
@@ -414,6 +560,8 @@ class SRRaGANModel(BaseModel):
                 self.step = (loaded_step + 1) * self.max_accumulation_steps
                 print('Resuming training with model for G [{:s}] ...'.format(os.path.join(models_dir, name)))
                 self.load_network(os.path.join(models_dir, name), self.netG, optimizer=self.optimizer_G)
+                if self.log_path is not None and os.path.exists(os.path.join(self.log_path, 'logs.npz')):
+                    self.load_log(max_step=loaded_step)       # the logs roll back with the weights (:746)
                 if self.D_exists:
                     print('Resuming training with model for D [{:s}] ...'.format(d_path))
                     self.load_network(d_path, self.netD, optimizer=self.optimizer_D)

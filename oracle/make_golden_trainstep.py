@@ -19,6 +19,10 @@ from make_golden import save  # noqa: E402
 
 PATCH, SCALE, BATCH = 32, 4, 4
 
+# the reference's load_log (SRRaGAN_model.py:653-675) reads object arrays it saved itself: numpy >= 1.16.3 needs allow_pickle for that
+_np_load = np.load
+np.load = lambda *a, **k: _np_load(*a, **{'allow_pickle': True, **k})
+
 
 class ND(dict):
     def __missing__(self, k):
@@ -70,14 +74,44 @@ VARIANTS = {
     'acc_d2_g1': dict(grad_accumulation_steps_D=2, grad_accumulation_steps_G=1),
     'no_gan': dict(gan_weight=None),
     'latent': dict(latent_weight=1.0, _latent=1),
+    'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
 }
 N_CALLS = 8
+
+
+class ValLoader:
+    """what perform_validation touches of a DataLoader: iteration over batched samples and `.dataset` (un-batched samples)"""
+
+    def __init__(self, lr, hr):
+        self.dataset = [{'LR': l, 'HR': h, 'HR_path': 'img%d.png' % i} for i, (l, h) in enumerate(zip(lr, hr))]
+
+    def __iter__(self):
+        for d in self.dataset:
+            yield {'LR': d['LR'].unsqueeze(0).clone(), 'HR': d['HR'].unsqueeze(0).clone(), 'HR_path': [d['HR_path']]}
+
+    def __len__(self):
+        return len(self.dataset)
+
+
+def run_validation(model, tmp, data):
+    from collections import OrderedDict
+    model.opt['path']['val_images'] = os.path.join(tmp, 'val_images')
+    os.makedirs(model.opt['path']['val_images'], exist_ok=True)
+    loader = ValLoader(data['LR'][0], data['HR'][0])
+    print_rlt = OrderedDict(psnr=0.0)
+    model.im_collages = []
+    model.gradient_step_num = 7
+    sr = model.perform_validation(data_loader=loader, cur_Z=0, print_rlt=print_rlt, first_eval=True, save_images=True)
+    files = sorted(os.listdir(model.opt['path']['val_images']))
+    return {'val:psnr': np.array(print_rlt['psnr']), 'val:sr_mean': np.array([float(np.mean(im)) for im in sr]), 'val:collage': model.im_collages[-1],
+            'val:n_files': np.array(len(files)), 'val:generator_changed': np.array(float(model.generator_changed))}
 
 
 def run(model_cls, networks, tmp, variant_name, data):
     variant = dict(VARIANTS[variant_name])
     rel = variant.pop('_relativistic', None)
     latent = bool(variant.pop('_latent', 0))
+    train_loop = bool(variant.pop('_loop', 0))
     opt = make_opt(tmp, variant, latent)
     patch = opt['datasets']['train']['patch_size']
     if rel is not None:
@@ -102,12 +136,26 @@ def run(model_cls, networks, tmp, variant_name, data):
         init.update({'D0:' + k: v.detach().clone().numpy() for k, v in model.netD.state_dict().items()})
     torch.manual_seed(5)      # feed_data draws the latent codes from the global generator
     key = 'lat' if latent else ''
+    lrs = []
     for it in range(N_CALLS):
+        if train_loop:      # what train.py:92-101,187-189 does around the step: checkpoint + log, then the loss-driven lr rule
+            model.gradient_step_num = model.step // model.max_accumulation_steps
+            model.save(model.gradient_step_num)
+            model.save_log()
         model.feed_data({'LR': data[key + 'LR'][it].clone(), 'HR': data[key + 'HR'][it].clone()})
         model.optimize_parameters()
+        if train_loop:
+            too_low = model.update_learning_rate(model.gradient_step_num)
+            lrs.append([model.step, model.optimizer_G.param_groups[0]['lr'], model.optimizer_D.param_groups[0]['lr'], float(too_low)])
     logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
             if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
                                     'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2')}
+    if train_loop:
+        logs['log:lrs'] = np.array(lrs, dtype=np.float64)
+        logs['log:D_loss_STD'] = np.array(model.log_dict['D_loss_STD'], dtype=np.float64)
+        logs['log:LR_decrease_steps'] = np.array([d[0] for d in model.log_dict['LR_decrease']], dtype=np.float64)
+    if variant_name == 'no_gan':      # the validation pass train.py:150-175 runs on the trained generator
+        logs.update(run_validation(model, tmp, data))
     final = {'G1:' + k: v.detach().numpy() for k, v in model.netG.state_dict().items()}
     if model.D_exists:
         final.update({'D1:' + k: v.detach().numpy() for k, v in model.netD.state_dict().items()})

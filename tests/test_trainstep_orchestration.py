@@ -48,7 +48,20 @@ VARIANTS = {
     'acc_d2_g1': dict(grad_accumulation_steps_D=2, grad_accumulation_steps_G=1),
     'no_gan': dict(gan_weight=None),
     'latent': dict(latent_weight=1.0, _latent=1),
+    'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
 }
+
+
+class ValLoader:
+    def __init__(self, lr, hr):
+        self.dataset = [{'LR': l, 'HR': h, 'HR_path': 'img%d.png' % i} for i, (l, h) in enumerate(zip(lr, hr))]
+
+    def __iter__(self):
+        for d in self.dataset:
+            yield {'LR': d['LR'].unsqueeze(0).clone(), 'HR': d['HR'].unsqueeze(0).clone(), 'HR_path': [d['HR_path']]}
+
+    def __len__(self):
+        return len(self.dataset)
 
 
 def _opt(tmp_path, variant, latent=False):
@@ -76,6 +89,7 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
     variant = dict(VARIANTS[name])
     rel = variant.pop('_relativistic', None)
     latent = bool(variant.pop('_latent', 0))
+    train_loop = bool(variant.pop('_loop', 0))
     opt = _opt(tmp_path, variant, latent)
     patch = opt['datasets']['train']['patch_size']
     if latent:      # the structure-tensor statistics kernel is CUDA-only: the oracle's restatement stands in for it here
@@ -103,9 +117,24 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
             assert np.array_equal(v.numpy(), g['%s/D0:%s' % (name, k)]), k
     torch.manual_seed(5)      # feed_data draws the latent codes from the global generator
     key = 'lat' if latent else ''
+    lrs = []
+    if train_loop:
+        import os
+        os.makedirs(str(tmp_path / 'models'), exist_ok=True)
     for it in range(g['LR'].shape[0]):
+        if train_loop:      # what train.py:92-101,187-189 does around the step: checkpoint + log, then the loss-driven lr rule
+            model.gradient_step_num = model.step // model.max_accumulation_steps
+            model.save(model.gradient_step_num)
+            model.save_log()
         model.feed_data({'LR': torch.from_numpy(g[key + 'LR'][it].astype(np.float32)), 'HR': torch.from_numpy(g[key + 'HR'][it].astype(np.float32))})
         model.optimize_parameters()
+        if train_loop:
+            too_low = model.update_learning_rate(model.gradient_step_num)
+            lrs.append([model.step, model.optimizer_G.param_groups[0]['lr'], model.optimizer_D.param_groups[0]['lr'], float(too_low)])
+    if train_loop:
+        assert np.allclose(np.array(lrs), g[name + '/log:lrs'], rtol=1e-6), (lrs, g[name + '/log:lrs'])      # steps rolled back, lrs halved at the same calls
+        assert np.allclose(np.array(model.log_dict['D_loss_STD'], dtype=np.float64), g[name + '/log:D_loss_STD'], rtol=1e-3, atol=1e-9)
+        assert [d[0] for d in model.log_dict['LR_decrease']] == list(g[name + '/log:LR_decrease_steps'])
     # the latent variant measures the structure tensor with a different summation order than the reference's conv filters: 1e-7
     # differences, and |measured - target| has kinks whose gradient sign Adam's first steps turn into full lr-size weight changes
     # (observed: agreement to 6e-7 through gradient step 3, 1e-3 from step 4 on) - it is compared over the first four steps
@@ -124,6 +153,20 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
         assert np.allclose(own[:, 1], ref[:, 1], rtol=rtol, atol=atol), (key, own[:, 1], ref[:, 1])
     if latent:
         return
+    if name == 'no_gan':      # the validation pass of train.py:150-175 on the trained generator: PSNR, collage, files written
+        import os
+        from collections import OrderedDict
+        model.opt['path']['val_images'] = str(tmp_path / 'val_images')
+        loader = ValLoader(torch.from_numpy(g['LR'][0].astype(np.float32)), torch.from_numpy(g['HR'][0].astype(np.float32)))
+        print_rlt = OrderedDict(psnr=0.0)
+        model.im_collages = []
+        model.gradient_step_num = 7
+        sr = model.perform_validation(data_loader=loader, cur_Z=0, print_rlt=print_rlt, first_eval=True, save_images=True)
+        assert abs(print_rlt['psnr'] - float(g[name + '/val:psnr'])) < 1e-3
+        assert np.allclose([float(np.mean(im)) for im in sr], g[name + '/val:sr_mean'], rtol=1e-4)
+        assert model.im_collages[-1].shape == g[name + '/val:collage'].shape
+        assert np.abs(model.im_collages[-1].astype(np.int32) - g[name + '/val:collage'].astype(np.int32)).max() <= 1
+        assert len(os.listdir(str(tmp_path / 'val_images'))) == int(g[name + '/val:n_files']) and model.generator_changed is False
     for k, v in model.netG.state_dict().items():
         assert np.allclose(v.numpy(), g['%s/G1:%s' % (name, k)], rtol=rtol, atol=atol), k
     if model.D_exists:
