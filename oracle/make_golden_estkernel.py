@@ -32,6 +32,18 @@ def main():
         cem = CEMnet(conf, upscale_kernel=k)
         arrays.update({tag + ':kernel': k, tag + ':ds_kernel': cem.ds_kernel, tag + ':inv_hTh': cem.inv_hTh,
                        tag + ':margins': np.array([cem.invalidity_margins_LR, cem.invalidity_margins_HR])})
+        # the filters applied (reference's dense depth-wise convs, CPU): what the rank > 1 separable CUDA path must reproduce
+        import torch
+        gen = torch.Generator().manual_seed(sf)
+        mod = cem.WrapArchitecture_PyTorch(None, None)
+        xl = torch.rand(1, 3, 14, 18, generator=gen)
+        gi = torch.rand(1, 3, 14 * sf, 18 * sf, generator=gen)
+        with torch.no_grad():
+            mod.train()
+            out_train = mod([xl, gi])
+            arrays.update({tag + ':x_lr': xl.numpy(), tag + ':g': gi.numpy(), tag + ':out_train': out_train.numpy(),
+                           tag + ':down': mod.DownscaleOP(gi).numpy(), tag + ':inv': mod.Conv_LR_with_Inv_hTh_OP(xl).numpy(),
+                           tag + ':up': mod.Upscale_OP(xl).numpy()})
         print(tag, cem.ds_kernel.shape, cem.inv_hTh.shape, cem.invalidity_margins_LR, cem.invalidity_margins_HR)
         imresize(None, [sf, sf], return_upscale_kernel=True, kernel='reset_2_default')
     save('cem_estimated_kernel', **arrays)
