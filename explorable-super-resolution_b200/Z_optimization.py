@@ -77,6 +77,49 @@ def TV_Loss(image):
 _UNBUILT = ['local', 'Mag', 'periodicity', 'hist', 'dict', 'scribble', 'VGG', 'Adversarial', 'desired_SVD', 'digit']
 
 
+def Patch_Indexes_2_Sparse_Mat(patches_indexes, mask_size, device):
+    """[n_patches, p*p] pixel indexes -> sparse 0/1 matrix [n_patches*p*p, mask_size]; row order: position-in-patch major, patch minor
+    (Z_optimization.py:267-271), so `mm(mat, image.view(-1,1)).view(p*p, n_patches)` lists every patch as a column"""
+    rows = np.arange(patches_indexes.size).reshape([-1])
+    cols = patches_indexes.transpose().reshape([-1])
+    return torch.sparse_coo_tensor(torch.from_numpy(np.stack([rows, cols]).astype(np.int64)), torch.ones(rows.size, dtype=torch.float32),
+                                   (patches_indexes.size, mask_size)).to(device)
+
+
+def ReturnPatchExtractionMat(mask, patch_size, device, patches_overlap=1, return_non_covered=False):
+    """All patch_size x patch_size patches lying inside `mask` as a sparse pixel-gathering matrix (Z_optimization.py:232-265; the GUI's
+    Estimate_DerivedControlIndicator, GUI.py:2408-2412).  patches_overlap < 1 keeps, scanning in raster order, only patches whose
+    share of already covered pixels does not exceed it (0: no shared pixel at all) and can return the uncovered pixels as a
+    second matrix.  Host-side index construction; the products with it are sparse mm."""
+    from scipy.ndimage import binary_opening
+    from sklearn.feature_extraction.image import extract_patches_2d
+    mask = binary_opening(mask, np.ones([patch_size, patch_size]).astype(bool))
+    numbered = np.multiply(mask, 1 + np.arange(mask.size).reshape(mask.shape))
+    patches_indexes = extract_patches_2d(numbered, (patch_size, patch_size)).reshape([-1, patch_size ** 2])
+    patches_indexes = patches_indexes[np.all(patches_indexes > 0, 1), :] - 1
+    non_covered_mat = None
+    if patches_overlap < 1:
+        unique_indexes = list(set(list(patches_indexes.reshape([-1]))))
+        lo = min(unique_indexes)
+        # (the reference sizes this one short and addresses it with "- lo - 1": the smallest index lands on the LAST slot; kept as is)
+        taken = np.zeros([max(unique_indexes) - lo]).astype(bool)
+        keep = np.ones([patches_indexes.shape[0]]).astype(bool)
+        for k in range(patches_indexes.shape[0]):
+            slots = patches_indexes[k, :] - lo - 1
+            if (patches_overlap == 0 and np.any(taken[slots])) or np.mean(taken[slots]) > patches_overlap:
+                keep[k] = False
+                continue
+            taken[slots] = True
+        patches_indexes = patches_indexes[keep]
+        print('%.3f of desired pixels are covered by assigned patches' % (taken[np.array(unique_indexes) - lo - 1].mean()))
+        if return_non_covered:
+            rest = np.array(unique_indexes)
+            rest = rest[np.logical_not(taken[rest - lo - 1])]
+            non_covered_mat = Patch_Indexes_2_Sparse_Mat(rest, mask.size, device)
+    mat = Patch_Indexes_2_Sparse_Mat(patches_indexes, mask.size, device)
+    return (mat, non_covered_mat) if return_non_covered else mat
+
+
 class Z_optimizer():
     MIN_LR = 1e-5
     PATCH_SIZE_4_STD = 7
