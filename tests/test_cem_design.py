@@ -70,3 +70,17 @@ def test_estimated_kernel_design_matches_reference(tag, s):
     finally:
         imresize(None, [s, s], return_upscale_kernel=True, kernel='reset_2_default')
     assert np.array_equal(CEMnet(Get_CEM_Conf(s)).ds_kernel, golden('cem_x%d' % s)['ds_kernel'])
+
+
+def test_imresize_matches_reference_on_images():
+    """CEM.imresize_CEM.imresize as an image resizer (data pipeline / GUI use) against the unmodified reference's outputs"""
+    from CEM.imresize_CEM import imresize
+    g = golden('imresize_cases')
+    cases = [('down4', dict(scale_factor=1 / 4)), ('up4', dict(scale_factor=4)), ('down2', dict(scale_factor=[0.5])), ('up3', dict(scale_factor=3)),
+             ('down3', dict(scale_factor=1 / 3)), ('down4_zero', dict(scale_factor=1 / 4, use_zero_padding=True)),
+             ('up2_center', dict(scale_factor=2, align_center=True)), ('down2_center', dict(scale_factor=0.5, align_center=True)),
+             ('up4_shape', dict(output_shape=[24, 28]))]
+    for tag, kw in cases:
+        out = imresize(g[tag + ':in'], **kw)
+        assert out.shape == g[tag + ':out'].shape, tag
+        assert np.abs(out - g[tag + ':out']).max() < 1e-12, (tag, np.abs(out - g[tag + ':out']).max())
