@@ -77,6 +77,16 @@ def TV_Loss(image):
 _UNBUILT = ['local', 'Mag', 'periodicity', 'hist', 'dict', 'scribble', 'VGG', 'Adversarial', 'desired_SVD', 'digit']
 
 
+class SoftHistogramLoss(torch.nn.Module):
+    """Kernel-density histogram / patch-dictionary objective of the GUI's imprinting tools (Z_optimization.py:24-230).  Not built: it is
+    an O(pixels x bins) double-precision distance computation that belongs in its own CUDA kernel; the name exists so
+    that `from Z_optimization import SoftHistogramLoss` resolves, and constructing it fails loudly (there is no PyTorch fallback)."""
+
+    def __init__(self, *args, **kwargs):
+        super(SoftHistogramLoss, self).__init__()
+        raise NotImplementedError('esr_b200: SoftHistogramLoss (hist / dict objectives of Z_optimizer) is not built yet')
+
+
 def Patch_Indexes_2_Sparse_Mat(patches_indexes, mask_size, device):
     """[n_patches, p*p] pixel indexes -> sparse 0/1 matrix [n_patches*p*p, mask_size]; row order: position-in-patch major, patch minor
     (Z_optimization.py:267-271), so `mm(mat, image.view(-1,1)).view(p*p, n_patches)` lists every patch as a column"""
