@@ -62,8 +62,8 @@ class SRRaGANModel(BaseModel):
             if train_opt['gan_weight'] is not None:
                 if train_opt['gan_type'] == 'wgan-gp':
                     unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
-                if train_opt['D_verification'] is not None or isinstance(train_opt['D_update_ratio'], list):
-                    unbuilt.append('D_verification / automatic D_update_ratio controller')
+                if isinstance(train_opt['D_update_ratio'], list):
+                    unbuilt.append('automatic D_update_ratio controller')
                 if (opt['network_D'] or {}).get('decomposed_input') or train_opt['hinge_threshold'] is not None:
                     unbuilt.append('decomposed_input / hinge_threshold')
             if unbuilt:
@@ -117,7 +117,13 @@ class SRRaGANModel(BaseModel):
         self.netG.train()
         self.l_gan_w = train_opt['gan_weight']
         self.D_exists = self.l_gan_w is not None
-        self.D_verified, self.verified_D_saved = True, True          # D_verification is None (SRRaGAN_model.py:74)
+        # D verification (SRRaGAN_model.py:71-76): the generator only steps on the adversarial term once the critic is judged good
+        # enough - by its recent log ('past'), by the current batch ('current') or by the flattening of its loss ('convergence')
+        self.D_verification = train_opt['D_verification']
+        assert self.D_verification in ['current', 'convergence', 'past', None]
+        self.D_verified, self.verified_D_saved = self.D_verification is None, self.D_verification is None
+        if self.D_verification == 'convergence':
+            self.D_converged = False
         if self.D_exists:
             self.relativistic_D = opt['network_D']['relativistic'] is None or bool(opt['network_D']['relativistic'])
             self.netD = networks.define_D(opt, CEM=self.CEM_net).to(self.device)
@@ -278,7 +284,10 @@ class SRRaGANModel(BaseModel):
             if first_acc_D:
                 self.discriminator_step = self.gradient_step_num >= -self.D_init_iters
                 if self.discriminator_step:
-                    self.discriminator_step = self.gradient_step_num % max([1, np.ceil(1 / self.global_D_update_ratio)]) == 0
+                    if not self.verified_D_saved:
+                        self.discriminator_step = True
+                    else:
+                        self.discriminator_step = self.gradient_step_num % max([1, np.ceil(1 / self.global_D_update_ratio)]) == 0
         # G forward: its graph is only kept when a generator step follows
         self.Set_Require_Grad_Status(self.netG, bool(not self.D_exists or self.generator_step))
         if self.CEM_net is not None:
@@ -316,6 +325,29 @@ class SRRaGANModel(BaseModel):
             self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
             self.D_fake_grad_step.append(torch.mean(pred_d_fake.detach()).item())
             self.D_logits_diff_grad_step.append(list(torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).cpu().numpy()))
+            if first_acc_D and self.generator_step:      # D verification (:377-393): may call this generator step off
+                tr = self.opt['train']
+                if self.D_verification == 'past' and tr['D_valid_Steps_4_G_update'] > 0:
+                    k = tr['D_valid_Steps_4_G_update']
+                    self.generator_step = len(self.log_dict['D_logits_diff']) >= k and \
+                        all([v[1] > np.log(tr['min_D_prob_ratio_4_G']) for v in self.log_dict['D_logits_diff'][-k:]]) and \
+                        all([v[1] > tr['min_mean_D_correct'] for v in self.log_dict['Correctly_distinguished'][-k:]])
+                elif self.D_verification == 'convergence':
+                    if not self.D_converged and self.gradient_step_num >= tr['steps_4_D_convergence']:
+                        std, slope = 0, 0
+                        for key in ['l_d_real', 'l_d_fake']:
+                            vals = [v[1] for v in self.log_dict[key] if v[0] >= self.gradient_step_num - tr['steps_4_loss_std']]
+                            [cur_slope, _], [[cur_var, _], _] = np.polyfit([i for i in range(len(vals))], vals, 1, cov=True)
+                            std += 0.5 * np.sqrt(cur_var)
+                            slope += 0.5 * cur_slope
+                        self.D_converged = -tr['lr_change_ratio'] * np.minimum(-1e-5, slope) < std
+                    self.generator_step = 1 * self.D_converged
+            if self.D_verification == 'current' and self.generator_step:
+                self.generator_step = all([v > 0 for v in self.D_logits_diff_grad_step[-1]]) \
+                    and np.mean(self.D_logits_diff_grad_step[-1]) > np.log(self.opt['train']['min_D_prob_ratio_4_G'])
+            self.generator_step = bool(self.generator_step)     # (numpy scalars above; under numpy 2 the reference's 'current' mode trips on exactly that)
+            if not self.generator_step:      # the generator's graph is not needed after all
+                self.fake_H = self.fake_H.detach()
             if last_acc_D:
                 parallel.average_gradients(self.netD.parameters())
                 self.optimizer_D.step()
