@@ -58,7 +58,7 @@ class SRRaGANModel(BaseModel):
         super(SRRaGANModel, self).__init__(opt)
         train_opt = opt['train'] if self.is_train else None
         if self.is_train:
-            unbuilt = [k for k in ('optimalZ_loss_weight',) if train_opt[k] is not None]
+            unbuilt = ['optimalZ_loss_type hist (SoftHistogramLoss)'] if (train_opt['optimalZ_loss_weight'] is not None and train_opt['optimalZ_loss_type'] == 'hist') else []
             if train_opt['gan_weight'] is not None:
                 if train_opt['gan_type'] == 'wgan-gp':
                     unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
@@ -77,7 +77,10 @@ class SRRaGANModel(BaseModel):
         self.cri_latent = None
         self.optimalZ_loss_type = None
         self.num_latent_channels = FilterLoss(latent_channels=opt['network_G']['latent_channels']).num_channels
+        self.cri_optimalZ = None
         if self.latent_input is not None and self.is_train:   # latent-control loss L_struct (SRRaGAN_model.py:37-40)
+            if train_opt['optimalZ_loss_type'] is not None and train_opt['optimalZ_loss_weight'] is not None:
+                self.optimalZ_loss_type = train_opt['optimalZ_loss_type']      # (:68-70)
             self.l_latent_w = train_opt['latent_weight']
             if self.l_latent_w is not None:
                 self.cri_latent = FilterLoss(latent_channels=opt['network_G']['latent_channels'])
@@ -103,7 +106,7 @@ class SRRaGANModel(BaseModel):
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
         logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'l_d_real_fake', 'D_real', 'D_fake', 'D_logits_diff',
-                       'Correctly_distinguished', 'psnr_val', 'LR_decrease'] + ['l_g_latent_%d' % i for i in range(self.num_latent_channels)]
+                       'Correctly_distinguished', 'psnr_val', 'LR_decrease', 'l_g_optimalZ', 'D_loss_STD'] + ['l_g_latent_%d' % i for i in range(self.num_latent_channels)]
         self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
         if not self.is_train:
             self.netG.eval()
@@ -140,6 +143,21 @@ class SRRaGANModel(BaseModel):
         else:
             print('Remove pixel loss.')
             self.cri_pix = None
+        if self.optimalZ_loss_type is not None:   # reference loss after optimising the latent input, L_map (:108-123)
+            from Z_optimization import Z_optimizer
+            self.l_g_optimalZ_w = train_opt['optimalZ_loss_weight']
+            self.Z_optimizer = Z_optimizer(objective=self.optimalZ_loss_type,
+                                           Z_size=2 * [int(opt['datasets']['train']['patch_size'] / (opt['scale'] / self.Z_size_factor))], model=self,
+                                           Z_range=1, max_iters=10, initial_LR=1, batch_size=opt['datasets']['train']['batch_size'],
+                                           HR_unpadder=self.CEM_net.HR_unpadder)
+            if self.optimalZ_loss_type == 'l2':
+                self.cri_optimalZ = nn.MSELoss().to(self.device)
+            elif self.optimalZ_loss_type == 'l1':
+                self.cri_optimalZ = nn.L1Loss().to(self.device)
+            else:
+                raise NotImplementedError('Loss type [{:s}] not recognized.'.format(self.optimalZ_loss_type))
+        else:
+            print('Remove reference loss with optimal Z.')
         if train_opt['range_weight'] is not None:
             self.cri_range = CreateRangeLoss(opt['range'])
             self.l_range_w = train_opt['range_weight']
@@ -198,6 +216,8 @@ class SRRaGANModel(BaseModel):
                 param_group['lr'] = self.lr_D
             if self.verified_D_saved:
                 self.lr_G = 1 * self.lr_D
+                if 'Z_optimizer' in self.__dict__:      # ... and a different number of Z iterations for the L_map step (:215-216)
+                    self.Z_optimizer.max_iters = self.opt['train']['Num_Z_iterations'][-1]
         for param_group in self.optimizer_G.param_groups:
             param_group['lr'] = self.lr_G
 
@@ -290,133 +310,154 @@ class SRRaGANModel(BaseModel):
                         self.discriminator_step = self.gradient_step_num % max([1, np.ceil(1 / self.global_D_update_ratio)]) == 0
         # G forward: its graph is only kept when a generator step follows
         self.Set_Require_Grad_Status(self.netG, bool(not self.D_exists or self.generator_step))
-        if self.CEM_net is not None:
-            self.var_H, self.var_ref = self.CEM_net.HR_unpadder(self.var_H), self.CEM_net.HR_unpadder(self.var_ref)
-        static_Z = self.GetLatent() if self.latent_input is not None else None
-        self.Prepare_Input(LR_image=self.var_L, latent_input=static_Z)
-        if self.D_exists and not self.generator_step:
-            with torch.no_grad():
-                self.fake_H = self.netG(self.model_input)
-        else:
-            self.fake_H = self.netG(self.model_input)
-        if self.CEM_net is not None:
-            self.fake_H = self.CEM_net.HR_unpadder(self.fake_H)
-        if not self.D_exists:
-            self.generator_step = self.gradient_step_num > 0   # one idle iteration first, to save the initial validation results
-        elif self.discriminator_step:
-            # ---- D step (:340-414)
-            self.Set_Require_Grad_Status(self.netD, True)
-            if first_acc_D:
-                self.optimizer_D.zero_grad()
-                self.l_d_real_grad_step, self.l_d_fake_grad_step, self.D_real_grad_step, self.D_fake_grad_step = [], [], [], []
-                self.D_logits_diff_grad_step = []
-            pred_d_real = self.netD(self.var_ref)
-            pred_d_fake = self.netD(self.fake_H.detach())   # detach to avoid BP to G
-            if self.relativistic_D:
-                l_d_real = self.cri_gan(pred_d_real - self._batch_mean(pred_d_fake), True)
-                l_d_fake = self.cri_gan(pred_d_fake - self._batch_mean(pred_d_real), False)
+        # with the optimised-Z reference loss (L_map) every batch is used twice once the generator has started learning (:314-330):
+        # first with Z optimised towards the ground truth by Z_optimizer, then with the Z that was fed
+        dual_steps = int(self.optimalZ_loss_type is not None and self.generator_started_learning) + 1
+        for dual_num in range(dual_steps):
+            optimized_Z_step = dual_num == (dual_steps - 2)
+            first_dual, last_dual = dual_num == 0, dual_num == (dual_steps - 1)
+            if self.CEM_net is not None and first_dual:
+                self.var_H, self.var_ref = self.CEM_net.HR_unpadder(self.var_H), self.CEM_net.HR_unpadder(self.var_ref)
+            if first_dual:
+                static_Z = self.GetLatent() if self.latent_input is not None else None
+            if optimized_Z_step:
+                self.Z_optimizer.feed_data({'LR': self.var_L, 'desired': self.var_H})
+                self.Z_optimizer.optimize()          # leaves self.fake_H = G(LR, optimised Z) with its graph
             else:
-                l_d_real = 2 * self.cri_gan(pred_d_real, True)
-                l_d_fake = 2 * self.cri_gan(pred_d_fake, False)
-            l_d_total = (l_d_real + l_d_fake) / 2 / acc_D
-            l_d_total.backward()
-            self.l_d_real_grad_step.append(l_d_real.item())
-            self.l_d_fake_grad_step.append(l_d_fake.item())
-            self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
-            self.D_fake_grad_step.append(torch.mean(pred_d_fake.detach()).item())
-            self.D_logits_diff_grad_step.append(list(torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).cpu().numpy()))
-            if first_acc_D and self.generator_step:      # D verification (:377-393): may call this generator step off
-                tr = self.opt['train']
-                if self.D_verification == 'past' and tr['D_valid_Steps_4_G_update'] > 0:
-                    k = tr['D_valid_Steps_4_G_update']
-                    self.generator_step = len(self.log_dict['D_logits_diff']) >= k and \
-                        all([v[1] > np.log(tr['min_D_prob_ratio_4_G']) for v in self.log_dict['D_logits_diff'][-k:]]) and \
-                        all([v[1] > tr['min_mean_D_correct'] for v in self.log_dict['Correctly_distinguished'][-k:]])
-                elif self.D_verification == 'convergence':
-                    if not self.D_converged and self.gradient_step_num >= tr['steps_4_D_convergence']:
-                        std, slope = 0, 0
-                        for key in ['l_d_real', 'l_d_fake']:
-                            vals = [v[1] for v in self.log_dict[key] if v[0] >= self.gradient_step_num - tr['steps_4_loss_std']]
-                            [cur_slope, _], [[cur_var, _], _] = np.polyfit([i for i in range(len(vals))], vals, 1, cov=True)
-                            std += 0.5 * np.sqrt(cur_var)
-                            slope += 0.5 * cur_slope
-                        self.D_converged = -tr['lr_change_ratio'] * np.minimum(-1e-5, slope) < std
-                    self.generator_step = 1 * self.D_converged
-            if self.D_verification == 'current' and self.generator_step:
-                self.generator_step = all([v > 0 for v in self.D_logits_diff_grad_step[-1]]) \
-                    and np.mean(self.D_logits_diff_grad_step[-1]) > np.log(self.opt['train']['min_D_prob_ratio_4_G'])
-            self.generator_step = bool(self.generator_step)     # (numpy scalars above; under numpy 2 the reference's 'current' mode trips on exactly that)
-            if not self.generator_step:      # the generator's graph is not needed after all
-                self.fake_H = self.fake_H.detach()
-            if last_acc_D:
-                parallel.average_gradients(self.netD.parameters())
-                self.optimizer_D.step()
-                self.log_dict['l_d_real'].append((self.gradient_step_num, np.mean(self.l_d_real_grad_step)))
-                self.log_dict['l_d_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step)))
-                self.log_dict['l_d_real_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step) + np.mean(self.l_d_real_grad_step)))
-                self.log_dict['D_real'].append((self.gradient_step_num, np.mean(self.D_real_grad_step)))
-                self.log_dict['D_fake'].append((self.gradient_step_num, np.mean(self.D_fake_grad_step)))
-                self.log_dict['D_logits_diff'].append((self.gradient_step_num, np.mean(self.D_logits_diff_grad_step)))
-                self.log_dict['Correctly_distinguished'].append((self.gradient_step_num, np.mean([v0 > 0 for v1 in self.D_logits_diff_grad_step for v0 in v1])))
-        if self.generator_step:
-            # ---- G step (:417-519)
-            self.generator_started_learning = True
-            if self.D_exists:
-                self.Set_Require_Grad_Status(self.netD, False)
-            self.Set_Require_Grad_Status(self.netG, True)
-            if first_acc:
-                self.optimizer_G.zero_grad()
-                self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step, self.l_g_gan_grad_step = [], [], [], []
-                self.l_g_latent_grad_step = []
-            l_g_total = 0
-            if self.cri_pix:
-                l_g_pix = self.cri_pix(self.fake_H, self.var_H)
-                l_g_total = l_g_total + self.l_pix_w * l_g_pix / acc_G
-            if self.cri_fea:   # perceptual loss: VGG features of the real image (no graph) and of the generated one
-                real_fea = self.netF(self.var_H).detach()
-                fake_fea = self.netF(self.fake_H)
-                l_g_fea = self.cri_fea(fake_fea, real_fea)
-                l_g_total = l_g_total + self.l_fea_w * l_g_fea / acc_G
-            if self.cri_range:
-                l_g_range = self.cri_range(self.fake_H)
-                l_g_total = l_g_total + self.l_range_w * l_g_range / acc_G
-            if self.cri_latent:   # latent-control loss (:455-461)
-                l_g_latent = self.cri_latent({'SR': self.fake_H, 'HR': self.var_H, 'Z': static_Z}).mean(0)
-                l_g_total = l_g_total + self.l_latent_w * l_g_latent.mean() / acc_G
-                self.l_g_latent_grad_step.append([v.item() for v in l_g_latent])
-            if self.D_exists:   # G gan loss (:466-479)
-                pred_g_fake = self.netD(self.fake_H)
-                if self.relativistic_D:
-                    pred_d_real = self.netD(self.var_ref).detach()
-                    l_g_gan = self.l_gan_w * (self.cri_gan(pred_d_real - self._batch_mean(pred_g_fake), False) +
-                                              self.cri_gan(pred_g_fake - self._batch_mean(pred_d_real), True)) / 2 / acc_G
+                self.Prepare_Input(LR_image=self.var_L, latent_input=static_Z)
+                if self.D_exists and not self.generator_step:
+                    with torch.no_grad():
+                        self.fake_H = self.netG(self.model_input)
                 else:
-                    l_g_gan = self.l_gan_w * self.cri_gan(pred_g_fake, True) / acc_G
-                l_g_total = l_g_total + l_g_gan
-            l_g_total.backward()
-            if self.cri_fea:
-                self.l_g_fea_grad_step.append(l_g_fea.item())
-            if self.cri_pix:
-                self.l_g_pix_grad_step.append(l_g_pix.item())
-            if self.cri_gan:
-                self.l_g_gan_grad_step.append(l_g_gan.item())
-            if self.cri_range:
-                self.l_g_range_grad_step.append(l_g_range.item())
-            if last_acc:
-                parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad])
-                self.optimizer_G.step()
-                self.generator_changed = True
+                    self.fake_H = self.netG(self.model_input)
+            if self.CEM_net is not None:
+                self.fake_H = self.CEM_net.HR_unpadder(self.fake_H)
+            if not self.D_exists:
+                self.generator_step = self.gradient_step_num > 0   # one idle iteration first, to save the initial validation results
+            elif self.discriminator_step:
+                # ---- D step (:340-414)
+                self.Set_Require_Grad_Status(self.netD, True)
+                if first_acc_D and first_dual:
+                    self.optimizer_D.zero_grad()
+                    self.l_d_real_grad_step, self.l_d_fake_grad_step, self.D_real_grad_step, self.D_fake_grad_step = [], [], [], []
+                    self.D_logits_diff_grad_step = []
+                if first_dual:
+                    pred_d_real = self.netD(self.var_ref)
+                pred_d_fake = self.netD(self.fake_H.detach())   # detach to avoid BP to G
+                if self.relativistic_D:
+                    l_d_real = self.cri_gan(pred_d_real - self._batch_mean(pred_d_fake), True)
+                    l_d_fake = self.cri_gan(pred_d_fake - self._batch_mean(pred_d_real), False)
+                else:
+                    if first_dual:
+                        l_d_real = 2 * self.cri_gan(pred_d_real, True)
+                    l_d_fake = 2 * self.cri_gan(pred_d_fake, False)
+                l_d_total = (l_d_real + l_d_fake) / 2 / (acc_D * dual_steps)
+                self.l_d_real_grad_step.append(l_d_real.item())
+                self.l_d_fake_grad_step.append(l_d_fake.item())
+                self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
+                self.D_fake_grad_step.append(torch.mean(pred_d_fake.detach()).item())
+                self.D_logits_diff_grad_step.append(list(torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).cpu().numpy()))
+                if first_acc_D and first_dual and self.generator_step:      # D verification (:377-393): may call this generator step off
+                    tr = self.opt['train']
+                    if self.D_verification == 'past' and tr['D_valid_Steps_4_G_update'] > 0:
+                        k = tr['D_valid_Steps_4_G_update']
+                        self.generator_step = len(self.log_dict['D_logits_diff']) >= k and \
+                            all([v[1] > np.log(tr['min_D_prob_ratio_4_G']) for v in self.log_dict['D_logits_diff'][-k:]]) and \
+                            all([v[1] > tr['min_mean_D_correct'] for v in self.log_dict['Correctly_distinguished'][-k:]])
+                    elif self.D_verification == 'convergence':
+                        if not self.D_converged and self.gradient_step_num >= tr['steps_4_D_convergence']:
+                            std, slope = 0, 0
+                            for key in ['l_d_real', 'l_d_fake']:
+                                vals = [v[1] for v in self.log_dict[key] if v[0] >= self.gradient_step_num - tr['steps_4_loss_std']]
+                                [cur_slope, _], [[cur_var, _], _] = np.polyfit([i for i in range(len(vals))], vals, 1, cov=True)
+                                std += 0.5 * np.sqrt(cur_var)
+                                slope += 0.5 * cur_slope
+                            self.D_converged = -tr['lr_change_ratio'] * np.minimum(-1e-5, slope) < std
+                        self.generator_step = 1 * self.D_converged
+                if self.D_verification == 'current' and self.generator_step:
+                    self.generator_step = all([v > 0 for v in self.D_logits_diff_grad_step[-1]]) \
+                        and np.mean(self.D_logits_diff_grad_step[-1]) > np.log(self.opt['train']['min_D_prob_ratio_4_G'])
+                self.generator_step = bool(self.generator_step)     # (numpy scalars above; under numpy 2 the reference's 'current' mode trips on exactly that)
+                if not self.generator_step:      # the generator's graph is not needed after all
+                    self.fake_H = self.fake_H.detach()
+                l_d_total.backward(retain_graph=not last_dual)      # the real batch's critic graph is shared by both dual steps
+                if last_acc_D and last_dual:
+                    parallel.average_gradients(self.netD.parameters())
+                    self.optimizer_D.step()
+                    self.log_dict['l_d_real'].append((self.gradient_step_num, np.mean(self.l_d_real_grad_step)))
+                    self.log_dict['l_d_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step)))
+                    self.log_dict['l_d_real_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step) + np.mean(self.l_d_real_grad_step)))
+                    self.log_dict['D_real'].append((self.gradient_step_num, np.mean(self.D_real_grad_step)))
+                    self.log_dict['D_fake'].append((self.gradient_step_num, np.mean(self.D_fake_grad_step)))
+                    self.log_dict['D_logits_diff'].append((self.gradient_step_num, np.mean(self.D_logits_diff_grad_step)))
+                    self.log_dict['Correctly_distinguished'].append((self.gradient_step_num, np.mean([v0 > 0 for v1 in self.D_logits_diff_grad_step for v0 in v1])))
+            if self.generator_step:
+                # ---- G step (:417-519)
+                self.generator_started_learning = True
+                if self.D_exists:
+                    self.Set_Require_Grad_Status(self.netD, False)
+                self.Set_Require_Grad_Status(self.netG, True)
+                if first_acc and first_dual:
+                    self.optimizer_G.zero_grad()
+                    self.l_g_pix_grad_step, self.l_g_range_grad_step, self.l_g_fea_grad_step, self.l_g_gan_grad_step = [], [], [], []
+                    self.l_g_latent_grad_step, self.l_g_optimalZ_grad_step = [], []
+                l_g_total = 0
                 if self.cri_pix:
-                    self.log_dict['l_g_pix'].append((self.gradient_step_num, np.mean(self.l_g_pix_grad_step)))
-                if self.cri_fea:
-                    self.log_dict['l_g_fea'].append((self.gradient_step_num, np.mean(self.l_g_fea_grad_step)))
+                    l_g_pix = self.cri_pix(self.fake_H, self.var_H)
+                    l_g_total = l_g_total + self.l_pix_w * l_g_pix / (acc_G * dual_steps)
+                if self.cri_fea:   # perceptual loss: VGG features of the real image (no graph) and of the generated one
+                    real_fea = self.netF(self.var_H).detach()
+                    fake_fea = self.netF(self.fake_H)
+                    l_g_fea = self.cri_fea(fake_fea, real_fea)
+                    l_g_total = l_g_total + self.l_fea_w * l_g_fea / (acc_G * dual_steps)
                 if self.cri_range:
-                    self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
+                    l_g_range = self.cri_range(self.fake_H)
+                    l_g_total = l_g_total + self.l_range_w * l_g_range / (acc_G * dual_steps)
+                if self.cri_latent and last_dual:   # latent-control loss, on the pass with the Z that was fed (:455-461)
+                    l_g_latent = self.cri_latent({'SR': self.fake_H, 'HR': self.var_H, 'Z': static_Z}).mean(0)
+                    l_g_total = l_g_total + self.l_latent_w * l_g_latent.mean() / acc_G
+                    self.l_g_latent_grad_step.append([v.item() for v in l_g_latent])
+                if self.cri_optimalZ and first_dual:   # L_map: with the optimised Z the output should reach the ground truth (:462-465)
+                    l_g_optimalZ = self.cri_optimalZ(self.fake_H, self.var_H)
+                    l_g_total = l_g_total + self.l_g_optimalZ_w * l_g_optimalZ / acc_G
+                    self.l_g_optimalZ_grad_step.append(l_g_optimalZ.item())
+                if self.D_exists:   # G gan loss (:466-479)
+                    pred_g_fake = self.netD(self.fake_H)
+                    if self.relativistic_D:
+                        # (the reference re-uses the D step's variable here, :474: with two dual steps the second D step therefore sees the
+                        #  real batch's logits DETACHED - mirrored, it changes the critic's gradient)
+                        pred_d_real = self.netD(self.var_ref).detach()
+                        l_g_gan = self.l_gan_w * (self.cri_gan(pred_d_real - self._batch_mean(pred_g_fake), False) +
+                                                  self.cri_gan(pred_g_fake - self._batch_mean(pred_d_real), True)) / 2 / (acc_G * dual_steps)
+                    else:
+                        l_g_gan = self.l_gan_w * self.cri_gan(pred_g_fake, True) / (acc_G * dual_steps)
+                    l_g_total = l_g_total + l_g_gan
+                l_g_total.backward()
+                if self.cri_fea:
+                    self.l_g_fea_grad_step.append(l_g_fea.item())
+                if self.cri_pix:
+                    self.l_g_pix_grad_step.append(l_g_pix.item())
                 if self.cri_gan:
-                    self.log_dict['l_g_gan'].append((self.gradient_step_num, np.mean(self.l_g_gan_grad_step)))
-                if self.cri_latent:
-                    for ch in range(self.num_latent_channels):
-                        self.log_dict['l_g_latent_%d' % ch].append((self.gradient_step_num, np.mean([v[ch] for v in self.l_g_latent_grad_step])))
+                    self.l_g_gan_grad_step.append(l_g_gan.item())
+                if self.cri_range:
+                    self.l_g_range_grad_step.append(l_g_range.item())
+                if last_acc and last_dual:
+                    parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad])
+                    self.optimizer_G.step()
+                    self.generator_changed = True
+                    if self.cri_pix:
+                        self.log_dict['l_g_pix'].append((self.gradient_step_num, np.mean(self.l_g_pix_grad_step)))
+                    if self.cri_fea:
+                        self.log_dict['l_g_fea'].append((self.gradient_step_num, np.mean(self.l_g_fea_grad_step)))
+                    if self.cri_range:
+                        self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
+                    if self.cri_gan:
+                        self.log_dict['l_g_gan'].append((self.gradient_step_num, np.mean(self.l_g_gan_grad_step)))
+                    if self.cri_latent:
+                        for ch in range(self.num_latent_channels):
+                            self.log_dict['l_g_latent_%d' % ch].append((self.gradient_step_num, np.mean([v[ch] for v in self.l_g_latent_grad_step])))
+                    if self.cri_optimalZ:
+                        self.log_dict['l_g_optimalZ'].append((self.gradient_step_num, np.mean(self.l_g_optimalZ_grad_step)))
         self.step += 1
 
     def test(self, prevent_grads_calc=True, **kwargs):

@@ -56,7 +56,7 @@ def make_opt(tmp, variant, latent=False):
     train.update(variant)
     patch = 96 if latent else PATCH
     return ND(model='srragan', scale=SCALE, gpu_ids=None, is_train=True, range=[0, 1], train=train,
-              datasets=ND(train=ND(patch_size=patch, batch_size=BATCH)),
+              datasets=ND(train=ND(patch_size=patch, batch_size=2 if latent else BATCH)),
               path=ND(models=os.path.join(tmp, 'models'), pretrained_model_G=None, pretrained_model_D=None, log=tmp, experiments_root=tmp),
               network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='all_layers' if latent else 'None', latent_input_domain='HR_downscaled',
                            latent_channels='SVDinNormedOut_structure_tensor' if latent else 0,
@@ -75,6 +75,7 @@ VARIANTS = {
     'no_gan': dict(gan_weight=None),
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
+    'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
 }
@@ -151,7 +152,7 @@ def run(model_cls, networks, tmp, variant_name, data):
             lrs.append([model.step, model.optimizer_G.param_groups[0]['lr'], model.optimizer_D.param_groups[0]['lr'], float(too_low)])
     logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
             if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
-                                    'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2')}
+                                    'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ')}
     if train_loop:
         logs['log:lrs'] = np.array(lrs, dtype=np.float64)
         logs['log:D_loss_STD'] = np.array(model.log_dict['D_loss_STD'], dtype=np.float64)
@@ -168,6 +169,15 @@ def main():
     import tempfile
     import models.networks as networks
     from models.SRRaGAN_model import SRRaGANModel
+    import Z_optimization as Zmod
+
+    class TorchProxy:       # Z_optimization.py hard-codes torch.device('cuda'): redirected in memory for this CPU run
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+        def device(self, *a, **k):
+            return torch.device('cpu')
+    Zmod.torch = TorchProxy()
     g = torch.Generator().manual_seed(31)
     q = lambda t: t.half().float()      # fp16-exact values: the fixture stores them in 16 bits
     data = {'LR': q(torch.rand(N_CALLS, BATCH, 3, PATCH // SCALE, PATCH // SCALE, generator=g)), 'HR': q(torch.rand(N_CALLS, BATCH, 3, PATCH, PATCH, generator=g))}

@@ -49,6 +49,7 @@ VARIANTS = {
     'no_gan': dict(gan_weight=None),
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
+    'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
 }
@@ -73,7 +74,7 @@ def _opt(tmp_path, variant, latent=False):
     train.update(variant)
     patch = 96 if latent else PATCH
     return ND(model='srragan', scale=SCALE, gpu_ids=None, is_train=True, range=[0, 1], train=train,
-              datasets=ND(train=ND(patch_size=patch, batch_size=BATCH)),
+              datasets=ND(train=ND(patch_size=patch, batch_size=2 if latent else BATCH)),
               path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, pretrained_model_D=None, log=str(tmp_path)),
               network_G=ND(which_model_G='RRDB_net', CEM_arch=0, latent_input='all_layers' if latent else 'None', latent_input_domain='HR_downscaled',
                            latent_channels='SVDinNormedOut_structure_tensor' if latent else 0,
@@ -98,6 +99,8 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
         import models.modules.loss as loss_mod
         from oracle import esr_oracle as O
         monkeypatch.setattr(loss_mod, 'structure_tensor_means', O.structure_tensor_means)
+        import Z_optimization as Zmod
+        monkeypatch.setattr(Zmod, '_dev', lambda: torch.device('cpu'))
     if rel is not None:
         opt['network_D']['relativistic'] = rel
 
@@ -143,7 +146,7 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
     rtol, atol = 1e-4, 1e-6
     last_step = 3 if latent else 10 ** 9
     for key in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
-                'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2'):
+                'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ'):
         if '%s/log:%s' % (name, key) not in g.files:
             assert len(model.log_dict.get(key, [])) == 0, key
             continue
