@@ -129,6 +129,7 @@ class SRRaGANModel(BaseModel):
             self.D_converged = False
         if self.D_exists:
             self.relativistic_D = opt['network_D']['relativistic'] is None or bool(opt['network_D']['relativistic'])
+            self.add_quantization_noise = bool(opt['network_D']['add_quantization_noise'])
             self.netD = networks.define_D(opt, CEM=self.CEM_net).to(self.device)
             self.netD.train()
         if train_opt['pixel_weight'] is not None:
@@ -270,6 +271,9 @@ class SRRaGANModel(BaseModel):
                 cur_Z = cur_Z.expand([self.var_L.size(0)] + list(cur_Z.shape[1:]))
         self.Prepare_Input(LR_image=self.var_L, latent_input=cur_Z)
         if need_GT:
+            if self.is_train and getattr(self, 'add_quantization_noise', False):
+                # keeps the critic from telling real from generated images by their 8-bit quantisation (:272-273)
+                data['HR'] += (torch.rand_like(data['HR']) - 0.5) / 255
             self.var_H = data['HR'].to(self.device)
             self.var_ref = (data['ref'] if 'ref' in data else data['HR']).to(self.device)
 
