@@ -111,6 +111,12 @@ class SRRaGANModel(BaseModel):
         if not self.is_train:
             self.netG.eval()
             self.Set_Require_Grad_Status(self.netG, False)
+            if init_Fnet:      # the GUI's feature-space / adversarial Z objectives ask for these next to the generator (:199-206)
+                self.netF = networks.define_F(opt, use_bn=False).to(self.device)
+                self.netF.eval()
+            if init_Dnet:
+                self.netD = networks.define_D(opt, CEM=self.CEM_net).to(self.device)
+                self.netD.eval()
             self.load()
             return
         # ---- training state (models/SRRaGAN_model.py:68-203, generator branch)
