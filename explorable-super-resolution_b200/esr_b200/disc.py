@@ -227,6 +227,7 @@ class _DiscFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable      # a second differentiation (WGAN-GP) must fail loudly, not return zeros
     def backward(ctx, g):
         want_params = any(ctx.needs_input_grad[2:])
         gx, plist = ctx.eng.backward(g, ctx.sv, want_input=ctx.needs_input_grad[0], want_params=want_params)

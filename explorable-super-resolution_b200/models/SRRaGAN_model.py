@@ -20,7 +20,7 @@ from torch.optim import lr_scheduler
 import CEM.CEMnet as CEMnet
 import models.networks as networks
 from esr_b200 import parallel
-from models.modules.loss import FilterLoss, CreateRangeLoss, GANLoss
+from models.modules.loss import FilterLoss, CreateRangeLoss, GANLoss, GradientPenaltyLoss
 from .base_model import BaseModel
 
 
@@ -60,8 +60,6 @@ class SRRaGANModel(BaseModel):
         if self.is_train:
             unbuilt = ['optimalZ_loss_type hist (SoftHistogramLoss)'] if (train_opt['optimalZ_loss_weight'] is not None and train_opt['optimalZ_loss_type'] == 'hist') else []
             if train_opt['gan_weight'] is not None:
-                if train_opt['gan_type'] == 'wgan-gp':
-                    unbuilt.append('gan_type wgan-gp (double backward through the critic, SURVEY 8f-2)')
                 if isinstance(train_opt['D_update_ratio'], list):
                     unbuilt.append('automatic D_update_ratio controller')
                 if (opt['network_D'] or {}).get('decomposed_input') or train_opt['hinge_threshold'] is not None:
@@ -106,7 +104,7 @@ class SRRaGANModel(BaseModel):
         self.netG = networks.define_G(opt, CEM=self.CEM_net, num_latent_channels=self.num_latent_channels)
         self.netG.to(self.device)
         logs_2_keep = ['l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'l_d_real_fake', 'D_real', 'D_fake', 'D_logits_diff',
-                       'Correctly_distinguished', 'psnr_val', 'LR_decrease', 'l_g_optimalZ', 'D_loss_STD'] + ['l_g_latent_%d' % i for i in range(self.num_latent_channels)]
+                       'Correctly_distinguished', 'psnr_val', 'LR_decrease', 'l_g_optimalZ', 'D_loss_STD', 'l_d_gp'] + ['l_g_latent_%d' % i for i in range(self.num_latent_channels)]
         self.log_dict = OrderedDict(zip(logs_2_keep, [[] for _ in logs_2_keep]))
         if not self.is_train:
             self.netG.eval()
@@ -138,6 +136,10 @@ class SRRaGANModel(BaseModel):
             self.add_quantization_noise = bool(opt['network_D']['add_quantization_noise'])
             self.netD = networks.define_D(opt, CEM=self.CEM_net).to(self.device)
             self.netD.train()
+            critic = self.netD.module if isinstance(self.netD, nn.DataParallel) else self.netD
+            if train_opt['gan_type'] == 'wgan-gp' and not getattr(critic, 'supports_double_backward', True):
+                raise NotImplementedError('esr_b200: gan_type wgan-gp needs a double backward through the critic, which the CUDA engine of '
+                                          'Discriminator_VGG_128 does not provide yet (SURVEY 8f-2, DESIGN 5b-6)')
         if train_opt['pixel_weight'] is not None:
             l_pix_type = train_opt['pixel_criterion']
             if l_pix_type == 'l1':
@@ -186,6 +188,9 @@ class SRRaGANModel(BaseModel):
             self.cri_fea = None
         if self.D_exists:   # GD gan loss (SRRaGAN_model.py:150-159)
             self.cri_gan = GANLoss(train_opt['gan_type'], 1.0, 0.0).to(self.device)
+            if train_opt['gan_type'] == 'wgan-gp':      # gradient penalty (:161-165)
+                self.cri_gp = GradientPenaltyLoss(device=self.device).to(self.device)
+                self.l_gp_w = train_opt['gp_weight']
             self.global_D_update_ratio = train_opt['D_update_ratio'] if train_opt['D_update_ratio'] is not None else 1
             self.D_init_iters = train_opt['D_init_iters'] if train_opt['D_init_iters'] else 0
         else:
@@ -361,7 +366,14 @@ class SRRaGANModel(BaseModel):
                     if first_dual:
                         l_d_real = 2 * self.cri_gan(pred_d_real, True)
                     l_d_fake = 2 * self.cri_gan(pred_d_fake, False)
-                l_d_total = (l_d_real + l_d_fake) / 2 / (acc_D * dual_steps)
+                l_d_total = (l_d_real + l_d_fake) / 2
+                if self.opt['train']['gan_type'] == 'wgan-gp':      # (:362-371) penalty at random interpolates of real and generated
+                    random_pt = torch.rand(self.var_ref.size(0), 1, 1, 1, device=self.var_ref.device)
+                    interp = random_pt * self.fake_H.detach() + (1 - random_pt) * self.var_ref
+                    interp.requires_grad = True
+                    l_d_gp = self.l_gp_w * self.cri_gp(interp, self.netD(interp))
+                    l_d_total = l_d_total + l_d_gp
+                l_d_total = l_d_total / (acc_D * dual_steps)
                 self.l_d_real_grad_step.append(l_d_real.item())
                 self.l_d_fake_grad_step.append(l_d_fake.item())
                 self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
@@ -397,6 +409,8 @@ class SRRaGANModel(BaseModel):
                     self.log_dict['l_d_real'].append((self.gradient_step_num, np.mean(self.l_d_real_grad_step)))
                     self.log_dict['l_d_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step)))
                     self.log_dict['l_d_real_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step) + np.mean(self.l_d_real_grad_step)))
+                    if self.opt['train']['gan_type'] == 'wgan-gp':
+                        self.log_dict['l_d_gp'].append((self.gradient_step_num, l_d_gp.item()))
                     self.log_dict['D_real'].append((self.gradient_step_num, np.mean(self.D_real_grad_step)))
                     self.log_dict['D_fake'].append((self.gradient_step_num, np.mean(self.D_fake_grad_step)))
                     self.log_dict['D_logits_diff'].append((self.gradient_step_num, np.mean(self.D_logits_diff_grad_step)))

@@ -76,6 +76,7 @@ VARIANTS = {
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
     'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
+    'wgan_gp': dict(gan_type='wgan-gp', gp_weight=10.0, _relativistic=0),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
 }
@@ -152,7 +153,7 @@ def run(model_cls, networks, tmp, variant_name, data):
             lrs.append([model.step, model.optimizer_G.param_groups[0]['lr'], model.optimizer_D.param_groups[0]['lr'], float(too_low)])
     logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
             if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
-                                    'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ')}
+                                    'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ', 'l_d_gp')}
     if train_loop:
         logs['log:lrs'] = np.array(lrs, dtype=np.float64)
         logs['log:D_loss_STD'] = np.array(model.log_dict['D_loss_STD'], dtype=np.float64)

@@ -138,3 +138,35 @@ def test_input_gradient_only_when_discriminator_is_frozen(monkeypatch):
     assert all(p.grad is None for p in net.parameters())
     with torch.no_grad():
         assert net(x.detach()).shape == (4, 1)
+
+
+def test_double_backward_fails_loudly(monkeypatch, tmp_path):
+    """WGAN-GP differentiates through the critic's input gradient: the CUDA engine does not provide that yet, and it must say so
+    (an error, never a silently missing gradient); SRRaGANModel refuses the configuration at construction."""
+    import disc_emul
+    import models.modules.architecture as arch
+    disc_emul.install(monkeypatch)
+    g = golden('disc_vgg128_nf8')
+    net = arch.Discriminator_VGG_128(in_nc=3, base_nf=8, input_patch_size=128)
+    net.load_state_dict(_sd(g), strict=True)
+    net.compute_dtype = torch.float32
+    x = torch.from_numpy(g['x'].astype(np.float32)).requires_grad_(True)
+    gx = torch.autograd.grad(net(x).sum(), x, create_graph=True)[0]
+    with pytest.raises(RuntimeError):
+        ((gx.flatten(1).norm(2, dim=1) - 1) ** 2).mean().backward()
+    assert net.supports_double_backward is False
+
+    class ND(dict):
+        def __missing__(self, k):
+            return None
+    from models import create_model
+    train = ND(pixel_weight=1.0, pixel_criterion='l1', gan_type='wgan-gp', gp_weight=10, gan_weight=5e-3, lr_G=1e-4, beta1_G=0.9, lr_D=1e-4, beta1_D=0.9,
+               lr_scheme='MultiStepLR', lr_steps=[10], lr_gamma=0.5, grad_accumulation_steps_G=1, grad_accumulation_steps_D=1)
+    opt = ND(model='srragan', scale=4, gpu_ids=None, is_train=True, range=[0, 1], train=train, datasets=ND(train=ND(patch_size=144, batch_size=2)),
+             path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, log=str(tmp_path)),
+             network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None, norm_type=None,
+                          mode='CNA', nf=8, nb=1, in_nc=3, out_nc=3, gc=32, scale=4),
+             network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3))
+    if not torch.cuda.is_available():
+        with pytest.raises(NotImplementedError):
+            create_model(opt)

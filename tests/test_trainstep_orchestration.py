@@ -50,6 +50,7 @@ VARIANTS = {
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
     'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
+    'wgan_gp': dict(gan_type='wgan-gp', gp_weight=10.0, _relativistic=0),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
 }
@@ -146,7 +147,7 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
     rtol, atol = 1e-4, 1e-6
     last_step = 3 if latent else 10 ** 9
     for key in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
-                'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ'):
+                'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ', 'l_d_gp'):
         if '%s/log:%s' % (name, key) not in g.files:
             assert len(model.log_dict.get(key, [])) == 0, key
             continue
