@@ -39,6 +39,15 @@ class GStand(nn.Module):
         return self.c2(nn.functional.interpolate(nn.functional.leaky_relu(self.c1(x), 0.2), scale_factor=SCALE, mode='nearest'))
 
 
+class FStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.features = nn.Sequential(nn.Conv2d(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(6, 6, 3, padding=1))
+
+    def forward(self, x):
+        return self.features(x)
+
+
 class DiscriminatorStand(nn.Module):
     def __init__(self, PATCH=PATCH):
         super().__init__()
@@ -76,6 +85,8 @@ VARIANTS = {
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
     'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
+    'feature': dict(feature_weight=1.0, feature_criterion='l1'),
+    'feature_l2': dict(feature_weight=0.5, feature_criterion='l2', pixel_criterion='l2', gan_weight=None),
     'wgan_gp': dict(gan_type='wgan-gp', gp_weight=10.0, _relativistic=0),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
@@ -128,13 +139,19 @@ def run(model_cls, networks, tmp, variant_name, data):
     def define_D(opt, **kw):
         torch.manual_seed(200)
         return DiscriminatorStand(patch - 80 if latent else patch)
-    old = networks.define_G, networks.define_D
-    networks.define_G, networks.define_D = define_G, define_D
+    def define_F(opt, **kw):
+        torch.manual_seed(400)
+        net = FStand()
+        for p_ in net.parameters():
+            p_.requires_grad = False
+        return net.eval()
+    old = networks.define_G, networks.define_D, networks.define_F
+    networks.define_G, networks.define_D, networks.define_F = define_G, define_D, define_F
     try:
         acc = max(opt['train']['grad_accumulation_steps_G'], opt['train']['grad_accumulation_steps_D'])
         model = model_cls(opt, accumulation_steps_per_batch=acc)
     finally:
-        networks.define_G, networks.define_D = old
+        networks.define_G, networks.define_D, networks.define_F = old
     init = {'G0:' + k: v.detach().clone().numpy() for k, v in model.netG.state_dict().items()}
     if model.D_exists:
         init.update({'D0:' + k: v.detach().clone().numpy() for k, v in model.netD.state_dict().items()})
@@ -152,7 +169,7 @@ def run(model_cls, networks, tmp, variant_name, data):
             too_low = model.update_learning_rate(model.gradient_step_num)
             lrs.append([model.step, model.optimizer_G.param_groups[0]['lr'], model.optimizer_D.param_groups[0]['lr'], float(too_low)])
     logs = {'log:' + k: np.array(v, dtype=np.float64) for k, v in model.log_dict.items()
-            if len(v) > 0 and k in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
+            if len(v) > 0 and k in ('l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
                                     'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ', 'l_d_gp')}
     if train_loop:
         logs['log:lrs'] = np.array(lrs, dtype=np.float64)

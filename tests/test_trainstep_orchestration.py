@@ -28,6 +28,15 @@ class GStand(nn.Module):
         return self.c2(nn.functional.interpolate(nn.functional.leaky_relu(self.c1(x), 0.2), scale_factor=SCALE, mode='nearest'))
 
 
+class FStand(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.features = nn.Sequential(nn.Conv2d(3, 6, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(6, 6, 3, padding=1))
+
+    def forward(self, x):
+        return self.features(x)
+
+
 class DiscriminatorStand(nn.Module):
     def __init__(self, PATCH=PATCH):
         super().__init__()
@@ -50,6 +59,8 @@ VARIANTS = {
     'latent': dict(latent_weight=1.0, _latent=1),
     'lr_drop': dict(steps_4_loss_std=2, std_4_lr_drop=1e-12, lr_gamma=0.5, _loop=1),
     'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
+    'feature': dict(feature_weight=1.0, feature_criterion='l1'),
+    'feature_l2': dict(feature_weight=0.5, feature_criterion='l2', pixel_criterion='l2', gan_weight=None),
     'wgan_gp': dict(gan_type='wgan-gp', gp_weight=10.0, _relativistic=0),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
@@ -112,6 +123,13 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
     def define_D(opt, **kw):
         torch.manual_seed(200)
         return DiscriminatorStand(patch - 80 if latent else patch)
+    def define_F(opt, **kw):
+        torch.manual_seed(400)
+        net = FStand()
+        for p_ in net.parameters():
+            p_.requires_grad = False
+        return net.eval()
+    monkeypatch.setattr(networks, 'define_F', define_F)
     monkeypatch.setattr(networks, 'define_G', define_G)
     monkeypatch.setattr(networks, 'define_D', define_D)
     acc = max(opt['train']['grad_accumulation_steps_G'], opt['train']['grad_accumulation_steps_D'])
@@ -146,7 +164,7 @@ def test_training_step_logic_matches_reference(monkeypatch, tmp_path, name):
     # (observed: agreement to 6e-7 through gradient step 3, 1e-3 from step 4 on) - it is compared over the first four steps
     rtol, atol = 1e-4, 1e-6
     last_step = 3 if latent else 10 ** 9
-    for key in ('l_g_pix', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
+    for key in ('l_g_pix', 'l_g_fea', 'l_g_range', 'l_g_gan', 'l_d_real', 'l_d_fake', 'D_real', 'D_fake', 'D_logits_diff', 'Correctly_distinguished',
                 'l_g_latent_0', 'l_g_latent_1', 'l_g_latent_2', 'l_g_optimalZ', 'l_d_gp'):
         if '%s/log:%s' % (name, key) not in g.files:
             assert len(model.log_dict.get(key, [])) == 0, key
