@@ -62,8 +62,8 @@ class SRRaGANModel(BaseModel):
             if train_opt['gan_weight'] is not None:
                 if isinstance(train_opt['D_update_ratio'], list):
                     unbuilt.append('automatic D_update_ratio controller')
-                if (opt['network_D'] or {}).get('decomposed_input') or train_opt['hinge_threshold'] is not None:
-                    unbuilt.append('decomposed_input / hinge_threshold')
+                if (opt['network_D'] or {}).get('decomposed_input'):
+                    unbuilt.append('decomposed_input')
             if unbuilt:
                 raise NotImplementedError('esr_b200: the training step is built for the pixel / feature / range / GAN losses; %s are '
                                           'not built' % ', '.join(unbuilt))
@@ -360,12 +360,13 @@ class SRRaGANModel(BaseModel):
                     pred_d_real = self.netD(self.var_ref)
                 pred_d_fake = self.netD(self.fake_H.detach())   # detach to avoid BP to G
                 if self.relativistic_D:
+                    assert self.opt['train']['hinge_threshold'] is None, 'Unsupported yet, should think whether it reuires special adaptation of hinge loss'
                     l_d_real = self.cri_gan(pred_d_real - self._batch_mean(pred_d_fake), True)
                     l_d_fake = self.cri_gan(pred_d_fake - self._batch_mean(pred_d_real), False)
-                else:
+                else:   # (x2: consistent with the SRGAN code, where the two losses are summed, :357-358)
                     if first_dual:
-                        l_d_real = 2 * self.cri_gan(pred_d_real, True)
-                    l_d_fake = 2 * self.cri_gan(pred_d_fake, False)
+                        l_d_real = 2 * self.cri_gan(pred_d_real, True, self.opt['train']['hinge_threshold'])
+                    l_d_fake = 2 * self.cri_gan(pred_d_fake, False, self.opt['train']['hinge_threshold'])
                 l_d_total = (l_d_real + l_d_fake) / 2
                 if self.opt['train']['gan_type'] == 'wgan-gp':      # (:362-371) penalty at random interpolates of real and generated
                     random_pt = torch.rand(self.var_ref.size(0), 1, 1, 1, device=self.var_ref.device)

@@ -87,6 +87,7 @@ VARIANTS = {
     'optimalZ': dict(latent_weight=1.0, optimalZ_loss_type='l1', optimalZ_loss_weight=10.0, Num_Z_iterations=[10, 3], _latent=1),
     'feature': dict(feature_weight=1.0, feature_criterion='l1'),
     'feature_l2': dict(feature_weight=0.5, feature_criterion='l2', pixel_criterion='l2', gan_weight=None),
+    'hinge': dict(hinge_threshold=0.05, _relativistic=0),
     'wgan_gp': dict(gan_type='wgan-gp', gp_weight=10.0, _relativistic=0),
     'verify_past': dict(D_verification='past', D_valid_Steps_4_G_update=2, min_D_prob_ratio_4_G=1.0, min_mean_D_correct=0.4, lr_D=2e-2),
     'verify_convergence': dict(D_verification='convergence', steps_4_D_convergence=3, steps_4_loss_std=3, lr_change_ratio=0.01, lr_D=2e-2),
