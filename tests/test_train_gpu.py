@@ -127,7 +127,7 @@ def test_srragan_model_refuses_unbuilt_losses(tmp_path):
     with pytest.raises(NotImplementedError):
         create_model(_train_opt(tmp_path, gan_weight=5e-3, gan_type='wgan-gp'))
     with pytest.raises(NotImplementedError):
-        create_model(_train_opt(tmp_path, optimalZ_loss_weight=1.0))
+        create_model(_train_opt(tmp_path, optimalZ_loss_weight=1.0, optimalZ_loss_type='hist'))
 
 
 def test_srragan_model_perceptual_training_step(tmp_path):
