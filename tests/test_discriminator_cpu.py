@@ -170,3 +170,29 @@ def test_double_backward_fails_loudly(monkeypatch, tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(NotImplementedError):
             create_model(opt)
+
+
+def test_engine_follows_weight_updates_in_place(monkeypatch):
+    """after an optimizer step the critic's packed weight objects are refreshed in place (same objects, new values): the
+    second forward must see the new weights"""
+    import disc_emul
+    import models.modules.architecture as arch
+    from oracle import esr_oracle as O
+    disc_emul.install(monkeypatch)
+    g = golden('disc_vgg128_nf8')
+    net = arch.Discriminator_VGG_128(in_nc=3, base_nf=8, input_patch_size=128)
+    net.load_state_dict(_sd(g), strict=True)
+    net.compute_dtype = torch.float32
+    net.train()
+    x = torch.from_numpy(g['x'].astype(np.float32))
+    with torch.no_grad():
+        out0 = net(x)
+        pk0 = list(net.engine()._pk)
+        for p in net.parameters():
+            if p.dim() == 4:
+                p.mul_(1.05)
+        out1 = net(x)
+        assert all(a is b for a, b in zip(pk0, net.engine()._pk))           # same packed objects
+        ref1 = O.discriminator_vgg128_forward(x, {k: v.detach().clone() for k, v in net.state_dict().items()}, training=True)
+    assert rel_err(out1, ref1)[0] < 1e-4
+    assert not torch.allclose(out0, out1)
