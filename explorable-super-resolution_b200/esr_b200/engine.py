@@ -319,6 +319,9 @@ class RRDBEngine:
             return out
         sv = _Saved()
         sv.B, sv.n, sv.h, sv.w, sv.h0, sv.w0, sv.pad, sv.cin = B, n, h, w, h0, w0, pad, cin
+        # the saved activations ARE the cached buffers: a later grad-enabled forward of the same shape overwrites them, so
+        # each one takes a generation number and `backward` refuses a stale record instead of returning wrong gradients
+        B['gen'] = sv.gen = B.get('gen', 0) + 1
         return out, sv
 
     # ---------------------------------------------------------------- backward
@@ -345,6 +348,9 @@ class RRDBEngine:
                 grads[idx] = ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale)
 
         B, n, h, w, pad = sv.B, sv.n, sv.h, sv.w, sv.pad
+        if B.get('gen') != sv.gen:
+            raise ops.L.EsrError('esr_b200: the activations saved for this backward were overwritten by a later grad-enabled forward of the '
+                                 'same shape (the engine keeps ONE saved set per shape: run backward before the next forward)')
         dev = g_out.device
         wt = self.packed_t()
         z = net.z_lead

@@ -65,6 +65,51 @@ def average_gradients(params, bucket_bytes=64 << 20, group=None):
     return calls
 
 
+def broadcast_parameters(module, src=0, group=None):
+    """every rank starts from rank `src`'s parameters and buffers (the reference's nn.DataParallel replicates GPU 0's weights
+    every forward, models/networks.py:122; with one process per GPU the replicas only agree if they start equal)"""
+    if world() == 1:
+        return 0
+    n = 0
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+            n += 1
+    return n
+
+
+def all_mean_scalars(values, group=None):
+    """mean over the ranks of a list of host floats (the loss / logit statistics the reference computes on the gathered global
+    batch, models/SRRaGAN_model.py:372-381; equal shard sizes make the mean of rank means the global mean).  Every statistic that
+    gates control flow (D verification, lr roll-back) goes through here so that all ranks take the same branch."""
+    if world() == 1 or len(values) == 0:
+        return [float(v) for v in values]
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [float(v) / world() for v in t.cpu()]
+
+
+def all_gather_cat(t, group=None):
+    """per-sample values of every rank, concatenated in rank order (equal shard sizes)"""
+    if world() == 1:
+        return t
+    out = [torch.empty_like(t) for _ in range(world())]
+    dist.all_gather(out, t.contiguous(), group=group)
+    return torch.cat(out, 0)
+
+
+def agree(flag, group=None):
+    """True only if `flag` is true on every rank (a safety net behind the shared statistics: ranks never split on a branch that
+    contains collectives)"""
+    if world() == 1:
+        return bool(flag)
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.cpu()[0]))
+
+
 def global_mean(local_values, group=None):
     """mean over the GLOBAL batch of per-sample values held rank by rank (unequal shard sizes allowed): one 2-scalar
     all-reduce (sum, count)"""

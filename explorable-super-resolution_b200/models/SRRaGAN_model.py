@@ -224,14 +224,20 @@ class SRRaGANModel(BaseModel):
         # learning rates after loading (SRRaGAN_model.py:208-218): once the adversarial term is in use (D verified, the default
         # without D_verification) the generator runs at the DISCRIMINATOR's learning rate
         if self.D_exists:
+            self.lr_D = float(self.lr_D)
             for param_group in self.optimizer_D.param_groups:
                 param_group['lr'] = self.lr_D
             if self.verified_D_saved:
                 self.lr_G = 1 * self.lr_D
                 if 'Z_optimizer' in self.__dict__:      # ... and a different number of Z iterations for the L_map step (:215-216)
                     self.Z_optimizer.max_iters = self.opt['train']['Num_Z_iterations'][-1]
+        self.lr_G = float(self.lr_G)
         for param_group in self.optimizer_G.param_groups:
             param_group['lr'] = self.lr_G
+        # one process per GPU: every replica starts from rank 0's weights (nn.DataParallel's per-forward replication, networks.py:122)
+        parallel.broadcast_parameters(self.netG)
+        if self.D_exists:
+            parallel.broadcast_parameters(self.netD)
 
     # ---- I/O of one batch -------------------------------------------------------------------------
     def Output_Batch(self, within_0_1):
@@ -375,11 +381,19 @@ class SRRaGANModel(BaseModel):
                     l_d_gp = self.l_gp_w * self.cri_gp(interp, self.netD(interp))
                     l_d_total = l_d_total + l_d_gp
                 l_d_total = l_d_total / (acc_D * dual_steps)
-                self.l_d_real_grad_step.append(l_d_real.item())
-                self.l_d_fake_grad_step.append(l_d_fake.item())
-                self.D_real_grad_step.append(torch.mean(pred_d_real.detach()).item())
-                self.D_fake_grad_step.append(torch.mean(pred_d_fake.detach()).item())
-                self.D_logits_diff_grad_step.append(list(torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).cpu().numpy()))
+                # logged statistics: ONE device->host read per D step, over the GLOBAL batch (the reference computes them on the
+                # outputs nn.DataParallel gathered, :372-381); they gate D verification and the lr roll-back, so every rank must
+                # see the same numbers
+                local = torch.cat([torch.stack([l_d_real.detach(), l_d_fake.detach(), torch.mean(pred_d_real.detach()),
+                                                torch.mean(pred_d_fake.detach())]).float().reshape(-1),
+                                   torch.mean(pred_d_real.detach() - pred_d_fake.detach(), dim=1).float().reshape(-1)])
+                allv = parallel.all_gather_cat(local.unsqueeze(0)).cpu().numpy()      # [ranks, 4 + local batch]
+                stats = [float(v) for v in allv[:, :4].astype(np.float64).mean(0)] + [float(v) for v in allv[:, 4:].reshape(-1)]
+                self.l_d_real_grad_step.append(stats[0])
+                self.l_d_fake_grad_step.append(stats[1])
+                self.D_real_grad_step.append(stats[2])
+                self.D_fake_grad_step.append(stats[3])
+                self.D_logits_diff_grad_step.append(list(np.asarray(stats[4:], dtype=np.float32)))
                 if first_acc_D and first_dual and self.generator_step:      # D verification (:377-393): may call this generator step off
                     tr = self.opt['train']
                     if self.D_verification == 'past' and tr['D_valid_Steps_4_G_update'] > 0:
@@ -458,14 +472,14 @@ class SRRaGANModel(BaseModel):
                         l_g_gan = self.l_gan_w * self.cri_gan(pred_g_fake, True) / (acc_G * dual_steps)
                     l_g_total = l_g_total + l_g_gan
                 l_g_total.backward()
-                if self.cri_fea:
-                    self.l_g_fea_grad_step.append(l_g_fea.item())
-                if self.cri_pix:
-                    self.l_g_pix_grad_step.append(l_g_pix.item())
-                if self.cri_gan:
-                    self.l_g_gan_grad_step.append(l_g_gan.item())
-                if self.cri_range:
-                    self.l_g_range_grad_step.append(l_g_range.item())
+                # logged scalars of the G step: one device->host read instead of one .item() sync per term
+                terms = [(self.cri_fea, 'l_g_fea_grad_step', l_g_fea if self.cri_fea else None), (self.cri_pix, 'l_g_pix_grad_step', l_g_pix if self.cri_pix else None),
+                         (self.cri_gan, 'l_g_gan_grad_step', l_g_gan if self.cri_gan else None), (self.cri_range, 'l_g_range_grad_step', l_g_range if self.cri_range else None)]
+                terms = [(name, v) for on, name, v in terms if on]
+                if terms:
+                    vals = torch.stack([v.detach().float().reshape(()) for _, v in terms]).cpu().tolist()
+                    for (name, _), v in zip(terms, vals):
+                        getattr(self, name).append(v)
                 if last_acc and last_dual:
                     parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad])
                     self.optimizer_G.step()
@@ -603,7 +617,9 @@ class SRRaGANModel(BaseModel):
         self.log_dict = OrderedDict((k, []) for k in self.log_dict.keys())
         for key in loaded.files:
             if key in ('D_verified', 'verified_D_saved', 'lr_G', 'lr_D'):
-                setattr(self, key, loaded[key])
+                # np.load hands back 0-d arrays: cast (reference: bool() at :209), or they end up pickled inside the optimizers'
+                # param_groups and the next checkpoint cannot be read back (torch.load weights_only)
+                setattr(self, key, bool(loaded[key]) if key in ('D_verified', 'verified_D_saved') else float(loaded[key]))
                 continue
             self.log_dict[key] = [tuple(v) for v in loaded[key]] if key == 'psnr_val' else list(loaded[key])
             if max_step is not None:

@@ -86,3 +86,31 @@ def test_inference_model_picks_latest_self_trained_generator(tmp_path):
     older = create_model(opt)
     older.load(max_step=5)
     assert older.gradient_step_num == 3
+
+
+def test_resume_save_resume_round_trip_with_logs(tmp_path):
+    """After a resume the scalars read back from logs.npz (lr_G, lr_D, D_verified, verified_D_saved) must be plain Python values:
+    as 0-d numpy arrays they get pickled into the optimizers' param_groups and the next checkpoint cannot be loaded
+    (reference casts with bool(), models/SRRaGAN_model.py:209)."""
+    from models import create_model
+    if torch.cuda.is_available():
+        return
+    torch.manual_seed(0)
+    model = create_model(_opt(tmp_path), accumulation_steps_per_batch=1)
+    _fake_adam_state(model.optimizer_G)
+    _fake_adam_state(model.optimizer_D)
+    os.makedirs(str(tmp_path / 'models'), exist_ok=True)
+    model.log_dict['l_d_real'].append((2, 0.7))
+    model.save(3)
+    model.save_log()
+    resumed = create_model(_opt(tmp_path, resume=1), accumulation_steps_per_batch=1)
+    assert type(resumed.lr_G) is float and type(resumed.lr_D) is float
+    assert type(resumed.D_verified) is bool and type(resumed.verified_D_saved) is bool
+    assert all(type(g['lr']) is float for o in resumed.optimizers for g in o.param_groups)
+    _fake_adam_state(resumed.optimizer_G)
+    resumed.save(5)
+    resumed.save_log()
+    again = create_model(_opt(tmp_path, resume=1), accumulation_steps_per_batch=1)      # raised UnpicklingError before the cast
+    assert again.step == 6 and len(again.optimizer_G.state) > 0
+    again.load(max_step=4, resume_train=True)                                            # the lr roll-back path of update_learning_rate
+    assert again.step == 4

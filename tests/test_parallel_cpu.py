@@ -48,6 +48,15 @@ def _worker(rank, world, port, q):
     ref_c.load_state_dict(critic.state_dict())
     rel_loss(ref_c(real), ref_c(fake), torch.mean).backward()
     err_rel = max(float((g - p.grad).abs().max()) for g, p in zip(got_c, ref_c.parameters()))
+    # control-flow statistics are identical on every rank; replicas start from rank 0's weights
+    stats = parallel.all_mean_scalars([float(rank), 2.0])
+    gathered = parallel.all_gather_cat(torch.full((2,), float(rank)))
+    lin = torch.nn.Linear(3, 2)
+    torch.nn.init.constant_(lin.weight, float(rank + 1))
+    parallel.broadcast_parameters(lin)
+    ok_all, ok_one = parallel.agree(True), parallel.agree(rank == 0)
+    assert stats == [0.5, 2.0] and gathered.tolist() == [0.0, 0.0, 1.0, 1.0] and float(lin.weight[0, 0]) == 1.0
+    assert ok_all is True and ok_one is False
     q.put((rank, max(err, err_rel), calls, gm, (a, b), (s, e)))
     dist.barrier()
     dist.destroy_process_group()
