@@ -346,14 +346,16 @@ def main():
             p_.requires_grad_(True)
         if world > 1:
             parallel.broadcast_parameters(model)
-        opt_g = torch.optim.Adam(params, lr=1e-4)
+        from esr_b200.losses import l1_mean
+        from esr_b200.optim import FlatAdam
+        opt_g = FlatAdam(params, lr=1e-4).register()      # torch.optim.Adam's arithmetic, one esr_adam_multi launch per step
         x_dev, hr_dev = lr_host.to(dev), hr_host.to(dev)
 
         def step_train():
             opt_g.zero_grad(set_to_none=True)
-            loss = (model(x_dev) - hr_dev).abs().mean()
+            loss = l1_mean(model(x_dev), hr_dev)            # nn.L1Loss on the esr_l1_reduce / esr_l1_grad kernels
             loss.backward()
-            parallel.average_gradients(params)
+            parallel.average_gradients(params, optimizer=opt_g)
             opt_g.step()
             return loss
 
@@ -621,7 +623,10 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             m4 = create_model(o4)
         regions, iters = 8, 100
-        data = {'LR': torch.rand(regions, 3, 64, 64, generator=gen), 'HR': torch.rand(regions, 3, 256, 256, generator=gen)}
+        data = {'LR': torch.rand(regions, 3, 64, 64, generator=gen).to(dev), 'desired': torch.rand(regions, 3, 256, 256, generator=gen).to(dev)}
+        m4.feed_data({'LR': data['LR'], 'Z': 0}, need_GT=False)      # what the GUI does before it builds a Z_optimizer (GUI.py:1689-1702)
+        m4.test()
+
         def once():
             with contextlib.redirect_stdout(io.StringIO()):
                 zo = Z_optimizer(objective='l1', Z_size=[256, 256], model=m4, Z_range=1, max_iters=iters, data=data, initial_LR=0.1,

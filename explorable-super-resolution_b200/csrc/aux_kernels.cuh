@@ -17,12 +17,43 @@ __device__ __forceinline__ float from16(uint16_t v, int dtype) {
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Split precision (esr_dtype ESR_BF16X3): a 16-bit tensor holds bf16 "hi" planes and, `lo` ELEMENTS further, the bf16 residuals
+// v - float(hi).  lo == 0 means a plain tensor of `dtype`.  store16x8 / load16x8 move 8 channels of one pixel-plane.
+__device__ __forceinline__ void store16x8(uint16_t* dst, const float* v, int dtype, size_t lo) {
+  uint16_t h[8];
+  const int dt = lo ? 1 : dtype;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) h[k] = to16(v[k], dt);
+  *reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                                              (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+  if (lo) {
+    uint16_t l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = to16(v[k] - from16(h[k], 1), 1);
+    *reinterpret_cast<uint4*>(dst + lo) = make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                                                     (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+  }
+}
+__device__ __forceinline__ void load16x8(const uint16_t* src, int dtype, size_t lo, float* v) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  const int dt = lo ? 1 : dtype;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = from16((uint16_t)((w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu), dt);
+  if (lo) {
+    const uint4 ql = __ldg(reinterpret_cast<const uint4*>(src + lo));
+    const uint32_t wl[4] = {ql.x, ql.y, ql.z, ql.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += from16((uint16_t)((wl[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu), 1);
+  }
+}
+
 // NCHW fp32 [n][c][h][w] -> planes [n][planes_total][h+2pad][w+2pad][8] (replicate padding), channels
 // beyond c are written as zeros.  One thread per (n, plane, y, x): 8 strided-by-HW reads (coalesced
 // over x), one 16 B (and optionally one 32 B) store.
 __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, int pad, int dtype,
                                  uint16_t* __restrict__ dst16, float* __restrict__ dst32, int planes_total,
-                                 int plane_off, int planes) {
+                                 int plane_off, int planes, size_t lo16) {
   const int ho = h + 2 * pad, wo = w + 2 * pad;
   const size_t total = (size_t)n * planes * ho * wo;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -39,14 +70,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
       v[k] = ch < c ? __ldg(src + (((size_t)img * c + ch) * h + sy) * w + sx) : 0.f;
     }
     const size_t o = ((((size_t)img * planes_total + plane_off + g) * ho + y) * wo + x) * 8;
-    if (dst16) {
-      uint4 pk;
-      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
-      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
-      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
-      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
-      *reinterpret_cast<uint4*>(dst16 + o) = pk;
-    }
+    if (dst16) store16x8(dst16 + o, v, dtype, lo16);
     if (dst32) {
       float4* op = reinterpret_cast<float4*>(dst32 + o);
       op[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -57,7 +81,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
 
 template <bool kIs16>
 __global__ void unpack_planes_kernel(const void* __restrict__ src, int dtype, int n, int c, int h, int w,
-                                     int planes_total, int plane_off, float* __restrict__ dst) {
+                                     int planes_total, int plane_off, float* __restrict__ dst, size_t lo16) {
   const size_t total = (size_t)n * c * h * w;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t r = idx;
@@ -66,8 +90,12 @@ __global__ void unpack_planes_kernel(const void* __restrict__ src, int dtype, in
     const int ch = r % c; r /= c;
     const int img = (int)r;
     const size_t o = ((((size_t)img * planes_total + plane_off + (ch >> 3)) * h + y) * w + x) * 8 + (ch & 7);
-    if (kIs16) dst[idx] = from16(reinterpret_cast<const uint16_t*>(src)[o], dtype);
-    else dst[idx] = reinterpret_cast<const float*>(src)[o];
+    if (kIs16) {
+      const uint16_t* sp = reinterpret_cast<const uint16_t*>(src);
+      dst[idx] = lo16 ? from16(sp[o], 1) + from16(sp[o + lo16], 1) : from16(sp[o], dtype);
+    } else {
+      dst[idx] = reinterpret_cast<const float*>(src)[o];
+    }
   }
 }
 
@@ -298,8 +326,9 @@ cem_up_add_kernel(const float* __restrict__ f, const float* __restrict__ g, int 
 // Adjoint of nearest x2 (block.py:299-300): dst[y][x] = sum of the 2x2 block of src.  Optionally multiplies by the
 // LeakyReLU derivative of the saved activation `act16` (given at the HIGH resolution, where it is stored 2x2
 // replicated) before the 16-bit store.  src fp32 planes [nplanes][2h][2w][8] -> dst32 / dst16 planes [nplanes][h][w][8].
+// Split precision: the 16-bit tensors (act16, dst16) have `planes` hi planes followed by as many lo planes per image.
 __global__ void downsum2x_kernel(const float4* __restrict__ src, size_t nplanes, int h, int w, const uint4* __restrict__ act16,
-                                 float slope, int dtype, float4* __restrict__ dst32, uint4* __restrict__ dst16) {
+                                 float slope, int dtype, float4* __restrict__ dst32, uint4* __restrict__ dst16, int planes, int split) {
   const size_t total = nplanes * h * w;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t r = idx;
@@ -315,8 +344,10 @@ __global__ void downsum2x_kernel(const float4* __restrict__ src, size_t nplanes,
         const float4 a = __ldg(sp), b = __ldg(sp + 1);
         v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
       }
+    // plane index inside a 16-bit tensor: split tensors hold twice the planes per image
+    const size_t r16 = split ? (r / planes) * (2 * (size_t)planes) + (r % planes) : r;
     if (act16) {
-      const uint4 q = __ldg(act16 + hi);
+      const uint4 q = __ldg(act16 + (r16 * (2 * (size_t)h) + 2 * y) * (2 * (size_t)w) + 2 * x);
       const uint32_t wq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -328,20 +359,15 @@ __global__ void downsum2x_kernel(const float4* __restrict__ src, size_t nplanes,
       dst32[idx * 2] = make_float4(v[0], v[1], v[2], v[3]);
       dst32[idx * 2 + 1] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    if (dst16) {
-      uint4 pk;
-      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
-      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
-      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
-      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
-      dst16[idx] = pk;
-    }
+    if (dst16)
+      store16x8(reinterpret_cast<uint16_t*>(dst16) + ((r16 * h + y) * w + x) * 8, v, dtype, split ? (size_t)planes * h * w * 8 : 0);
   }
 }
 
 // out = a + b on fp32 planes; optional 16-bit copy
+// (split precision: per_img = pixel-planes of one image in the fp32 tensors; the 16-bit output holds twice as many)
 __global__ void planes_add_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t n8, int dtype,
-                                  float4* __restrict__ out32, uint4* __restrict__ out16) {
+                                  float4* __restrict__ out32, uint4* __restrict__ out16, size_t per_img, int split) {
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n8; idx += (size_t)gridDim.x * blockDim.x) {
     const float4 a0 = __ldg(a + 2 * idx), a1 = __ldg(a + 2 * idx + 1), b0 = __ldg(b + 2 * idx), b1 = __ldg(b + 2 * idx + 1);
     const float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
@@ -350,12 +376,8 @@ __global__ void planes_add_kernel(const float4* __restrict__ a, const float4* __
       out32[2 * idx + 1] = make_float4(v[4], v[5], v[6], v[7]);
     }
     if (out16) {
-      uint4 pk;
-      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
-      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
-      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
-      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
-      out16[idx] = pk;
+      const size_t o = split ? (idx / per_img) * (2 * per_img) + (idx % per_img) : idx;
+      store16x8(reinterpret_cast<uint16_t*>(out16) + o * 8, v, dtype, split ? per_img * 8 : 0);
     }
   }
 }
@@ -469,7 +491,7 @@ __global__ void latent_grad_lr_kernel(const float* __restrict__ gz_lr, int n, in
 // (x - mean) / std of VGGFeatureExtractor.forward (:719-720).  One thread per (n, plane, y, x).
 __global__ void pack_nchw_affine_kernel(const float* __restrict__ src, int n, int c, int h, int w, const float* __restrict__ scale,
                                         const float* __restrict__ shift, int dtype, uint16_t* __restrict__ dst16, int planes_total,
-                                        int plane_off, int planes) {
+                                        int plane_off, int planes, size_t lo16) {
   const size_t total = (size_t)n * planes * h * w;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t r = idx;
@@ -477,18 +499,42 @@ __global__ void pack_nchw_affine_kernel(const float* __restrict__ src, int n, in
     const int y = r % h; r /= h;
     const int g = r % planes; r /= planes;
     const int img = (int)r;
-    uint32_t pk[4] = {0, 0, 0, 0};
+    float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = g * 8 + k;
-      const float v = ch < c ? fmaf(__ldg(src + (((size_t)img * c + ch) * h + y) * w + x), __ldg(scale + ch), __ldg(shift + ch)) : 0.f;
-      pk[k >> 1] |= (uint32_t)to16(v, dtype) << ((k & 1) * 16);
+      v[k] = ch < c ? fmaf(__ldg(src + (((size_t)img * c + ch) * h + y) * w + x), __ldg(scale + ch), __ldg(shift + ch)) : 0.f;
     }
-    *reinterpret_cast<uint4*>(dst16 + ((((size_t)img * planes_total + plane_off + g) * h + y) * w + x) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    store16x8(dst16 + ((((size_t)img * planes_total + plane_off + g) * h + y) * w + x) * 8, v, dtype, lo16);
   }
 }
 
 // 2x2 / stride 2 max pooling of 16-bit planes (nn.MaxPool2d(2, 2) inside torchvision's vgg19.features).
+// split precision: `planes` hi planes + as many lo planes per image (nplanes counts the hi planes of all images); a window's
+// maximum is decided on hi + lo and both halves of the winner are carried over
+__global__ void maxpool2x2_split_kernel(const uint16_t* __restrict__ src, size_t nplanes, int planes, int h, int w, uint16_t* __restrict__ dst) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = nplanes * ho * wo;
+  const size_t lo_in = (size_t)planes * h * w * 8, lo_out = (size_t)planes * ho * wo * 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % wo; r /= wo;
+    const int y = r % ho; r /= ho;
+    const size_t r16 = (r / planes) * (2 * (size_t)planes) + (r % planes);
+    const uint16_t* sp = src + ((r16 * h + 2 * y) * w + 2 * x) * 8;
+    float best[8], v[8];
+    load16x8(sp, 1, lo_in, best);
+    const size_t offs[3] = {8, (size_t)w * 8, (size_t)w * 8 + 8};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      load16x8(sp + offs[t], 1, lo_in, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) best[k] = v[k] > best[k] ? v[k] : best[k];
+    }
+    store16x8(dst + ((r16 * ho + y) * wo + x) * 8, best, 1, lo_out);
+  }
+}
+
 __global__ void maxpool2x2_kernel(const uint4* __restrict__ src, size_t nplanes, int h, int w, int dtype, uint4* __restrict__ dst) {
   const int ho = h / 2, wo = w / 2;
   const size_t total = nplanes * ho * wo;
@@ -551,6 +597,40 @@ __global__ void maxpool2x2_bwd_kernel(const uint4* __restrict__ gout, const uint
     gin[base + 1] = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
     gin[base + w] = make_uint4(o[2][0], o[2][1], o[2][2], o[2][3]);
     gin[base + w + 1] = make_uint4(o[3][0], o[3][1], o[3][2], o[3][3]);
+  }
+}
+
+// split-precision variant of the pooling backward: argmax on hi + lo of the saved activation, the gradient's hi and lo halves
+// both go to the winner
+__global__ void maxpool2x2_bwd_split_kernel(const uint16_t* __restrict__ gout, const uint16_t* __restrict__ act, size_t nplanes, int planes,
+                                            int h, int w, uint16_t* __restrict__ gin) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = nplanes * ho * wo;
+  const size_t lo_in = (size_t)planes * h * w * 8, lo_out = (size_t)planes * ho * wo * 8;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % wo; r /= wo;
+    const int y = r % ho; r /= ho;
+    const size_t r16 = (r / planes) * (2 * (size_t)planes) + (r % planes);
+    const size_t base = ((r16 * h + 2 * y) * w + 2 * x) * 8;
+    const size_t offs[4] = {0, 8, (size_t)w * 8, (size_t)w * 8 + 8};
+    float a[4][8], g[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) load16x8(act + base + offs[t], 1, lo_in, a[t]);
+    load16x8(gout + ((r16 * ho + y) * wo + x) * 8, 1, lo_out, g);
+    float o[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int arg = 0;
+      float best = a[0][k];
+#pragma unroll
+      for (int t = 1; t < 4; ++t)
+        if (a[t][k] > best) { best = a[t][k]; arg = t; }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) o[t][k] = (t == arg && best > 0.f) ? g[k] : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) store16x8(gin + base + offs[t], o[t], 1, lo_in);
   }
 }
 

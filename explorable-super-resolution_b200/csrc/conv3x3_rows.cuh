@@ -144,9 +144,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
       int s = 0;
       uint32_t ph = 0;
       const size_t plane16 = hw * 16;
-      const int npl_last = p.cin_planes - (p.nchunks - 1) * kRowsKch;
-      const int nld_last = (npl_last + 1) & ~1;   // K steps take plane pairs: an odd tail re-loads its last plane (zero weights)
-      const size_t last_plane_off = (size_t)((p.nchunks - 1) * kRowsKch + (lane < npl_last ? lane : npl_last - 1)) * plane16;
+      // chunks per plane segment (split precision: three segments hi | lo | hi, else one); the last chunk of a segment may be
+      // partial.  K steps take plane pairs: an odd tail re-loads its last plane (zero weights)
+      const int cps = p.split ? p.cps : p.nchunks;
+      const int npl_last = p.cin_planes - (cps - 1) * kRowsKch;
+      const int nld_last = (npl_last + 1) & ~1;
+      const int lane_last = lane < npl_last ? lane : npl_last - 1;
       const uint32_t lane_dst = (uint32_t)lane * kRowBytes;
       int u_img, x0, ya, yb;
       long long u = u0;
@@ -156,14 +159,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
         const uint32_t cnt_bytes = (uint32_t)(xe - xs) * 16u, dst_off = (uint32_t)(xs - (x0 - 1)) * 16u + lane_dst;
         const bool zl = x0 == 0, zr = x0 + 129 > p.w;   // image border inside this strip: the halo pixel is zero padding
         const uint32_t zr_off = (uint32_t)(p.w - (x0 - 1)) * 16u + lane_dst;
-        const uint8_t* colp = p.in + (((size_t)u_img * p.in_pt + p.in_plane_off) * hw + xs) * 16;
+        const uint8_t* colp = p.in + (((size_t)u_img * p.in_pt) * hw + xs) * 16;
         int seg_uses = 0;
         for (int yi = yi0; yi <= yi1; ++yi) {
           const uint8_t* rowp = colp + (size_t)yi * p.w * 16;
-          const uint8_t* src = rowp + (size_t)lane * plane16;
+          int cc = 0, sg = 0;
           for (int c = 0; c < p.nchunks; ++c) {
-            const bool last = c == p.nchunks - 1;
+            const bool last = cc == cps - 1;
             const int nld = last ? nld_last : kRowsKch;
+            const int plane = (p.split ? p.seg_base[sg] : p.in_plane_off) + cc * kRowsKch + (last ? lane_last : lane);
             mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
             const uint32_t sa = stage0 + s * kRowsStageBytes;
             if ((zl || zr) && seg_uses < p.stages) {
@@ -177,10 +181,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
             }
             if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)nld * cnt_bytes);
             __syncwarp();
-            if (lane < nld) bulk_load(sa + dst_off, last ? rowp + last_plane_off : src, cnt_bytes, bar_full + 8 * s);
-            src += (size_t)kRowsKch * plane16;
+            if (lane < nld) bulk_load(sa + dst_off, rowp + (size_t)plane * plane16, cnt_bytes, bar_full + 8 * s);
             ++seg_uses;
             if (++s == p.stages) { s = 0; ph ^= 1u; }
+            if (++cc == cps) { cc = 0; ++sg; }
           }
         }
       }
@@ -195,7 +199,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
         const uint64_t adesc_t = make_smem_desc(0u, kRowBytes, 128u);
         const uint64_t bdesc_t = make_smem_desc(0u, (uint32_t)N3 * 16u, 128u) + (uint64_t)(wres >> 4);
         const int nchunks = p.nchunks, stages = p.stages;
-        const int nk_last = (p.cin_planes - (nchunks - 1) * kRowsKch + 1) >> 1;
+        const int cps = p.split ? p.cps : nchunks;
+        const int nk_last = (p.cin_planes - (cps - 1) * kRowsKch + 1) >> 1;
         const uint32_t id1 = p.idesc_n[0], id2 = p.idesc_n[1], id3 = p.idesc_n[2];
         if (u0 < u1) {
           mbar_wait(bar_w, 0u, 5u);
@@ -232,13 +237,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
             const uint32_t dA = tmem_base + (uint32_t)(slot0 * NBN), dB = tmem_base;
             const uint32_t idA = nA == 3 ? id3 : (nA == 2 ? id2 : id1), idB = nB == 2 ? id2 : id1;
             const uint64_t bA = bdesc_t + (uint64_t)(ky_lo * NBN), bB = bdesc_t + (uint64_t)((ky_lo + nA) * NBN);
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = 0, cc = 0; c < nchunks; ++c) {
+              const bool last_of_seg = ++cc == cps;
+              if (last_of_seg) cc = 0;
               if (kmod == iw) {
                 mbar_wait(bar_full + 8 * s, ph, 3u);
                 tc_fence_after();
                 const uint64_t ad0 = adesc_t + (uint64_t)((stage0 + s * kRowsStageBytes) >> 4);
                 const uint64_t wo = (uint64_t)(c * (kChunkW >> 4));
-                const int nk = c == nchunks - 1 ? nk_last : kRowsKch / 2;
+                const int nk = last_of_seg ? nk_last : kRowsKch / 2;
                 if (nB == 0) rows_issue_chunk<N3, false>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
                 else rows_issue_chunk<N3, true>(ad0, bA + wo, bB + wo, dA, dB, idA, idB, nk);
                 umma_commit(bar_empty + 8 * s);
@@ -319,8 +326,10 @@ __device__ __forceinline__ uint16_t pack_weights_rows_elem(const float* __restri
   const int nn = r % n3; r /= n3;
   const int j = r % kRowsKch; r /= kRowsKch;
   const int dx = r % 3; r /= 3;
-  const int c = r % nchunks; r /= nchunks;
+  int c = r % nchunks; r /= nchunks;
   const int nb = (int)r;
+  int seg = 0;
+  if (dtype == 2) { const int cps = nchunks / 3; seg = c / cps; c -= seg * cps; }
   const int ky = nn / nb_n;
   int o = nb * nb_n + (nn - ky * nb_n);
   int i = (c * kRowsKch + j) * 8 + ci8;
@@ -336,6 +345,7 @@ __device__ __forceinline__ uint16_t pack_weights_rows_elem(const float* __restri
     if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + dx];
     else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - dx)];
   }
+  if (dtype == 2) return split_weight_bits(val, seg);
   return (uint16_t)(pack2(val, 0.f, dtype) & 0xFFFFu);
 }
 

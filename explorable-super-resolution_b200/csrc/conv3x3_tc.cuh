@@ -73,7 +73,21 @@ struct ConvParams {
   uint16_t* out16; int out16_pt, out16_po, out16_up2, out16_ps;
   float* out32; int out32_pt, out32_po;
   float* out_nchw; int out_nchw_c;
+  // split precision (esr_dtype ESR_BF16X3): every 16-bit tensor carries bf16 hi planes and, `*_lo` elements further, the bf16
+  // residual v - hi ("lo") planes; the K loop runs over three plane segments (hi, lo, hi) against weights packed as
+  // (w_hi, w_hi, w_lo), i.e. x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation: 16 mantissa bits per operand on
+  // the kind::f16 tensor pipe.  cps = K chunks per segment, seg_base = first input plane of each segment.
+  int split, cps;
+  int seg_base[3];
+  size_t out16_lo, res1_lo;
 };
+
+// first input plane of K chunk c (K = planes per chunk of the calling kernel)
+__device__ __forceinline__ int conv_chunk_plane(const ConvParams& p, int c, int K) {
+  if (!p.split) return p.in_plane_off + c * K;
+  const int s = c / p.cps;
+  return p.seg_base[s] + (c - s * p.cps) * K;
+}
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
   if (dtype == 0) {
@@ -104,6 +118,24 @@ __device__ __forceinline__ void unpack8(const uint4& q, int dtype, float (&a)[8]
       a[2 * k] = f.x; a[2 * k + 1] = f.y;
     }
   }
+}
+
+// 8 fp32 values -> 8 16-bit values (`hi`); split mode also returns the bf16 residuals v - float(hi) (`lo`)
+__device__ __forceinline__ void pack8_hl(const float (&v)[8], int dtype, int split, uint4& hi, uint4& lo) {
+  hi.x = pack2(v[0], v[1], dtype); hi.y = pack2(v[2], v[3], dtype); hi.z = pack2(v[4], v[5], dtype); hi.w = pack2(v[6], v[7], dtype);
+  if (split) {
+    float h[8];
+    unpack8(hi, 1, h);
+    lo.x = pack2(v[0] - h[0], v[1] - h[1], 1); lo.y = pack2(v[2] - h[2], v[3] - h[3], 1);
+    lo.z = pack2(v[4] - h[4], v[5] - h[5], 1); lo.w = pack2(v[6] - h[6], v[7] - h[7], 1);
+  }
+}
+// a[k] += lo part of a split 16-bit tensor (8 channels at `ptr`, the lo planes `lo_elems` further)
+__device__ __forceinline__ void add_lo8(const uint16_t* ptr, size_t lo_elems, float (&a)[8]) {
+  float l[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(ptr + lo_elems)), 1, l);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] += l[k];
 }
 
 // Epilogue of one accumulator row of one thread (= one output pixel): TMEM -> registers -> bias / LeakyReLU /
@@ -203,6 +235,8 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
           float a[8];
           if (p.res1_is16) {
             unpack8(q1[g], p.dtype, a);
+            if (p.split)
+              add_lo8(reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gp) * hw + pix) * 8, p.res1_lo, a);
           } else {
             a[0] = f1[g][0].x; a[1] = f1[g][0].y; a[2] = f1[g][0].z; a[3] = f1[g][0].w;
             a[4] = f1[g][1].x; a[5] = f1[g][1].y; a[6] = f1[g][1].z; a[7] = f1[g][1].w;
@@ -243,15 +277,12 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
             for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
           }
           if (p.out16_ps == 0) {
-            uint4 o;
-            o.x = pack2(v[0], v[1], p.dtype);
-            o.y = pack2(v[2], v[3], p.dtype);
-            o.z = pack2(v[4], v[5], p.dtype);
-            o.w = pack2(v[6], v[7], p.dtype);
+            uint4 o, ol;
+            pack8_hl(v, p.dtype, p.split, o, ol);
             if (!p.out16_up2) {
-              uint4* op = reinterpret_cast<uint4*>(
-                  p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * hw + pix) * 8);
-              *op = o;
+              uint16_t* op = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * hw + pix) * 8;
+              *reinterpret_cast<uint4*>(op) = o;
+              if (p.split) *reinterpret_cast<uint4*>(op + p.out16_lo) = ol;
             } else {
               const size_t w2 = 2 * (size_t)p.w;
               uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gp) * (4 * hw) +
@@ -259,6 +290,11 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
               uint4* o0 = reinterpret_cast<uint4*>(basep);
               uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
               o0[0] = o; o0[1] = o; o1[0] = o; o1[1] = o;
+              if (p.split) {
+                uint4* l0 = reinterpret_cast<uint4*>(basep + p.out16_lo);
+                uint4* l1 = reinterpret_cast<uint4*>(basep + p.out16_lo + w2 * 8);
+                l0[0] = ol; l0[1] = ol; l1[0] = ol; l1[1] = ol;
+              }
             }
           } else {
             // pixel shuffle (block.py:287): conv channel c*r*r + i*r + j -> channel c at (r*y+i, r*x+j).
@@ -274,6 +310,10 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
                                         (size_t)(rs * y + i) * wr + (rs * x + j)) * 8 + (oc & 7);
               const uint32_t pk = pack2(v[k], 0.f, p.dtype);
               *op = (uint16_t)(pk & 0xFFFFu);
+              if (p.split) {
+                const float hv = __bfloat162float(__ushort_as_bfloat16((uint16_t)(pk & 0xFFFFu)));
+                op[p.out16_lo] = (uint16_t)(pack2(v[k] - hv, 0.f, 1) & 0xFFFFu);
+              }
             }
           }
         }
@@ -367,6 +407,8 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
         } else {
           float a[8];
           unpack8(q1[g], p.dtype, a);
+          if (p.split)
+            add_lo8(reinterpret_cast<const uint16_t*>(p.res1) + (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8, p.res1_lo, a);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = fmaf(p.beta1, a[k], v[k] * p.alpha);
           if (has2) {
@@ -381,19 +423,23 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
             op[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
-        uint4 o;
-        o.x = pack2(v[0], v[1], p.dtype);
-        o.y = pack2(v[2], v[3], p.dtype);
-        o.z = pack2(v[4], v[5], p.dtype);
-        o.w = pack2(v[6], v[7], p.dtype);
+        uint4 o, ol;
+        pack8_hl(v, p.dtype, p.split, o, ol);
         if (kMode == 1 && p.out16_up2) {
           const size_t w2 = 2 * (size_t)p.w;
           uint16_t* basep = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * (4 * hw) + (size_t)(2 * y) * w2 + 2 * x) * 8;
           uint4* o0 = reinterpret_cast<uint4*>(basep);
           uint4* o1 = reinterpret_cast<uint4*>(basep + w2 * 8);
           o0[0] = o; o0[1] = o; o1[0] = o; o1[1] = o;
+          if (p.split) {
+            uint4* l0 = reinterpret_cast<uint4*>(basep + p.out16_lo);
+            uint4* l1 = reinterpret_cast<uint4*>(basep + p.out16_lo + w2 * 8);
+            l0[0] = ol; l0[1] = ol; l1[0] = ol; l1[1] = ol;
+          }
         } else {
-          *reinterpret_cast<uint4*>(p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * hw + pix) * 8) = o;
+          uint16_t* op = p.out16 + (((size_t)img * p.out16_pt + p.out16_po + gu + g) * hw + pix) * 8;
+          *reinterpret_cast<uint4*>(op) = o;
+          if (p.split) *reinterpret_cast<uint4*>(op + p.out16_lo) = ol;
         }
       }
     }
@@ -496,7 +542,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
           const uint32_t sa = stage0 + s * p.stage_bytes;
           mbar_expect_tx(bar_full + 8 * s, p.w_resident ? p.a_bytes : p.a_bytes + p.b_bytes);
-          tma_load_4d(sa, &tmA, bar_full + 8 * s, (x0 - 1) * 8, y0 - 1, p.in_plane_off + c * p.kcp, img);
+          tma_load_4d(sa, &tmA, bar_full + 8 * s, (x0 - 1) * 8, y0 - 1, conv_chunk_plane(p, c, p.kcp), img);
           if (!p.w_resident) bulk_load(sa + p.a_alloc, wsrc + (size_t)c * p.b_bytes, p.b_bytes, bar_full + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -593,6 +639,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // weight packing: OIHW fp32 -> [n_block][chunk][tap][plane-in-chunk][cout-in-block][8 cin] 16-bit
 // ---------------------------------------------------------------------------------------------
 // one element of the packed image (shared by the per-conv kernel and the batched one)
+// split mode (dtype 2): the chunk index runs over three segments of nchunks/3 chunks each; segments 0 and 1 hold bf16(w) (they meet
+// the hi and lo activation planes), segment 2 holds the bf16 residual w - bf16(w) (it meets the hi planes again)
+__device__ __forceinline__ uint16_t split_weight_bits(float val, int seg) {
+  const float hi = __bfloat162float(__float2bfloat16_rn(val));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(seg == 2 ? val - hi : hi));
+}
+
 __device__ __forceinline__ uint16_t pack_weights_elem(const float* __restrict__ w, int cout, int cin, int lead, int kcp, int nb_n, int nchunks,
                                                       int dtype, int transpose_flip, size_t idx) {
   // logical conv: out channels = (transpose_flip ? cin : cout) of the source tensor
@@ -604,8 +657,10 @@ __device__ __forceinline__ uint16_t pack_weights_elem(const float* __restrict__ 
   const int n = r % nb_n; r /= nb_n;
   const int j = r % kcp; r /= kcp;
   const int tap = r % 9; r /= 9;
-  const int c = r % nchunks; r /= nchunks;
+  int c = r % nchunks; r /= nchunks;
   const int nb = (int)r;
+  int seg = 0;
+  if (dtype == 2) { const int cps = nchunks / 3; seg = c / cps; c -= seg * cps; }
   int o = nb * nb_n + n;
   int i = (c * kcp + j) * 8 + ci8;
   // channel position in plane space -> source channel: the `lead` latent channels sit in their own zero-padded
@@ -623,6 +678,7 @@ __device__ __forceinline__ uint16_t pack_weights_elem(const float* __restrict__ 
     if (!transpose_flip) val = w[(((size_t)o * cin + i) * 3 + ky) * 3 + kx];
     else val = w[(((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - kx)];
   }
+  if (dtype == 2) return split_weight_bits(val, seg);
   return (uint16_t)(pack2(val, 0.f, dtype) & 0xFFFFu);
 }
 

@@ -115,7 +115,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part, int chunks, i
 // and / or NCHW fp32 (the classifier's input).  One thread per (img, plane, y, x).
 __global__ void bn_lrelu_apply_kernel(const float* __restrict__ y32, const float* __restrict__ scale, const float* __restrict__ shift,
                                       float slope, int n, int P, int h, int w, int C, int dtype, uint16_t* __restrict__ dst16, int s2d,
-                                      float* __restrict__ dst_nchw) {
+                                      float* __restrict__ dst_nchw, int split) {
   const size_t total = (size_t)n * P * h * w;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t r = idx;
@@ -133,14 +133,9 @@ __global__ void bn_lrelu_apply_kernel(const float* __restrict__ y32, const float
       float t = fmaf(v[k], sc[k], sh[k]);
       v[k] = t > 0.f ? t : t * slope;
     }
-    if (dst16) {
-      uint4 pk;
-      pk.x = (uint32_t)to16(v[0], dtype) | ((uint32_t)to16(v[1], dtype) << 16);
-      pk.y = (uint32_t)to16(v[2], dtype) | ((uint32_t)to16(v[3], dtype) << 16);
-      pk.z = (uint32_t)to16(v[4], dtype) | ((uint32_t)to16(v[5], dtype) << 16);
-      pk.w = (uint32_t)to16(v[6], dtype) | ((uint32_t)to16(v[7], dtype) << 16);
-      const size_t o = grad_offset(s2d ? 1 : 0, img, g, yy, x, P, h, w, C);
-      *reinterpret_cast<uint4*>(dst16 + o) = pk;
+    if (dst16) {   // (split precision: hi and lo halves per image, so the image stride doubles; both layouts hold P*h*w*8 per half)
+      const size_t o = grad_offset(s2d ? 1 : 0, split ? 2 * img : img, g, yy, x, P, h, w, C);
+      store16x8(dst16 + o, v, dtype, split ? (size_t)P * h * w * 8 : 0);
     }
     if (dst_nchw) {
       const size_t hw = (size_t)h * w;
@@ -218,7 +213,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int chunk
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int layout, const float* __restrict__ y32, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ c1, const float* __restrict__ c2, float slope, int n, int P, int h, int w, int C,
-                                    int dtype, uint16_t* __restrict__ gy16) {
+                                    int dtype, uint16_t* __restrict__ gy16, int split) {
   const size_t total = (size_t)n * P * h * w;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     size_t r = idx;
@@ -241,12 +236,9 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int layout, con
         o[k] = 0.f;
       }
     }
-    uint4 pk;
-    pk.x = (uint32_t)to16(o[0], dtype) | ((uint32_t)to16(o[1], dtype) << 16);
-    pk.y = (uint32_t)to16(o[2], dtype) | ((uint32_t)to16(o[3], dtype) << 16);
-    pk.z = (uint32_t)to16(o[4], dtype) | ((uint32_t)to16(o[5], dtype) << 16);
-    pk.w = (uint32_t)to16(o[6], dtype) | ((uint32_t)to16(o[7], dtype) << 16);
-    *reinterpret_cast<uint4*>(gy16 + idx * 8) = pk;
+    const size_t per_img = (size_t)P * h * w;
+    const size_t o16 = split ? (size_t)img * 2 * per_img + (idx - (size_t)img * per_img) : idx;
+    store16x8(gy16 + o16 * 8, o, dtype, split ? per_img * 8 : 0);
   }
 }
 

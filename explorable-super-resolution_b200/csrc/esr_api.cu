@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -19,6 +20,7 @@
 #include "conv3x3_rows.cuh"
 #include "conv3x3_wgrad.cuh"
 #include "disc_kernels.cuh"
+#include "train_kernels.cuh"
 
 namespace {
 
@@ -109,8 +111,8 @@ int nblock_for(int cout, int* cout_pad) {
 const uint32_t kSmemMax = 232448u;
 
 // n-block of the row-streaming kernel for (cin_planes, cout); 0 = this conv cannot use it
-int rows_nbn_for(int cin_planes, int cout) {
-  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+int rows_nbn_for(int cin_planes, int cout, int segs = 1) {
+  const int nchunks = segs * ((cin_planes + esr::kRowsKch - 1) / esr::kRowsKch);
   auto fits = [&](int nbn, int min_stages) {
     const size_t wb = (size_t)nchunks * 3 * esr::kRowsKch * 3 * nbn * 16;
     return esr::kSmemHeader + 128u + wb + (size_t)min_stages * esr::kRowsStageBytes <= kSmemMax;
@@ -243,12 +245,15 @@ int esr_device_check(void) {
   return ESR_OK;
 }
 
-size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out) {
+size_t esr_conv3x3_packed_bytes_ex(int cin_planes, int cout, int kcp, int dtype, int* cout_pad_out) {
   int cout_pad = 0;
   nblock_for(cout, &cout_pad);
   if (cout_pad_out) *cout_pad_out = cout_pad;
-  const int nchunks = (cin_planes + kcp - 1) / kcp;
+  const int nchunks = (dtype == ESR_BF16X3 ? 3 : 1) * ((cin_planes + kcp - 1) / kcp);
   return (size_t)nchunks * 9 * kcp * cout_pad * 16;
+}
+size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out) {
+  return esr_conv3x3_packed_bytes_ex(cin_planes, cout, kcp, ESR_F16, cout_pad_out);
 }
 
 int esr_conv3x3_cin_planes(int cin, int lead) { return (lead + 7) / 8 + (cin - lead + 7) / 8; }
@@ -266,7 +271,7 @@ int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, i
   const int nb_n = nblock_for(lc_out_planespace, &cout_pad);
   const int n_blocks = cout_pad / nb_n;
   const int cin_planes = transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(cin, lead);
-  const int nchunks = (cin_planes + kcp - 1) / kcp;
+  const int nchunks = (dtype == ESR_BF16X3 ? 3 : 1) * ((cin_planes + kcp - 1) / kcp);
   const size_t total = (size_t)n_blocks * nchunks * 9 * kcp * nb_n * 8;
   cudaStream_t st = (cudaStream_t)stream;
   esr::pack_weights_kernel<<<grid_for(total, 256), 256, 0, st>>>(w_oihw, cout, cin, lead, kcp, nb_n, n_blocks, nchunks, dtype,
@@ -286,7 +291,12 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   if (!a->in || !a->wpacked || !a->bias) return fail(ESR_ERR_INVALID, "conv3x3: null in/weights/bias");
   if (a->n <= 0 || a->h <= 0 || a->w <= 0) return fail(ESR_ERR_INVALID, "conv3x3: bad shape %dx%dx%d", a->n, a->h, a->w);
   if (a->kcp != 2 && a->kcp != 4) return fail(ESR_ERR_INVALID, "conv3x3: kcp must be 2 or 4");
-  if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "conv3x3: bad dtype");
+  if (a->dtype != ESR_F16 && a->dtype != ESR_BF16 && a->dtype != ESR_BF16X3) return fail(ESR_ERR_INVALID, "conv3x3: bad dtype");
+  const int split = a->dtype == ESR_BF16X3 ? 1 : 0;
+  const int edt = split ? (int)ESR_BF16 : a->dtype;     // element format of the 16-bit operands
+  const int segs = split ? 3 : 1;
+  if (split && ((a->in_planes_total & 1) || (a->out16 && (a->out16_planes_total & 1)) || (a->res1 && a->res1_is16 && (a->res1_planes_total & 1))))
+    return fail(ESR_ERR_INVALID, "conv3x3: split-precision tensors hold hi and lo halves: planes_total must be even");
   if (!a->out16 && !a->out32 && !a->out_nchw && !a->lead_acc) return fail(ESR_ERR_INVALID, "conv3x3: no output requested");
   if (a->out16_up2 && a->out16_pixel_shuffle) return fail(ESR_ERR_INVALID, "conv3x3: up2 and pixel_shuffle are exclusive");
   if (((uintptr_t)a->in & 15) || ((uintptr_t)a->wpacked & 15) || ((uintptr_t)a->bias & 15))
@@ -313,8 +323,17 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.tiles_y = (a->h + p.R - 1) / p.R;
   p.num_tiles = p.tiles_x * p.tiles_y * a->n;
   p.kcp = a->kcp;
-  p.nchunks = (a->cin_planes + a->kcp - 1) / a->kcp;
+  p.split = split;
+  p.cps = (a->cin_planes + a->kcp - 1) / a->kcp;
+  p.nchunks = segs * p.cps;
   p.in_plane_off = a->in_plane_off;
+  p.seg_base[0] = p.seg_base[2] = a->in_plane_off;
+  p.seg_base[1] = a->in_plane_off + a->in_planes_total / 2;
+  {
+    const size_t f = a->out16_up2 ? 2 : (a->out16_pixel_shuffle ? a->out16_pixel_shuffle : 1);
+    p.out16_lo = (size_t)(a->out16_planes_total / 2) * f * f * a->h * a->w * 8;
+    p.res1_lo = (size_t)(a->res1_planes_total / 2) * a->h * a->w * 8;
+  }
   p.plane_stride = (uint32_t)(p.R + 2) * p.P * 16u;
   p.a_bytes = p.kcp * p.plane_stride;
   p.b_bytes = 9u * p.kcp * p.nb_n * 16u;
@@ -332,7 +351,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.stages = stages;
   const uint32_t smem_bytes = fixed + (uint32_t)stages * p.stage_bytes;
   // instruction descriptor: D=f32, A/B = f16|bf16, K-major both, N, M=128
-  p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | ((uint32_t)(p.nb_n >> 3) << 17) |
+  p.idesc = (1u << 4) | ((uint32_t)edt << 7) | ((uint32_t)edt << 10) | ((uint32_t)(p.nb_n >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   uint32_t cols = 2u * p.MT * p.nb_n, alloc = 32;
   while (alloc < cols) alloc <<= 1;
@@ -341,7 +360,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.wts = (const uint8_t*)a->wpacked;
   p.bias = a->bias;
   p.cout = a->cout;
-  p.dtype = a->dtype;
+  p.dtype = edt;
   p.lrelu = a->lrelu; p.slope = a->slope; p.alpha = a->alpha;
   p.res1 = a->res1; p.res1_is16 = a->res1_is16; p.res1_pt = a->res1_planes_total; p.res1_po = a->res1_plane_off; p.beta1 = a->beta1;
   p.res2 = a->res2; p.res2_pt = a->res2_planes_total; p.res2_po = a->res2_plane_off; p.beta2 = a->beta2;
@@ -374,7 +393,8 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
     p.nb_n = nbn;
     p.n_blocks = (a->cout + nbn - 1) / nbn;
-    p.nchunks = (a->cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+    p.cps = (a->cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+    p.nchunks = segs * p.cps;
     p.cin_planes = a->cin_planes;
     p.w_bytes = (uint32_t)p.nchunks * 3u * esr::kRowsKch * 3u * nbn * 16u;
     const uint32_t fixed = esr::kSmemHeader + 128u + p.w_bytes;
@@ -397,7 +417,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     p.in_pt = a->in_planes_total;
     p.wts = (const uint8_t*)a->wpacked_rows;
     for (int k = 0; k < 3; ++k)
-      p.idesc_n[k] = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | ((uint32_t)(((k + 1) * nbn) >> 3) << 17) |
+      p.idesc_n[k] = (1u << 4) | ((uint32_t)edt << 7) | ((uint32_t)edt << 10) | ((uint32_t)(((k + 1) * nbn) >> 3) << 17) |
                      ((uint32_t)(128 >> 4) << 24);
     int rc = set_max_smem_once((const void*)rk);
     if (rc) return rc;
@@ -439,14 +459,18 @@ int esr_conv3x3_fwd_batch(const esr_conv3x3_args* args, int count, void* stream,
   return ESR_OK;
 }
 
-int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out) {
-  const int nbn = rows_nbn_for(cin_planes, cout);
+int esr_conv3x3_rows_config_ex(int cin_planes, int cout, int dtype, int* nbn_out, size_t* bytes_out) {
+  const int segs = dtype == ESR_BF16X3 ? 3 : 1;
+  const int nbn = rows_nbn_for(cin_planes, cout, segs);
   if (nbn_out) *nbn_out = nbn;
   if (!nbn) return fail(ESR_ERR_INVALID, "conv3x3 rows: weights of (cin_planes %d, cout %d) do not fit in shared memory", cin_planes, cout);
-  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+  const int nchunks = segs * ((cin_planes + esr::kRowsKch - 1) / esr::kRowsKch);
   const int n_blocks = (cout + nbn - 1) / nbn;
   if (bytes_out) *bytes_out = (size_t)n_blocks * nchunks * 3 * esr::kRowsKch * 3 * nbn * 16;
   return ESR_OK;
+}
+int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out) {
+  return esr_conv3x3_rows_config_ex(cin_planes, cout, ESR_F16, nbn_out, bytes_out);
 }
 
 int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int lead, int dtype, int transpose_flip, int nbn,
@@ -457,7 +481,7 @@ int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int le
   const int lc_out = transpose_flip ? esr_conv3x3_cin_planes(cin, lead) * 8 : cout;
   const int lc_in = transpose_flip ? cout : cin;
   const int cin_planes = transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(cin, lead);
-  const int nchunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+  const int nchunks = (dtype == ESR_BF16X3 ? 3 : 1) * ((cin_planes + esr::kRowsKch - 1) / esr::kRowsKch);
   const int n_blocks = (lc_out + nbn - 1) / nbn;
   const size_t total = (size_t)n_blocks * nchunks * 3 * esr::kRowsKch * 3 * nbn * 8;
   esr::pack_weights_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, cout, cin, lead, nbn, nchunks, dtype,
@@ -508,7 +532,8 @@ int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* 
     const int nb_n = nblock_for(lc_out_planespace, &cout_pad);
     const int n_blocks = cout_pad / nb_n;
     const int cin_planes = it->transpose_flip ? (lc_in + 7) / 8 : esr_conv3x3_cin_planes(it->cin, it->lead);
-    const int nchunks = (cin_planes + it->kcp - 1) / it->kcp;
+    const int segs = it->dtype == ESR_BF16X3 ? 3 : 1;
+    const int nchunks = segs * ((cin_planes + it->kcp - 1) / it->kcp);
     jb.w = it->w_oihw; jb.cout = it->cout; jb.cin = it->cin; jb.lead = it->lead; jb.kcp = it->kcp; jb.nb_n = nb_n; jb.nchunks = nchunks;
     jb.dtype = it->dtype; jb.transpose_flip = it->transpose_flip;
     jb.dst = (uint16_t*)it->wpacked;
@@ -517,7 +542,7 @@ int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* 
       const int nbn = it->rows_nbn;
       if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "pack batch: row n-block must be 16, 32 or 64 (item %d)", i);
       const int rows_out = it->transpose_flip ? esr_conv3x3_cin_planes(it->cin, it->lead) * 8 : it->cout;
-      const int rows_chunks = (cin_planes + esr::kRowsKch - 1) / esr::kRowsKch;
+      const int rows_chunks = segs * ((cin_planes + esr::kRowsKch - 1) / esr::kRowsKch);
       const int rows_blocks = (rows_out + nbn - 1) / nbn;
       jb.rows_nb_n = nbn; jb.rows_nchunks = rows_chunks; jb.rows_dst = (uint16_t*)it->wpacked_rows;
       jb.rows_total = (unsigned long long)rows_blocks * rows_chunks * 3 * esr::kRowsKch * 3 * nbn * 8;
@@ -548,6 +573,25 @@ size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout) {
 
 int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
   if (!a || !a->x || !a->gy || !a->workspace) return fail(ESR_ERR_INVALID, "wgrad: null pointer");
+  if (a->dtype == ESR_BF16X3) {
+    // split precision: dW = x_hi (*) gy_hi + x_lo (*) gy_hi + x_hi (*) gy_lo, three accumulating launches of the bf16 kernel
+    if ((a->x_planes_total & 1) || (a->gy_planes_total & 1)) return fail(ESR_ERR_INVALID, "wgrad: split tensors need an even planes_total");
+    esr_conv3x3_wgrad_args b = *a;
+    b.dtype = ESR_BF16;
+    int rc = esr_conv3x3_wgrad(&b, stream);
+    if (rc) return rc;
+    b.accumulate = 1;
+    if (a->dw) {
+      b.db = nullptr;
+      b.x_plane_off = a->x_plane_off + a->x_planes_total / 2;
+      rc = esr_conv3x3_wgrad(&b, stream);
+      if (rc) return rc;
+    }
+    b.db = a->db;
+    b.x_plane_off = a->x_plane_off;
+    b.gy_plane_off = a->gy_plane_off + a->gy_planes_total / 2;
+    return esr_conv3x3_wgrad(&b, stream);
+  }
   if (!a->dw && !a->db) return fail(ESR_ERR_INVALID, "wgrad: no output requested");
   if (a->n <= 0 || a->h <= 0 || a->w <= 0) return fail(ESR_ERR_INVALID, "wgrad: bad shape %dx%dx%d", a->n, a->h, a->w);
   if (a->dtype != ESR_F16 && a->dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "wgrad: bad dtype");
@@ -651,8 +695,11 @@ int esr_pack_nchw(const float* src, int n, int c, int h, int w, int pad, int dty
   const int planes = (c + 7) / 8;
   if (plane_off + planes > planes_total) return fail(ESR_ERR_INVALID, "pack_nchw: planes out of range");
   const size_t total = (size_t)n * planes * (h + 2 * pad) * (w + 2 * pad);
-  esr::pack_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, pad, dtype, (uint16_t*)dst16,
-                                                                              dst32, planes_total, plane_off, planes);
+  const bool split = dtype == ESR_BF16X3 && dst16;
+  if (split && ((planes_total & 1) || plane_off + planes > planes_total / 2)) return fail(ESR_ERR_INVALID, "pack_nchw: bad split layout");
+  const size_t lo16 = split ? (size_t)(planes_total / 2) * (h + 2 * pad) * (w + 2 * pad) * 8 : 0;
+  esr::pack_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, pad, split ? 1 : dtype, (uint16_t*)dst16,
+                                                                              dst32, planes_total, plane_off, planes, lo16);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -664,8 +711,11 @@ int esr_pack_nchw_affine(const float* src, int n, int c, int h, int w, const flo
   const int planes = (c + 7) / 8;
   if (plane_off + planes > planes_total) return fail(ESR_ERR_INVALID, "pack_nchw_affine: planes out of range");
   const size_t total = (size_t)n * planes * h * w;
-  esr::pack_nchw_affine_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, scale, shift, dtype, (uint16_t*)dst16,
-                                                                                     planes_total, plane_off, planes);
+  const bool split = dtype == ESR_BF16X3;
+  if (split && ((planes_total & 1) || plane_off + planes > planes_total / 2)) return fail(ESR_ERR_INVALID, "pack_nchw_affine: bad split layout");
+  esr::pack_nchw_affine_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, scale, shift, split ? 1 : dtype, (uint16_t*)dst16,
+                                                                                     planes_total, plane_off, planes,
+                                                                                     split ? (size_t)(planes_total / 2) * h * w * 8 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -674,6 +724,15 @@ int esr_pack_nchw_affine(const float* src, int n, int c, int h, int w, const flo
 int esr_maxpool2x2_planes16(const void* src, int dtype, int n, int planes, int h, int w, void* dst, void* stream) {
   if (!src || !dst) return fail(ESR_ERR_INVALID, "maxpool2x2: null pointer");
   if ((h & 1) || (w & 1)) return fail(ESR_ERR_INVALID, "maxpool2x2: odd size %dx%d", h, w);
+  if (dtype == ESR_BF16X3) {
+    if (planes & 1) return fail(ESR_ERR_INVALID, "maxpool2x2: split tensors need an even plane count");
+    const size_t tot = (size_t)n * (planes / 2) * (h / 2) * (w / 2);
+    esr::maxpool2x2_split_kernel<<<grid_for(tot, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, (size_t)n * (planes / 2), planes / 2, h, w,
+                                                                                    (uint16_t*)dst);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ESR_OK;
+  }
   const size_t total = (size_t)n * planes * (h / 2) * (w / 2);
   esr::maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (size_t)n * planes, h, w, dtype, (uint4*)dst);
   g_launches++;
@@ -684,6 +743,15 @@ int esr_maxpool2x2_planes16(const void* src, int dtype, int n, int planes, int h
 int esr_maxpool2x2_bwd_planes16(const void* gout, const void* act, int dtype, int n, int planes, int h, int w, void* gin, void* stream) {
   if (!gout || !act || !gin) return fail(ESR_ERR_INVALID, "maxpool2x2_bwd: null pointer");
   if ((h & 1) || (w & 1)) return fail(ESR_ERR_INVALID, "maxpool2x2_bwd: odd size %dx%d", h, w);
+  if (dtype == ESR_BF16X3) {
+    if (planes & 1) return fail(ESR_ERR_INVALID, "maxpool2x2_bwd: split tensors need an even plane count");
+    const size_t tot = (size_t)n * (planes / 2) * (h / 2) * (w / 2);
+    esr::maxpool2x2_bwd_split_kernel<<<grid_for(tot, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)gout, (const uint16_t*)act,
+                                                                                        (size_t)n * (planes / 2), planes / 2, h, w, (uint16_t*)gin);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ESR_OK;
+  }
   const size_t total = (size_t)n * planes * (h / 2) * (w / 2);
   esr::maxpool2x2_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)gout, (const uint4*)act, (size_t)n * planes, h, w,
                                                                                    dtype, (uint4*)gin);
@@ -696,8 +764,8 @@ int esr_unpack_planes16(const void* src16, int dtype, int n, int c, int h, int w
                         float* dst, void* stream) {
   if (!src16 || !dst) return fail(ESR_ERR_INVALID, "unpack16: null pointer");
   const size_t total = (size_t)n * c * h * w;
-  esr::unpack_planes_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src16, dtype, n, c, h, w,
-                                                                                       planes_total, plane_off, dst);
+  esr::unpack_planes_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src16, dtype == ESR_BF16X3 ? 1 : dtype, n, c, h, w, planes_total, plane_off, dst, dtype == ESR_BF16X3 ? (size_t)(planes_total / 2) * h * w * 8 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -708,7 +776,7 @@ int esr_unpack_planes32(const float* src32, int n, int c, int h, int w, int plan
   if (!src32 || !dst) return fail(ESR_ERR_INVALID, "unpack32: null pointer");
   const size_t total = (size_t)n * c * h * w;
   esr::unpack_planes_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src32, 0, n, c, h, w,
-                                                                                        planes_total, plane_off, dst);
+                                                                                        planes_total, plane_off, dst, 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -739,17 +807,25 @@ int esr_downsum2x_planes(const float* src32, int n, int planes, int h, int w, co
   if (!src32 || (!dst32 && !dst16)) return fail(ESR_ERR_INVALID, "downsum2x: null pointer");
   const size_t total = (size_t)n * planes * h * w;
   esr::downsum2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src32, (size_t)n * planes, h, w,
-                                                                              (const uint4*)act16_hi, slope, dtype, (float4*)dst32,
-                                                                              (uint4*)dst16);
+                                                                              (const uint4*)act16_hi, slope, dtype == ESR_BF16X3 ? 1 : dtype,
+                                                                              (float4*)dst32, (uint4*)dst16, planes, dtype == ESR_BF16X3 ? 1 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
 }
 
 int esr_planes_add(const float* a32, const float* b32, size_t n_groups8, int dtype, float* out32, void* out16, void* stream) {
+  return esr_planes_add_ex(a32, b32, n_groups8, 0, dtype, out32, out16, stream);
+}
+
+int esr_planes_add_ex(const float* a32, const float* b32, size_t n_groups8, size_t per_image_groups8, int dtype, float* out32, void* out16,
+                      void* stream) {
   if (!a32 || !b32 || (!out32 && !out16)) return fail(ESR_ERR_INVALID, "planes_add: null pointer");
+  const bool split = dtype == ESR_BF16X3 && out16;
+  if (split && (per_image_groups8 == 0 || n_groups8 % per_image_groups8)) return fail(ESR_ERR_INVALID, "planes_add: split output needs the per-image size");
   esr::planes_add_kernel<<<grid_for(n_groups8, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a32, (const float4*)b32, n_groups8,
-                                                                                   dtype, (float4*)out32, (uint4*)out16);
+                                                                                   split ? 1 : dtype, (float4*)out32, (uint4*)out16,
+                                                                                   per_image_groups8, split ? 1 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -888,11 +964,12 @@ int esr_bn_lrelu_fwd(const float* y32, int n, int planes, int h, int w, int c, c
                      int dtype, void* dst16, int space_to_depth, float* dst_nchw, void* stream) {
   if (!y32 || !scale || !shift || (!dst16 && !dst_nchw)) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: null pointer");
   if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: bad shape");
-  if (dtype != ESR_F16 && dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: bad dtype");
+  if (dtype != ESR_F16 && dtype != ESR_BF16 && dtype != ESR_BF16X3) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: bad dtype");
   if (space_to_depth && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_lrelu_fwd: space-to-depth needs an even size, got %dx%d", h, w);
   const size_t total = (size_t)n * planes * h * w;
-  esr::bn_lrelu_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y32, scale, shift, slope, n, planes, h, w, c, dtype,
-                                                                                  (uint16_t*)dst16, space_to_depth, dst_nchw);
+  esr::bn_lrelu_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y32, scale, shift, slope, n, planes, h, w, c,
+                                                                                  dtype == ESR_BF16X3 ? 1 : dtype, (uint16_t*)dst16, space_to_depth,
+                                                                                  dst_nchw, dtype == ESR_BF16X3 ? 1 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -916,7 +993,7 @@ int esr_bn_lrelu_bwd(const float* g, int g_layout, const float* y32, int n, int 
   if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad shape");
   if (g_layout < 0 || g_layout > 2) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad gradient layout %d", g_layout);
   if (g_layout == 1 && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: space-to-depth gradient needs an even size");
-  if (dtype != ESR_F16 && dtype != ESR_BF16) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad dtype");
+  if (dtype != ESR_F16 && dtype != ESR_BF16 && dtype != ESR_BF16X3) return fail(ESR_ERR_INVALID, "bn_lrelu_bwd: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t m = (size_t)n * h * w;
   if (has_bn) {
@@ -932,7 +1009,7 @@ int esr_bn_lrelu_bwd(const float* g, int g_layout, const float* y32, int n, int 
   }
   const size_t total = (size_t)n * planes * h * w;
   esr::bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(g, g_layout, y32, scale, shift, save_mean, save_invstd, c1, c2, slope, n, planes,
-                                                                h, w, c, dtype, (uint16_t*)gy16);
+                                                                h, w, c, dtype == ESR_BF16X3 ? 1 : dtype, (uint16_t*)gy16, dtype == ESR_BF16X3 ? 1 : 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -991,6 +1068,87 @@ int esr_structure_tensor_bwd(const float* img, const float* g, int n, int c, int
   const size_t total = (size_t)n * c * h * w;
   esr::structure_tensor_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, g, n, c, h, w,
                                                                                        (float)(1.0 / ((double)c * (h - 1) * (w - 1))), grad_img);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+// ---- training step outside the networks: Adam, L1, relativistic BCE --------------------------------------------------------------
+size_t esr_adam_scratch_bytes(int count) { return count > 0 ? (size_t)count * sizeof(esr::AdamTensor) : 0; }
+
+int esr_adam_multi(const esr_adam_tensor* tensors_host, int count, void* scratch, size_t scratch_bytes, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  static_assert(sizeof(esr_adam_tensor) == sizeof(esr::AdamTensor), "esr_adam_tensor layout");
+  if (count <= 0) return ESR_OK;
+  if (!scratch || scratch_bytes < esr_adam_scratch_bytes(count)) return fail(ESR_ERR_INVALID, "adam: scratch of %zu bytes needed", esr_adam_scratch_bytes(count));
+  if (step < 1) return fail(ESR_ERR_INVALID, "adam: step counts from 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long nmax = 0;
+  if (tensors_host) {     // NULL: the table uploaded by an earlier call is still in `scratch` (same tensors, e.g. flat buffers)
+    for (int i = 0; i < count; ++i) {
+      if (!tensors_host[i].p || !tensors_host[i].g || !tensors_host[i].m || !tensors_host[i].v) return fail(ESR_ERR_INVALID, "adam: null pointer in tensor %d", i);
+      if (tensors_host[i].n > nmax) nmax = tensors_host[i].n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(scratch, tensors_host, sizeof(esr::AdamTensor) * (size_t)count, cudaMemcpyHostToDevice, st));
+  } else {
+    nmax = count == 1 ? (1ull << 40) : (1ull << 18);
+  }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), bc2_sqrt = (float)sqrt(bc2);
+  // blocks per tensor: enough for the largest one at 4 elements per thread, capped so that the grid stays a few waves
+  unsigned long long bx = (nmax / 4 + 255) / 256;
+  const unsigned long long cap = count == 1 ? 148ull * 8 : 16ull;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  for (int i0 = 0; i0 < count; i0 += 65535) {
+    const int n = count - i0 < 65535 ? count - i0 : 65535;
+    esr::adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, st>>>((const esr::AdamTensor*)scratch + i0, beta1, beta2, eps, weight_decay,
+                                                                          step_size, bc2_sqrt, grad_scale);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return ESR_OK;
+}
+
+size_t esr_l1_workspace_bytes(void) { return (size_t)esr::kL1Blocks * sizeof(float); }
+
+int esr_l1_reduce(const float* a, const float* b, size_t n, float* workspace, size_t workspace_bytes, float* out_mean, void* stream) {
+  if (!a || !b || !workspace || !out_mean || n == 0) return fail(ESR_ERR_INVALID, "l1_reduce: bad arguments");
+  if (workspace_bytes < esr_l1_workspace_bytes()) return fail(ESR_ERR_INVALID, "l1_reduce: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > esr::kL1Blocks) blocks = esr::kL1Blocks;
+  if (blocks < 1) blocks = 1;
+  esr::l1_partial_kernel<<<blocks, 256, 0, st>>>(a, b, n, workspace);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  esr::sum_partials_kernel<<<1, 256, 0, st>>>(workspace, blocks, 1.0 / (double)n, out_mean);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_l1_grad(const float* a, const float* b, size_t n, const float* gout, float* ga, float* gb, void* stream) {
+  if (!a || !b || !gout || (!ga && !gb) || n == 0) return fail(ESR_ERR_INVALID, "l1_grad: bad arguments");
+  esr::l1_grad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, gout, (float)(1.0 / (double)n), ga, gb);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_bce_rel_loss(const float* a, const float* b, int n, const float* sums_global, float n_global, float target_a, float target_b, float* out4,
+                     float* ea, float* eb, void* stream) {
+  if (!a || !b || !out4 || !ea || !eb || n <= 0) return fail(ESR_ERR_INVALID, "bce_rel_loss: bad arguments");
+  esr::bce_rel_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, b, n, sums_global, sums_global ? n_global : (float)n, target_a, target_b, out4, ea, eb);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_bce_rel_loss_bwd(const float* ea, const float* eb, int n, const float* S_global, float n_global, const float* ga_up, const float* gb_up,
+                         float* ga, float* gb, void* stream) {
+  if (!ea || !eb || !S_global || (!ga && !gb) || n <= 0) return fail(ESR_ERR_INVALID, "bce_rel_loss_bwd: bad arguments");
+  esr::bce_rel_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ea, eb, n, S_global, n_global, ga_up, gb_up, ga, gb);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;

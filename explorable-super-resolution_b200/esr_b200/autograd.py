@@ -19,9 +19,10 @@ def _params(net):
 
 
 def _engine_for(net, params):
-    """training (some generator parameter wants a gradient) runs in bf16, the frozen generator in net.compute_dtype"""
+    """training (some generator parameter wants a gradient) runs in bf16, the frozen generator in net.compute_dtype;
+    the parity mode of esr_b200.precision runs both in split precision"""
     training = any(p.requires_grad for p in params)
-    return net.engine(torch.bfloat16 if training else None)
+    return net.engine(training=training)
 
 
 def _flat_grads(ctx, grads, n_params):
@@ -30,6 +31,8 @@ def _flat_grads(ctx, grads, n_params):
     for k in range(n_params):
         need = ctx.needs_input_grad[ctx.first_param + k]
         g = grads[k // 2][k % 2] if (grads is not None and need) else None
+        if isinstance(g, str):      # engine.DIRECT: already written into the parameter's registered flat-buffer view (.grad points at it)
+            g = None
         flat.append(g)
     return flat
 

@@ -11,8 +11,10 @@ process, like each replica of the reference's nn.DataParallel) and updates the r
 import torch
 
 from . import ops
+from . import optim as flat
 
 SLOPE = 0.2
+DIRECT = 'direct'      # this gradient was written straight into the parameter's FlatAdam-registered gradient view
 
 
 _K4_INDEX = {}
@@ -183,38 +185,81 @@ class DiscEngine:
         dev = feat.device
         g_out = g_out.float().contiguous()
         grads = {}
-        g_h1, dw2, db2 = ops.linear_bwd(g_out, None, h1, self.fc2.weight.detach(), want_w=want_params)
-        flat = feat.reshape(n, -1)
-        g_flat, dw1, db1 = ops.linear_bwd(g_h1, h1, flat, self.fc1.weight.detach(), slope=SLOPE, want_w=want_params)
+        pending = []
+
+        def target(*params):
+            """the parameters' flat gradient views when every one of them is registered and its .grad is unset or already that view:
+            (views, accumulate) - else (None, False)"""
+            views = [flat.grad_view(p) for p in params]
+            if not want_params or any(v is None for v in views):
+                return None, False
+            if not all(p.grad is None or p.grad is v or p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, views)):
+                return None, False
+            states = {p.grad is None for p in params}
+            if len(states) != 1:
+                return None, False
+            pending.extend(zip(params, views))
+            return views, not states.pop()
+
+        v2, acc2 = target(self.fc2.weight, self.fc2.bias)
+        g_h1, dw2, db2 = ops.linear_bwd(g_out, None, h1, self.fc2.weight.detach(), want_w=want_params, dw=v2[0] if v2 else None,
+                                        db=v2[1] if v2 else None, accumulate=acc2)
+        flat_in = feat.reshape(n, -1)
+        v1, acc1 = target(self.fc1.weight, self.fc1.bias)
+        g_flat, dw1, db1 = ops.linear_bwd(g_h1, h1, flat_in, self.fc1.weight.detach(), slope=SLOPE, want_w=want_params, dw=v1[0] if v1 else None,
+                                          db=v1[1] if v1 else None, accumulate=acc1)
         if want_params:
-            grads[id(self.fc1.weight)], grads[id(self.fc1.bias)] = dw1, db1
-            grads[id(self.fc2.weight)], grads[id(self.fc2.bias)] = dw2, db2
+            grads[id(self.fc1.weight)], grads[id(self.fc1.bias)] = (DIRECT, DIRECT) if v1 else (dw1, db1)
+            grads[id(self.fc2.weight)], grads[id(self.fc2.bias)] = (DIRECT, DIRECT) if v2 else (dw2, db2)
         g, layout = g_flat.reshape(feat.shape), 2
         gx = None
+        split = ops.is_split(self.dtype)
         for li in range(len(self.layers) - 1, -1, -1):
             L = self.layers[li]
             cur, y32, mean, invstd, scale, shift, use_batch = saved[li]
             dgamma = dbeta = None
+            vbn, accbn = None, False
             if L.bn is not None and want_params:
-                dgamma = torch.empty(L.cout, dtype=torch.float32, device=dev)
-                dbeta = torch.empty(L.cout, dtype=torch.float32, device=dev)
+                vbn, accbn = target(L.bn.weight, L.bn.bias)
+                if vbn:
+                    dgamma, dbeta = vbn
+                else:
+                    dgamma = torch.empty(L.cout, dtype=torch.float32, device=dev)
+                    dbeta = torch.empty(L.cout, dtype=torch.float32, device=dev)
             gy16 = ops.bn_lrelu_bwd(g, layout, y32, L.cout, scale, shift, mean, invstd, SLOPE, self.dtype, has_bn=L.bn is not None,
-                                    train=use_batch, dgamma=dgamma, dbeta=dbeta)
+                                    train=use_batch, dgamma=dgamma, dbeta=dbeta, accumulate=accbn)
             if want_params:
                 if L.bn is not None:
-                    grads[id(L.bn.weight)], grads[id(L.bn.bias)] = dgamma, dbeta
+                    grads[id(L.bn.weight)], grads[id(L.bn.bias)] = (DIRECT, DIRECT) if vbn else (dgamma, dbeta)
                 cin3 = 4 * L.cin if L.k4 else L.cin
-                dw, db = ops.conv3x3_wgrad(cur, gy16, L.cout, cin3)
-                grads[id(L.conv.weight)] = k3x3_to_k4s2(dw) if L.k4 else dw
-                grads[id(L.conv.bias)] = db
+                vc, accc = target(L.conv.weight, L.conv.bias)
+                if vc and not L.k4:
+                    ops.conv3x3_wgrad(cur, gy16, L.cout, cin3, split=split, dw=vc[0], db=vc[1], accumulate=accc)
+                    grads[id(L.conv.weight)], grads[id(L.conv.bias)] = DIRECT, DIRECT
+                elif vc:       # 4x4 stride-2 conv: the tensor cores produce dW of its 3x3 space-to-depth form; one gather puts it in place
+                    dw, db = ops.conv3x3_wgrad(cur, gy16, L.cout, cin3, split=split)
+                    if accc:
+                        vc[0].add_(k3x3_to_k4s2(dw))
+                        vc[1].add_(db)
+                    else:
+                        vc[0].copy_(k3x3_to_k4s2(dw))
+                        vc[1].copy_(db)
+                    grads[id(L.conv.weight)], grads[id(L.conv.bias)] = DIRECT, DIRECT
+                else:
+                    dw, db = ops.conv3x3_wgrad(cur, gy16, L.cout, cin3, split=split)
+                    grads[id(L.conv.weight)] = k3x3_to_k4s2(dw) if L.k4 else dw
+                    grads[id(L.conv.bias)] = db
             if li == 0:
                 if want_input:
                     gx = torch.zeros((n, L.cin, H, W), dtype=torch.float32, device=dev)
                     ops.conv3x3(gy16, pkt[0], out_nchw=gx)
                 break
-            g = torch.empty((n, cur.shape[1], cur.shape[2], cur.shape[3], 8), dtype=torch.float32, device=dev)
+            g = torch.empty((n, ops.logical_planes(cur, self.dtype), cur.shape[2], cur.shape[3], 8), dtype=torch.float32, device=dev)
             ops.conv3x3(gy16, pkt[li], out32=g)
             layout = 1 if L.k4 else 0
+        for prm, view in pending:
+            if prm.grad is None:
+                prm.grad = view
         plist = [grads.get(id(p)) for p in self.params()] if want_params else None
         return gx, plist
 
@@ -231,7 +276,7 @@ class _DiscFn(torch.autograd.Function):
     def backward(ctx, g):
         want_params = any(ctx.needs_input_grad[2:])
         gx, plist = ctx.eng.backward(g, ctx.sv, want_input=ctx.needs_input_grad[0], want_params=want_params)
-        pg = tuple((plist[k] if (want_params and ctx.needs_input_grad[2 + k]) else None) for k in range(ctx.n_params))
+        pg = tuple((plist[k] if (want_params and ctx.needs_input_grad[2 + k] and not isinstance(plist[k], str)) else None) for k in range(ctx.n_params))
         return (gx, None) + pg
 
 

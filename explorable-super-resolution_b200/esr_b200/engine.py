@@ -22,8 +22,10 @@ channels' gradient is accumulated by every launch into one plane (`lead_acc`).
 import torch
 
 from . import ops
+from . import optim as flat
 
 SLOPE = 0.2
+DIRECT = 'direct'      # marker: this gradient was written straight into the parameter's registered flat-buffer view
 
 
 def _param_version(mods):
@@ -176,7 +178,7 @@ class RRDBEngine:
         nfp, gcp = net.nf // 8, net.gc // 8
         nb = len(net.model[1].sub) - 1
         dense_planes = zp + nfp + 4 * gcp
-        z16 = lambda *s: torch.zeros(s, dtype=self.dtype, device=dev)
+        z16 = lambda n_, planes, hh, ww, _8: ops.alloc16(self.dtype, n_, planes, hh, ww, dev, zero=True)
         z32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         b = {
             'in16': z16(n, zp + 1, h, w, 8),
@@ -288,14 +290,15 @@ class RRDBEngine:
             # architecture.py:284), so the padding is folded into the resize kernel, not applied after it
             z_lr = ops.latent_downscale(z_hr, S, pad_hr=pad * S)
             img = x[:, zc:].contiguous()
-            ops.pack_nchw(z_lr, dst16=B['in16'], plane_off=0)
-            ops.pack_nchw(img, pad=pad, dst16=B['in16'], plane_off=1)
+            dt = self.dtype
+            ops.pack_nchw(z_lr, dst16=B['in16'], plane_off=0, dtype=dt)
+            ops.pack_nchw(img, pad=pad, dst16=B['in16'], plane_off=1, dtype=dt)
             for d in B['D']:
-                ops.pack_nchw(z_lr, dst16=d, plane_off=0)
-            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_a'], plane_off=0)
-            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_b'], plane_off=0)
+                ops.pack_nchw(z_lr, dst16=d, plane_off=0, dtype=dt)
+            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_a'], plane_off=0, dtype=dt)
+            ops.pack_nchw(z_hr, pad=pad * S, dst16=B['hr_b'], plane_off=0, dtype=dt)
         else:
-            ops.pack_nchw(x, pad=pad, dst16=B['in16'], plane_off=0)
+            ops.pack_nchw(x, pad=pad, dst16=B['in16'], plane_off=0, dtype=self.dtype)
 
         out = torch.empty((n, net.out_nc, h * S, w * S), dtype=torch.float32, device=dev)
         if ops.PLAN_REPLAY:
@@ -342,10 +345,31 @@ class RRDBEngine:
         leads = self._leads(convs)
         grads = [None] * len(convs) if wgrad else None
 
-        def wg(idx, x16, gy16, gy_off=0, scale=1.0):
-            if wgrad:
-                cout, cin = int(convs[idx].weight.shape[0]), int(convs[idx].weight.shape[1])
-                grads[idx] = ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale)
+        pending = []      # (parameter, flat view) pairs whose .grad must point at the view once the launches are issued
+
+        def wg(idx, x16, gy16, gy_off=0, scale=1.0, bias_from_nchw=None):
+            """weight / bias gradient of conv `idx`.  With a FlatAdam-registered parameter pair the launches write (or accumulate, when
+            .grad already is that view: gradient accumulation, SRRaGAN_model.py:392-396) straight into the flat gradient buffer."""
+            if not wgrad:
+                return
+            conv = convs[idx]
+            cout, cin = int(conv.weight.shape[0]), int(conv.weight.shape[1])
+            gw, gb = flat.grad_view(conv.weight), flat.grad_view(conv.bias)
+            split = ops.is_split(self.dtype)
+            own = lambda p, v: p.grad is None or p.grad is v or p.grad.data_ptr() == v.data_ptr()
+            if gw is not None and gb is not None and own(conv.weight, gw) and own(conv.bias, gb) and (conv.weight.grad is None) == (conv.bias.grad is None):
+                acc = conv.weight.grad is not None
+                if bias_from_nchw is None:
+                    ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale, split=split, dw=gw, db=gb, accumulate=acc)
+                else:
+                    ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale, split=split, dw=gw, db=False, accumulate=acc)
+                    ops.sum_nchw(bias_from_nchw, out=gb, accumulate=acc)
+                pending.extend([(conv.weight, gw), (conv.bias, gb)])
+                grads[idx] = (DIRECT, DIRECT)
+                return
+            grads[idx] = ops.conv3x3_wgrad(x16, gy16, cout, cin, lead=leads[idx], gy_off=gy_off, scale=scale, split=split)
+            if bias_from_nchw is not None:
+                grads[idx] = (grads[idx][0], ops.sum_nchw(bias_from_nchw))
 
         B, n, h, w, pad = sv.B, sv.n, sv.h, sv.w, sv.pad
         if B.get('gen') != sv.gen:
@@ -364,7 +388,7 @@ class RRDBEngine:
         # engine in bf16 because fp16 gradients underflow (a dense block's inner gradients sit 3-4 decades below the trunk's)
         gdt = self.dtype
         f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        f16 = lambda *s: torch.zeros(s, dtype=gdt, device=dev)
+        f16 = lambda n_, planes, hh, ww, _8: ops.alloc16(gdt, n_, planes, hh, ww, dev, zero=True)
         gz_hr = f32(n, 1, H, W, 8) if z else None
         gz_lr = f32(n, 1, h, w, 8) if z else None
         lead = dict(lead_planes=zp, lead_acc=gz_hr) if z else {}
@@ -374,9 +398,7 @@ class RRDBEngine:
         # HR_conv1^T, HR_conv0^T (LeakyReLU derivative of the conv below comes from its saved output)
         g_out = g_out.float().contiguous()
         g16, _ = ops.pack_nchw(g_out, dtype=gdt)
-        wg(idx_hr0 + 1, B['hr_b'], g16)
-        if wgrad:   # the last conv's bias gradient from the unrounded dL/dG (a sum with heavy cancellation)
-            grads[idx_hr0 + 1] = (grads[idx_hr0 + 1][0], ops.sum_nchw(g_out))
+        wg(idx_hr0 + 1, B['hr_b'], g16, bias_from_nchw=g_out)    # the last conv's bias gradient from the unrounded dL/dG (heavy cancellation)
         g_b = f16(n, nfp, H, W, 8)
         ops.conv3x3(g16, wt[idx_hr0 + 1], mask16=B['hr_b'], mask_off=zp, mask_slope=SLOPE, out16=g_b, **lead)
         wg(idx_hr0, B['hr_a'], g_b)
@@ -440,4 +462,7 @@ class RRDBEngine:
             gx[:, :sv.cin - 3] = gz.view(n, z * S * S, sv.h0, sv.w0)
         if pad == 0:
             gx[:, sv.cin - 3:] = g_img
+        for prm, view in pending:
+            if prm.grad is None:
+                prm.grad = view
         return gx, grads

@@ -10,7 +10,7 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 LIB_PATH = os.path.join(PKG_ROOT, "libesr_b200.so")
 CSRC = os.path.join(PKG_ROOT, "csrc")
 
-ESR_F16, ESR_BF16 = 0, 1
+ESR_F16, ESR_BF16, ESR_BF16X3 = 0, 1, 2
 
 
 class EsrError(RuntimeError):
@@ -58,6 +58,11 @@ class PackItem(C.Structure):
                 ("wpacked_rows", C.c_void_p), ("rows_nbn", C.c_int)]
 
 
+class AdamTensor(C.Structure):
+    """mirror of esr_adam_tensor"""
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_ulonglong)]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     "esr_last_error": (C.c_char_p, []),
@@ -68,12 +73,14 @@ SIGNATURES = {
     "esr_conv3x3_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "esr_conv3x3_fwd_batch": (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "esr_conv3x3_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "esr_conv3x3_packed_bytes_ex": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "esr_conv3x3_cin_planes": (C.c_int, [C.c_int, C.c_int]),
     "esr_pack_conv3x3_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esr_pack_batch_scratch_bytes": (C.c_size_t, [C.c_int]),
     "esr_pack_conv3x3_weights_batch": (C.c_int, [C.POINTER(PackItem), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int)]),
     "esr_conv3x3_rows_config": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "esr_conv3x3_rows_config_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "esr_pack_conv3x3_weights_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_conv3x3_wgrad_workspace": (C.c_size_t, [C.c_int, C.c_int]),
     "esr_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
@@ -89,6 +96,7 @@ SIGNATURES = {
     "esr_downsum2x_planes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "esr_planes_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_planes_add_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "esr_sep_adjoint_1d": (C.c_int, [C.c_void_p] + [C.c_int] * 12 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "esr_latent_grad": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "esr_cem_down": (C.c_int, [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -111,6 +119,15 @@ SIGNATURES = {
     "esr_structure_tensor_workspace_bytes": (C.c_size_t, [C.c_int]),
     "esr_structure_tensor_fwd": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "esr_structure_tensor_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "esr_adam_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "esr_adam_multi": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.c_void_p, C.c_size_t] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
+    "esr_l1_workspace_bytes": (C.c_size_t, []),
+    "esr_l1_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "esr_l1_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "esr_bce_rel_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
+    "esr_bce_rel_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",

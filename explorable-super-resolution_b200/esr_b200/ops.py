@@ -11,6 +11,33 @@ from . import lib as L
 
 _TORCH2ESR = {torch.float16: L.ESR_F16, torch.bfloat16: L.ESR_BF16}
 
+# Split precision ("parity mode", esr_dtype ESR_BF16X3): a 16-bit tensor [N, 2P, H, W, 8] holds P bf16 hi planes and P bf16 lo planes
+# (lo = bf16(v - hi)); convs run x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation.  Engines select it by passing SPLIT
+# where they would pass torch.float16 / torch.bfloat16.
+SPLIT = 'bf16x3'
+
+
+def is_split(dt):
+    return dt == SPLIT
+
+
+def elem_dtype(dt):
+    return torch.bfloat16 if dt == SPLIT else dt
+
+
+def esr_dtype(dt):
+    return L.ESR_BF16X3 if dt == SPLIT else _TORCH2ESR[dt]
+
+
+def alloc16(dt, n, planes, h, w, dev, zero=False):
+    """16-bit planes tensor of `planes` logical planes in precision `dt` (split tensors hold twice the planes)"""
+    shape = (n, planes * (2 if dt == SPLIT else 1), h, w, 8)
+    return (torch.zeros if zero else torch.empty)(shape, dtype=elem_dtype(dt), device=dev)
+
+
+def logical_planes(t, dt):
+    return t.shape[1] // 2 if dt == SPLIT else t.shape[1]
+
 # engines replay recorded launch sequences (LaunchPlan) when True; False launches every conv through its own host call
 PLAN_REPLAY = True
 
@@ -39,15 +66,15 @@ _cfg_cache = {}
 _pack_scratch = {}
 
 
-def _pack_config(cin_planes, cout, kcp, want_rows):
+def _pack_config(cin_planes, cout, kcp, want_rows, edt=L.ESR_F16):
     """(packed bytes, cout_pad, row-image n-block, row-image bytes) - pure functions of the shape, memoised"""
-    key = (cin_planes, cout, kcp, want_rows)
+    key = (cin_planes, cout, kcp, want_rows, edt == L.ESR_BF16X3)
     if key not in _cfg_cache:
         lib = L.load()
         cp = C.c_int(0)
-        nbytes = int(lib.esr_conv3x3_packed_bytes(cin_planes, cout, kcp, C.byref(cp)))
+        nbytes = int(lib.esr_conv3x3_packed_bytes_ex(cin_planes, cout, kcp, edt, C.byref(cp)))
         nbn, nb = C.c_int(0), C.c_size_t(0)
-        ok = want_rows and lib.esr_conv3x3_rows_config(cin_planes, cout, C.byref(nbn), C.byref(nb)) == 0
+        ok = want_rows and lib.esr_conv3x3_rows_config_ex(cin_planes, cout, edt, C.byref(nbn), C.byref(nb)) == 0
         _cfg_cache[key] = (nbytes, cp.value, nbn.value if ok else 0, nb.value if ok else 0)
     return _cfg_cache[key]
 
@@ -81,8 +108,9 @@ class PackedConv:
         require_cuda(weight, bias)
         cout, cin = int(weight.shape[0]), int(weight.shape[1])
         assert tuple(weight.shape[2:]) == (3, 3), "only 3x3 kernels"
-        self.dtype = dtype
-        self.esr_dtype = _TORCH2ESR[dtype]
+        self.split = dtype == SPLIT
+        self.dtype = elem_dtype(dtype)
+        self.esr_dtype = esr_dtype(dtype)
         self.lead = lead
         self.transpose_flip = bool(transpose_flip)
         self._w_shape = (cout, cin, 3, 3)
@@ -97,7 +125,7 @@ class PackedConv:
         if kcp is None:
             kcp = 4 if self.cin_planes >= 4 else 2
         self.kcp = kcp
-        nbytes, self.cout_pad, self.rows_nbn, rows_bytes = _pack_config(self.cin_planes, self.cout, kcp, bool(rows))
+        nbytes, self.cout_pad, self.rows_nbn, rows_bytes = _pack_config(self.cin_planes, self.cout, kcp, bool(rows), self.esr_dtype)
         self.wpacked = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
         self.bias = torch.empty(self.cout_pad, dtype=torch.float32, device=weight.device)
         # second image for the row-streaming kernel (used for images wide enough for 128-pixel strips)
@@ -139,6 +167,7 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     a.n, a.h, a.w, a.dtype = n, h, w, pc.esr_dtype
     a.in_, a.in_planes_total, a.in_plane_off = x16.data_ptr(), pt, in_plane_off
     a.cin_planes = pc.cin_planes if cin_planes is None else cin_planes
+    assert a.cin_planes == pc.cin_planes or not pc.split      # the packed image's chunk structure is that of its own cin
     a.wpacked, a.bias = pc.wpacked.data_ptr(), pc.bias.data_ptr()
     a.cout, a.cout_pad, a.kcp = pc.cout, pc.cout_pad, pc.kcp
     a.lrelu, a.slope, a.alpha = int(lrelu), slope, alpha
@@ -210,7 +239,7 @@ def _wgrad_ws_bytes(cp, cout):
     return _wgrad_ws_size[key]
 
 
-def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, db=None, scale=1.0, accumulate=False):
+def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, db=None, scale=1.0, accumulate=False, split=False):
     """Weight / bias gradient of a 3x3 conv: x16 = the conv's input planes, gy16 = gradient of its (pre-activation)
     output.  Returns (dw [cout,cin,3,3] fp32, db [cout] fp32); pass dw/db tensors to accumulate into them."""
     require_cuda(x16, gy16, dw, db)
@@ -223,7 +252,10 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
         accumulate = False
     if db is None:
         db = torch.empty((cout,), dtype=torch.float32, device=dev)
-    assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3) and db.dtype == torch.float32
+    elif db is False:      # no bias gradient wanted
+        db = None
+    assert dw.dtype == torch.float32 and tuple(dw.shape) == (cout, cin, 3, 3) and (db is None or db.dtype == torch.float32)
+    assert dw.is_contiguous() and (db is None or db.is_contiguous())
     # wide convs are covered in input-channel slices of at most 208 channels (5 M chunks of (row, plane) groups)
     cp_all = _cin_planes(cin, lead)
     if cp_all <= 26:
@@ -243,23 +275,24 @@ def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, d
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _wgrad_ws[key] = ws
         a = L.WgradArgs()
-        a.n, a.h, a.w, a.dtype = n, h, w, _TORCH2ESR[x16.dtype]
+        a.n, a.h, a.w, a.dtype = n, h, w, (L.ESR_BF16X3 if split else _TORCH2ESR[x16.dtype])
         a.x, a.x_planes_total, a.x_plane_off = x16.data_ptr(), xpt, xo
         a.gy, a.gy_planes_total, a.gy_plane_off = gy16.data_ptr(), gy16.shape[1], gy_off
         a.cout, a.cin, a.lead = cout, cs, ld
         a.cin_total, a.cin_off = cin, c0
-        a.dw, a.db, a.scale, a.accumulate = dw.data_ptr(), (db.data_ptr() if si == 0 else None), scale, int(accumulate)
+        a.dw, a.db, a.scale, a.accumulate = dw.data_ptr(), (db.data_ptr() if (si == 0 and db is not None) else None), scale, int(accumulate)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         L.check(lib.esr_conv3x3_wgrad(C.byref(a), _stream()))
     return dw, db
 
 
-def sum_nchw(src, scale=1.0):
-    """per-channel sum of an NCHW fp32 tensor -> [C] fp32"""
-    require_cuda(src)
+def sum_nchw(src, scale=1.0, out=None, accumulate=False):
+    """per-channel sum of an NCHW fp32 tensor -> [C] fp32 (written or accumulated into `out` when given)"""
+    require_cuda(src, out)
     n, c, h, w = src.shape
-    out = torch.empty((c,), dtype=torch.float32, device=src.device)
-    L.check(L.load().esr_sum_nchw(_ptr(src), n, c, h, w, scale, 0, _ptr(out), _stream()))
+    if out is None:
+        out, accumulate = torch.empty((c,), dtype=torch.float32, device=src.device), False
+    L.check(L.load().esr_sum_nchw(_ptr(src), n, c, h, w, scale, int(accumulate), _ptr(out), _stream()))
     return out
 
 
@@ -274,14 +307,15 @@ def pack_nchw(src, *, pad=0, dtype=torch.float16, dst16=None, dst32=None, plane_
     n, c, h, w = src.shape
     planes = planes_for(c)
     ho, wo = h + 2 * pad, w + 2 * pad
+    split = dtype == SPLIT
     if dst16 is None and want16:
-        dst16 = torch.empty((n, planes, ho, wo, 8), dtype=dtype, device=src.device)
+        dst16 = alloc16(dtype, n, planes, ho, wo, src.device)
     if dst32 is None and want32:
         dst32 = torch.empty((n, planes, ho, wo, 8), dtype=torch.float32, device=src.device)
     pt = (dst16 if dst16 is not None else dst32).shape[1]
-    if dst16 is not None:
+    if dst16 is not None and not split:
         dtype = dst16.dtype
-    L.check(L.load().esr_pack_nchw(_ptr(src), n, c, h, w, pad, _TORCH2ESR[dtype], _ptr(dst16), _ptr(dst32), pt, plane_off,
+    L.check(L.load().esr_pack_nchw(_ptr(src), n, c, h, w, pad, esr_dtype(dtype), _ptr(dst16), _ptr(dst32), pt, plane_off,
                                    _stream()))
     return dst16, dst32
 
@@ -291,39 +325,41 @@ def pack_nchw_affine(src, scale, shift, dtype=torch.float16):
     require_cuda(src, scale, shift)
     src = src.float().contiguous()
     n, c, h, w = src.shape
-    dst = torch.empty((n, planes_for(c), h, w, 8), dtype=dtype, device=src.device)
-    L.check(L.load().esr_pack_nchw_affine(_ptr(src), n, c, h, w, _ptr(scale), _ptr(shift), _TORCH2ESR[dtype], _ptr(dst), dst.shape[1], 0,
+    dst = alloc16(dtype, n, planes_for(c), h, w, src.device)
+    L.check(L.load().esr_pack_nchw_affine(_ptr(src), n, c, h, w, _ptr(scale), _ptr(shift), esr_dtype(dtype), _ptr(dst), dst.shape[1], 0,
                                           _stream()))
     return dst
 
 
-def maxpool2x2(src16):
+def maxpool2x2(src16, split=False):
     require_cuda(src16)
     n, pt, h, w, _ = src16.shape
     dst = torch.empty((n, pt, h // 2, w // 2, 8), dtype=src16.dtype, device=src16.device)
-    L.check(L.load().esr_maxpool2x2_planes16(_ptr(src16), _TORCH2ESR[src16.dtype], n, pt, h, w, _ptr(dst), _stream()))
+    L.check(L.load().esr_maxpool2x2_planes16(_ptr(src16), L.ESR_BF16X3 if split else _TORCH2ESR[src16.dtype], n, pt, h, w, _ptr(dst), _stream()))
     return dst
 
 
-def maxpool2x2_bwd(gout16, act16):
+def maxpool2x2_bwd(gout16, act16, split=False):
     """gradient w.r.t. the pre-activation that fed ReLU -> MaxPool2d(2,2); act16 = the pooling's (post-ReLU) input"""
     require_cuda(gout16, act16)
     n, pt, h, w, _ = act16.shape
     assert gout16.dtype == act16.dtype and tuple(gout16.shape) == (n, pt, h // 2, w // 2, 8)
     gin = torch.empty_like(act16)
-    L.check(L.load().esr_maxpool2x2_bwd_planes16(_ptr(gout16), _ptr(act16), _TORCH2ESR[act16.dtype], n, pt, h, w, _ptr(gin), _stream()))
+    L.check(L.load().esr_maxpool2x2_bwd_planes16(_ptr(gout16), _ptr(act16), L.ESR_BF16X3 if split else _TORCH2ESR[act16.dtype], n, pt, h, w,
+                                                 _ptr(gin), _stream()))
     return gin
 
 
-def unpack_planes(src, c, plane_off=0):
-    """planar-8 -> NCHW fp32 (first c channels starting at plane_off)."""
+def unpack_planes(src, c, plane_off=0, split=False):
+    """planar-8 -> NCHW fp32 (first c channels starting at plane_off; split tensors return hi + lo)."""
     require_cuda(src)
     n, pt, h, w, _ = src.shape
     dst = torch.empty((n, c, h, w), dtype=torch.float32, device=src.device)
     if src.dtype == torch.float32:
         L.check(L.load().esr_unpack_planes32(_ptr(src), n, c, h, w, pt, plane_off, _ptr(dst), _stream()))
     else:
-        L.check(L.load().esr_unpack_planes16(_ptr(src), _TORCH2ESR[src.dtype], n, c, h, w, pt, plane_off, _ptr(dst), _stream()))
+        L.check(L.load().esr_unpack_planes16(_ptr(src), L.ESR_BF16X3 if split else _TORCH2ESR[src.dtype], n, c, h, w, pt, plane_off, _ptr(dst),
+                                             _stream()))
     return dst
 
 
@@ -376,10 +412,10 @@ def downsum2x(src32, act16_hi=None, slope=0.2, dtype=torch.float16, want32=True,
     n, pt, h2, w2, _ = src32.shape
     h, w = h2 // 2, w2 // 2
     d32 = torch.empty((n, pt, h, w, 8), dtype=torch.float32, device=src32.device) if want32 else None
-    d16 = torch.empty((n, pt, h, w, 8), dtype=dtype, device=src32.device) if want16 else None
-    if act16_hi is not None:
-        assert act16_hi.shape == src32.shape and act16_hi.dtype in _TORCH2ESR   # only the sign is read
-    L.check(L.load().esr_downsum2x_planes(_ptr(src32), n, pt, h, w, _ptr(act16_hi), slope, _TORCH2ESR[dtype], _ptr(d32), _ptr(d16),
+    d16 = alloc16(dtype, n, pt, h, w, src32.device) if want16 else None
+    if act16_hi is not None:   # only the sign is read (the hi half of a split tensor)
+        assert tuple(act16_hi.shape[2:]) == tuple(src32.shape[2:]) and act16_hi.shape[1] == pt * (2 if dtype == SPLIT else 1)
+    L.check(L.load().esr_downsum2x_planes(_ptr(src32), n, pt, h, w, _ptr(act16_hi), slope, esr_dtype(dtype), _ptr(d32), _ptr(d16),
                                           _stream()))
     return d32, d16
 
@@ -388,8 +424,9 @@ def planes_add(a32, b32, dtype=torch.float16, want32=True, want16=True):
     require_cuda(a32, b32)
     assert a32.shape == b32.shape and a32.dtype == b32.dtype == torch.float32
     o32 = torch.empty_like(a32) if want32 else None
-    o16 = torch.empty(a32.shape, dtype=dtype, device=a32.device) if want16 else None
-    L.check(L.load().esr_planes_add(_ptr(a32), _ptr(b32), a32.numel() // 8, _TORCH2ESR[dtype], _ptr(o32), _ptr(o16), _stream()))
+    o16 = alloc16(dtype, a32.shape[0], a32.shape[1], a32.shape[2], a32.shape[3], a32.device) if want16 else None
+    L.check(L.load().esr_planes_add_ex(_ptr(a32), _ptr(b32), a32.numel() // 8, a32[0].numel() // 8, esr_dtype(dtype), _ptr(o32), _ptr(o16),
+                                       _stream()))
     return o32, o16
 
 
@@ -461,10 +498,9 @@ def bn_lrelu_fwd(y32, c, scale, shift, slope, dtype, space_to_depth=False, want1
     n, p, h, w, _ = y32.shape
     d16 = None
     if want16:
-        shape = (n, 4 * p, h // 2, w // 2, 8) if space_to_depth else (n, p, h, w, 8)
-        d16 = torch.empty(shape, dtype=dtype, device=y32.device)
+        d16 = alloc16(dtype, n, 4 * p, h // 2, w // 2, y32.device) if space_to_depth else alloc16(dtype, n, p, h, w, y32.device)
     dn = torch.empty((n, c, h, w), dtype=torch.float32, device=y32.device) if want_nchw else None
-    L.check(L.load().esr_bn_lrelu_fwd(_ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), slope, _TORCH2ESR[dtype], _ptr(d16),
+    L.check(L.load().esr_bn_lrelu_fwd(_ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), slope, esr_dtype(dtype), _ptr(d16),
                                       int(space_to_depth), _ptr(dn), _stream()))
     return d16, dn
 
@@ -484,13 +520,13 @@ def bn_lrelu_bwd(g, g_layout, y32, c, scale, shift, mean, invstd, slope, dtype, 
     require_cuda(g, y32, scale, shift, mean, invstd, dgamma, dbeta)
     n, p, h, w, _ = y32.shape
     assert g.dtype == torch.float32 and g.numel() == (n * c * h * w if g_layout == 2 else y32.numel())
-    gy16 = torch.empty((n, p, h, w, 8), dtype=dtype, device=y32.device)
+    gy16 = alloc16(dtype, n, p, h, w, y32.device)
     if scratch is None:
         scratch = torch.zeros((2, c), dtype=torch.float32, device=y32.device)
     ws = _bn_workspace(y32.device, p) if has_bn else None
     L.check(L.load().esr_bn_lrelu_bwd(_ptr(g), g_layout, _ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), slope,
                                       int(has_bn), int(train), gscale, int(accumulate), _ptr(dgamma), _ptr(dbeta), _ptr(scratch[0]),
-                                      _ptr(scratch[1]), _TORCH2ESR[dtype], _ptr(gy16), _ptr(ws), (ws.numel() * 4 if ws is not None else 0),
+                                      _ptr(scratch[1]), esr_dtype(dtype), _ptr(gy16), _ptr(ws), (ws.numel() * 4 if ws is not None else 0),
                                       _stream()))
     return gy16
 
@@ -505,16 +541,20 @@ def linear_fwd(x, weight, bias, lrelu=False, slope=0.2):
     return out
 
 
-def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1.0):
-    """-> (gx [B,K] | None, dW [J,K] | None, db [J] | None); act = the layer's LeakyReLU output (None for a linear layer)"""
-    require_cuda(g, act, x, weight)
+def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1.0, dw=None, db=None, accumulate=False):
+    """-> (gx [B,K] | None, dW [J,K] | None, db [J] | None); act = the layer's LeakyReLU output (None for a linear layer).
+    dw / db given: written (or accumulated) in place."""
+    require_cuda(g, act, x, weight, dw, db)
     b, k = x.shape
     j = weight.shape[0]
     assert g.dtype == torch.float32 and tuple(g.shape) == (b, j)
     gx = torch.empty((b, k), dtype=torch.float32, device=x.device) if want_gx else None
-    dw = torch.empty((j, k), dtype=torch.float32, device=x.device) if want_w else None
-    db = torch.empty((j,), dtype=torch.float32, device=x.device) if want_w else None
-    L.check(L.load().esr_linear_bwd(_ptr(g), _ptr(act), slope, _ptr(x), _ptr(weight), b, k, j, gscale, 0, _ptr(gx), _ptr(dw), _ptr(db), _stream()))
+    if want_w and dw is None:
+        dw, db, accumulate = torch.empty((j, k), dtype=torch.float32, device=x.device), torch.empty((j,), dtype=torch.float32, device=x.device), False
+    if not want_w:
+        dw = db = None
+    L.check(L.load().esr_linear_bwd(_ptr(g), _ptr(act), slope, _ptr(x), _ptr(weight), b, k, j, gscale, int(accumulate), _ptr(gx), _ptr(dw), _ptr(db),
+                                    _stream()))
     return gx, dw, db
 
 

@@ -28,13 +28,28 @@ def shard_batch(n, world_size=None, r=None):
     return start, start + base + (1 if r < rem else 0)
 
 
-def average_gradients(params, bucket_bytes=64 << 20, group=None):
+def average_gradients(params, bucket_bytes=64 << 20, group=None, optimizer=None):
     """In-place average of .grad over all ranks, in flat buckets of about `bucket_bytes` (a 17 M-parameter generator is two
     buckets: the all-reduce is latency-bound on NVLink).  Parameters without a gradient contribute zeros so
-    that every rank issues the same collectives.  Returns the number of all-reduce calls."""
+    that every rank issues the same collectives.  Returns the number of all-reduce calls.
+    With a FlatAdam `optimizer` whose gradients already live in its flat buffer (the engines write them there) the buffer itself is
+    reduced in place: no concatenation, no copy back."""
     params = [p for p in params if p.requires_grad]
     if world() == 1 or not params:
         return 0
+    if optimizer is not None and hasattr(optimizer, 'flat_grad'):
+        calls = 0
+        flat_ok = True
+        for gi in range(len(optimizer.param_groups)):
+            flat_ok = flat_ok and optimizer.flat_grad(gi) is not None and optimizer.grads_in_place(gi)
+        flat_ok = agree(flat_ok, group=group)      # every rank takes the same path
+        if flat_ok:
+            for gi in range(len(optimizer.param_groups)):
+                buf = optimizer.flat_grad(gi)
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+                buf.div_(world())
+                calls += 1
+            return calls
     calls, bucket, size = 0, [], 0
 
     def flush():

@@ -77,7 +77,7 @@ class VGGEngine:
                 hh, ww = cur.shape[2], cur.shape[3]
                 relu_next = li + 1 < len(self.layers) and self.layers[li + 1][0] == 'relu'
                 if relu_next:
-                    o = torch.empty((n, ops.planes_for(cout), hh, ww, 8), dtype=self.dtype, device=dev)
+                    o = ops.alloc16(self.dtype, n, ops.planes_for(cout), hh, ww, dev)
                     ops.conv3x3(cur, pk[k], lrelu=True, slope=0.0, out16=o)
                     cur = o
                 else:   # the feature map itself: pre-activation, fp32 NCHW
@@ -88,10 +88,10 @@ class VGGEngine:
             elif kind == 'pool':
                 if cur.shape[2] % 2 or cur.shape[3] % 2:
                     raise ops.L.EsrError('VGGFeatureExtractor: image size must be divisible by 2 at every pooling stage')
-                cur = ops.maxpool2x2(cur)
+                cur = ops.maxpool2x2(cur, split=ops.is_split(self.dtype))
             # 'relu' is fused into the conv in front of it
         if out is None:   # feature_layer ends on a ReLU / pooling layer
-            out = ops.unpack_planes(cur, self.layers[-1][3])
+            out = ops.unpack_planes(cur, self.layers[-1][3], split=ops.is_split(self.dtype))
         return (out, saved) if save else out
 
     @torch.no_grad()
@@ -121,14 +121,14 @@ class VGGEngine:
                 return gx / scale
             prev = layers[li - 1][0]
             if prev == 'relu':      # conv <- relu <- conv: mask with the (post-ReLU) activation this conv read
-                o = torch.empty((n, ops.planes_for(cin), hh, ww, 8), dtype=self.dtype, device=dev)
+                o = ops.alloc16(self.dtype, n, ops.planes_for(cin), hh, ww, dev)
                 ops.conv3x3(g, pkt[k], mask16=inp, mask_slope=0.0, out16=o)
                 g = o
                 li -= 2
             else:                   # conv <- pool <- relu <- conv
-                o = torch.empty((n, ops.planes_for(cin), hh, ww, 8), dtype=self.dtype, device=dev)
+                o = ops.alloc16(self.dtype, n, ops.planes_for(cin), hh, ww, dev)
                 ops.conv3x3(g, pkt[k], out16=o)
-                g = ops.maxpool2x2_bwd(o, saved[li - 1])
+                g = ops.maxpool2x2_bwd(o, saved[li - 1], split=ops.is_split(self.dtype))
                 li -= 3
             k -= 1
 

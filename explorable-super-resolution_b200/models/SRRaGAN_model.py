@@ -5,9 +5,9 @@ Built: construction for inference / latent exploration (CEM + generator + checkp
 `Feed_n_Run_model` and `Z_optimizer.optimize` call — and the training step (`optimize_parameters`,
 models/SRRaGAN_model.py:280-519): discriminator step (Discriminator_VGG_128, vanilla / lsgan / wgan losses, relativistic by
 default) and generator step (pixel + VGG-feature + range + GAN + latent-control losses), gradient accumulation for both, Adam, MultiStepLR,
-D_update_ratio / D_init_iters scheduling.  Configurations that need WGAN-GP's double backward, the decomposed-output
-critic, D verification, the optimised-Z reference loss or non-structure-tensor latent descriptors raise NotImplementedError at construction: those are not built and
-there is no PyTorch fallback."""
+D_update_ratio / D_init_iters scheduling, D verification ('past' / 'current' / 'convergence') and the optimised-Z reference loss
+L_map.  Configurations that need the decomposed-output critic, the automatic D_update_ratio controller or the histogram
+reference loss raise NotImplementedError at construction: those are not built and there is no PyTorch fallback."""
 import os
 import re
 from collections import OrderedDict
@@ -20,6 +20,8 @@ from torch.optim import lr_scheduler
 import CEM.CEMnet as CEMnet
 import models.networks as networks
 from esr_b200 import parallel
+from esr_b200.losses import L1Loss as EsrL1Loss, relativistic_bce
+from esr_b200.optim import FlatAdam
 from models.modules.loss import FilterLoss, CreateRangeLoss, GANLoss, GradientPenaltyLoss
 from .base_model import BaseModel
 
@@ -119,6 +121,9 @@ class SRRaGANModel(BaseModel):
             return
         # ---- training state (models/SRRaGAN_model.py:68-203, generator branch)
         self.max_accumulation_steps = accumulation_steps_per_batch
+        for mod in self.netG.modules():      # D-only steps feed the critic from no-grad forwards: same arithmetic as the training passes
+            if hasattr(mod, 'z_lead'):
+                mod.train_precision_always = True
         self.grad_accumulation_steps_G = train_opt['grad_accumulation_steps_G'] or 1
         self.grad_accumulation_steps_D = train_opt['grad_accumulation_steps_D'] or 1
         self.netG.train()
@@ -143,7 +148,7 @@ class SRRaGANModel(BaseModel):
         if train_opt['pixel_weight'] is not None:
             l_pix_type = train_opt['pixel_criterion']
             if l_pix_type == 'l1':
-                self.cri_pix = nn.L1Loss().to(self.device)
+                self.cri_pix = EsrL1Loss().to(self.device)      # esr_l1_reduce kernel on CUDA tensors
             elif l_pix_type == 'l2':
                 self.cri_pix = nn.MSELoss().to(self.device)
             else:
@@ -162,7 +167,7 @@ class SRRaGANModel(BaseModel):
             if self.optimalZ_loss_type == 'l2':
                 self.cri_optimalZ = nn.MSELoss().to(self.device)
             elif self.optimalZ_loss_type == 'l1':
-                self.cri_optimalZ = nn.L1Loss().to(self.device)
+                self.cri_optimalZ = EsrL1Loss().to(self.device)
             else:
                 raise NotImplementedError('Loss type [{:s}] not recognized.'.format(self.optimalZ_loss_type))
         else:
@@ -176,7 +181,7 @@ class SRRaGANModel(BaseModel):
         if train_opt['feature_weight'] is not None:   # G feature loss (SRRaGAN_model.py:124-138)
             l_fea_type = train_opt['feature_criterion']
             if l_fea_type == 'l1':
-                self.cri_fea = nn.L1Loss().to(self.device)
+                self.cri_fea = EsrL1Loss().to(self.device)
             elif l_fea_type == 'l2':
                 self.cri_fea = nn.MSELoss().to(self.device)
             else:
@@ -204,15 +209,16 @@ class SRRaGANModel(BaseModel):
             else:
                 print('WARNING: params [{:s}] will not optimize.'.format(k))
         self.lr_G = train_opt['lr_G']
-        self.optimizer_G = torch.optim.Adam(optim_params, lr=self.lr_G, weight_decay=wd_G,
-                                            betas=(train_opt['beta1_G'], train_opt['beta2_G'] if train_opt['beta2_G'] is not None else 0.999))
+        # torch.optim.Adam's arithmetic and state-dict layout, one fused launch per step (esr_b200.optim)
+        self.optimizer_G = FlatAdam(optim_params, lr=self.lr_G, weight_decay=wd_G,
+                                    betas=(train_opt['beta1_G'], train_opt['beta2_G'] if train_opt['beta2_G'] is not None else 0.999))
         self.optimizers.append(self.optimizer_G)
         self.optimizer_D = None
         if self.D_exists:
             wd_D = train_opt['weight_decay_D'] if train_opt['weight_decay_D'] else 0
             self.lr_D = train_opt['lr_D']
-            self.optimizer_D = torch.optim.Adam(self.netD.parameters(), lr=self.lr_D, weight_decay=wd_D,
-                                                betas=(train_opt['beta1_D'], train_opt['beta2_D'] if train_opt['beta2_D'] is not None else 0.999))
+            self.optimizer_D = FlatAdam(self.netD.parameters(), lr=self.lr_D, weight_decay=wd_D,
+                                        betas=(train_opt['beta1_D'], train_opt['beta2_D'] if train_opt['beta2_D'] is not None else 0.999))
             self.optimizers.append(self.optimizer_D)
         if train_opt['lr_scheme'] == 'MultiStepLR':
             for optimizer in self.optimizers:
@@ -238,6 +244,9 @@ class SRRaGANModel(BaseModel):
         parallel.broadcast_parameters(self.netG)
         if self.D_exists:
             parallel.broadcast_parameters(self.netD)
+        if self.device.type == 'cuda':      # parameters, gradients and Adam moments move into flat buffers; the engines write gradients there
+            for optimizer in self.optimizers:
+                optimizer.register()
 
     # ---- I/O of one batch -------------------------------------------------------------------------
     def Output_Batch(self, within_0_1):
@@ -301,6 +310,14 @@ class SRRaGANModel(BaseModel):
         if parallel.world() == 1:
             return torch.mean(t)
         return parallel.global_mean_autograd(t)
+
+    def _relativistic_terms(self, pred_a, pred_b, target_a, target_b):
+        """(cri_gan(pred_a - mean(pred_b), target_a), cri_gan(pred_b - mean(pred_a), target_b)), means over the global batch
+        (models/SRRaGAN_model.py:353-354,475-476).  The vanilla (BCE-with-logits) loss on CUDA logits is one fused kernel each way."""
+        if self.cri_gan.gan_type == 'vanilla' and pred_a.is_cuda and pred_a.shape == pred_b.shape:
+            return relativistic_bce(pred_a, pred_b, self.cri_gan.real_label_val if target_a else self.cri_gan.fake_label_val,
+                                    self.cri_gan.real_label_val if target_b else self.cri_gan.fake_label_val)
+        return (self.cri_gan(pred_a - self._batch_mean(pred_b), target_a), self.cri_gan(pred_b - self._batch_mean(pred_a), target_b))
 
     def optimize_parameters(self):
         """models/SRRaGAN_model.py:280-519: forward through CEM(G) and crop the invalid margins; discriminator step
@@ -367,8 +384,7 @@ class SRRaGANModel(BaseModel):
                 pred_d_fake = self.netD(self.fake_H.detach())   # detach to avoid BP to G
                 if self.relativistic_D:
                     assert self.opt['train']['hinge_threshold'] is None, 'Unsupported yet, should think whether it reuires special adaptation of hinge loss'
-                    l_d_real = self.cri_gan(pred_d_real - self._batch_mean(pred_d_fake), True)
-                    l_d_fake = self.cri_gan(pred_d_fake - self._batch_mean(pred_d_real), False)
+                    l_d_real, l_d_fake = self._relativistic_terms(pred_d_real, pred_d_fake, True, False)
                 else:   # (x2: consistent with the SRGAN code, where the two losses are summed, :357-358)
                     if first_dual:
                         l_d_real = 2 * self.cri_gan(pred_d_real, True, self.opt['train']['hinge_threshold'])
@@ -419,7 +435,7 @@ class SRRaGANModel(BaseModel):
                     self.fake_H = self.fake_H.detach()
                 l_d_total.backward(retain_graph=not last_dual)      # the real batch's critic graph is shared by both dual steps
                 if last_acc_D and last_dual:
-                    parallel.average_gradients(self.netD.parameters())
+                    parallel.average_gradients(self.netD.parameters(), optimizer=self.optimizer_D)
                     self.optimizer_D.step()
                     self.log_dict['l_d_real'].append((self.gradient_step_num, np.mean(self.l_d_real_grad_step)))
                     self.log_dict['l_d_fake'].append((self.gradient_step_num, np.mean(self.l_d_fake_grad_step)))
@@ -466,8 +482,8 @@ class SRRaGANModel(BaseModel):
                         # (the reference re-uses the D step's variable here, :474: with two dual steps the second D step therefore sees the
                         #  real batch's logits DETACHED - mirrored, it changes the critic's gradient)
                         pred_d_real = self.netD(self.var_ref).detach()
-                        l_g_gan = self.l_gan_w * (self.cri_gan(pred_d_real - self._batch_mean(pred_g_fake), False) +
-                                                  self.cri_gan(pred_g_fake - self._batch_mean(pred_d_real), True)) / 2 / (acc_G * dual_steps)
+                        l_g_real, l_g_fake = self._relativistic_terms(pred_d_real, pred_g_fake, False, True)
+                        l_g_gan = self.l_gan_w * (l_g_real + l_g_fake) / 2 / (acc_G * dual_steps)
                     else:
                         l_g_gan = self.l_gan_w * self.cri_gan(pred_g_fake, True) / (acc_G * dual_steps)
                     l_g_total = l_g_total + l_g_gan
@@ -481,7 +497,7 @@ class SRRaGANModel(BaseModel):
                     for (name, _), v in zip(terms, vals):
                         getattr(self, name).append(v)
                 if last_acc and last_dual:
-                    parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad])
+                    parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad], optimizer=self.optimizer_G)
                     self.optimizer_G.step()
                     self.generator_changed = True
                     if self.cri_pix:

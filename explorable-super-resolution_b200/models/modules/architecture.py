@@ -63,11 +63,18 @@ class RRDBNet(nn.Module):
     def up_factors(self):
         return [3] if self.upscale == 3 else [2] * self._n_upscale
 
-    def engine(self, dtype=None):
+    def engine(self, dtype=None, training=False):
         """engine for `dtype` (default: self.compute_dtype, fp16).  Training (weight gradients) uses the bf16 engine:
-        fp16 gradients underflow, and the tensor cores want activations, weights and gradients in one format."""
+        fp16 gradients underflow, and the tensor cores want activations, weights and gradients in one format.  In the
+        'parity' arithmetic mode (esr_b200.precision) every pass runs the split-precision engine."""
+        from esr_b200 import ops, precision
         from esr_b200.engine import RRDBEngine
-        key = self.compute_dtype if dtype is None else dtype
+        if dtype is not None:
+            key = dtype
+        elif precision.parity():
+            key = ops.SPLIT
+        else:
+            key = torch.bfloat16 if training else self.compute_dtype
         if key not in self._engines:
             self._engines[key] = RRDBEngine(self, dtype=key)
         return self._engines[key]
@@ -79,7 +86,8 @@ class RRDBNet(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             from esr_b200.autograd import rrdb_forward_with_grad
             return rrdb_forward_with_grad(self, x, pad)
-        return self.engine().forward(x, pad=pad)
+        # a model under training feeds its critic from no-grad forwards too (D-only steps): same precision as its training passes
+        return self.engine(training=bool(getattr(self, 'train_precision_always', False) and self.training)).forward(x, pad=pad)
 
 
 class VGGFeatureExtractor(nn.Module):
@@ -121,10 +129,12 @@ class VGGFeatureExtractor(nn.Module):
         self._engines = {}
 
     def engine(self):
+        from esr_b200 import ops, precision
         from esr_b200.vgg import VGGEngine
-        if self.compute_dtype not in self._engines:
-            self._engines[self.compute_dtype] = VGGEngine(self, dtype=self.compute_dtype)
-        return self._engines[self.compute_dtype]
+        key = ops.SPLIT if precision.parity() else self.compute_dtype
+        if key not in self._engines:
+            self._engines[key] = VGGEngine(self, dtype=key)
+        return self._engines[key]
 
     def forward(self, x):
         from esr_b200.vgg import vgg_forward
@@ -165,10 +175,12 @@ class Discriminator_VGG_128(nn.Module):
         self._engines = {}
 
     def engine(self):
+        from esr_b200 import ops, precision
         from esr_b200.disc import DiscEngine
-        if self.compute_dtype not in self._engines:
-            self._engines[self.compute_dtype] = DiscEngine(self, dtype=self.compute_dtype)
-        return self._engines[self.compute_dtype]
+        key = ops.SPLIT if precision.parity() else self.compute_dtype
+        if key not in self._engines:
+            self._engines[key] = DiscEngine(self, dtype=key)
+        return self._engines[key]
 
     def forward(self, x):
         from esr_b200.disc import disc_forward

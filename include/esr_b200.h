@@ -32,7 +32,12 @@ typedef enum {
   ESR_ERR_UNSUPPORTED = -3  /* device is not sm_100                                        */
 } esr_status;
 
-typedef enum { ESR_F16 = 0, ESR_BF16 = 1 } esr_dtype;
+/* element format of the 16-bit tensor-core operands.
+ * ESR_BF16X3 ("split precision", the parity mode): every 16-bit tensor holds planes_total/2 bf16 "hi" planes per image followed by
+ * as many bf16 "lo" planes (lo = bf16(v - hi)); plane offsets always address the hi half.  Convolutions run
+ * x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo on the kind::f16 tensor pipe with fp32 accumulation (16 mantissa bits per operand,
+ * fp32 exponent range): the arithmetic class of the reference's fp32 convs (models/modules/block.py:141-146), 3x the MMAs. */
+typedef enum { ESR_F16 = 0, ESR_BF16 = 1, ESR_BF16X3 = 2 } esr_dtype;
 
 const char* esr_last_error(void);
 int esr_version(void);
@@ -110,8 +115,10 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream);
  * *failed_index (may be NULL) receives its position. */
 int esr_conv3x3_fwd_batch(const esr_conv3x3_args* args, int count, void* stream, int* failed_index);
 
-/* bytes of the packed weight image for (cin_planes, cout) with chunk size kcp */
+/* bytes of the packed weight image for (cin_planes, cout) with chunk size kcp (_ex: for a given esr_dtype; ESR_BF16X3 images hold
+ * the three segments w_hi | w_hi | w_lo) */
 size_t esr_conv3x3_packed_bytes(int cin_planes, int cout, int kcp, int* cout_pad_out);
+size_t esr_conv3x3_packed_bytes_ex(int cin_planes, int cout, int kcp, int dtype, int* cout_pad_out);
 /* OIHW fp32 [cout][cin][3][3] (device) -> packed tensor-core image (device).
  * Layout [n_block][chunk][tap][plane-in-chunk][cout-in-block][8 cin], zero padded.
  * `transpose_flip` = 1 packs the dgrad operand (I/O swapped, taps rotated 180 degrees).
@@ -127,6 +134,7 @@ int esr_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, int lead, i
  * kernel) and the size of the packed image [n_block][chunk][dx][plane-in-chunk (4)][ky*nbn + cout-in-block][8 cin];
  * for a dgrad operand pass cout = 8 * esr_conv3x3_cin_planes(cin, lead) and cin_planes = ceil(cout_fwd / 8). */
 int esr_conv3x3_rows_config(int cin_planes, int cout, int* nbn_out, size_t* bytes_out);
+int esr_conv3x3_rows_config_ex(int cin_planes, int cout, int dtype, int* nbn_out, size_t* bytes_out);
 int esr_pack_conv3x3_weights_rows(const float* w_oihw, int cout, int cin, int lead, int dtype, int transpose_flip,
                                   int nbn, void* wpacked_rows, void* stream);
 /* ------------------------------------------------------------------------------------------------
@@ -230,6 +238,9 @@ int esr_downsum2x_planes(const float* src32, int n, int planes, int h, int w, co
 /* out = a + b on fp32 planes (n_groups8 groups of 8 floats), optional 16-bit copy */
 int esr_planes_add(const float* a32, const float* b32, size_t n_groups8, int dtype, float* out32, void* out16,
                    void* stream);
+/* same with the groups of one image stated (a split-precision out16 holds hi and lo halves per image) */
+int esr_planes_add_ex(const float* a32, const float* b32, size_t n_groups8, size_t per_image_groups8, int dtype, float* out32,
+                      void* out16, void* stream);
 /* adjoint of one 1-D pass of a clamp-addressed strided filter (the building block of the CEM backward):
  *   forward out[o] = sum_t k[t]*in[clamp(a_stride*o + t + c_off, 0, n_in-1)];  produces gin at logical positions
  *   m = m_stride*mi + m_phase, mi < n_store.  Tensor viewed as [imgs][outer][axis][inner].
@@ -305,6 +316,32 @@ size_t esr_structure_tensor_workspace_bytes(int n);
 int esr_structure_tensor_fwd(const float* img, int n, int c, int h, int w, float* out, float* workspace, size_t workspace_bytes,
                              void* stream);
 int esr_structure_tensor_bwd(const float* img, const float* g, int n, int c, int h, int w, float* grad_img, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The training step outside the networks.
+ * ---------------------------------------------------------------------------------------------- */
+/* Fused multi-tensor Adam: ONE launch per optimizer step (models/SRRaGAN_model.py:182,188 build torch.optim.Adam for G and D; :403,499
+ * step them).  Exactly torch.optim.Adam's arithmetic (amsgrad off): g' = grad_scale*g + wd*p; m += (g'-m)(1-b1); v = b2 v + (1-b2) g'^2;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  grad_scale folds the 1/world of a summed all-reduce.  `tensors_host` is a HOST
+ * array copied into `scratch` (device, esr_adam_scratch_bytes); pass NULL to reuse the table a previous call uploaded. */
+typedef struct { float* p; const float* g; float* m; float* v; unsigned long long n; } esr_adam_tensor;
+size_t esr_adam_scratch_bytes(int count);
+int esr_adam_multi(const esr_adam_tensor* tensors_host, int count, void* scratch, size_t scratch_bytes, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* nn.L1Loss (mean) of the pixel and VGG-feature criteria (models/SRRaGAN_model.py:98,129,434,448-451): out_mean[0] = mean |a - b|
+ * (two-stage, deterministic), and its gradient ga = sign(a-b) * gout[0] / n, gb = -ga (either may be NULL). */
+size_t esr_l1_workspace_bytes(void);
+int esr_l1_reduce(const float* a, const float* b, size_t n, float* workspace, size_t workspace_bytes, float* out_mean, void* stream);
+int esr_l1_grad(const float* a, const float* b, size_t n, const float* gout, float* ga, float* gb, void* stream);
+/* Relativistic average GAN terms on logits (models/SRRaGAN_model.py:353-354 D step, :475-476 G step; GANLoss 'vanilla' =
+ * BCEWithLogitsLoss, models/modules/loss.py:212-246):  la = mean_i bce(a_i - mean(b), target_a), lb = mean_i bce(b_i - mean(a), target_b).
+ * out4 = [sum_i bce_a, sum_i bce_b, S_a, S_b] over the n LOCAL samples (S = sum of the bce derivatives, kept per sample in ea / eb);
+ * sums_global = [sum a, sum b] over the global batch of n_global samples (NULL: local).  The backward gives d(ga_up*la + gb_up*lb)
+ * with respect to a and b (either output may be NULL = that input is detached), S_global = [S_a, S_b] over the global batch. */
+int esr_bce_rel_loss(const float* a, const float* b, int n, const float* sums_global, float n_global, float target_a, float target_b,
+                     float* out4, float* ea, float* eb, void* stream);
+int esr_bce_rel_loss_bwd(const float* ea, const float* eb, int n, const float* S_global, float n_global, const float* ga_up,
+                         const float* gb_up, float* ga, float* gb, void* stream);
 
 #ifdef __cplusplus
 }

@@ -125,9 +125,14 @@ def linear_fwd(x, weight, bias, lrelu=False, slope=0.2):
     return F.leaky_relu(y, slope) if lrelu else y
 
 
-def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1.0):
+def linear_bwd(g, act, x, weight, slope=0.2, want_gx=True, want_w=True, gscale=1.0, dw=None, db=None, accumulate=False):
     gm = g if act is None else torch.where(act > 0, g, g * slope)
-    return (gm @ weight if want_gx else None), (gscale * gm.t() @ x if want_w else None), (gscale * gm.sum(0) if want_w else None)
+    gw, gb = (gscale * gm.t() @ x if want_w else None), (gscale * gm.sum(0) if want_w else None)
+    if want_w and dw is not None:       # written / accumulated in place, like the C-ABI call
+        dw.copy_(dw + gw if accumulate else gw)
+        db.copy_(db + gb if accumulate else gb)
+        gw, gb = dw, db
+    return (gm @ weight if want_gx else None), gw, gb
 
 
 def conv3x3_wgrad(x16, gy16, cout, cin, **kw):
