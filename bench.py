@@ -523,23 +523,32 @@ def main():
         barrier()
         ms_f = a.elapsed_time(b) / args.steps
         nl = (lib.launch_count() - l0) // args.steps
-        conv_ev = []
-        real_conv = ops.conv3x3
+        conv_ev, cem_ev = [], []
+        real_ops = {k: getattr(ops, k) for k in ('conv3x3', 'cem_down', 'cem_inv', 'cem_up_add')}
 
-        def tconv(*aa, **kk):
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            real_conv(*aa, **kk)
-            c1.record()
-            conv_ev.append((c0, c1))
-        ops.conv3x3, ops.PLAN_REPLAY = tconv, False
+        def timed_into(lst, fn):
+            def f(*aa, **kk):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                r = fn(*aa, **kk)
+                c1.record()
+                lst.append((c0, c1))
+                return r
+            return f
+        ops.conv3x3, ops.PLAN_REPLAY = timed_into(conv_ev, real_ops['conv3x3']), False
+        for k in ('cem_down', 'cem_inv', 'cem_up_add'):
+            setattr(ops, k, timed_into(cem_ev, real_ops[k]))
         try:
             for _ in range(3):
                 fwd()
             barrier()
         finally:
-            ops.conv3x3, ops.PLAN_REPLAY = real_conv, True
+            ops.PLAN_REPLAY = True
+            for k, fn in real_ops.items():
+                setattr(ops, k, fn)
         conv_ms = sum(c0.elapsed_time(c1) for c0, c1 in conv_ev) / 3
+        cem_ms = sum(c0.elapsed_time(c1) for c0, c1 in cem_ev) / 3
+        cem_alg = B * 3 * 4.0 * (2 * HRP * HRP + LR * LR)         # read G, read x, write out: 24.75 B per HR pixel
         copy_stream, h2d_stream = torch.cuda.Stream(), torch.cuda.Stream()
         keep = [None, None]
 
@@ -573,7 +582,10 @@ def main():
                 'gpu_launches_per_step': nl, 'dtype': 'f16 operands, f32 accumulate/trunk',
                 'e2e': {'value': mp_step / (ms_fe * 1e-3), 'ms_per_step': ms_fe, 'h2d_bytes_per_step': lr_host.numel() * 4,
                         'd2h_bytes_per_step': y_hosts[0].numel() * 4},
-                'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'kernel_ms_per_step': conv_ms}}
+                'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'kernel_ms_per_step': conv_ms},
+                'cem_projection': {'bound': 'hbm', 'kernels': 'cem_down_fast + cem_inv_fast + cem_up_add_fast', 'ms_per_step': cem_ms,
+                                   'launches': len(cem_ev) // 3, 'algorithmic_bytes': cem_alg, 'achieved_gbs': cem_alg / (cem_ms * 1e-3) / 1e9,
+                                   'peak_gbs': peak_bw, 'frac': cem_alg / (cem_ms * 1e-3) / 1e9 / peak_bw}}
 
     def leg_gan():
         """C3: full SRRaGAN step at the per-GPU shape (batch 4 of 52x52 LR -> 208x208, critic and VGG on 128x128 crops)"""

@@ -1,0 +1,222 @@
+// CEM projection, HBM-bound fast path for rank-1 (separable) filters: out = G + Up(Inv(x - Down(G)))   (CEM/CEMnet.py:303-310 by
+// linearity; the reference runs five dense depth-wise convs on zero-stuffed / un-decimated HR tensors plus three pad copies).
+//
+//   cem_down_fast   : e = x - Down(G)      reads G once (float4, halo 1.3x through L2), writes the LR residual
+//   cem_inv_fast    : f = Inv(e)           27-tap separable on the LR grid (16x fewer pixels than HR)
+//   cem_up_add_fast : out = G + Up(f)      polyphase (every s-th tap meets a sample of the zero-stuffed image), float4 G read and
+//                                          float4 store, 128 x 32 output tiles, optional crop (eval mode's HR_unpadder)
+// Algorithmic bytes per HR pixel (fp32, x4): 12 (G) + 12 (G again, for the add) + 12 (out) + 5 x 0.75 (LR tensors) = 39.75 B for the
+// three-kernel form against 24.75 B for a (not tile-able: 68-pixel receptive radius) single pass.
+// Interior tiles take index-arithmetic-free paths; tiles touching the image border reproduce the replicate padding of the
+// reference's three pads by clamped addressing (same code path as the general kernels in aux_kernels.cuh).
+#pragma once
+#include "aux_kernels.cuh"
+
+namespace esr {
+
+constexpr int kDnTJ = 32, kDnTI = 16;      // LR output tile of the down kernel
+constexpr int kInvTJ = 64, kInvTI = 32;    // LR tile of the inverse filter
+constexpr int kUpTX = 128, kUpTY = 32;     // HR output tile of the up kernel
+constexpr int kCemMaxTaps = 64;
+
+// e[i][j] = sub_from[i][j] - sum_{a,b} kv[a] kh[b] G[clamp(s i + phase + a - r)][clamp(s j + phase + b - r)]     (sub_from optional)
+__global__ void __launch_bounds__(256)
+cem_down_fast_kernel(const float* __restrict__ g, int hh, int wh, int s, int phase, const float* __restrict__ kv, const float* __restrict__ kh,
+                     int len, const float* __restrict__ sub_from, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
+  const int hl = hh / s, wl = wh / s;
+  const int rows = (kDnTI - 1) * s + len, cols = (kDnTJ - 1) * s + len;
+  const int pitch = ((cols + 3 + 3) & ~3) | 1;      // room for the alignment shift; odd: the strided row walk is bank-conflict free
+  float* tile = sm;                                 // [rows][pitch]
+  float* hbuf = sm + rows * pitch;                  // [rows][kDnTJ + 1]
+  const int nc = blockIdx.z;
+  const int i0 = blockIdx.y * kDnTI, j0 = blockIdx.x * kDnTJ;
+  const int r = len / 2;
+  const float* gp = g + (size_t)nc * hh * wh;
+  const int ybase = s * i0 + phase - r, xbase = s * j0 + phase - r;
+  if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
+  const int xa = xbase & ~3;                        // 16-byte aligned start of the window (xbase may be negative: two's complement floor)
+  const int shift = xbase - xa;                     // 0..3: the window starts `shift` floats into the first float4
+  const int nvec = (shift + cols + 3) >> 2;
+  const bool interior = ybase >= 0 && ybase + rows <= hh && xa >= 0 && xa + 4 * nvec <= wh && (wh & 3) == 0 && (((uintptr_t)gp) & 15) == 0;
+  if (interior) {
+    for (int e = threadIdx.x; e < rows * nvec; e += 256) {
+      const int rr = e / nvec, v = e - rr * nvec;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(ybase + rr) * wh + xa) + v);
+      float* d = tile + rr * pitch + 4 * v;         // stored un-shifted: the horizontal pass adds `shift`
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    }
+  } else {
+    for (int e = threadIdx.x; e < rows * cols; e += 256) {
+      const int rr = e / cols, cc = e - rr * cols;
+      tile[rr * pitch + shift + cc] = __ldg(gp + (size_t)clampi(ybase + rr, 0, hh - 1) * wh + clampi(xbase + cc, 0, wh - 1));
+    }
+  }
+  __syncthreads();
+  // horizontal pass: consecutive threads walk down the rows (pitch is odd)
+  for (int e = threadIdx.x; e < rows * kDnTJ; e += 256) {
+    const int jj = e / rows, rr = e - jj * rows;
+    const float* tp = tile + rr * pitch + shift + jj * s;
+    float a = 0.f;
+    for (int b = 0; b < len; ++b) a = fmaf(th[b], tp[b], a);
+    hbuf[rr * (kDnTJ + 1) + jj] = a;
+  }
+  __syncthreads();
+  const int tj = threadIdx.x & (kDnTJ - 1);
+  for (int ti = threadIdx.x / kDnTJ; ti < kDnTI; ti += 256 / kDnTJ) {
+    float acc = 0.f;
+    const float* hp = hbuf + (ti * s) * (kDnTJ + 1) + tj;
+    for (int a = 0; a < len; ++a) acc = fmaf(tv[a], hp[a * (kDnTJ + 1)], acc);
+    const int i = i0 + ti, j = j0 + tj;
+    if (i < hl && j < wl) {
+      const size_t o = (size_t)nc * hl * wl + (size_t)i * wl + j;
+      out[o] = sub_from ? (__ldg(sub_from + o) - acc) : acc;
+    }
+  }
+}
+
+// f = replicate-padded correlation of e with kv (x) kh on the LR grid
+__global__ void __launch_bounds__(256)
+cem_inv_fast_kernel(const float* __restrict__ e_in, int hl, int wl, const float* __restrict__ kv, const float* __restrict__ kh, int len,
+                    float* __restrict__ out) {
+  extern __shared__ float sm[];
+  __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
+  const int rows = kInvTI + len - 1, cols = kInvTJ + len - 1;
+  const int pitch = cols | 1;
+  float* tile = sm;                        // [rows][pitch]
+  float* hbuf = sm + rows * pitch;         // [rows][kInvTJ]
+  const int nc = blockIdx.z;
+  const int i0 = blockIdx.y * kInvTI, j0 = blockIdx.x * kInvTJ;
+  const int r = len / 2;
+  const float* ep = e_in + (size_t)nc * hl * wl;
+  if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
+  for (int e = threadIdx.x; e < rows * cols; e += 256) {
+    const int rr = e / cols, cc = e - rr * cols;
+    tile[rr * pitch + cc] = __ldg(ep + (size_t)clampi(i0 - r + rr, 0, hl - 1) * wl + clampi(j0 - r + cc, 0, wl - 1));
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < rows * kInvTJ; e += 256) {
+    const int rr = e / kInvTJ, jj = e - rr * kInvTJ;
+    const float* tp = tile + rr * pitch + jj;
+    float a = 0.f;
+    for (int b = 0; b < len; ++b) a = fmaf(th[b], tp[b], a);
+    hbuf[e] = a;
+  }
+  __syncthreads();
+  const int tj = threadIdx.x & (kInvTJ - 1);
+  for (int ti = threadIdx.x / kInvTJ; ti < kInvTI; ti += 256 / kInvTJ) {
+    float acc = 0.f;
+    for (int a = 0; a < len; ++a) acc = fmaf(tv[a], hbuf[(ti + a) * kInvTJ + tj], acc);
+    const int i = i0 + ti, j = j0 + tj;
+    if (i < hl && j < wl) out[(size_t)nc * hl * wl + (size_t)i * wl + j] = acc;
+  }
+}
+
+// out[Y - crop][X - crop] = G[Y][X] + sum_{a,b} kv[a] kh[b] S[clamp(Y + a - r)][clamp(X + b - r)],  S = F zero-stuffed at `phase`
+__global__ void __launch_bounds__(256)
+cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g, int hl, int wl, int s, int phase, const float* __restrict__ kv,
+                       const float* __restrict__ kh, int len, int crop, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
+  const int hh = hl * s, wh = wl * s;
+  const int ho = hh - 2 * crop, wo = wh - 2 * crop;
+  const int r = len / 2;
+  const int nc = blockIdx.z;
+  const int Y0 = blockIdx.y * kUpTY + crop, X0 = blockIdx.x * kUpTX + crop;     // tile origin in the un-cropped HR domain
+  const int maxni = (kUpTY + len) / s + 2, maxnj = (kUpTX + len) / s + 2;
+  float* ft = sm;                           // [maxni][maxnj]   LR window
+  float* hb = sm + maxni * maxnj;           // [maxni][kUpTX]   horizontally filtered rows
+  if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
+  const int ylo = clampi(Y0 - r, 0, hh - 1), yhi = clampi(Y0 + kUpTY - 1 + r, 0, hh - 1);
+  const int xlo = clampi(X0 - r, 0, wh - 1), xhi = clampi(X0 + kUpTX - 1 + r, 0, wh - 1);
+  const int ilo = max((ylo - phase + s - 1) / s, 0), ihi = min((yhi - phase) / s, hl - 1);
+  const int jlo = max((xlo - phase + s - 1) / s, 0), jhi = min((xhi - phase) / s, wl - 1);
+  const int ni = max(ihi - ilo + 1, 0), nj = max(jhi - jlo + 1, 0);
+  const bool interior_y = Y0 - r >= 0 && Y0 + kUpTY - 1 + r <= hh - 1;
+  const bool interior_x = X0 - r >= 0 && X0 + kUpTX - 1 + r <= wh - 1;
+  const float* fp = f + (size_t)nc * hl * wl;
+  for (int e = threadIdx.x; e < ni * nj; e += 256) {
+    const int ii = e / nj, jj = e - ii * nj;
+    ft[ii * maxnj + jj] = __ldg(fp + (size_t)(ilo + ii) * wl + (jlo + jj));
+  }
+  __syncthreads();
+  // horizontal pass: one column X per thread pair (the phase arithmetic is done once per thread)
+  {
+    const int xx = threadIdx.x & (kUpTX - 1), half = threadIdx.x / kUpTX;      // 128 columns x 2 row halves
+    const int X = X0 + xx;
+    if (interior_x) {
+      const int b0 = (((phase + r - X) % s) + s) % s;
+      const int jb = (X + b0 - r - phase) / s - jlo;
+      for (int ii = half; ii < ni; ii += 256 / kUpTX) {
+        const float* fr = ft + ii * maxnj + jb;
+        float a = 0.f;
+        int j = 0;
+        for (int b = b0; b < len; b += s, ++j) a = fmaf(th[b], fr[j], a);
+        hb[ii * kUpTX + xx] = a;
+      }
+    } else {
+      for (int ii = half; ii < ni; ii += 256 / kUpTX) {
+        float a = 0.f;
+        for (int b = 0; b < len; ++b) {
+          const int xs = clampi(X + b - r, 0, wh - 1) - phase;
+          if (xs >= 0 && xs % s == 0) {
+            const int j = xs / s - jlo;
+            if (j >= 0 && j < nj) a = fmaf(th[b], ft[ii * maxnj + j], a);
+          }
+        }
+        hb[ii * kUpTX + xx] = a;
+      }
+    }
+  }
+  __syncthreads();
+  // vertical pass + G + store: a thread owns 4 consecutive X of rows ty, ty+8, ty+16, ty+24
+  const int xg = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int X = X0 + 4 * xg;
+  const bool vec = (crop & 3) == 0 && (wo & 3) == 0 && (wh & 3) == 0 && X + 3 < wh && (X - crop) + 3 < wo &&
+                   ((((uintptr_t)out) | (g ? (uintptr_t)g : 0)) & 15) == 0;
+#pragma unroll
+  for (int k = 0; k < kUpTY / 8; ++k) {
+    const int Y = Y0 + ty + 8 * k;
+    const int yo = Y - crop;
+    if (yo >= ho || Y >= hh) continue;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (interior_y) {
+      const int a0 = (((phase + r - Y) % s) + s) % s;
+      int i = (Y + a0 - r - phase) / s - ilo;
+      for (int a = a0; a < len; a += s, ++i) {
+        const float4 h4 = *reinterpret_cast<const float4*>(hb + i * kUpTX + 4 * xg);
+        const float t = tv[a];
+        acc[0] = fmaf(t, h4.x, acc[0]); acc[1] = fmaf(t, h4.y, acc[1]); acc[2] = fmaf(t, h4.z, acc[2]); acc[3] = fmaf(t, h4.w, acc[3]);
+      }
+    } else {
+      for (int a = 0; a < len; ++a) {
+        const int ys = clampi(Y + a - r, 0, hh - 1) - phase;
+        if (ys >= 0 && ys % s == 0) {
+          const int i = ys / s - ilo;
+          if (i >= 0 && i < ni) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hb + i * kUpTX + 4 * xg);
+            const float t = tv[a];
+            acc[0] = fmaf(t, h4.x, acc[0]); acc[1] = fmaf(t, h4.y, acc[1]); acc[2] = fmaf(t, h4.z, acc[2]); acc[3] = fmaf(t, h4.w, acc[3]);
+          }
+        }
+      }
+    }
+    const float* gp = g ? g + (size_t)nc * hh * wh + (size_t)Y * wh + X : nullptr;
+    float* op = out + (size_t)nc * ho * wo + (size_t)yo * wo + (X - crop);
+    if (vec) {
+      if (gp) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(gp));
+        acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+      }
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (X + q < wh && (X + q - crop) < wo) op[q] = acc[q] + (gp ? __ldg(gp + q) : 0.f);
+      }
+    }
+  }
+}
+
+}  // namespace esr

@@ -242,6 +242,188 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ g, int layout, con
   }
 }
 
+// ---- second-order pass of the gradient penalty (WGAN-GP, models/modules/loss.py:260-279) ------------------------------------------
+// L_gp = mean_b (||g_b|| - 1)^2 with g = d(sum D(x))/dx.  Its parameter gradient is  grad_theta [ D'(x; theta)[v] ],  v = dL_gp/dg: the
+// directional derivative of the critic along v (a forward-mode tangent through the layers) differentiated by an ordinary backward pass
+// over the (primal, tangent) pair of streams.  Convolutions are linear (tangent = the same conv without bias), LeakyReLU has a zero
+// second derivative (tangent and both adjoints take the primal's mask); the only second-order arithmetic is BatchNorm's, whose
+// batch statistics couple all pixels of a channel:
+//   primal   yh = (y - mu) r,  z = gamma yh + beta                       r = 1 / sqrt(var + eps)
+//   tangent  w  = gamma r A,   A = t - mean(t) - yh c,   c = mean(yh t)   (the BatchNorm Jacobian applied to the conv's tangent t)
+// bn_tangent_apply_kernel: LeakyReLU'(z) * w  -> 16-bit planes (plain / space-to-depth) and / or NCHW fp32.  c1 = mean(t), c2 = c
+// come from bn_bwd_partial_kernel (slope 1) + bn_bwd_finalize_kernel.  Layers without normalisation pass scale 1, c1 = c2 = 0.
+__global__ void bn_tangent_apply_kernel(const float* __restrict__ t32, const float* __restrict__ y32, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                        const float* __restrict__ c1, const float* __restrict__ c2, float slope, int n, int P, int h, int w, int C,
+                                        int dtype, uint16_t* __restrict__ dst16, int s2d, float* __restrict__ dst_nchw, int split) {
+  const size_t total = (size_t)n * P * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int yy = r % h; r /= h;
+    const int g = r % P; r /= P;
+    const int img = (int)r;
+    float v[8], t[8], o[8];
+    load8(y32 + idx * 8, v);
+    load8(t32 + idx * 8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = g * 8 + k;
+      if (c < C) {
+        const float sc = __ldg(scale + c);
+        const float xh = (v[k] - __ldg(mean + c)) * __ldg(invstd + c);
+        const float wv = sc * (t[k] - __ldg(c1 + c) - xh * __ldg(c2 + c));
+        o[k] = fmaf(v[k], sc, __ldg(shift + c)) > 0.f ? wv : wv * slope;
+      } else {
+        o[k] = 0.f;
+      }
+    }
+    if (dst16) {
+      const size_t off = grad_offset(s2d ? 1 : 0, split ? 2 * img : img, g, yy, x, P, h, w, C);
+      store16x8(dst16 + off, o, dtype, split ? (size_t)P * h * w * 8 : 0);
+    }
+    if (dst_nchw) {
+      const size_t hw = (size_t)h * w;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+        if (c < C) dst_nchw[((size_t)img * C + c) * hw + (size_t)yy * w + x] = o[k];
+      }
+    }
+  }
+}
+
+// Backward of the pair (z, w) above.  Incoming adjoints: zb (of the primal activation) and wb (of the tangent activation), both in
+// one of the three gradient layouts; either may be NULL (= zero).  With m = LeakyReLU'(z): p = m zb, q = m wb.  Per channel
+//   sums  S0 = sum p, S1 = sum p yh, S2 = sum q, S3 = sum q yh, S4 = sum q A
+//   tb  = gamma r (q - S2/N - yh S3/N)                                   adjoint of the conv's tangent t
+//   yb  = gamma r (p - S0/N - yh S1/N) - gamma r^2 [ (S4/N) yh + c (q - S2/N - yh S3/N) + (S3/N) A ]      adjoint of the conv's output y
+//   dgamma = S1 + r S4,  dbeta = S0
+// partial kernel: grid (chunks, P) -> part[(g*chunks + chunk)*40 + 8*j + k]
+__global__ void bn_dbl_partial_kernel(const float* __restrict__ zb, const float* __restrict__ wb, int layout, const float* __restrict__ y32,
+                                      const float* __restrict__ t32, const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ c1,
+                                      const float* __restrict__ c2, float slope, int n, int P, int h, int w, int C, float* __restrict__ part,
+                                      int chunks) {
+  const int gi = blockIdx.y, chunk = blockIdx.x;
+  const size_t hw = (size_t)h * w, M = (size_t)n * hw;
+  const size_t per = (M + chunks - 1) / chunks;
+  const size_t m0 = (size_t)chunk * per, m1 = m0 + per < M ? m0 + per : M;
+  float sc[8], sh[8], mu[8], is[8], tm[8], tc[8], acc[40];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = gi * 8 + k;
+    const bool on = c < C;
+    sc[k] = on ? scale[c] : 0.f; sh[k] = on ? shift[c] : 0.f; mu[k] = on ? mean[c] : 0.f; is[k] = on ? invstd[c] : 0.f;
+    tm[k] = on ? c1[c] : 0.f; tc[k] = on ? c2[c] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 40; ++k) acc[k] = 0.f;
+  for (size_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+    const int img = (int)(m / hw);
+    const int pix = (int)(m - (size_t)img * hw);
+    const int yy = pix / w, x = pix - yy * w;
+    float v[8], t[8], pz[8], qw[8];
+    const size_t o = (((size_t)img * P + gi) * hw + pix) * 8;
+    load8(y32 + o, v);
+    load8(t32 + o, t);
+    if (zb) load_grad8(zb, layout, img, gi, yy, x, P, h, w, C, pz);
+    if (wb) load_grad8(wb, layout, img, gi, yy, x, P, h, w, C, qw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float msk = fmaf(v[k], sc[k], sh[k]) > 0.f ? 1.f : slope;
+      const float xh = (v[k] - mu[k]) * is[k];
+      const float p = zb ? pz[k] * msk : 0.f, q = wb ? qw[k] * msk : 0.f;
+      const float A = t[k] - tm[k] - xh * tc[k];
+      acc[k] += p; acc[8 + k] = fmaf(p, xh, acc[8 + k]);
+      acc[16 + k] += q; acc[24 + k] = fmaf(q, xh, acc[24 + k]); acc[32 + k] = fmaf(q, A, acc[32 + k]);
+    }
+  }
+  // block-level sums of the 40 accumulators
+  __shared__ float smem[8][40];
+#pragma unroll
+  for (int k = 0; k < 40; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 40; ++k) smem[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 40) {
+    float sum = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) sum += smem[wv][threadIdx.x];
+    part[((size_t)gi * chunks + chunk) * 40 + threadIdx.x] = sum;
+  }
+}
+
+// coef[j*C + c] = S_j / N for j = 0..4; dgamma / dbeta (+= when accumulate), scaled by gscale
+__global__ void bn_dbl_finalize_kernel(const float* __restrict__ part, int chunks, int C, double M, const float* __restrict__ invstd, int has_bn,
+                                       float gscale, int accumulate, float* dgamma, float* dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double S[5] = {0, 0, 0, 0, 0};
+  const float* pp = part + (size_t)(c >> 3) * chunks * 40 + (c & 7);
+  for (int k = 0; k < chunks; ++k)
+    for (int j = 0; j < 5; ++j) S[j] += pp[(size_t)k * 40 + 8 * j];
+  if (has_bn) {
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)(S[0] * gscale);
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)((S[1] + (double)invstd[c] * S[4]) * gscale);
+  }
+  for (int j = 0; j < 5; ++j) coef[j * C + c] = has_bn ? (float)(S[j] / M) : 0.f;
+}
+
+// tb16 / yb16 (16-bit planes, operands of the dgrad and wgrad launches of the layer's conv)
+__global__ void bn_dbl_apply_kernel(const float* __restrict__ zb, const float* __restrict__ wb, int layout, const float* __restrict__ y32,
+                                    const float* __restrict__ t32, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ c1,
+                                    const float* __restrict__ c2, const float* __restrict__ coef, int has_bn, float slope, int n, int P, int h, int w,
+                                    int C, int dtype, uint16_t* __restrict__ tb16, uint16_t* __restrict__ yb16, int split) {
+  const size_t total = (size_t)n * P * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int yy = r % h; r /= h;
+    const int gi = r % P; r /= P;
+    const int img = (int)r;
+    float v[8], t[8], pz[8], qw[8], ot[8], oy[8];
+    load8(y32 + idx * 8, v);
+    load8(t32 + idx * 8, t);
+    if (zb) load_grad8(zb, layout, img, gi, yy, x, P, h, w, C, pz);
+    if (wb) load_grad8(wb, layout, img, gi, yy, x, P, h, w, C, qw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = gi * 8 + k;
+      if (c < C) {
+        const float sc = __ldg(scale + c), is = __ldg(invstd + c);
+        const float msk = fmaf(v[k], sc, __ldg(shift + c)) > 0.f ? 1.f : slope;
+        const float p = zb ? pz[k] * msk : 0.f, q = wb ? qw[k] * msk : 0.f;
+        if (has_bn) {
+          const float xh = (v[k] - __ldg(mean + c)) * is;
+          const float cc = __ldg(c2 + c);
+          const float A = t[k] - __ldg(c1 + c) - xh * cc;
+          const float s0 = __ldg(coef + c), s1 = __ldg(coef + C + c), s2 = __ldg(coef + 2 * C + c), s3 = __ldg(coef + 3 * C + c),
+                      s4 = __ldg(coef + 4 * C + c);
+          const float qc = q - s2 - xh * s3;
+          ot[k] = sc * qc;                                                    // sc = gamma r
+          oy[k] = sc * (p - s0 - xh * s1) - sc * is * (s4 * xh + cc * qc + s3 * A);
+        } else {
+          ot[k] = q;
+          oy[k] = p;
+        }
+      } else {
+        ot[k] = 0.f; oy[k] = 0.f;
+      }
+    }
+    const size_t per_img = (size_t)P * h * w;
+    const size_t o16 = split ? (size_t)img * 2 * per_img + (idx - (size_t)img * per_img) : idx;
+    if (tb16) store16x8(tb16 + o16 * 8, ot, dtype, split ? per_img * 8 : 0);
+    if (yb16) store16x8(yb16 + o16 * 8, oy, dtype, split ? per_img * 8 : 0);
+  }
+}
+
 // ---- fully connected layers (fp32; 8192 -> 100 -> 1 at the reference's sizes: a few MFLOP, weight-read bound) ---------------------
 // out[b][j] = act(bias[j] + sum_k x[b][k] * W[j][k]); one block per output feature, batch in groups of 8
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias, int B, int K, int J,

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "cem_kernels.cuh"
 #include "conv3x3_tc.cuh"
 #include "conv3x3_rows.cuh"
 #include "conv3x3_wgrad.cuh"
@@ -375,7 +376,11 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   p.out_nchw = a->out_nchw; p.out_nchw_c = a->out_nchw_c;
 
   const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
-  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w, bwd))) {
+  // (the gradient-slice launches of the dense-block backward have the forward-type fast epilogue: same width rule as forward launches)
+  const bool mask_only_shape = bwd && a->rows_nbn == 32 && a->cout % 32 == 0 && a->mask16 && a->out16 && !a->lead_planes && !a->res1 && !a->res2 &&
+                               !a->res3 && !a->out32 && !a->out_nchw && !a->out16_up2 && !a->out16_pixel_shuffle && a->tail_first_plane == 0 &&
+                               a->alpha == 1.0f && !a->lrelu;
+  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w, bwd && !mask_only_shape))) {
     // ---- row-streaming kernel (conv3x3_rows.cuh)
     const int nbn = a->rows_nbn;
     if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "conv3x3: rows_nbn must be 16, 32 or 64");
@@ -615,9 +620,9 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     if (ranges < 1) return fail(ESR_ERR_INVALID, "wgrad: too many n-blocks (%d)", w.n_blocks);
     if ((long long)ranges > p.units) ranges = (int)p.units;
     // small images: every CTA dumps a full partial (mt*128*3*nbn floats) whatever its share of rows, and the reduce reads all of
-    // them (profiles/r01c_launches_c3_step.csv: the reduce costs as much as the wgrad at ~1.4 rows per CTA).  ESR_WGRAD_MIN_ROWS=k
-    // gives every CTA at least k row units (default 1 = one range per SM as measured so far; to be tuned on the GPU).
-    static const int min_rows = [] { const char* e = getenv("ESR_WGRAD_MIN_ROWS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    // them (profiles/r01c_launches_c3_step.csv: at ~1.4 rows per CTA the reduce cost as much as the wgrad itself).  Every CTA gets
+    // at least ESR_WGRAD_MIN_ROWS row units (default 6: a row unit is 0.6-1.1 us of MMAs, a partial 60-250 KB).
+    static const int min_rows = [] { const char* e = getenv("ESR_WGRAD_MIN_ROWS"); const int v = e ? atoi(e) : 6; return v < 1 ? 1 : v; }();
     if (min_rows > 1 && p.units / min_rows < ranges) ranges = (int)(p.units / min_rows > 0 ? p.units / min_rows : 1);
     p.ranges = ranges;
     p.x = (const uint8_t*)a->x; p.x_pt = a->x_planes_total; p.x_po = a->x_plane_off; p.cp = cp;
@@ -866,6 +871,12 @@ int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, in
   return ESR_OK;
 }
 
+// rank-1 filters take the HBM-bound kernels of cem_kernels.cuh (ESR_CEM_FAST=0: the general kernels, which also cover rank > 1)
+static bool cem_fast(int rank, int len) {
+  static const bool on = [] { const char* e = getenv("ESR_CEM_FAST"); return !(e && e[0] == '0'); }();
+  return on && rank == 1 && len <= esr::kCemMaxTaps;
+}
+
 static int set_smem_attr(const void* fn, size_t bytes) {
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -880,6 +891,20 @@ int esr_cem_down(const float* g, int n, int c, int hh, int wh, int s, int phase,
   if (s < 1 || hh % s || wh % s) return fail(ESR_ERR_INVALID, "cem_down: HR size %dx%d not divisible by scale %d", hh, wh, s);
   if (phase < 0 || phase >= s || kd_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_down: bad phase/filter");
   const int hl = hh / s, wl = wh / s;
+  if (cem_fast(rank, kd_len)) {
+    const int frows = (esr::kDnTI - 1) * s + kd_len, fcols = (esr::kDnTJ - 1) * s + kd_len;
+    const int pitch = ((fcols + 3 + 3) & ~3) | 1;
+    const size_t fsmem = sizeof(float) * ((size_t)frows * pitch + (size_t)frows * (esr::kDnTJ + 1));
+    if (fsmem <= 200 * 1024) {
+      int rc = set_smem_attr((const void*)esr::cem_down_fast_kernel, fsmem);
+      if (rc) return rc;
+      dim3 grid((wl + esr::kDnTJ - 1) / esr::kDnTJ, (hl + esr::kDnTI - 1) / esr::kDnTI, n * c);
+      esr::cem_down_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(g, hh, wh, s, phase, kd_v, kd_h, kd_len, sub_from, out_lr);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      return ESR_OK;
+    }
+  }
   const int rows = (esr::kCemTI - 1) * s + kd_len, cols = (esr::kCemTJ - 1) * s + kd_len;
   const size_t smem = sizeof(float) * ((size_t)rows * cols + (size_t)rows * esr::kCemTJ);
   if (smem > 227 * 1024) return fail(ESR_ERR_INVALID, "cem_down: filter too large for shared memory");
@@ -897,6 +922,17 @@ int esr_cem_inv(const float* e, int n, int c, int hl, int wl, const float* ki_v,
                 float* out_lr, void* stream) {
   if (!e || !ki_v || !ki_h || !out_lr) return fail(ESR_ERR_INVALID, "cem_inv: null pointer");
   if (ki_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_inv: bad filter");
+  if (cem_fast(rank, ki_len)) {
+    const int frows = esr::kInvTI + ki_len - 1, fcols = esr::kInvTJ + ki_len - 1;
+    const size_t fsmem = sizeof(float) * ((size_t)frows * (fcols | 1) + (size_t)frows * esr::kInvTJ);
+    int rc = set_smem_attr((const void*)esr::cem_inv_fast_kernel, fsmem);
+    if (rc) return rc;
+    dim3 grid((wl + esr::kInvTJ - 1) / esr::kInvTJ, (hl + esr::kInvTI - 1) / esr::kInvTI, n * c);
+    esr::cem_inv_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(e, hl, wl, ki_v, ki_h, ki_len, out_lr);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ESR_OK;
+  }
   const int rows = esr::kCemTI + ki_len - 1, cols = esr::kCemTJ + ki_len - 1;
   const size_t smem = sizeof(float) * ((size_t)rows * cols + (size_t)rows * esr::kCemTJ);
   if (smem > 227 * 1024) return fail(ESR_ERR_INVALID, "cem_inv: filter too large for shared memory");
@@ -916,6 +952,17 @@ int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl,
   const int hh = hl * s, wh = wl * s;
   if (crop < 0 || 2 * crop >= hh || 2 * crop >= wh) return fail(ESR_ERR_INVALID, "cem_up_add: crop %d too large", crop);
   const int ho = hh - 2 * crop, wo = wh - 2 * crop;
+  if (cem_fast(rank, ku_len)) {
+    const int maxni = (esr::kUpTY + ku_len) / s + 2, maxnj = (esr::kUpTX + ku_len) / s + 2;
+    const size_t fsmem = sizeof(float) * ((size_t)maxni * maxnj + (size_t)maxni * esr::kUpTX);
+    int rc = set_smem_attr((const void*)esr::cem_up_add_fast_kernel, fsmem);
+    if (rc) return rc;
+    dim3 grid((wo + esr::kUpTX - 1) / esr::kUpTX, (ho + esr::kUpTY - 1) / esr::kUpTY, n * c);
+    esr::cem_up_add_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(f, g, hl, wl, s, phase, ku_v, ku_h, ku_len, crop, out_hr);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ESR_OK;
+  }
   const int maxn = (esr::kUpT + ku_len) / s + 2;
   const size_t smem = sizeof(float) * ((size_t)maxn * maxn + (size_t)maxn * esr::kUpT);
   int rc = set_smem_attr((const void*)esr::cem_up_add_kernel, smem);

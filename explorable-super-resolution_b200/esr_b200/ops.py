@@ -242,7 +242,7 @@ def _wgrad_ws_bytes(cp, cout):
 def conv3x3_wgrad(x16, gy16, cout, cin, *, lead=0, x_off=0, gy_off=0, dw=None, db=None, scale=1.0, accumulate=False, split=False):
     """Weight / bias gradient of a 3x3 conv: x16 = the conv's input planes, gy16 = gradient of its (pre-activation)
     output.  Returns (dw [cout,cin,3,3] fp32, db [cout] fp32); pass dw/db tensors to accumulate into them."""
-    require_cuda(x16, gy16, dw, db)
+    require_cuda(x16, gy16, dw, db if db is not False else None)
     lib = L.load()
     n, xpt, h, w, e = x16.shape
     assert e == 8 and gy16.dtype == x16.dtype and tuple(gy16.shape[2:]) == (h, w, 8) and gy16.shape[0] == n

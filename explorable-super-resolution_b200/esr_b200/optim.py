@@ -101,6 +101,15 @@ class FlatAdam(torch.optim.Adam):
                     break
         return flat if ok else self._build(gi, group)
 
+    def state_dict(self):
+        """torch.optim.Adam's layout.  Internally every parameter of a group references ONE step counter; a checkpoint must not carry that
+        sharing (torch's own Adam increments `step` once per parameter), so each entry gets its own copy here."""
+        sd = super(FlatAdam, self).state_dict()
+        for st in sd['state'].values():
+            if 'step' in st and torch.is_tensor(st['step']):
+                st['step'] = st['step'].clone()
+        return sd
+
     def flat_grad(self, gi=0):
         """the flat gradient buffer of parameter group gi (None until the first step / register()), for the all-reduce"""
         flat = self._flat.get(gi)
@@ -161,6 +170,9 @@ class FlatAdam(torch.optim.Adam):
                     flat['uploaded'] = True
                 L.check(lib.esr_adam_multi(arg, 1, C.c_void_p(flat['scratch'].data_ptr()), flat['scratch'].numel(), *hyper, t, float(grad_scale), stream))
                 flat['step'] += 1
+                # the kernel wrote the parameters behind autograd's back: bump their version counters (the engines re-pack their
+                # tensor-core weight images when a parameter's version changes, exactly as after torch.optim.Adam's in-place update)
+                torch.autograd.graph.increment_version(flat['params'])
             else:
                 # torch skips parameters without a gradient (a zero gradient would still decay their moments), and a loaded checkpoint
                 # may hold unequal step counts: one table entry per tensor that has a gradient, grouped by step count
@@ -180,6 +192,7 @@ class FlatAdam(torch.optim.Adam):
                     L.check(lib.esr_adam_multi(tab, len(ents), C.c_void_p(scratch.data_ptr()), scratch.numel(), *hyper, int(t0) + 1, float(grad_scale), stream))
                     for p, _, _, _ in ents:
                         self.state[p]['step'] += 1
+                    torch.autograd.graph.increment_version([p for p, _, _, _ in ents])
         if cpu_groups:
             if float(grad_scale) != 1.0:
                 for group in cpu_groups:

@@ -116,22 +116,30 @@ def test_engine_writes_gradients_into_the_flat_buffer():
     pb = [p for n_, p in mb.named_parameters() if 'Filter_OP' not in n_]
     opt = FlatAdam(pa, lr=1e-4).register()
     x, hr = torch.rand(2, 3, 24, 40, device=DEV), torch.rand(2, 3, 96, 160, device=DEV)
+    with torch.no_grad():
+        y0 = ma(x)
     for m in (ma, mb):
         (m(x) - hr).abs().mean().backward()
-    for p, q in zip(pa, pb):
-        assert p.grad is grad_view(p) and torch.equal(p.grad, q.grad)
+    for p, q in zip(pa, pb):      # (two launches of the bf16 row kernel differ in summation order: equal to operand precision, not bit for bit)
+        assert p.grad is grad_view(p)
+        assert torch.allclose(p.grad, q.grad, rtol=0, atol=2e-2 * float(q.grad.abs().max()))
     flat = opt.flat_grad().clone()
     (ma(x) - hr).abs().mean().backward()          # gradient accumulation: in place, into the same views
-    assert torch.allclose(opt.flat_grad(), 2 * flat, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(opt.flat_grad(), 2 * flat, rtol=0, atol=4e-2 * float(flat.abs().max()))      # (bf16 launches: summation order varies)
     assert opt.grads_in_place()
     w0 = pa[0].detach().clone()
     opt.step()
     assert not torch.equal(w0, pa[0].detach()) and float(opt.state[pa[0]]['step']) == 1
     opt.zero_grad()
     assert pa[0].grad is None
-    with torch.no_grad():                         # the engine picks the updated weights up (parameters moved into the flat buffer)
-        y1 = ma(x)
-    assert torch.isfinite(y1).all()
+    # the engine picks the updated weights up (version counters bumped by the step): same output as a torch.optim.Adam twin
+    opt_b = torch.optim.Adam(pb, lr=1e-4)
+    for p in pb:
+        p.grad = p.grad * 2
+    opt_b.step()
+    with torch.no_grad():
+        y1, y2 = ma(x), mb(x)
+    assert torch.isfinite(y1).all() and float((y1 - y2).abs().max()) < 2e-3 and float((y1 - y2).abs().max()) < 0.5 * float((y1 - y0).abs().max())
 
 
 def test_backward_after_a_second_forward_is_refused():
