@@ -409,9 +409,9 @@ __global__ void bn_dbl_apply_kernel(const float* __restrict__ zb, const float* _
           const float qc = q - s2 - xh * s3;
           ot[k] = sc * qc;                                                    // sc = gamma r
           oy[k] = sc * (p - s0 - xh * s1) - sc * is * (s4 * xh + cc * qc + s3 * A);
-        } else {
-          ot[k] = q;
-          oy[k] = p;
+        } else {      // no normalisation (scale = 1) or running statistics (a fixed affine map: scale = gamma * invstd)
+          ot[k] = sc * q;
+          oy[k] = sc * p;
         }
       } else {
         ot[k] = 0.f; oy[k] = 0.f;

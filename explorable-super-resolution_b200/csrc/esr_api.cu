@@ -1062,6 +1062,73 @@ int esr_bn_lrelu_bwd(const float* g, int g_layout, const float* y32, int n, int 
   return ESR_OK;
 }
 
+// ---- gradient penalty (WGAN-GP): tangent forward and double backward of BatchNorm + LeakyReLU ----------------------------------------
+size_t esr_bn_dbl_workspace_bytes(int planes) { return planes > 0 ? (size_t)planes * esr::kBnMaxChunks * 40 * sizeof(float) : 0; }
+
+int esr_bn_tangent_fwd(const float* t32, const float* y32, int n, int planes, int h, int w, int c, const float* scale, const float* shift,
+                       const float* save_mean, const float* save_invstd, float slope, int has_bn, float* c1, float* c2, int dtype, void* dst16,
+                       int space_to_depth, float* dst_nchw, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!t32 || !y32 || !scale || !shift || !save_mean || !save_invstd || !c1 || !c2 || (!dst16 && !dst_nchw)) return fail(ESR_ERR_INVALID, "bn_tangent_fwd: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_tangent_fwd: bad shape");
+  if (dtype != ESR_F16 && dtype != ESR_BF16 && dtype != ESR_BF16X3) return fail(ESR_ERR_INVALID, "bn_tangent_fwd: bad dtype");
+  if (space_to_depth && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_tangent_fwd: space-to-depth needs an even size");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)n * h * w;
+  if (has_bn) {     // c1 = mean(t), c2 = mean(yh t): the reductions of the BatchNorm backward with the mask switched off (slope 1)
+    if (!workspace || workspace_bytes < esr_bn_workspace_bytes(planes)) return fail(ESR_ERR_INVALID, "bn_tangent_fwd: workspace too small");
+    const int chunks = bn_chunks(m);
+    esr::bn_bwd_partial_kernel<<<dim3((unsigned)chunks, (unsigned)planes), 256, 0, st>>>(t32, 0, y32, scale, shift, save_mean, save_invstd, 1.0f, n,
+                                                                                        planes, h, w, c, workspace, chunks);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    esr::bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(workspace, chunks, c, (double)m, 1, 1.0f, 0, nullptr, nullptr, c1, c2);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    CUDA_TRY(cudaMemsetAsync(c1, 0, sizeof(float) * c, st));
+    CUDA_TRY(cudaMemsetAsync(c2, 0, sizeof(float) * c, st));
+  }
+  const size_t total = (size_t)n * planes * h * w;
+  esr::bn_tangent_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(t32, y32, scale, shift, save_mean, save_invstd, c1, c2, slope, n, planes, h, w, c,
+                                                                    dtype == ESR_BF16X3 ? 1 : dtype, (uint16_t*)dst16, space_to_depth, dst_nchw,
+                                                                    dtype == ESR_BF16X3 ? 1 : 0);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_bn_double_bwd(const float* zb, const float* wb, int g_layout, const float* y32, const float* t32, int n, int planes, int h, int w, int c,
+                      const float* scale, const float* shift, const float* save_mean, const float* save_invstd, const float* c1, const float* c2,
+                      float slope, int has_bn, float gscale, int accumulate, float* dgamma, float* dbeta, float* coef, int dtype, void* tb16,
+                      void* yb16, float* workspace, size_t workspace_bytes, void* stream) {
+  if ((!zb && !wb) || !y32 || !t32 || !scale || !shift || !save_mean || !save_invstd || !c1 || !c2 || !coef || (!tb16 && !yb16))
+    return fail(ESR_ERR_INVALID, "bn_double_bwd: null pointer");
+  if (n <= 0 || planes <= 0 || h <= 0 || w <= 0 || c <= 0 || c > planes * 8) return fail(ESR_ERR_INVALID, "bn_double_bwd: bad shape");
+  if (g_layout < 0 || g_layout > 2) return fail(ESR_ERR_INVALID, "bn_double_bwd: bad gradient layout %d", g_layout);
+  if (g_layout == 1 && ((h & 1) || (w & 1))) return fail(ESR_ERR_INVALID, "bn_double_bwd: space-to-depth gradient needs an even size");
+  if (dtype != ESR_F16 && dtype != ESR_BF16 && dtype != ESR_BF16X3) return fail(ESR_ERR_INVALID, "bn_double_bwd: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t m = (size_t)n * h * w;
+  if (has_bn) {
+    if (!workspace || workspace_bytes < esr_bn_dbl_workspace_bytes(planes)) return fail(ESR_ERR_INVALID, "bn_double_bwd: workspace too small");
+    const int chunks = bn_chunks(m);
+    esr::bn_dbl_partial_kernel<<<dim3((unsigned)chunks, (unsigned)planes), 256, 0, st>>>(zb, wb, g_layout, y32, t32, scale, shift, save_mean, save_invstd,
+                                                                                        c1, c2, slope, n, planes, h, w, c, workspace, chunks);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    esr::bn_dbl_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(workspace, chunks, c, (double)m, save_invstd, 1, gscale, accumulate, dgamma, dbeta, coef);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  const size_t total = (size_t)n * planes * h * w;
+  esr::bn_dbl_apply_kernel<<<grid_for(total, 256), 256, 0, st>>>(zb, wb, g_layout, y32, t32, scale, shift, save_mean, save_invstd, c1, c2, coef, has_bn,
+                                                                slope, n, planes, h, w, c, dtype == ESR_BF16X3 ? 1 : dtype, (uint16_t*)tb16,
+                                                                (uint16_t*)yb16, dtype == ESR_BF16X3 ? 1 : 0);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 int esr_linear_fwd(const float* x, const float* weight, const float* bias, int batch, int in_features, int out_features, int lrelu,
                    float slope, float* out, void* stream) {
   if (!x || !weight || !out) return fail(ESR_ERR_INVALID, "linear_fwd: null pointer");

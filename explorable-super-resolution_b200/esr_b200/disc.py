@@ -264,6 +264,119 @@ class DiscEngine:
         return gx, plist
 
 
+    # ---- second-order pass of the gradient penalty (WGAN-GP) ----------------------------------------------------------------------
+    def _zero_bias(self, n, dev):
+        key = ('zb', str(dev))
+        if key not in self._const or self._const[key].numel() < n:
+            self._const[key] = torch.zeros(max(n, 1024), dtype=torch.float32, device=dev)
+        return self._const[key]
+
+    @torch.no_grad()
+    def input_gradient(self, sv):
+        """g = d(sum of the logits) / d(image): what GradientPenaltyLoss takes the norm of (models/modules/loss.py:271-273)"""
+        saved, feat, h1, _ = sv
+        ones = torch.ones((feat.shape[0], 1), dtype=torch.float32, device=feat.device)
+        return self.backward(ones, sv, want_input=True, want_params=False)[0]
+
+    @torch.no_grad()
+    def second_order_param_grads(self, v, sv, gscale=1.0):
+        """Parameter gradient of  s(theta) = sum_b D'(x; theta)[v]_b,  the critic's directional derivative along v (an image-shaped tensor,
+        constant here).  With v = dL_gp/dg this is d L_gp / d theta, the double backward of models/modules/loss.py:271-278.  Two passes
+        over the layers: the tangent forward (same conv launches without bias, BatchNorm's Jacobian, the primal LeakyReLU masks) and the
+        backward over the (primal, tangent) pair (esr_bn_double_bwd + the dgrad / wgrad launches, each conv's dW = wgrad(a, yb) + wgrad(u, tb)).
+        Returns the gradients in module.parameters() order, scaled by gscale."""
+        saved, feat, h1, (H, W) = sv
+        pk, pkt = self._packed()
+        n, dev = feat.shape[0], feat.device
+        split = ops.is_split(self.dtype)
+        for L, (_, _, _, _, _, _, use_batch) in zip(self.layers, saved):
+            if L.bn is not None and not use_batch:
+                raise NotImplementedError('esr_b200: the gradient penalty through BatchNorm in eval mode (running statistics) is not built')
+        # ---- tangent forward
+        cur_u, _ = ops.pack_nchw(v.float().contiguous(), dtype=self.dtype)
+        tang, fdot = [], None
+        for li, L in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            cur_a, y32, mean, invstd, scale, shift, use_batch = saved[li]
+            t32 = torch.empty_like(y32)
+            ops.conv3x3(cur_u, pk[li], out32=t32, bias=self._zero_bias(pk[li].cout_pad, dev))
+            nxt_k4 = (not last) and self.layers[li + 1].k4
+            w16, w_nchw, c1, c2 = ops.bn_tangent_fwd(t32, y32, L.cout, scale, shift, mean, invstd, SLOPE, self.dtype, has_bn=L.bn is not None,
+                                                     space_to_depth=nxt_k4, want16=not last, want_nchw=last)
+            tang.append((cur_u, t32, c1, c2))
+            cur_u, fdot = w16, w_nchw
+        fdot = fdot.reshape(n, -1)
+        W1, W2 = self.fc1.weight.detach(), self.fc2.weight.detach()
+        t1 = ops.linear_fwd(fdot, W1, None)
+        hdot = torch.where(h1 > 0, t1, t1 * SLOPE)          # tangent of the hidden LeakyReLU ([B, 100] glue)
+        # ---- backward of s = sum_b (W2 hdot)_b over the (primal, tangent) pair; the primal adjoint is zero until the first BatchNorm
+        grads = {}
+        ones = torch.ones((n, 1), dtype=torch.float32, device=dev)
+        hbar, dw2, _ = ops.linear_bwd(ones, None, hdot, W2, gscale=gscale)
+        fbar, dw1, _ = ops.linear_bwd(hbar, h1, fdot, W1, slope=SLOPE, gscale=gscale)
+        grads[id(self.fc2.weight)], grads[id(self.fc2.bias)] = dw2, torch.zeros_like(self.fc2.bias)
+        grads[id(self.fc1.weight)], grads[id(self.fc1.bias)] = dw1, torch.zeros_like(self.fc1.bias)
+        wb, zb, layout = fbar.reshape(feat.shape), None, 2
+        for li in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[li]
+            cur_a, y32, mean, invstd, scale, shift, use_batch = saved[li]
+            cur_u, t32, c1, c2 = tang[li]
+            dgamma = dbeta = None
+            if L.bn is not None:
+                dgamma, dbeta = torch.empty(L.cout, dtype=torch.float32, device=dev), torch.empty(L.cout, dtype=torch.float32, device=dev)
+            tb16, yb16 = ops.bn_double_bwd(zb, wb, layout, y32, t32, L.cout, scale, shift, mean, invstd, c1, c2, SLOPE, self.dtype,
+                                           has_bn=L.bn is not None, gscale=gscale, dgamma=dgamma, dbeta=dbeta)
+            if L.bn is not None:
+                grads[id(L.bn.weight)], grads[id(L.bn.bias)] = dgamma, dbeta
+            cin3 = 4 * L.cin if L.k4 else L.cin
+            dw, db = ops.conv3x3_wgrad(cur_a, yb16, L.cout, cin3, split=split, scale=gscale)
+            ops.conv3x3_wgrad(cur_u, tb16, L.cout, cin3, split=split, scale=gscale, dw=dw, db=False, accumulate=True)
+            grads[id(L.conv.weight)] = k3x3_to_k4s2(dw) if L.k4 else dw
+            grads[id(L.conv.bias)] = db
+            if li == 0:
+                break
+            lp = ops.logical_planes(cur_a, self.dtype)
+            zb = torch.empty((n, lp, cur_a.shape[2], cur_a.shape[3], 8), dtype=torch.float32, device=dev)
+            wb = torch.empty_like(zb)
+            ops.conv3x3(yb16, pkt[li], out32=zb)
+            ops.conv3x3(tb16, pkt[li], out32=wb)
+            layout = 1 if L.k4 else 0
+        return [grads.get(id(p)) for p in self.params()]
+
+
+class _GradPenaltyFn(torch.autograd.Function):
+    """L_gp = mean_b (||d(sum D(x)) / dx_b||_2 - 1)^2 and its gradient with respect to the critic's parameters, for a critic forward
+    that ran on this engine (models/modules/loss.py:260-279; models/SRRaGAN_model.py:362-371).  `crit` ties the node behind the critic's
+    forward; the saved activations of that forward are passed as `sv`."""
+
+    @staticmethod
+    def forward(ctx, crit, eng, sv, *params):
+        gx = eng.input_gradient(sv)
+        norms = gx.reshape(gx.shape[0], -1).norm(2, dim=1)
+        ctx.eng, ctx.sv, ctx.n_params = eng, sv, len(params)
+        ctx.save_for_backward(gx, norms)
+        return ((norms - 1) ** 2).mean()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        gx, norms = ctx.saved_tensors
+        b = gx.shape[0]
+        v = gx * ((2.0 / b) * (norms - 1) / norms.clamp_min(1e-30)).view(b, 1, 1, 1)        # dL_gp / dg
+        plist = ctx.eng.second_order_param_grads(v, ctx.sv)
+        g = g.float()
+        pg = tuple((plist[k] * g if (ctx.needs_input_grad[3 + k] and plist[k] is not None) else None) for k in range(ctx.n_params))
+        return (None, None, None) + pg
+
+
+def gradient_penalty(interp_crit):
+    """fused WGAN-GP penalty for logits produced by this engine (None if `interp_crit` did not come from it)"""
+    node = interp_crit.grad_fn
+    if node is None or not hasattr(node, 'eng') or not hasattr(node, 'sv'):
+        return None
+    return _GradPenaltyFn.apply(interp_crit, node.eng, node.sv, *node.eng.params())
+
+
 class _DiscFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eng, *params):

@@ -157,7 +157,7 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
             res1=None, res1_off=0, beta1=1.0, res2=None, res2_off=0, beta2=1.0, res3=None, res3_off=0, beta3=1.0,
             out16=None, out16_off=0, up2=False, pixel_shuffle=0, out32=None, out32_off=0,
             out_nchw=None, lead_planes=0, lead_acc=None, mask16=None, mask_off=0, mask_slope=0.2, tail_first=0,
-            tile_p=0, tile_mt=0, rows=True, plan=None):
+            tile_p=0, tile_mt=0, rows=True, plan=None, bias=None):
     """One fused conv launch.  x16: [N, planes, H, W, 8] operand tensor.  With `plan` (a list) the filled argument struct is
     appended instead of launched: `LaunchPlan` replays such a recording with one host call."""
     require_cuda(x16, res1, res2, res3, out16, out32, out_nchw, lead_acc, mask16)
@@ -168,7 +168,8 @@ def conv3x3(x16, pc, *, in_plane_off=0, cin_planes=None, lrelu=False, slope=0.2,
     a.in_, a.in_planes_total, a.in_plane_off = x16.data_ptr(), pt, in_plane_off
     a.cin_planes = pc.cin_planes if cin_planes is None else cin_planes
     assert a.cin_planes == pc.cin_planes or not pc.split      # the packed image's chunk structure is that of its own cin
-    a.wpacked, a.bias = pc.wpacked.data_ptr(), pc.bias.data_ptr()
+    a.wpacked, a.bias = pc.wpacked.data_ptr(), (pc.bias if bias is None else bias).data_ptr()      # bias: override (e.g. zeros for a tangent)
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() >= pc.cout_pad and bias.is_cuda)
     a.cout, a.cout_pad, a.kcp = pc.cout, pc.cout_pad, pc.kcp
     a.lrelu, a.slope, a.alpha = int(lrelu), slope, alpha
     if res1 is not None:
@@ -529,6 +530,49 @@ def bn_lrelu_bwd(g, g_layout, y32, c, scale, shift, mean, invstd, slope, dtype, 
                                       _ptr(scratch[1]), esr_dtype(dtype), _ptr(gy16), _ptr(ws), (ws.numel() * 4 if ws is not None else 0),
                                       _stream()))
     return gy16
+
+
+_bn_dbl_ws = {}
+
+
+def bn_tangent_fwd(t32, y32, c, scale, shift, mean, invstd, slope, dtype, *, has_bn, space_to_depth=False, want16=True, want_nchw=False):
+    """tangent of LeakyReLU(BatchNorm(y)) along the conv tangent t (WGAN-GP second-order pass) -> (w16 | None, w_nchw | None, c1, c2)"""
+    require_cuda(t32, y32, scale, shift, mean, invstd)
+    n, p, h, w, _ = y32.shape
+    assert t32.shape == y32.shape and t32.dtype == y32.dtype == torch.float32
+    d16 = None
+    if want16:
+        d16 = alloc16(dtype, n, 4 * p, h // 2, w // 2, y32.device) if space_to_depth else alloc16(dtype, n, p, h, w, y32.device)
+    dn = torch.empty((n, c, h, w), dtype=torch.float32, device=y32.device) if want_nchw else None
+    cc = torch.empty((2, c), dtype=torch.float32, device=y32.device)
+    ws = _bn_workspace(y32.device, p) if has_bn else None
+    L.check(L.load().esr_bn_tangent_fwd(_ptr(t32), _ptr(y32), n, p, h, w, c, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), slope, int(has_bn),
+                                        _ptr(cc[0]), _ptr(cc[1]), esr_dtype(dtype), _ptr(d16), int(space_to_depth), _ptr(dn), _ptr(ws),
+                                        (ws.numel() * 4 if ws is not None else 0), _stream()))
+    return d16, dn, cc[0], cc[1]
+
+
+def bn_double_bwd(zb, wb, g_layout, y32, t32, c, scale, shift, mean, invstd, c1, c2, slope, dtype, *, has_bn, gscale=1.0, dgamma=None, dbeta=None,
+                  accumulate=False):
+    """adjoints (tb16, yb16) of the conv's tangent and output from the adjoints of the tangent / primal activations; fills dgamma / dbeta"""
+    require_cuda(zb, wb, y32, t32, scale, shift, mean, invstd, c1, c2, dgamma, dbeta)
+    n, p, h, w, _ = y32.shape
+    dev = y32.device
+    tb16, yb16 = alloc16(dtype, n, p, h, w, dev), alloc16(dtype, n, p, h, w, dev)
+    coef = torch.empty((5, c), dtype=torch.float32, device=dev)
+    ws = None
+    if has_bn:
+        nbytes = int(L.load().esr_bn_dbl_workspace_bytes(p))
+        key = (str(dev), torch.cuda.current_stream().cuda_stream)
+        ws = _bn_dbl_ws.get(key)
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            _bn_dbl_ws[key] = ws
+    L.check(L.load().esr_bn_double_bwd(_ptr(zb), _ptr(wb), g_layout, _ptr(y32), _ptr(t32), n, p, h, w, c, _ptr(scale), _ptr(shift), _ptr(mean),
+                                       _ptr(invstd), _ptr(c1), _ptr(c2), slope, int(has_bn), gscale, int(accumulate), _ptr(dgamma), _ptr(dbeta),
+                                       _ptr(coef), esr_dtype(dtype), _ptr(tb16), _ptr(yb16), _ptr(ws), (ws.numel() * 4 if ws is not None else 0),
+                                       _stream()))
+    return tb16, yb16
 
 
 def linear_fwd(x, weight, bias, lrelu=False, slope=0.2):

@@ -171,7 +171,7 @@ class Discriminator_VGG_128(nn.Module):
         self.last_FC_layers = True
         self.classifier = nn.Sequential(nn.Linear(base_nf * 8 * int(size) ** 2, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
         self.compute_dtype = torch.bfloat16   # training precision of the step (BASELINE config 3); fp16 is a switch for inference use
-        self.supports_double_backward = False  # WGAN-GP differentiates through the input gradient: not built for this engine yet
+        self.supports_double_backward = True   # WGAN-GP's second-order pass: esr_b200.disc.DiscEngine.second_order_param_grads
         self._engines = {}
 
     def engine(self):

@@ -132,14 +132,18 @@ def CreateRangeLoss(legit_range, chroma_mode=False):
 
 class GradientPenaltyLoss(nn.Module):
     """WGAN-GP penalty ((||d crit / d interp||_2 - 1)^2).mean() (loss.py:260-279).  It differentiates THROUGH the critic's input
-    gradient (create_graph=True), so the critic must support a double backward: plain torch modules do; esr_b200's
-    Discriminator_VGG_128 does not yet (its backward is marked once-differentiable and SRRaGANModel refuses `gan_type: wgan-gp`
-    with it at construction - DESIGN 5b-6)."""
+    gradient.  For logits of esr_b200's Discriminator_VGG_128 the penalty and its parameter gradient are computed by the engine
+    (esr_b200.disc._GradPenaltyFn: a tangent forward along dL/dg, then a backward over the primal / tangent pair - BatchNorm's
+    double backward is its own kernel); any other critic (plain torch modules) takes autograd's create_graph route as in the reference."""
 
     def __init__(self, device=torch.device('cpu')):
         super(GradientPenaltyLoss, self).__init__()
 
     def forward(self, interp, interp_crit):
+        from esr_b200.disc import gradient_penalty      # logits of the CUDA critic: tangent-forward + double-backward launches
+        fused = gradient_penalty(interp_crit)
+        if fused is not None:
+            return fused
         grad_interp = torch.autograd.grad(outputs=interp_crit, inputs=interp, grad_outputs=torch.ones_like(interp_crit),
                                           create_graph=True, retain_graph=True, only_inputs=True)[0]
         grad_interp_norm = grad_interp.view(grad_interp.size(0), -1).norm(2, dim=1)

@@ -317,6 +317,24 @@ int esr_structure_tensor_fwd(const float* img, int n, int c, int h, int w, float
                              void* stream);
 int esr_structure_tensor_bwd(const float* img, const float* g, int n, int c, int h, int w, float* grad_img, void* stream);
 
+/* Second-order pass of the gradient penalty (WGAN-GP: GradientPenaltyLoss, models/modules/loss.py:260-279, differentiates THROUGH the
+ * critic's input gradient; models/SRRaGAN_model.py:362-371).  d L_gp / d theta = grad_theta of the critic's directional derivative along
+ * v = dL_gp/dg: a forward-mode tangent through the layers, then an ordinary backward over the (primal, tangent) pair.  Convolutions and
+ * linear layers reuse the launches above; these two entry points are the BatchNorm2d (batch statistics) + LeakyReLU part:
+ *   esr_bn_tangent_fwd : w = LeakyReLU'(z) * gamma r (t - mean(t) - yh mean(yh t)) from the conv's tangent t (fp32 planes) and the saved
+ *                        primal output y32 / statistics; also returns c1 = mean(t), c2 = mean(yh t) per channel.  has_bn = 0: w = mask * t.
+ *   esr_bn_double_bwd  : adjoints of the conv's output (yb16) and of the conv's tangent (tb16) from the adjoints zb / wb of the primal and
+ *                        tangent activations (gradient layouts as esr_bn_lrelu_bwd; either may be NULL = zero), plus dgamma / dbeta.
+ *                        coef: [5*c] fp32 scratch for the per-channel sums. */
+size_t esr_bn_dbl_workspace_bytes(int planes);
+int esr_bn_tangent_fwd(const float* t32, const float* y32, int n, int planes, int h, int w, int c, const float* scale, const float* shift,
+                       const float* save_mean, const float* save_invstd, float slope, int has_bn, float* c1, float* c2, int dtype, void* dst16,
+                       int space_to_depth, float* dst_nchw, float* workspace, size_t workspace_bytes, void* stream);
+int esr_bn_double_bwd(const float* zb, const float* wb, int g_layout, const float* y32, const float* t32, int n, int planes, int h, int w, int c,
+                      const float* scale, const float* shift, const float* save_mean, const float* save_invstd, const float* c1, const float* c2,
+                      float slope, int has_bn, float gscale, int accumulate, float* dgamma, float* dbeta, float* coef, int dtype, void* tb16,
+                      void* yb16, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * The training step outside the networks.
  * ---------------------------------------------------------------------------------------------- */

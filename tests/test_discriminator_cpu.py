@@ -140,9 +140,9 @@ def test_input_gradient_only_when_discriminator_is_frozen(monkeypatch):
         assert net(x.detach()).shape == (4, 1)
 
 
-def test_double_backward_fails_loudly(monkeypatch, tmp_path):
-    """WGAN-GP differentiates through the critic's input gradient: the CUDA engine does not provide that yet, and it must say so
-    (an error, never a silently missing gradient); SRRaGANModel refuses the configuration at construction."""
+def test_generic_double_backward_fails_loudly(monkeypatch):
+    """a generic second differentiation THROUGH the engine's backward is an error, never a silently missing gradient (the supported
+    second-order use, WGAN-GP, goes through GradientPenaltyLoss -> esr_b200.disc.gradient_penalty)"""
     import disc_emul
     import models.modules.architecture as arch
     disc_emul.install(monkeypatch)
@@ -154,8 +154,41 @@ def test_double_backward_fails_loudly(monkeypatch, tmp_path):
     gx = torch.autograd.grad(net(x).sum(), x, create_graph=True)[0]
     with pytest.raises(RuntimeError):
         ((gx.flatten(1).norm(2, dim=1) - 1) ** 2).mean().backward()
-    assert net.supports_double_backward is False
+    assert net.supports_double_backward is True
 
+
+def test_gradient_penalty_host_logic_against_reference(monkeypatch):
+    """GradientPenaltyLoss on the engine (tangent forward + backward over the primal / tangent pair, esr_b200.disc) against the UNMODIFIED
+    reference's double backward (oracle/make_golden_gp.py): penalty value and the gradient of every critic parameter.  The CUDA
+    kernels are replaced by torch stand-ins here (tests/disc_emul.py); the GPU suite runs the same comparison on the kernels."""
+    import disc_emul
+    import models.modules.architecture as arch
+    from models.modules.loss import GradientPenaltyLoss
+    disc_emul.install(monkeypatch)
+    g = golden('wgan_gp_nf8_kf')
+    w = golden('disc_vgg128_nf8_kf')
+    net = arch.Discriminator_VGG_128(in_nc=3, base_nf=8, input_patch_size=128)
+    net.load_state_dict(_sd(w), strict=True)
+    net.compute_dtype = torch.float32
+    net.train()
+    interp = torch.from_numpy(g['interp']).requires_grad_(True)
+    l_gp = GradientPenaltyLoss()(interp, net(interp))
+    assert abs(float(l_gp) - float(g['l_gp'])) < 1e-4 * float(g['l_gp'])
+    (10.0 * l_gp).backward()
+    worst = 0.0
+    for name, p in net.named_parameters():
+        ref = 10.0 * torch.from_numpy(g['g:' + name])
+        scale = float(ref.abs().max())
+        if scale < 1e-9:
+            assert float(p.grad.abs().max()) < 1e-7, name
+            continue
+        worst = max(worst, rel_err(p.grad, ref)[0])
+        assert rel_err(p.grad, ref)[0] < 2e-3, (name, rel_err(p.grad, ref))
+    print('gradient penalty, host logic vs reference: worst parameter gradient error %.2e' % worst)
+
+
+def test_wgan_gp_model_constructs(tmp_path):
+    """the reference's explorable-SR training configuration (gan_type wgan-gp, options/train/train_explorable_SR.json:87) constructs"""
     class ND(dict):
         def __missing__(self, k):
             return None
@@ -166,10 +199,10 @@ def test_double_backward_fails_loudly(monkeypatch, tmp_path):
              path=ND(models=str(tmp_path / 'models'), pretrained_model_G=None, log=str(tmp_path)),
              network_G=ND(which_model_G='RRDB_net', CEM_arch=1, latent_input=None, latent_input_domain=None, latent_channels=None, norm_type=None,
                           mode='CNA', nf=8, nb=1, in_nc=3, out_nc=3, gc=32, scale=4),
-             network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3))
+             network_D=ND(which_model_D='discriminator_vgg_128', norm_type='batch', act_type='leakyrelu', mode='CNA', nf=8, in_nc=3, relativistic=0))
     if not torch.cuda.is_available():
-        with pytest.raises(NotImplementedError):
-            create_model(opt)
+        model = create_model(opt)
+        assert model.cri_gp is not None and model.l_gp_w == 10
 
 
 def test_engine_follows_weight_updates_in_place(monkeypatch):
