@@ -406,25 +406,31 @@ __global__ void sep_adjoint_1d_kernel(const float* __restrict__ gout, int imgs, 
     const float* gp = gout + (((size_t)img * outer + ou) * o_cnt) * inner + in_i;
     const int o_hi = o_lo + o_cnt;
     float acc = 0.f;
-    for (int t = 0; t < len; ++t) {
-      const float kt = __ldg(k + t);
-      const int num = m - t - c;  // A*o == num for the un-clamped hit
-      float ssum = 0.f;
-      if (num >= 0 && num % A == 0) {
-        const int o = num / A;
-        if (o >= o_lo && o < o_hi) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+    // un-clamped hits: A*o + t + c == m.  Only every A-th tap can hit (t == (m - c) mod A): walk those, o falls by one per step -
+    // no division inside the loop (the strided Down^T pass touches ceil(len / A) taps per output instead of len).
+    {
+      int t = (m - c) % A;
+      if (t < 0) t += A;
+      int o = (m - t - c) / A;            // exact
+      for (; t < len && o >= o_lo; t += A, --o)
+        if (o < o_hi) acc = fmaf(__ldg(k + t), __ldg(gp + (size_t)(o - o_lo) * inner), acc);
+    }
+    if (m == 0 || m == n_in - 1) {        // border positions also collect everything the replicate padding clamped onto them
+      for (int t = 0; t < len; ++t) {
+        const float kt = __ldg(k + t);
+        float ssum = 0.f;
+        if (m == 0) {            // everything that fell off the low end was clamped onto index 0
+          for (int o = o_lo; o < o_hi && A * o + t + c < 0; ++o) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+        }
+        if (m == n_in - 1) {     // ... and off the high end onto index n_in-1
+          int o0 = (n_in - 1 - t - c) / A + 1;
+          if (o0 < o_lo) o0 = o_lo;
+          while (o0 > o_lo && A * (o0 - 1) + t + c > n_in - 1) --o0;
+          for (int o = o0; o < o_hi; ++o)
+            if (A * o + t + c > n_in - 1) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
+        }
+        acc = fmaf(kt, ssum, acc);
       }
-      if (m == 0) {            // everything that fell off the low end was clamped onto index 0
-        for (int o = o_lo; o < o_hi && A * o + t + c < 0; ++o) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
-      }
-      if (m == n_in - 1) {     // ... and off the high end onto index n_in-1
-        int o0 = (n_in - 1 - t - c) / A + 1;
-        if (o0 < o_lo) o0 = o_lo;
-        while (o0 > o_lo && A * (o0 - 1) + t + c > n_in - 1) --o0;
-        for (int o = o0; o < o_hi; ++o)
-          if (A * o + t + c > n_in - 1) ssum += __ldg(gp + (size_t)(o - o_lo) * inner);
-      }
-      acc = fmaf(kt, ssum, acc);
     }
     if (sub_from) {  // x-axis pass only (inner == 1): dst = crop_adjoint(sub_from) - acc
       const int y = ou, x = mi;

@@ -20,32 +20,50 @@ constexpr int kUpTX = 128, kUpTY = 32;     // HR output tile of the up kernel
 constexpr int kCemMaxTaps = 64;
 
 // e[i][j] = sub_from[i][j] - sum_{a,b} kv[a] kh[b] G[clamp(s i + phase + a - r)][clamp(s j + phase + b - r)]     (sub_from optional)
+// S and LEN are compile-time (bicubic: (2,9) (3,11) (4,17) (8,33)): the taps live in registers and both passes are register-blocked -
+// a thread computes 4 horizontally adjacent / 2 vertically adjacent outputs from one sliding window, 3-5x fewer shared-memory loads
+// than one output per thread (the un-blocked kernel was LSU-bound at 1.2 TB/s).
+template <int S, int LEN>
 __global__ void __launch_bounds__(256)
-cem_down_fast_kernel(const float* __restrict__ g, int hh, int wh, int s, int phase, const float* __restrict__ kv, const float* __restrict__ kh,
-                     int len, const float* __restrict__ sub_from, float* __restrict__ out) {
+cem_down_fast_kernel(const float* __restrict__ g, int hh, int wh, int phase, const float* __restrict__ kv, const float* __restrict__ kh,
+                     const float* __restrict__ sub_from, float* __restrict__ out) {
   extern __shared__ float sm[];
-  __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
-  const int hl = hh / s, wl = wh / s;
-  const int rows = (kDnTI - 1) * s + len, cols = (kDnTJ - 1) * s + len;
-  const int pitch = ((cols + 3 + 3) & ~3) | 1;      // room for the alignment shift; odd: the strided row walk is bank-conflict free
+  constexpr int rows = (kDnTI - 1) * S + LEN, cols = (kDnTJ - 1) * S + LEN;
+  constexpr int pitch = ((cols + 3 + 3) & ~3) | 1;  // room for the alignment shift; odd: the strided row walk is bank-conflict free
+  constexpr int hp = kDnTJ + 1;
+  const int hl = hh / S, wl = wh / S;
   float* tile = sm;                                 // [rows][pitch]
-  float* hbuf = sm + rows * pitch;                  // [rows][kDnTJ + 1]
+  float* hbuf = sm + rows * pitch;                  // [rows][hp]
   const int nc = blockIdx.z;
   const int i0 = blockIdx.y * kDnTI, j0 = blockIdx.x * kDnTJ;
-  const int r = len / 2;
+  constexpr int r = LEN / 2;
   const float* gp = g + (size_t)nc * hh * wh;
-  const int ybase = s * i0 + phase - r, xbase = s * j0 + phase - r;
-  if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
-  const int xa = xbase & ~3;                        // 16-byte aligned start of the window (xbase may be negative: two's complement floor)
-  const int shift = xbase - xa;                     // 0..3: the window starts `shift` floats into the first float4
+  const int ybase = S * i0 + phase - r, xbase = S * j0 + phase - r;
+  const int xa = xbase & ~3;                        // 16-byte aligned start of the window (two's complement floor for negative xbase)
+  const int shift = xbase - xa;                     // 0..3
   const int nvec = (shift + cols + 3) >> 2;
   const bool interior = ybase >= 0 && ybase + rows <= hh && xa >= 0 && xa + 4 * nvec <= wh && (wh & 3) == 0 && (((uintptr_t)gp) & 15) == 0;
   if (interior) {
-    for (int e = threadIdx.x; e < rows * nvec; e += 256) {
-      const int rr = e / nvec, v = e - rr * nvec;
-      const float4 q = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(ybase + rr) * wh + xa) + v);
-      float* d = tile + rr * pitch + 4 * v;         // stored un-shifted: the horizontal pass adds `shift`
-      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+    const int total = rows * nvec;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 256 * 4) {      // four 16-byte loads in flight per thread
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        if (e < total) {
+          const int rr = e / nvec, v = e - rr * nvec;
+          q[k] = __ldg(reinterpret_cast<const float4*>(gp + (size_t)(ybase + rr) * wh + xa) + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        if (e < total) {
+          const int rr = e / nvec, v = e - rr * nvec;
+          float* d = tile + rr * pitch + 4 * v;
+          d[0] = q[k].x; d[1] = q[k].y; d[2] = q[k].z; d[3] = q[k].w;
+        }
+      }
     }
   } else {
     for (int e = threadIdx.x; e < rows * cols; e += 256) {
@@ -53,63 +71,105 @@ cem_down_fast_kernel(const float* __restrict__ g, int hh, int wh, int s, int pha
       tile[rr * pitch + shift + cc] = __ldg(gp + (size_t)clampi(ybase + rr, 0, hh - 1) * wh + clampi(xbase + cc, 0, wh - 1));
     }
   }
+  float th[LEN], tv[LEN];
+#pragma unroll
+  for (int b = 0; b < LEN; ++b) { th[b] = __ldg(kh + b); tv[b] = __ldg(kv + b); }
   __syncthreads();
-  // horizontal pass: consecutive threads walk down the rows (pitch is odd)
-  for (int e = threadIdx.x; e < rows * kDnTJ; e += 256) {
-    const int jj = e / rows, rr = e - jj * rows;
-    const float* tp = tile + rr * pitch + shift + jj * s;
-    float a = 0.f;
-    for (int b = 0; b < len; ++b) a = fmaf(th[b], tp[b], a);
-    hbuf[rr * (kDnTJ + 1) + jj] = a;
+  // horizontal pass: a thread produces 4 adjacent outputs of one row from a window of 3 S + LEN inputs
+  constexpr int HB = 4, quads = kDnTJ / HB;
+  for (int e = threadIdx.x; e < rows * quads; e += 256) {
+    const int qd = e / rows, rr = e - qd * rows;
+    const float* tp = tile + rr * pitch + shift + qd * HB * S;
+    float win[(HB - 1) * S + LEN];
+#pragma unroll
+    for (int k = 0; k < (HB - 1) * S + LEN; ++k) win[k] = tp[k];
+    float acc[HB];
+#pragma unroll
+    for (int o = 0; o < HB; ++o) {
+      acc[o] = 0.f;
+#pragma unroll
+      for (int b = 0; b < LEN; ++b) acc[o] = fmaf(th[b], win[o * S + b], acc[o]);
+      hbuf[rr * hp + qd * HB + o] = acc[o];
+    }
   }
   __syncthreads();
+  // vertical pass: a thread produces 2 vertically adjacent outputs of one column
+  constexpr int VB = 2;
   const int tj = threadIdx.x & (kDnTJ - 1);
-  for (int ti = threadIdx.x / kDnTJ; ti < kDnTI; ti += 256 / kDnTJ) {
-    float acc = 0.f;
-    const float* hp = hbuf + (ti * s) * (kDnTJ + 1) + tj;
-    for (int a = 0; a < len; ++a) acc = fmaf(tv[a], hp[a * (kDnTJ + 1)], acc);
-    const int i = i0 + ti, j = j0 + tj;
-    if (i < hl && j < wl) {
-      const size_t o = (size_t)nc * hl * wl + (size_t)i * wl + j;
-      out[o] = sub_from ? (__ldg(sub_from + o) - acc) : acc;
+  for (int tp2 = threadIdx.x / kDnTJ; tp2 < kDnTI / VB; tp2 += 256 / kDnTJ) {
+    const int ti = tp2 * VB;
+    const float* hq = hbuf + (ti * S) * hp + tj;
+    float win[(VB - 1) * S + LEN];
+#pragma unroll
+    for (int k = 0; k < (VB - 1) * S + LEN; ++k) win[k] = hq[k * hp];
+#pragma unroll
+    for (int o = 0; o < VB; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < LEN; ++a) acc = fmaf(tv[a], win[o * S + a], acc);
+      const int i = i0 + ti + o, j = j0 + tj;
+      if (i < hl && j < wl) {
+        const size_t oo = (size_t)nc * hl * wl + (size_t)i * wl + j;
+        out[oo] = sub_from ? (__ldg(sub_from + oo) - acc) : acc;
+      }
     }
   }
 }
 
-// f = replicate-padded correlation of e with kv (x) kh on the LR grid
+// f = replicate-padded correlation of e with kv (x) kh on the LR grid; LEN compile-time, 8 outputs per thread in both passes
+template <int LEN>
 __global__ void __launch_bounds__(256)
-cem_inv_fast_kernel(const float* __restrict__ e_in, int hl, int wl, const float* __restrict__ kv, const float* __restrict__ kh, int len,
+cem_inv_fast_kernel(const float* __restrict__ e_in, int hl, int wl, const float* __restrict__ kv, const float* __restrict__ kh,
                     float* __restrict__ out) {
   extern __shared__ float sm[];
-  __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
-  const int rows = kInvTI + len - 1, cols = kInvTJ + len - 1;
-  const int pitch = cols | 1;
+  constexpr int rows = kInvTI + LEN - 1, cols = kInvTJ + LEN - 1;
+  constexpr int pitch = cols | 1;
+  constexpr int hp = kInvTJ + 1;
   float* tile = sm;                        // [rows][pitch]
-  float* hbuf = sm + rows * pitch;         // [rows][kInvTJ]
+  float* hbuf = sm + rows * pitch;         // [rows][hp]
   const int nc = blockIdx.z;
   const int i0 = blockIdx.y * kInvTI, j0 = blockIdx.x * kInvTJ;
-  const int r = len / 2;
+  constexpr int r = LEN / 2;
   const float* ep = e_in + (size_t)nc * hl * wl;
-  if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
   for (int e = threadIdx.x; e < rows * cols; e += 256) {
     const int rr = e / cols, cc = e - rr * cols;
     tile[rr * pitch + cc] = __ldg(ep + (size_t)clampi(i0 - r + rr, 0, hl - 1) * wl + clampi(j0 - r + cc, 0, wl - 1));
   }
+  float th[LEN], tv[LEN];
+#pragma unroll
+  for (int b = 0; b < LEN; ++b) { th[b] = __ldg(kh + b); tv[b] = __ldg(kv + b); }
   __syncthreads();
-  for (int e = threadIdx.x; e < rows * kInvTJ; e += 256) {
-    const int rr = e / kInvTJ, jj = e - rr * kInvTJ;
-    const float* tp = tile + rr * pitch + jj;
-    float a = 0.f;
-    for (int b = 0; b < len; ++b) a = fmaf(th[b], tp[b], a);
-    hbuf[e] = a;
+  constexpr int B8 = 8;
+  for (int e = threadIdx.x; e < rows * (kInvTJ / B8); e += 256) {       // consecutive threads walk down the rows (odd pitch)
+    const int oc = e / rows, rr = e - oc * rows;
+    const float* tp = tile + rr * pitch + oc * B8;
+    float win[B8 + LEN - 1];
+#pragma unroll
+    for (int k = 0; k < B8 + LEN - 1; ++k) win[k] = tp[k];
+#pragma unroll
+    for (int o = 0; o < B8; ++o) {
+      float a = 0.f;
+#pragma unroll
+      for (int b = 0; b < LEN; ++b) a = fmaf(th[b], win[o + b], a);
+      hbuf[rr * hp + oc * B8 + o] = a;
+    }
   }
   __syncthreads();
   const int tj = threadIdx.x & (kInvTJ - 1);
-  for (int ti = threadIdx.x / kInvTJ; ti < kInvTI; ti += 256 / kInvTJ) {
-    float acc = 0.f;
-    for (int a = 0; a < len; ++a) acc = fmaf(tv[a], hbuf[(ti + a) * kInvTJ + tj], acc);
-    const int i = i0 + ti, j = j0 + tj;
-    if (i < hl && j < wl) out[(size_t)nc * hl * wl + (size_t)i * wl + j] = acc;
+  for (int tg = threadIdx.x / kInvTJ; tg < kInvTI / B8; tg += 256 / kInvTJ) {
+    const int ti = tg * B8;
+    const float* hq = hbuf + ti * hp + tj;
+    float win[B8 + LEN - 1];
+#pragma unroll
+    for (int k = 0; k < B8 + LEN - 1; ++k) win[k] = hq[k * hp];
+#pragma unroll
+    for (int o = 0; o < B8; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < LEN; ++a) acc = fmaf(tv[a], win[o + a], acc);
+      const int i = i0 + ti + o, j = j0 + tj;
+      if (i < hl && j < wl) out[(size_t)nc * hl * wl + (size_t)i * wl + j] = acc;
+    }
   }
 }
 
@@ -135,6 +195,18 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
   const int ni = max(ihi - ilo + 1, 0), nj = max(jhi - jlo + 1, 0);
   const bool interior_y = Y0 - r >= 0 && Y0 + kUpTY - 1 + r <= hh - 1;
   const bool interior_x = X0 - r >= 0 && X0 + kUpTX - 1 + r <= wh - 1;
+  // the thread's four G vectors go in flight first: their latency hides behind the filter passes
+  const int xg = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int X = X0 + 4 * xg;
+  const bool vec = (crop & 3) == 0 && (wo & 3) == 0 && (wh & 3) == 0 && X + 3 < wh && (X - crop) + 3 < wo &&
+                   ((((uintptr_t)out) | (g ? (uintptr_t)g : 0)) & 15) == 0;
+  float4 gq[kUpTY / 8];
+#pragma unroll
+  for (int k = 0; k < kUpTY / 8; ++k) {
+    const int Y = Y0 + ty + 8 * k;
+    gq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && g && Y < hh && Y - crop < ho) gq[k] = __ldg(reinterpret_cast<const float4*>(g + (size_t)nc * hh * wh + (size_t)Y * wh + X));
+  }
   const float* fp = f + (size_t)nc * hl * wl;
   for (int e = threadIdx.x; e < ni * nj; e += 256) {
     const int ii = e / nj, jj = e - ii * nj;
@@ -171,10 +243,6 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
   }
   __syncthreads();
   // vertical pass + G + store: a thread owns 4 consecutive X of rows ty, ty+8, ty+16, ty+24
-  const int xg = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int X = X0 + 4 * xg;
-  const bool vec = (crop & 3) == 0 && (wo & 3) == 0 && (wh & 3) == 0 && X + 3 < wh && (X - crop) + 3 < wo &&
-                   ((((uintptr_t)out) | (g ? (uintptr_t)g : 0)) & 15) == 0;
 #pragma unroll
   for (int k = 0; k < kUpTY / 8; ++k) {
     const int Y = Y0 + ty + 8 * k;
@@ -205,11 +273,7 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
     const float* gp = g ? g + (size_t)nc * hh * wh + (size_t)Y * wh + X : nullptr;
     float* op = out + (size_t)nc * ho * wo + (size_t)yo * wo + (X - crop);
     if (vec) {
-      if (gp) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(gp));
-        acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
-      }
-      *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(op) = make_float4(acc[0] + gq[k].x, acc[1] + gq[k].y, acc[2] + gq[k].z, acc[3] + gq[k].w);
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {

@@ -329,6 +329,8 @@ __device__ __forceinline__ void conv_epilogue_px(const ConvParams& p, uint32_t t
 //            LR_conv + ShortcutBlock add)
 //   kMode 2: v = alpha*(acc + bias) + beta1*res1(16-bit) [+ beta2*res2(fp32)] -> out16 [+ out32]   (conv5 of a dense block)
 //   kMode 4: out16 = acc * (act > 0 ? 1 : mask_slope)   no bias                (gradient slices of the dense-block backward)
+//   kMode 5: v = acc + beta3*res3(fp32) [+ beta1*res1(fp32)] -> out32 and out16, no bias   (closing launch of the dense-block backward:
+//            the block's input gradient plus what arrives at its output; 43 % of the backward's FLOPs)
 template <int NBN, int kMode>
 __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t trow, int img, int y, int x, bool valid, int nblk) {
   const size_t hw = (size_t)p.h * p.w;
@@ -342,10 +344,10 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
     const int gu = chu >> 3;
     uint4 q1[4];
     float4 f2[4][2], bb[4][2];
-    const bool has2 = (kMode == 2 && p.res2 != nullptr) || (kMode == 1 && p.res1 != nullptr);
+    const bool has2 = (kMode == 2 && p.res2 != nullptr) || (kMode == 1 && p.res1 != nullptr) || kMode == 5;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      if (kMode == 4) {
+      if (kMode == 4 || kMode == 5) {
         bb[g][0] = make_float4(0.f, 0.f, 0.f, 0.f);
         bb[g][1] = bb[g][0];
       } else {
@@ -364,6 +366,14 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
       for (int g = 0; g < 4; ++g) {
         f2[g][0] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8));
         f2[g][1] = __ldg(reinterpret_cast<const float4*>(r2 + (size_t)g * hw * 8) + 1);
+      }
+    }
+    if (kMode == 5 && valid) {   // what arrives at the block's output (fp32 trunk gradient) rides in the f2 registers
+      const float* r3 = p.res3 + (((size_t)img * p.res3_pt + p.res3_po + gu) * hw + pix) * 8;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        f2[g][0] = __ldg(reinterpret_cast<const float4*>(r3 + (size_t)g * hw * 8));
+        f2[g][1] = __ldg(reinterpret_cast<const float4*>(r3 + (size_t)g * hw * 8) + 1);
       }
     }
     if (kMode == 2 && valid) {
@@ -395,6 +405,21 @@ __device__ __forceinline__ void conv_epilogue_fast(const ConvParams& p, uint32_t
           unpack8(q1[g], p.dtype, a);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = a[k] > 0.f ? v[k] : v[k] * p.mask_slope;
+        } else if (kMode == 5) {
+          v[0] = fmaf(p.beta3, f2[g][0].x, v[0]); v[1] = fmaf(p.beta3, f2[g][0].y, v[1]);
+          v[2] = fmaf(p.beta3, f2[g][0].z, v[2]); v[3] = fmaf(p.beta3, f2[g][0].w, v[3]);
+          v[4] = fmaf(p.beta3, f2[g][1].x, v[4]); v[5] = fmaf(p.beta3, f2[g][1].y, v[5]);
+          v[6] = fmaf(p.beta3, f2[g][1].z, v[6]); v[7] = fmaf(p.beta3, f2[g][1].w, v[7]);
+          if (p.res1) {     // the RRDB skip connection's gradient (first block of an RRDB), fp32
+            const float4* r1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res1) +
+                                                               (((size_t)img * p.res1_pt + p.res1_po + gu + g) * hw + pix) * 8);
+            const float4 a0 = __ldg(r1), a1 = __ldg(r1 + 1);
+            v[0] = fmaf(p.beta1, a0.x, v[0]); v[1] = fmaf(p.beta1, a0.y, v[1]); v[2] = fmaf(p.beta1, a0.z, v[2]); v[3] = fmaf(p.beta1, a0.w, v[3]);
+            v[4] = fmaf(p.beta1, a1.x, v[4]); v[5] = fmaf(p.beta1, a1.y, v[5]); v[6] = fmaf(p.beta1, a1.z, v[6]); v[7] = fmaf(p.beta1, a1.w, v[7]);
+          }
+          float4* op = reinterpret_cast<float4*>(p.out32 + (((size_t)img * p.out32_pt + p.out32_po + gu + g) * hw + pix) * 8);
+          op[0] = make_float4(v[0], v[1], v[2], v[3]);
+          op[1] = make_float4(v[4], v[5], v[6], v[7]);
         } else if (kMode == 1) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;

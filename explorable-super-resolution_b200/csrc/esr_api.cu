@@ -141,6 +141,8 @@ RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
     case 32 * 8 + 1: return esr::conv3x3_rows_kernel<32, false, 1>;
     case 32 * 8 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
     case 32 * 8 + 4: return esr::conv3x3_rows_kernel<32, false, 4>;
+    case 32 * 8 + 5: return esr::conv3x3_rows_kernel<32, false, 5>;
+    case 64 * 8 + 5: return esr::conv3x3_rows_kernel<64, false, 5>;
     case 64 * 8 + 0: return esr::conv3x3_rows_kernel<64, false, 0>;
     case 64 * 8 + 1: return esr::conv3x3_rows_kernel<64, false, 1>;
     case 64 * 8 + 2: return esr::conv3x3_rows_kernel<64, false, 2>;
@@ -380,7 +382,11 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
   const bool mask_only_shape = bwd && a->rows_nbn == 32 && a->cout % 32 == 0 && a->mask16 && a->out16 && !a->lead_planes && !a->res1 && !a->res2 &&
                                !a->res3 && !a->out32 && !a->out_nchw && !a->out16_up2 && !a->out16_pixel_shuffle && a->tail_first_plane == 0 &&
                                a->alpha == 1.0f && !a->lrelu;
-  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 && (a->rows_mode > 0 || rows_shape_ok(a->w, bwd && !mask_only_shape))) {
+  const bool closing_shape = bwd && a->rows_nbn >= 32 && a->cout % 32 == 0 && !a->mask16 && !a->lead_planes && a->res3 && !a->res2 && a->out32 && a->out16 &&
+                             !a->out_nchw && !a->out16_up2 && !a->out16_pixel_shuffle && a->tail_first_plane == 0 && a->alpha == 1.0f && !a->lrelu &&
+                             (!a->res1 || !a->res1_is16);
+  if (a->wpacked_rows && a->rows_nbn > 0 && a->rows_mode >= 0 &&
+      (a->rows_mode > 0 || rows_shape_ok(a->w, bwd && !mask_only_shape && !closing_shape))) {
     // ---- row-streaming kernel (conv3x3_rows.cuh)
     const int nbn = a->rows_nbn;
     if (nbn != 16 && nbn != 32 && nbn != 64) return fail(ESR_ERR_INVALID, "conv3x3: rows_nbn must be 16, 32 or 64");
@@ -394,7 +400,10 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     // gradient slice of the dense-block backward: mask * acc -> 16-bit planes, nothing else
     const bool mask_only = bwd && nbn == 32 && a->cout % 32 == 0 && p.mask16 && p.out16 && !p.lead_planes && !p.res1 && !p.res2 && !p.res3 &&
                            !p.out32 && !p.out_nchw && !p.out16_up2 && !p.out16_ps && p.tail_first == 0 && p.alpha == 1.0f && !p.lrelu;
-    RowsKernelFn rk = mask_only ? select_rows_kernel(32, false, 4) : select_rows_kernel(nbn, bwd, epi);
+    // closing launch of the dense-block backward: acc + beta3*res3 (+ beta1*res1 fp32) -> fp32 planes and 16-bit planes
+    const bool closing = bwd && nbn >= 32 && a->cout % 32 == 0 && !p.mask16 && !p.lead_planes && p.res3 && !p.res2 && p.out32 && p.out16 && !p.out_nchw &&
+                         !p.out16_up2 && !p.out16_ps && p.tail_first == 0 && p.alpha == 1.0f && !p.lrelu && (!p.res1 || !p.res1_is16);
+    RowsKernelFn rk = mask_only ? select_rows_kernel(32, false, 4) : (closing ? select_rows_kernel(nbn, false, 5) : select_rows_kernel(nbn, bwd, epi));
     if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
     p.nb_n = nbn;
     p.n_blocks = (a->cout + nbn - 1) / nbn;
@@ -892,14 +901,20 @@ int esr_cem_down(const float* g, int n, int c, int hh, int wh, int s, int phase,
   if (phase < 0 || phase >= s || kd_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_down: bad phase/filter");
   const int hl = hh / s, wl = wh / s;
   if (cem_fast(rank, kd_len)) {
-    const int frows = (esr::kDnTI - 1) * s + kd_len, fcols = (esr::kDnTJ - 1) * s + kd_len;
-    const int pitch = ((fcols + 3 + 3) & ~3) | 1;
-    const size_t fsmem = sizeof(float) * ((size_t)frows * pitch + (size_t)frows * (esr::kDnTJ + 1));
-    if (fsmem <= 200 * 1024) {
-      int rc = set_smem_attr((const void*)esr::cem_down_fast_kernel, fsmem);
+    typedef void (*DownFn)(const float*, int, int, int, const float*, const float*, const float*, float*);
+    DownFn fn = nullptr;
+    if (s == 2 && kd_len == 9) fn = esr::cem_down_fast_kernel<2, 9>;
+    else if (s == 3 && kd_len == 11) fn = esr::cem_down_fast_kernel<3, 11>;
+    else if (s == 4 && kd_len == 17) fn = esr::cem_down_fast_kernel<4, 17>;
+    else if (s == 8 && kd_len == 33) fn = esr::cem_down_fast_kernel<8, 33>;
+    if (fn) {
+      const int frows = (esr::kDnTI - 1) * s + kd_len, fcols = (esr::kDnTJ - 1) * s + kd_len;
+      const int pitch = ((fcols + 3 + 3) & ~3) | 1;
+      const size_t fsmem = sizeof(float) * ((size_t)frows * pitch + (size_t)frows * (esr::kDnTJ + 1));
+      int rc = set_smem_attr((const void*)fn, fsmem);
       if (rc) return rc;
       dim3 grid((wl + esr::kDnTJ - 1) / esr::kDnTJ, (hl + esr::kDnTI - 1) / esr::kDnTI, n * c);
-      esr::cem_down_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(g, hh, wh, s, phase, kd_v, kd_h, kd_len, sub_from, out_lr);
+      fn<<<grid, 256, fsmem, (cudaStream_t)stream>>>(g, hh, wh, phase, kd_v, kd_h, sub_from, out_lr);
       g_launches++;
       CUDA_TRY(cudaGetLastError());
       return ESR_OK;
@@ -922,13 +937,14 @@ int esr_cem_inv(const float* e, int n, int c, int hl, int wl, const float* ki_v,
                 float* out_lr, void* stream) {
   if (!e || !ki_v || !ki_h || !out_lr) return fail(ESR_ERR_INVALID, "cem_inv: null pointer");
   if (ki_len < 1 || rank < 1) return fail(ESR_ERR_INVALID, "cem_inv: bad filter");
-  if (cem_fast(rank, ki_len)) {
-    const int frows = esr::kInvTI + ki_len - 1, fcols = esr::kInvTJ + ki_len - 1;
-    const size_t fsmem = sizeof(float) * ((size_t)frows * (fcols | 1) + (size_t)frows * esr::kInvTJ);
-    int rc = set_smem_attr((const void*)esr::cem_inv_fast_kernel, fsmem);
+  if (cem_fast(rank, ki_len) && ki_len == 27) {
+    constexpr int LEN = 27;
+    const int frows = esr::kInvTI + LEN - 1, fcols = esr::kInvTJ + LEN - 1;
+    const size_t fsmem = sizeof(float) * ((size_t)frows * (fcols | 1) + (size_t)frows * (esr::kInvTJ + 1));
+    int rc = set_smem_attr((const void*)esr::cem_inv_fast_kernel<LEN>, fsmem);
     if (rc) return rc;
     dim3 grid((wl + esr::kInvTJ - 1) / esr::kInvTJ, (hl + esr::kInvTI - 1) / esr::kInvTI, n * c);
-    esr::cem_inv_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(e, hl, wl, ki_v, ki_h, ki_len, out_lr);
+    esr::cem_inv_fast_kernel<LEN><<<grid, 256, fsmem, (cudaStream_t)stream>>>(e, hl, wl, ki_v, ki_h, out_lr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ESR_OK;

@@ -122,10 +122,10 @@ def test_engine_writes_gradients_into_the_flat_buffer():
         (m(x) - hr).abs().mean().backward()
     for p, q in zip(pa, pb):      # (two launches of the bf16 row kernel differ in summation order: equal to operand precision, not bit for bit)
         assert p.grad is grad_view(p)
-        assert torch.allclose(p.grad, q.grad, rtol=0, atol=2e-2 * float(q.grad.abs().max()))
+        assert float((p.grad - q.grad).norm()) < 3e-2 * float(q.grad.norm())
     flat = opt.flat_grad().clone()
     (ma(x) - hr).abs().mean().backward()          # gradient accumulation: in place, into the same views
-    assert torch.allclose(opt.flat_grad(), 2 * flat, rtol=0, atol=4e-2 * float(flat.abs().max()))      # (bf16 launches: summation order varies)
+    assert float((opt.flat_grad() - 2 * flat).norm()) < 3e-2 * float((2 * flat).norm())      # (bf16 launches: summation order varies)
     assert opt.grads_in_place()
     w0 = pa[0].detach().clone()
     opt.step()

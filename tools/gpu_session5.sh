@@ -1,15 +1,9 @@
 #!/bin/bash
-OUT=gpurun_out/s5
+OUT=gpurun_out/s6
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -s -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
 echo "pytest rc=$?" > $OUT/summary.txt
 tail -n 15 $OUT/pytest_gpu.log >> $OUT/summary.txt
-for mr in 1 4 6 10 16; do
-  echo "== ESR_WGRAD_MIN_ROWS=$mr" >> $OUT/summary.txt
-  ESR_WGRAD_MIN_ROWS=$mr timeout 300 python tools/bench_configs.py C3 2>/dev/null | tail -n 1 | cut -c1-260 >> $OUT/summary.txt
-done
 timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err
 echo "bench rc=$?" >> $OUT/summary.txt
-timeout 300 ncu --kernel-name regex:cem_ --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $OUT/ncu_cem.csv python tools/stress_legs.py fwd --iters 2 --batch 16 --lr 256 > $OUT/ncu_cem.log 2>&1
-echo "ncu rc=$?" >> $OUT/summary.txt
 cat $OUT/summary.txt
