@@ -7,9 +7,10 @@ underneath `model.test(prevent_grads_calc=False)` / `Z_loss.backward()`: a singl
 tcgen05 forward launches and, in backward, the dgrad launches + the exact CEM adjoint (esr_b200.autograd) instead of
 ~1800 autograd nodes over cuDNN calls.
 
-Objectives built: 'l1' (optionally masked), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' / 'STD_decrease' (global),
-'random_l1' (+ '_limited').  The patch-based ('local', 'Mag', 'periodicity'), histogram/dictionary, scribble, VGG,
-Adversarial, desired_SVD and digit objectives are SURVEY §8(f)-1 and raise NotImplementedError."""
+Objectives built: 'l1' (optionally masked), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' / 'STD_decrease' (global, or 'local_' over
+7x7 patches through ReturnPatchExtractionMat), 'Mag' (local magnitude), 'hist' / 'dict' (+ 'patch', 'noDC', 'no_localSTD', 'localSTD':
+SoftHistogramLoss on the esr_soft_hist kernels), 'VGG' (perceptual distance through the VGG19 engine), 'Adversarial' (the critic
+engine), 'random_l1' (+ '_limited').  Periodicity, scribble, desired_SVD and digit raise NotImplementedError."""
 import time
 
 import numpy as np
@@ -74,17 +75,180 @@ def TV_Loss(image):
     return (image[:, :, :, :-1] - image[:, :, :, 1:]).abs().mean(dim=(1, 2, 3)) + (image[:, :, :-1, :] - image[:, :, 1:, :]).abs().mean(dim=(1, 2, 3))
 
 
-_UNBUILT = ['local', 'Mag', 'periodicity', 'hist', 'dict', 'scribble', 'VGG', 'Adversarial', 'desired_SVD', 'digit']
+_UNBUILT = ['periodicity', 'scribble', 'desired_SVD', 'digit']
+
+
+class _SoftHistFn(torch.autograd.Function):
+    """esr_soft_hist_fwd / _bwd: x [D, P] fp64 -> hist [B] (mean_p E[p][b]) or, dictionary mode, [P] (-log mean_b E[p][b])"""
+
+    @staticmethod
+    def forward(ctx, x, bins, vmax, eps, temperature, dictionary):
+        import ctypes as C
+        from esr_b200 import lib as L
+        x, bins = x.double().contiguous(), bins.double().contiguous()
+        if not x.is_cuda:
+            raise L.EsrError('esr_b200: SoftHistogramLoss needs CUDA tensors (there is no CPU fallback)')
+        D, P = x.shape
+        B = bins.shape[1]
+        out = torch.empty(P if dictionary else B, dtype=torch.float64, device=x.device)
+        sum_e = torch.empty(P, dtype=torch.float64, device=x.device) if dictionary else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        L.check(L.load().esr_soft_hist_fwd(ptr(x), D, P, ptr(bins), B, float(vmax), float(eps), float(temperature), int(dictionary), ptr(out), ptr(sum_e),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx.save_for_backward(x, bins, sum_e if dictionary else out)
+        ctx.cfg = (float(vmax), float(eps), float(temperature), bool(dictionary))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from esr_b200 import lib as L
+        x, bins, aux = ctx.saved_tensors
+        vmax, eps, temperature, dictionary = ctx.cfg
+        D, P = x.shape
+        g = g.double().contiguous()
+        dx = torch.empty_like(x)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+        L.check(L.load().esr_soft_hist_bwd(ptr(x), D, P, ptr(bins), bins.shape[1], vmax, eps, temperature, ptr(None if dictionary else g),
+                                           ptr(g if dictionary else None), ptr(aux if dictionary else None), ptr(dx),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return dx, None, None, None, None, None
 
 
 class SoftHistogramLoss(torch.nn.Module):
-    """Kernel-density histogram / patch-dictionary objective of the GUI's imprinting tools (Z_optimization.py:24-230).  Not built: it is
-    an O(pixels x bins) double-precision distance computation that belongs in its own CUDA kernel; the name exists so
-    that `from Z_optimization import SoftHistogramLoss` resolves, and constructing it fails loudly (there is no PyTorch fallback)."""
+    """Kernel-density histogram / patch-dictionary objective of the GUI's imprinting tools (Z_optimization.py:24-230): the grey-level
+    (or patch) distribution of the edited region is pulled towards that of a desired image region - KL divergence between soft
+    histograms (`hist`), or mean distance to the nearest desired patch (`dict`).  Same constructor and semantics as the reference for
+    grey-scale inputs (the only mode Z_optimizer uses, :536-539); the O(dims x pixels x bins) distance tensor the reference
+    materialises in double precision is one CUDA kernel here (esr_soft_hist_fwd / _bwd, fp64 as well).  The automatic temperature
+    search differentiates through the generator's backward (a double backward) and is not built."""
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, bins, min, max, desired_hist_image_mask=None, desired_hist_image=None, gray_scale=True, input_im_HR_mask=None, patch_size=1,
+                 automatic_temperature=False, image_Z=None, temperature=0.05, dictionary_not_histogram=False, no_patch_DC=False, no_patch_STD=False):
         super(SoftHistogramLoss, self).__init__()
-        raise NotImplementedError('esr_b200: SoftHistogramLoss (hist / dict objectives of Z_optimizer) is not built yet')
+        if automatic_temperature:
+            raise NotImplementedError('esr_b200 SoftHistogramLoss: the automatic temperature search needs a double backward through the generator')
+        if not gray_scale:
+            raise NotImplementedError('esr_b200 SoftHistogramLoss: colour histograms are not built (Z_optimizer only asks for gray_scale=True)')
+        assert no_patch_DC or not no_patch_STD, 'Not supporting removing of only patch STD without DC'
+        self.exp_power, self.SQRT_EPSILON = 2, 1e-7
+        self.device = _dev()
+        self.bin_width = (max - min) / (bins - 1)          # min / max are the CENTRES of the first / last bin
+        self.max = max
+        self.no_patch_DC, self.no_patch_STD = no_patch_DC, no_patch_STD
+        self.temperature = float(temperature)
+        self.gray_scale, self.patch_size = gray_scale, patch_size
+        self.dictionary_not_histogram = dictionary_not_histogram
+        self.num_dims = 1
+        self.KDE = patch_size > 1           # kernel density estimation over the desired samples instead of a fixed-bin histogram
+        self.bins = torch.linspace(min, max, bins).view(1, -1).double().to(self.device)        # [dims, bins]
+        if desired_hist_image is not None:
+            desired_hist_image = [im.mean(1, keepdim=True).view([-1, 1]) for im in desired_hist_image]
+        if patch_size > 1:
+            assert desired_hist_image is not None, 'Not supporting patch histograms for model training loss for now'
+            self.num_dims = patch_size ** 2
+            overlap = (self.num_dims - patch_size) / self.num_dims        # an entire patch but one row / column
+            mats = [ReturnPatchExtractionMat(m, patch_size=patch_size, device=self.device, patches_overlap=overlap) for m in desired_hist_image_mask]
+            desired = torch.cat([torch.sparse.mm(mats[i], desired_hist_image[i].to(self.device)).view([self.num_dims, -1, 1])
+                                 for i in range(len(desired_hist_image))], 1)
+            if no_patch_DC:
+                desired = desired - torch.mean(desired, dim=0, keepdim=True)
+                if no_patch_STD:
+                    std = torch.max(torch.std(desired, dim=0, keepdim=True), other=torch.tensor(1 / 255).to(self.device))
+                    self.mean_patches_STD = 1 * std.mean().item()
+                    desired = desired / std * self.mean_patches_STD      # keeps the dynamic range, hence the kernel support
+            self.desired_hist_image_mask = None
+            desired_hist_image = desired
+        else:
+            if desired_hist_image is not None and len(desired_hist_image) > 1:
+                print('Not supproting multiple hist image versions for non-patch histogram/dictionary. Removing extra image versions.')
+            if desired_hist_image is not None:
+                desired_hist_image = 1 * desired_hist_image[0].view([self.num_dims, -1, 1]).to(self.device)
+            m = desired_hist_image_mask[0] if desired_hist_image_mask is not None else None
+            self.desired_hist_image_mask = torch.from_numpy(np.asarray(m)).view([-1]).bool().to(self.device) if m is not None else None
+        if self.KDE:
+            if self.desired_hist_image_mask is not None:
+                desired_hist_image = desired_hist_image[:, self.desired_hist_image_mask, :]
+            self.bins = self.Desired_Im_2_Bins(desired_hist_image)[:, 0, :].contiguous()        # the desired samples are the bins
+        if not dictionary_not_histogram:
+            self.loss = torch.nn.KLDivLoss()
+        if patch_size > 1:
+            self.patch_extraction_mat = ReturnPatchExtractionMat(input_im_HR_mask.data.cpu().numpy(), patch_size=patch_size, device=self.device,
+                                                                 patches_overlap=0.5)
+            self.image_mask = None
+        else:
+            self.image_mask = input_im_HR_mask.view([-1]).bool().to(self.device) if input_im_HR_mask is not None else None
+        if not dictionary_not_histogram:
+            if desired_hist_image is not None:
+                with torch.no_grad():
+                    self.desired_hists_list = [self.ComputeSoftHistogram(desired_hist_image, image_mask=self.desired_hist_image_mask, return_log_hist=False,
+                                                                         reshape_image=False, compute_hist_normalizer=True).detach()]
+            else:
+                self.desired_hist_image = desired_hist_image
+
+    def Feed_Desired_Hist_Im(self, desired_hist_image):
+        self.desired_hists_list = []
+        for desired_im in desired_hist_image:
+            desired_im = desired_im.mean(0, keepdim=True).view([1, -1, 1])
+            with torch.no_grad():
+                self.desired_hists_list.append(self.ComputeSoftHistogram(desired_im, image_mask=self.desired_hist_image_mask, return_log_hist=False,
+                                                                         reshape_image=False, compute_hist_normalizer=True).detach())
+
+    def Desired_Im_2_Bins(self, desired_im):
+        """the desired samples [dims, n, 1] with near-duplicates (every coordinate within half a bin of a LATER sample) removed
+        (Z_optimization.py:105-133) -> [dims, 1, n_kept] fp64"""
+        im = desired_im.view([self.num_dims, -1])
+        n = im.size(1)
+        keep = torch.ones(n, dtype=torch.bool, device=im.device)
+        step = 2048
+        for a in range(0, n, step):        # row blocks instead of the reference's all-at-once n x n matrix (and its retry on out-of-memory)
+            close = ((im[:, a:a + step].unsqueeze(2) - im.unsqueeze(1)).abs() < self.bin_width / 2).all(0)      # [block, n]
+            idx = torch.arange(a, min(a + step, n), device=im.device).unsqueeze(1)
+            later = torch.arange(n, device=im.device).unsqueeze(0) > idx
+            keep[a:a + step] = ~(close & later).any(1)
+        return im[:, keep].view([self.num_dims, 1, -1]).double()
+
+    def ComputeSoftHistogram(self, image, image_mask, return_log_hist, reshape_image, compute_hist_normalizer, temperature=None):
+        if temperature is None:
+            temperature = 1 * self.temperature
+        if reshape_image:
+            if self.patch_size > 1:
+                image = torch.sparse.mm(self.patch_extraction_mat, image.view([-1, 1])).view([self.num_dims, -1])
+                if self.no_patch_DC:
+                    image = image - torch.mean(image, dim=0, keepdim=True)
+                    if self.no_patch_STD:
+                        image = image / torch.max(torch.std(image, dim=0, keepdim=True), other=torch.tensor(1 / 255).to(self.device)) * self.mean_patches_STD
+            else:
+                image = image.contiguous().view([self.num_dims, -1])
+                if image_mask is not None:
+                    image = image[:, image_mask]
+        else:
+            image = image.view([self.num_dims, -1])
+            if image_mask is not None and not self.KDE:
+                pass        # (the reference applies the desired image's mask only in the KDE branch of the constructor, :90-91)
+        n_samples = image.size(1)
+        res = _SoftHistFn.apply(image.to(self.device), self.bins, self.max, self.SQRT_EPSILON, float(temperature), self.dictionary_not_histogram)
+        if self.dictionary_not_histogram:
+            return res.view([1, -1])
+        hist = res
+        if compute_hist_normalizer or not self.KDE:
+            self.normalizer = hist.sum() / n_samples
+        hist = (hist / self.normalizer / n_samples).float()
+        if self.KDE:        # another "bin" accounts for everything the desired samples do not cover
+            hist = torch.cat([hist, (1 - torch.min(torch.tensor(1, dtype=hist.dtype, device=hist.device), hist.sum())).view([1])])
+        if return_log_hist:
+            return torch.log(hist + torch.finfo(hist.dtype).eps).view([1, -1])
+        return hist.view([1, -1])
+
+    def forward(self, cur_images):
+        hists = []
+        for cur_image in cur_images:
+            cur_image = cur_image.mean(0, keepdim=True)
+            hists.append(self.ComputeSoftHistogram(cur_image, self.image_mask, return_log_hist=True, reshape_image=True, compute_hist_normalizer=False,
+                                                   temperature=self.temperature))
+        if self.dictionary_not_histogram:
+            return torch.cat(hists, 0).mean(1).float()
+        return self.loss(torch.cat(hists, 0), torch.cat(self.desired_hists_list, 0)).float()
 
 
 def Patch_Indexes_2_Sparse_Mat(patches_indexes, mask_size, device):
@@ -185,6 +349,10 @@ class Z_optimizer():
                 self.constraining_loss = lambda produced_im: F.l1_loss(input=produced_im * self.constraining_mask,
                                                                        target=self.initial_output * self.constraining_mask)
                 self.constraining_loss_weight = 0.1
+        if 'local' in objective:      # relative STD change over patches (Z_optimization.py:391-397)
+            desired_overlap = 1 if 'STD' in objective else 0.5
+            self.patch_extraction_map, self.non_covered_indexes_extraction_mat = ReturnPatchExtractionMat(
+                mask=image_mask, patch_size=self.PATCH_SIZE_4_STD, device=model.fake_H.device, patches_overlap=desired_overlap, return_non_covered=True)
         if not self.model_training:
             self.initial_STD = self.Masked_STD(first_image_only=True)
             print('Initial STD: %.3e' % (self.initial_STD.mean().item()))
@@ -199,8 +367,36 @@ class Z_optimizer():
                     self.loss = lambda produced_im, GT_im: torch.stack(
                         [F.l1_loss(input=produced_im[i].unsqueeze(0) * loss_mask, target=GT_im * loss_mask) for i in range(produced_im.size(0))], 0)
                     self.constraining_loss_weight = 1
+            elif 'Mag' in objective:      # local magnitude: patches keep their mean, their STD moves by STD_increment (:450-455)
+                self.desired_patches = torch.sparse.mm(self.patch_extraction_map, self.initial_output.mean(dim=1).view([-1, 1])).view(
+                    [self.PATCH_SIZE_4_STD ** 2, -1])
+                desired_STD = torch.max(torch.std(self.desired_patches, dim=0, keepdim=True), torch.tensor(1 / 255).to(self.device))
+                mean = torch.mean(self.desired_patches, dim=0, keepdim=True)
+                self.desired_patches = (self.desired_patches - mean) / desired_STD * \
+                    (desired_STD + data['STD_increment'] * (1 if 'increase' in objective else -1)) + mean
+                self.constraining_loss_weight = 255 / 10 * data['STD_increment'] ** 2
+            elif 'VGG' in objective and 'random' not in objective:      # perceptual distance to the desired image (:505-509)
+                self.desired_im = data['desired']
+                self.GT_HR_VGG = model.netF(self.desired_im.to(self.device)).detach().to(self.device)
+                from esr_b200.losses import L1Loss
+                self.loss = L1Loss().to(self.device)
+            elif any(p in objective for p in ['hist', 'dict']):       # imprinting tools (:510-542)
+                if auto_set_hist_temperature:
+                    raise NotImplementedError('esr_b200: auto_set_hist_temperature needs a double backward through the generator')
+                self.STD_PRESERVING_WEIGHT = 1e4
+                optimal_temperature = 5e-4 if 'hist' in objective else 1e-3
+                self.loss = SoftHistogramLoss(bins=256, min=0, max=1, desired_hist_image=self.data['desired'] if self.data is not None else None,
+                                              desired_hist_image_mask=data['Desired_Im_Mask'] if self.data is not None else None,
+                                              input_im_HR_mask=self.image_mask, gray_scale=True, patch_size=6 if 'patch' in objective else 1,
+                                              temperature=optimal_temperature, dictionary_not_histogram='dict' in objective,
+                                              no_patch_DC='noDC' in objective, no_patch_STD='no_localSTD' in objective)
+                self.constraining_loss_weight = 10
+            elif 'Adversarial' in objective:      # fool the critic (:543-545)
+                from models.modules.loss import GANLoss
+                self.netD = model.netD
+                self.loss = GANLoss('wgan-gp', 1.0, 0.0).to(self.device)
             elif 'STD' in objective and 'TV' not in objective:
-                assert self.objective in ['max_STD', 'min_STD', 'STD_increase', 'STD_decrease']
+                assert self.objective.replace('local_', '') in ['max_STD', 'min_STD', 'STD_increase', 'STD_decrease']
                 if any(p in objective for p in ['increase', 'decrease']):
                     STD_CHANGE_FACTOR = 1.05
                     self.desired_STD = self.initial_STD
@@ -233,6 +429,14 @@ class Z_optimizer():
 
     def Masked_STD(self, first_image_only=False):
         model_output = self.model.Output_Batch(within_0_1=True)
+        if 'local' in self.objective:      # STD of every 7x7 patch inside the mask (+ of the pixels no patch covers), per image (:618-625)
+            values = []
+            for im_num in range(1 if first_image_only else model_output.size(0)):
+                gray = model_output[im_num].mean(dim=0).view([-1, 1])
+                values.append(torch.sparse.mm(self.patch_extraction_map, gray).view([self.PATCH_SIZE_4_STD ** 2, -1]).std(dim=0))
+                if self.non_covered_indexes_extraction_mat is not None:
+                    values[-1] = torch.cat([values[-1], torch.sparse.mm(self.non_covered_indexes_extraction_mat, gray).std(dim=0)], 0)
+            return torch.stack(values, 1)
         return torch.std(model_output * self.image_mask, dim=(1, 2, 3)).view(1, -1)
 
     def feed_data(self, data):
@@ -273,8 +477,24 @@ class Z_optimizer():
             if self.Z_mask is not None:
                 Z_loss = Z_loss * self.image_mask
             Z_loss = -1 * Z_loss.mean(dim=(1, 2, 3))
+            if 'local' in self.objective:
+                Z_loss = Z_loss + self.STD_PRESERVING_WEIGHT * ((self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean()
         elif 'l1' in self.objective:
             Z_loss = self.loss(self.output_image.to(self.device), self.desired_im.to(self.device))
+        elif any(p in self.objective for p in ['hist', 'dict']):
+            Z_loss = self.loss(self.output_image.to(self.device))
+            if 'localSTD' in self.objective:
+                Z_loss = Z_loss + (self.STD_PRESERVING_WEIGHT * (self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean(0).to(self.device)
+        elif 'Adversarial' in self.objective:
+            Z_loss = self.loss(self.netD(self.model.CEM_net.HR_unpadder(self.output_image).to(self.device)), True)
+        elif 'Mag' in self.objective:
+            values = []
+            for im_num in range(self.output_image.size(0)):
+                patches = torch.sparse.mm(self.patch_extraction_map, self.output_image[im_num].mean(dim=0).view([-1, 1])).view([self.PATCH_SIZE_4_STD ** 2, -1])
+                values.append(((patches - self.desired_patches) ** 2).mean())
+            Z_loss = torch.stack(values, 0)
+        elif 'VGG' in self.objective:
+            Z_loss = self.loss(self.model.netF(self.output_image).to(self.device), self.GT_HR_VGG)
         elif 'STD' in self.objective and 'TV' not in self.objective:
             Z_loss = self.Masked_STD(first_image_only=False)
             if any(p in self.objective for p in ['increase', 'decrease']):
@@ -315,6 +535,7 @@ class Z_optimizer():
         graph, static = None, None
         self._graph_ok = (self._own_optimizer and torch.cuda.is_available() and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0'
                           and not self.model_training and self.loggers is None
+                          and not any(p in self.objective for p in ['local', 'Mag', 'hist', 'dict'])      # (sparse products: eager iterations)
                           and (self.max_iters < 0 or self.max_iters >= self.GRAPH_WARMUP_ITERS + 4))
         if self._graph_ok:
             self._side_stream = torch.cuda.Stream()

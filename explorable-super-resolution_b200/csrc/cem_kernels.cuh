@@ -193,8 +193,8 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
   const int ilo = max((ylo - phase + s - 1) / s, 0), ihi = min((yhi - phase) / s, hl - 1);
   const int jlo = max((xlo - phase + s - 1) / s, 0), jhi = min((xhi - phase) / s, wl - 1);
   const int ni = max(ihi - ilo + 1, 0), nj = max(jhi - jlo + 1, 0);
-  const bool interior_y = Y0 - r >= 0 && Y0 + kUpTY - 1 + r <= hh - 1;
-  const bool interior_x = X0 - r >= 0 && X0 + kUpTX - 1 + r <= wh - 1;
+  // (the replicate-padding path is decided per column / per row, not per tile: only the r pixels next to an image border pay for it -
+  //  with per-tile flags a quarter of the tiles ran 17 clamped taps per sample and the kernel was instruction-bound at 1 TB/s)
   // the thread's four G vectors go in flight first: their latency hides behind the filter passes
   const int xg = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int X = X0 + 4 * xg;
@@ -217,7 +217,7 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
   {
     const int xx = threadIdx.x & (kUpTX - 1), half = threadIdx.x / kUpTX;      // 128 columns x 2 row halves
     const int X = X0 + xx;
-    if (interior_x) {
+    if (X - r >= 0 && X + r <= wh - 1) {
       const int b0 = (((phase + r - X) % s) + s) % s;
       const int jb = (X + b0 - r - phase) / s - jlo;
       for (int ii = half; ii < ni; ii += 256 / kUpTX) {
@@ -249,7 +249,7 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
     const int yo = Y - crop;
     if (yo >= ho || Y >= hh) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (interior_y) {
+    if (Y - r >= 0 && Y + r <= hh - 1) {
       const int a0 = (((phase + r - Y) % s) + s) % s;
       int i = (Y + a0 - r - phase) / s - ilo;
       for (int a = a0; a < len; a += s, ++i) {

@@ -22,6 +22,7 @@
 #include "conv3x3_wgrad.cuh"
 #include "disc_kernels.cuh"
 #include "train_kernels.cuh"
+#include "hist_kernels.cuh"
 
 namespace {
 
@@ -1279,6 +1280,42 @@ int esr_bce_rel_loss_bwd(const float* ea, const float* eb, int n, const float* S
                          float* ga, float* gb, void* stream) {
   if (!ea || !eb || !S_global || (!ga && !gb) || n <= 0) return fail(ESR_ERR_INVALID, "bce_rel_loss_bwd: bad arguments");
   esr::bce_rel_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ea, eb, n, S_global, n_global, ga_up, gb_up, ga, gb);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+// ---- soft histogram / dictionary objective of the latent-exploration tools --------------------------------------------------------
+int esr_soft_hist_fwd(const double* x, int dims, int n_samples, const double* bins, int n_bins, double vmax, double eps, double temperature,
+                      int dictionary, double* out, double* sum_e, void* stream) {
+  if (!x || !bins || !out) return fail(ESR_ERR_INVALID, "soft_hist_fwd: null pointer");
+  if (dims < 1 || dims > esr::kHistMaxD || n_samples < 1 || n_bins < 1 || !(temperature > 0)) return fail(ESR_ERR_INVALID, "soft_hist_fwd: bad shape (dims %d, samples %d, bins %d)", dims, n_samples, n_bins);
+  if (dictionary && !sum_e) return fail(ESR_ERR_INVALID, "soft_hist_fwd: dictionary mode needs sum_e");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double inv_DT = 1.0 / ((double)dims * temperature);
+  if (dictionary) {
+    esr::soft_dict_fwd_kernel<<<(n_samples + 127) / 128, 128, 0, st>>>(x, dims, n_samples, bins, n_bins, vmax, eps, inv_DT, out, sum_e);
+  } else {
+    CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * n_bins, st));
+    const int bx = (n_bins + esr::kHistTileB - 1) / esr::kHistTileB;
+    int chunks = (148 * 4 + bx - 1) / bx;                       // a few waves of blocks whatever the bin count
+    int per = (n_samples + chunks - 1) / chunks;
+    per = (per + esr::kHistTileP - 1) / esr::kHistTileP * esr::kHistTileP;
+    chunks = (n_samples + per - 1) / per;
+    esr::soft_hist_fwd_kernel<<<dim3((unsigned)bx, (unsigned)chunks), esr::kHistTileB, 0, st>>>(x, dims, n_samples, bins, n_bins, vmax, eps, inv_DT, per, out);
+  }
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
+int esr_soft_hist_bwd(const double* x, int dims, int n_samples, const double* bins, int n_bins, double vmax, double eps, double temperature,
+                      const double* g_hist, const double* g_out, const double* sum_e, double* dx, void* stream) {
+  if (!x || !bins || !dx || (!g_hist && !g_out) || (g_out && !sum_e)) return fail(ESR_ERR_INVALID, "soft_hist_bwd: null pointer");
+  if (dims < 1 || dims > esr::kHistMaxD || n_samples < 1 || n_bins < 1 || !(temperature > 0)) return fail(ESR_ERR_INVALID, "soft_hist_bwd: bad shape");
+  const double inv_DT = 1.0 / ((double)dims * temperature);
+  esr::soft_hist_bwd_kernel<<<(n_samples + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, dims, n_samples, bins, n_bins, vmax, eps, inv_DT, g_hist, g_out,
+                                                                                     sum_e, dx);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;

@@ -125,6 +125,10 @@ SIGNATURES = {
     "esr_structure_tensor_workspace_bytes": (C.c_size_t, [C.c_int]),
     "esr_structure_tensor_fwd": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "esr_structure_tensor_bwd": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
+    "esr_soft_hist_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "esr_soft_hist_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "esr_adam_scratch_bytes": (C.c_size_t, [C.c_int]),
     "esr_adam_multi": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.c_void_p, C.c_size_t] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
     "esr_l1_workspace_bytes": (C.c_size_t, []),

@@ -361,6 +361,20 @@ int esr_bce_rel_loss(const float* a, const float* b, int n, const float* sums_gl
 int esr_bce_rel_loss_bwd(const float* ea, const float* eb, int n, const float* S_global, float n_global, const float* ga_up,
                          const float* gb_up, float* ga, float* gb, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-density soft histogram / dictionary distance (SoftHistogramLoss.ComputeSoftHistogram, Z_optimization.py:180-216: the `hist` /
+ * `dict` objectives of the GUI's imprinting tools).  x: [dims][n_samples] fp64 (grey levels, or dims = patch_size^2 patch entries),
+ * bins: [dims][n_bins] fp64.  E[p][b] = exp(-(1/dims) sum_d (cyclic|x - bins| + eps)^2 / temperature).
+ *   dictionary == 0: out[n_bins]    = mean_p E[p][b]
+ *   dictionary == 1: out[n_samples] = -log(mean_b E[p][b]),  sum_e[n_samples] = sum_b E[p][b] (kept for the backward)
+ * The backward returns d/dx of  sum_b g_hist[b] out[b]  (histogram)  or  sum_p g_out[p] out[p]  (dictionary).  The [dims, P, B]
+ * distance tensor the reference materialises never exists.
+ * ---------------------------------------------------------------------------------------------- */
+int esr_soft_hist_fwd(const double* x, int dims, int n_samples, const double* bins, int n_bins, double vmax, double eps, double temperature,
+                      int dictionary, double* out, double* sum_e, void* stream);
+int esr_soft_hist_bwd(const double* x, int dims, int n_samples, const double* bins, int n_bins, double vmax, double eps, double temperature,
+                      const double* g_hist, const double* g_out, const double* sum_e, double* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

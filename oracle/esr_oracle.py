@@ -250,3 +250,40 @@ def filter_loss_structure_tensor(sr, hr, z, history, latent_channels='SVDinNorme
         ub, lb = np.percentile(history[i], 95), np.percentile(history[i], 5)
         target.append(cur_z[:, i] / 2 * (ub - lb) + np.mean([ub, lb]))
     return (torch.stack(measured, 1) - torch.stack(target, 1)).abs()
+
+
+# ---- soft histogram / dictionary objective (latent-exploration tools) -------------------------------------------------------------
+def soft_histogram(x, bins, vmax, temperature, dictionary, eps=1e-7):
+    """SoftHistogramLoss.ComputeSoftHistogram's kernel (Z_optimization.py:196-210) with the [dims, samples, bins] tensor materialised in
+    double precision like the reference: cyclic distance min(|d|, |d - max|, |d + max|), -(dist + eps)^2 / T, mean over dims, exp; then
+    mean over the samples (histogram, -> [bins]) or -log of the mean over the bins (dictionary, -> [samples]).  x: [dims, P], bins: [dims, B]."""
+    x, bins = x.double().unsqueeze(-1), bins.double().unsqueeze(1)
+    d = (x - bins).abs()
+    d = torch.min(d, (x - bins - vmax).abs())
+    d = torch.min(d, (x - bins + vmax).abs())
+    e = torch.exp((-((d + eps) ** 2) / temperature).mean(0))          # [P, B]
+    return -torch.log(e.mean(1)) if dictionary else e.mean(0)
+
+
+def soft_histogram_loss_gray(cur_images, desired, image_mask, temperature, dictionary, n_bins=256):
+    """SoftHistogramLoss(bins=256, min=0, max=1, gray_scale=True, patch_size=1).forward (Z_optimization.py:218-230 with :36-101,180-216):
+    grey levels of every image inside image_mask against the grey levels of the WHOLE desired image (its mask is only applied in the
+    kernel-density branch, :90-91): KL divergence between the normalised soft histograms, or the mean dictionary distance per image."""
+    bins = torch.linspace(0, 1, n_bins).view(1, -1)
+    mask = image_mask.reshape(-1) > 0
+    des = desired.mean(1, keepdim=True).reshape(1, -1)
+    h_des = soft_histogram(des, bins, 1.0, temperature, False)
+    normalizer = h_des.sum() / des.shape[1]
+    h_des = (h_des / normalizer / des.shape[1]).float()
+    out = []
+    for im in cur_images:
+        xs = im.mean(0, keepdim=True).reshape(1, -1)[:, mask]
+        if dictionary:
+            out.append(soft_histogram(xs, bins, 1.0, temperature, True).mean().float())
+        else:
+            h = soft_histogram(xs, bins, 1.0, temperature, False)
+            h = (h / (h.sum() / xs.shape[1]) / xs.shape[1]).float()        # fixed-bin mode re-computes the normaliser on every call (:211-212)
+            out.append(torch.log(h + torch.finfo(h.dtype).eps).view(1, -1))
+    if dictionary:
+        return torch.stack(out)
+    return F.kl_div(torch.cat(out, 0), h_des.view(1, -1).expand(len(out), -1), reduction='mean')
