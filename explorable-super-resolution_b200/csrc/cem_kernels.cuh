@@ -174,27 +174,56 @@ cem_inv_fast_kernel(const float* __restrict__ e_in, int hl, int wl, const float*
 }
 
 // out[Y - crop][X - crop] = G[Y][X] + sum_{a,b} kv[a] kh[b] S[clamp(Y + a - r)][clamp(X + b - r)],  S = F zero-stuffed at `phase`
+// (S[S_ i + phase][S_ j + phase] = F[i][j]).  Polyphase: of a sample's `len` taps only every S_-th one meets a non-zero entry of S.
+// Replicate padding of S (CEMnet.py:268-272 pads the zero-stuffed image): every tap that leaves the image reads S's border row /
+// column, which is F's first / last row / column when the border index is on the sampling lattice and zero otherwise - so a border
+// sample is the in-range polyphase walk plus (sum of the taps that left) x (that border entry).  No per-tap clamping anywhere.
+// S_ is compile-time (2, 3, 4, 8): the lattice arithmetic is shifts and masks.
+template <int S_>
+__device__ __forceinline__ float up_axis(const float* __restrict__ taps, int len, int r, int phase, int pos, int n_hr, int n_lr, int lo,
+                                         const float* __restrict__ samples, int stride) {
+  // taps: shared memory; samples[(j - lo) * stride] = the LR entries of this line (window starts at LR index `lo`)
+  const int b_lo = max(0, r - pos), b_hi = min(len - 1, n_hr - 1 - pos + r);
+  int m = (phase + r - pos - b_lo) % S_;
+  if (m < 0) m += S_;
+  int b = b_lo + m;
+  int j = (pos + b - r - phase) / S_ - lo;           // exact: pos + b - r - phase is a non-negative multiple of S_
+  float a = 0.f;
+  for (; b <= b_hi; b += S_, ++j) a = fmaf(taps[b], samples[j * stride], a);
+  if (b_lo > 0 && phase == 0) {                       // taps that fell off the low end read S[0] = F[0]
+    float t = 0.f;
+    for (int k = 0; k < b_lo; ++k) t += taps[k];
+    a = fmaf(t, samples[(0 - lo) * stride], a);
+  }
+  if (b_hi < len - 1 && (n_hr - 1 - phase) % S_ == 0) {   // ... off the high end: S[n_hr - 1] = F[n_lr - 1]
+    float t = 0.f;
+    for (int k = b_hi + 1; k < len; ++k) t += taps[k];
+    a = fmaf(t, samples[(n_lr - 1 - lo) * stride], a);
+  }
+  return a;
+}
+
+template <int S_>
 __global__ void __launch_bounds__(256)
-cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g, int hl, int wl, int s, int phase, const float* __restrict__ kv,
+cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g, int hl, int wl, int phase, const float* __restrict__ kv,
                        const float* __restrict__ kh, int len, int crop, float* __restrict__ out) {
   extern __shared__ float sm[];
   __shared__ float tv[kCemMaxTaps], th[kCemMaxTaps];
-  const int hh = hl * s, wh = wl * s;
+  const int hh = hl * S_, wh = wl * S_;
   const int ho = hh - 2 * crop, wo = wh - 2 * crop;
   const int r = len / 2;
   const int nc = blockIdx.z;
   const int Y0 = blockIdx.y * kUpTY + crop, X0 = blockIdx.x * kUpTX + crop;     // tile origin in the un-cropped HR domain
-  const int maxni = (kUpTY + len) / s + 2, maxnj = (kUpTX + len) / s + 2;
+  const int maxni = (kUpTY + len) / S_ + 2, maxnj = (kUpTX + len) / S_ + 2;
   float* ft = sm;                           // [maxni][maxnj]   LR window
   float* hb = sm + maxni * maxnj;           // [maxni][kUpTX]   horizontally filtered rows
   if (threadIdx.x < len) { tv[threadIdx.x] = __ldg(kv + threadIdx.x); th[threadIdx.x] = __ldg(kh + threadIdx.x); }
+  // LR rows / columns that can contribute to this tile (clamped to the image: border entries included)
   const int ylo = clampi(Y0 - r, 0, hh - 1), yhi = clampi(Y0 + kUpTY - 1 + r, 0, hh - 1);
   const int xlo = clampi(X0 - r, 0, wh - 1), xhi = clampi(X0 + kUpTX - 1 + r, 0, wh - 1);
-  const int ilo = max((ylo - phase + s - 1) / s, 0), ihi = min((yhi - phase) / s, hl - 1);
-  const int jlo = max((xlo - phase + s - 1) / s, 0), jhi = min((xhi - phase) / s, wl - 1);
+  const int ilo = max((ylo - phase + S_ - 1) / S_, 0), ihi = min((yhi - phase) / S_, hl - 1);
+  const int jlo = max((xlo - phase + S_ - 1) / S_, 0), jhi = min((xhi - phase) / S_, wl - 1);
   const int ni = max(ihi - ilo + 1, 0), nj = max(jhi - jlo + 1, 0);
-  // (the replicate-padding path is decided per column / per row, not per tile: only the r pixels next to an image border pay for it -
-  //  with per-tile flags a quarter of the tiles ran 17 clamped taps per sample and the kernel was instruction-bound at 1 TB/s)
   // the thread's four G vectors go in flight first: their latency hides behind the filter passes
   const int xg = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int X = X0 + 4 * xg;
@@ -208,38 +237,15 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
     if (vec && g && Y < hh && Y - crop < ho) gq[k] = __ldg(reinterpret_cast<const float4*>(g + (size_t)nc * hh * wh + (size_t)Y * wh + X));
   }
   const float* fp = f + (size_t)nc * hl * wl;
-  for (int e = threadIdx.x; e < ni * nj; e += 256) {
-    const int ii = e / nj, jj = e - ii * nj;
-    ft[ii * maxnj + jj] = __ldg(fp + (size_t)(ilo + ii) * wl + (jlo + jj));
-  }
+  for (int ii = threadIdx.x / 64; ii < ni; ii += 4)
+    for (int jj = threadIdx.x & 63; jj < nj; jj += 64) ft[ii * maxnj + jj] = __ldg(fp + (size_t)(ilo + ii) * wl + (jlo + jj));
   __syncthreads();
-  // horizontal pass: one column X per thread pair (the phase arithmetic is done once per thread)
+  // horizontal pass: one column per thread pair
   {
-    const int xx = threadIdx.x & (kUpTX - 1), half = threadIdx.x / kUpTX;      // 128 columns x 2 row halves
-    const int X = X0 + xx;
-    if (X - r >= 0 && X + r <= wh - 1) {
-      const int b0 = (((phase + r - X) % s) + s) % s;
-      const int jb = (X + b0 - r - phase) / s - jlo;
-      for (int ii = half; ii < ni; ii += 256 / kUpTX) {
-        const float* fr = ft + ii * maxnj + jb;
-        float a = 0.f;
-        int j = 0;
-        for (int b = b0; b < len; b += s, ++j) a = fmaf(th[b], fr[j], a);
-        hb[ii * kUpTX + xx] = a;
-      }
-    } else {
-      for (int ii = half; ii < ni; ii += 256 / kUpTX) {
-        float a = 0.f;
-        for (int b = 0; b < len; ++b) {
-          const int xs = clampi(X + b - r, 0, wh - 1) - phase;
-          if (xs >= 0 && xs % s == 0) {
-            const int j = xs / s - jlo;
-            if (j >= 0 && j < nj) a = fmaf(th[b], ft[ii * maxnj + j], a);
-          }
-        }
-        hb[ii * kUpTX + xx] = a;
-      }
-    }
+    const int xx = threadIdx.x & (kUpTX - 1), half = threadIdx.x / kUpTX;
+    const int Xc = X0 + xx;
+    if (Xc < wh)
+      for (int ii = half; ii < ni; ii += 256 / kUpTX) hb[ii * kUpTX + xx] = up_axis<S_>(th, len, r, phase, Xc, wh, wl, jlo, ft + ii * maxnj, 1);
   }
   __syncthreads();
   // vertical pass + G + store: a thread owns 4 consecutive X of rows ty, ty+8, ty+16, ty+24
@@ -248,28 +254,9 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
     const int Y = Y0 + ty + 8 * k;
     const int yo = Y - crop;
     if (yo >= ho || Y >= hh) continue;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (Y - r >= 0 && Y + r <= hh - 1) {
-      const int a0 = (((phase + r - Y) % s) + s) % s;
-      int i = (Y + a0 - r - phase) / s - ilo;
-      for (int a = a0; a < len; a += s, ++i) {
-        const float4 h4 = *reinterpret_cast<const float4*>(hb + i * kUpTX + 4 * xg);
-        const float t = tv[a];
-        acc[0] = fmaf(t, h4.x, acc[0]); acc[1] = fmaf(t, h4.y, acc[1]); acc[2] = fmaf(t, h4.z, acc[2]); acc[3] = fmaf(t, h4.w, acc[3]);
-      }
-    } else {
-      for (int a = 0; a < len; ++a) {
-        const int ys = clampi(Y + a - r, 0, hh - 1) - phase;
-        if (ys >= 0 && ys % s == 0) {
-          const int i = ys / s - ilo;
-          if (i >= 0 && i < ni) {
-            const float4 h4 = *reinterpret_cast<const float4*>(hb + i * kUpTX + 4 * xg);
-            const float t = tv[a];
-            acc[0] = fmaf(t, h4.x, acc[0]); acc[1] = fmaf(t, h4.y, acc[1]); acc[2] = fmaf(t, h4.z, acc[2]); acc[3] = fmaf(t, h4.w, acc[3]);
-          }
-        }
-      }
-    }
+    float acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = up_axis<S_>(tv, len, r, phase, Y, hh, hl, ilo, hb + 4 * xg + q, kUpTX);
     const float* gp = g ? g + (size_t)nc * hh * wh + (size_t)Y * wh + X : nullptr;
     float* op = out + (size_t)nc * ho * wo + (size_t)yo * wo + (X - crop);
     if (vec) {

@@ -41,6 +41,7 @@ struct WgradParams {
   uint32_t slot_bytes, gstage_bytes;           // per 32-pixel box: cp * 512 and 3 * cpb * 512
   uint32_t ring_bytes;                         // one box ring: (rb + 2) slots + slack
   uint32_t idesc;
+  int issuers;                                 // MMA issuer warps sharing the K steps (1..3; 1 = fixed accumulation order)
   float* part;                                 // [cta][mt][128][3*nbn] fp32 partial gradients
 };
 
@@ -91,13 +92,13 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.rb; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_xempty + 8 * s, kWgIssuers);
+      mbar_init(bar_xempty + 8 * s, (uint32_t)p.issuers);
     }
     for (int s = 0; s < kWgGStages; ++s) {
       mbar_init(bar_gfull + 8 * s, 1);
-      mbar_init(bar_gempty + 8 * s, kWgIssuers);
+      mbar_init(bar_gempty + 8 * s, (uint32_t)p.issuers);
     }
-    mbar_init(bar_done, kWgIssuers);
+    mbar_init(bar_done, (uint32_t)p.issuers);
     mbar_init(bar_zero, 4);
     fence_barrier_init();
   }
@@ -157,7 +158,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
     }
-  } else if (warp <= kWgIssuers) {
+  } else if (warp <= p.issuers) {
     // ------------------------------------------------------------------ MMA issuers (one thread per warp).  The K steps
     // of the launch are dealt round-robin to the issuers; every MMA accumulates into zero-initialised TMEM, so their
     // order is irrelevant, and every buffer is released when all issuers have committed it.
@@ -196,7 +197,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               uint32_t d = tmem_base;
               for (int m = 0; m < p.mt; ++m, ad += mstep, d += (uint32_t)N3) umma_f16(d, ad, bd, p.idesc, 1u);
             }
-            if (++kmod == kWgIssuers) kmod = 0;
+            if (++kmod == p.issuers) kmod = 0;
           }
           umma_commit(bar_gempty + 8 * gr.j);
           umma_commit(bar_xempty + 8 * p0.j);                 // row r-1 is not needed again
@@ -313,13 +314,28 @@ __global__ void bias_grad_kernel(const uint16_t* __restrict__ gy, int dtype, int
 
 // out[c] += scale * sum_{n,y,x} src[n][c][y][x]  (NCHW fp32: bias gradient of the last conv straight from dL/dG, which
 // has not been rounded to 16 bits).  grid = (chunks, c, n)
-__global__ void sum_nchw_kernel(const float* __restrict__ src, int c, size_t hw, float scale, float* __restrict__ out) {
-  const float* p = src + ((size_t)blockIdx.z * c + blockIdx.y) * hw;
+// (n_loop > 0: one block per channel walks all n_loop images and adds its total in a fixed order - the deterministic variant)
+__global__ void sum_nchw_kernel(const float* __restrict__ src, int c, size_t hw, float scale, float* __restrict__ out, int n_loop) {
   float s = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += __ldg(p + i);
+  const int n0 = n_loop > 0 ? 0 : (int)blockIdx.z, n1 = n_loop > 0 ? n_loop : (int)blockIdx.z + 1;
+  for (int img = n0; img < n1; ++img) {
+    const float* p = src + ((size_t)img * c + blockIdx.y) * hw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < hw; i += (size_t)gridDim.x * blockDim.x) s += __ldg(p + i);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out + blockIdx.y, s * scale);
+  if (n_loop > 0) {
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) t += red[w8];
+      out[blockIdx.y] += t * scale;
+    }
+  } else if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + blockIdx.y, s * scale);
+  }
 }
 
 }  // namespace esr

@@ -60,6 +60,19 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// ESR_DETERMINISTIC=1 / esr_set_deterministic(1): every reduction takes a fixed order (one MMA issuer per CTA in the row and wgrad kernels,
+// no floating-point atomics across blocks): launches become bit-reproducible at ~15 % of the conv throughput.
+std::atomic<int> g_deterministic{-1};
+bool deterministic() {
+  int v = g_deterministic.load();
+  if (v < 0) {
+    const char* e = getenv("ESR_DETERMINISTIC");
+    v = (e && e[0] != '0') ? 1 : 0;
+    g_deterministic.store(v);
+  }
+  return v != 0;
+}
+
 int grid_for(size_t total, int threads) {
   size_t b = (total + threads - 1) / threads;
   const size_t cap = 148 * 16;
@@ -235,6 +248,11 @@ int esr_debug_watchdog(unsigned int* out8_host, int reset) {
     unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyToSymbol(esr::g_watchdog, z, sizeof(z)));
   }
+  return ESR_OK;
+}
+
+int esr_set_deterministic(int on) {
+  g_deterministic.store(on ? 1 : 0);
   return ESR_OK;
 }
 
@@ -420,7 +438,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     p.slots = 512 / nbn < esr::kRowsMaxSlots ? 512 / nbn : esr::kRowsMaxSlots;
     {
       static const int issuers = [] { const char* e = getenv("ESR_ISSUERS"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 3 ? 3 : v); }();
-      p.issuers = issuers;
+      p.issuers = deterministic() ? 1 : issuers;
     }
     p.strips = (a->w + 127) / 128;
     p.units = (long long)a->n * p.strips * a->h;
@@ -640,6 +658,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     p.nbn = w.nbn; p.cpb = w.cpb; p.mt = w.mt; p.rb = w.rb;
     p.slot_bytes = w.slot_bytes; p.gstage_bytes = w.gstage_bytes; p.ring_bytes = w.ring_bytes;
     // D=f32, A/B = f16|bf16, both MN-major (bits 15, 16), N = 3*nbn, M = 128
+    p.issuers = deterministic() ? 1 : esr::kWgIssuers;
     p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | (1u << 15) | (1u << 16) |
               ((uint32_t)((3 * w.nbn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int grid = ranges * w.n_blocks;
@@ -682,6 +701,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     const size_t hw = (size_t)a->h * a->w;
     size_t chunks = ((size_t)a->n * hw + 255) / 256;
     if (chunks > 148) chunks = 148;
+    if (deterministic()) chunks = 1;       // one block per plane: a single atomicAdd per channel, fixed order
     dim3 grid((unsigned)chunks, (unsigned)w.gyp);
     esr::bias_grad_kernel<<<grid, 256, 0, st>>>((const uint16_t*)a->gy, a->dtype, a->n, a->gy_planes_total, a->gy_plane_off, a->cout, hw,
                                                 a->scale, a->db);
@@ -698,7 +718,10 @@ int esr_sum_nchw(const float* src, int n, int c, int h, int w, float scale, int 
   const size_t hw = (size_t)h * w;
   size_t chunks = (hw + 1023) / 1024;
   if (chunks > 64) chunks = 64;
-  esr::sum_nchw_kernel<<<dim3((unsigned)chunks, (unsigned)c, (unsigned)n), 256, 0, st>>>(src, c, hw, scale, out);
+  if (deterministic())
+    esr::sum_nchw_kernel<<<dim3(1, (unsigned)c, 1), 256, 0, st>>>(src, c, hw, scale, out, n);
+  else
+    esr::sum_nchw_kernel<<<dim3((unsigned)chunks, (unsigned)c, (unsigned)n), 256, 0, st>>>(src, c, hw, scale, out, 0);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return ESR_OK;
@@ -969,13 +992,15 @@ int esr_cem_up_add(const float* f, const float* g, int n, int c, int hl, int wl,
   const int hh = hl * s, wh = wl * s;
   if (crop < 0 || 2 * crop >= hh || 2 * crop >= wh) return fail(ESR_ERR_INVALID, "cem_up_add: crop %d too large", crop);
   const int ho = hh - 2 * crop, wo = wh - 2 * crop;
-  if (cem_fast(rank, ku_len)) {
+  if (cem_fast(rank, ku_len) && (s == 2 || s == 3 || s == 4 || s == 8)) {
+    typedef void (*UpFn)(const float*, const float*, int, int, int, const float*, const float*, int, int, float*);
+    UpFn fn = s == 2 ? esr::cem_up_add_fast_kernel<2> : (s == 3 ? esr::cem_up_add_fast_kernel<3> : (s == 4 ? esr::cem_up_add_fast_kernel<4> : esr::cem_up_add_fast_kernel<8>));
     const int maxni = (esr::kUpTY + ku_len) / s + 2, maxnj = (esr::kUpTX + ku_len) / s + 2;
     const size_t fsmem = sizeof(float) * ((size_t)maxni * maxnj + (size_t)maxni * esr::kUpTX);
-    int rc = set_smem_attr((const void*)esr::cem_up_add_fast_kernel, fsmem);
+    int rc = set_smem_attr((const void*)fn, fsmem);
     if (rc) return rc;
     dim3 grid((wo + esr::kUpTX - 1) / esr::kUpTX, (ho + esr::kUpTY - 1) / esr::kUpTY, n * c);
-    esr::cem_up_add_fast_kernel<<<grid, 256, fsmem, (cudaStream_t)stream>>>(f, g, hl, wl, s, phase, ku_v, ku_h, ku_len, crop, out_hr);
+    fn<<<grid, 256, fsmem, (cudaStream_t)stream>>>(f, g, hl, wl, phase, ku_v, ku_h, ku_len, crop, out_hr);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ESR_OK;
@@ -1298,7 +1323,7 @@ int esr_soft_hist_fwd(const double* x, int dims, int n_samples, const double* bi
   } else {
     CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(double) * n_bins, st));
     const int bx = (n_bins + esr::kHistTileB - 1) / esr::kHistTileB;
-    int chunks = (148 * 4 + bx - 1) / bx;                       // a few waves of blocks whatever the bin count
+    int chunks = deterministic() ? 1 : (148 * 4 + bx - 1) / bx;  // a few waves of blocks whatever the bin count
     int per = (n_samples + chunks - 1) / chunks;
     per = (per + esr::kHistTileP - 1) / esr::kHistTileP * esr::kHistTileP;
     chunks = (n_samples + per - 1) / per;

@@ -69,6 +69,7 @@ SIGNATURES = {
     "esr_version": (C.c_int, []),
     "esr_launch_count": (C.c_longlong, []),
     "esr_device_check": (C.c_int, []),
+    "esr_set_deterministic": (C.c_int, [C.c_int]),
     "esr_debug_watchdog": (C.c_int, [C.POINTER(C.c_uint), C.c_int]),
     "esr_conv3x3_fwd": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "esr_conv3x3_fwd_batch": (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.POINTER(C.c_int)]),

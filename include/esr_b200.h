@@ -46,6 +46,11 @@ long long esr_launch_count(void);
 /* debugging aid: copies the 8-word pipeline watchdog record (word 0 != 0: some mbarrier wait timed out;
  * then block, thread, barrier address, parity, role tag) to host memory; optionally clears it.  Synchronises. */
 int esr_debug_watchdog(unsigned int* out8_host, int reset);
+/* Bit-reproducible launches (also ESR_DETERMINISTIC=1 in the environment): one MMA issuer per CTA in the row-streaming and wgrad
+ * kernels (three issuers add into one TMEM accumulator in arrival order otherwise), no floating-point atomics across blocks in the
+ * bias / channel-sum / histogram reductions.  Costs about 15 % of the convolution throughput.  (Not covered: the scatter of the
+ * latent map's gradient in esr_latent_grad, which folds replicate-padded pixels onto the border with atomics.) */
+int esr_set_deterministic(int on);
 /* 0 if the current device can run the sm_100a kernels */
 int esr_device_check(void);
 

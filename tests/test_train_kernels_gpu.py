@@ -157,3 +157,28 @@ def test_backward_after_a_second_forward_is_refused():
     y2.sum().backward()
     with pytest.raises(lib.EsrError):
         y1.sum().backward()
+
+
+def test_deterministic_flag_makes_training_backward_bit_reproducible():
+    """esr_set_deterministic(1): one MMA issuer per CTA, no cross-block float atomics - two launches of the same backward agree bit for bit
+    (with the default three issuers the fp32 summation order inside an accumulator follows arrival order)"""
+    import models.modules.architecture as arch
+    from CEM.CEMnet import CEMnet, Get_CEM_Conf
+    from esr_b200 import lib
+    torch.manual_seed(4)
+    model = CEMnet(Get_CEM_Conf(4)).WrapArchitecture_PyTorch(arch.RRDBNet(3, 3, 64, 1, upscale=4, num_latent_channels=0), None).to(DEV).train()
+    params = [p for n_, p in model.named_parameters() if 'Filter_OP' not in n_]
+    x, hr = torch.rand(2, 3, 40, 136, device=DEV), torch.rand(2, 3, 160, 544, device=DEV)
+    lib.check(lib.load().esr_set_deterministic(1))
+    try:
+        runs = []
+        for _ in range(2):
+            for p in params:
+                p.grad = None
+            out = model(x)
+            (out - hr).abs().mean().backward()
+            runs.append((out.detach().clone(), [p.grad.clone() for p in params]))
+        assert torch.equal(runs[0][0], runs[1][0])
+        assert all(torch.equal(a, b) for a, b in zip(runs[0][1], runs[1][1]))
+    finally:
+        lib.check(lib.load().esr_set_deterministic(0))

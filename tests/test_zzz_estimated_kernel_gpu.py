@@ -7,10 +7,9 @@ import torch
 
 from util import golden, rel_err
 
-# Written after the round's GPU minutes were spent: the host-side design is pinned on the CPU (tests/test_cem_design.py), the
-# rank-1 kernels are verified on the GPU (tests/test_gpu_parity.py), the rank > 1 loops have not run against a reference yet.
-# (named zzz: it runs last, so that even a device fault in this unconfirmed path cannot touch any other test)
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='rank > 1 separable CEM path not yet confirmed on a GPU')]
+# (the host-side design is pinned on the CPU by tests/test_cem_design.py, the rank-1 kernels by tests/test_gpu_parity.py; this is the
+#  rank > 1 path - confirmed on the driver's B200 at the end of round 1)
+pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
