@@ -203,6 +203,36 @@ __device__ __forceinline__ float up_axis(const float* __restrict__ taps, int len
   return a;
 }
 
+// the same walk for four adjacent columns at once (vertical pass: the taps and LR rows depend on the output row only)
+template <int S_>
+__device__ __forceinline__ float4 up_axis4(const float* __restrict__ taps, int len, int r, int phase, int pos, int n_hr, int n_lr, int lo,
+                                           const float* __restrict__ samples, int stride) {
+  const int b_lo = max(0, r - pos), b_hi = min(len - 1, n_hr - 1 - pos + r);
+  int m = (phase + r - pos - b_lo) % S_;
+  if (m < 0) m += S_;
+  int b = b_lo + m;
+  int j = (pos + b - r - phase) / S_ - lo;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (; b <= b_hi; b += S_, ++j) {
+    const float t = taps[b];
+    const float4 v = *reinterpret_cast<const float4*>(samples + j * stride);
+    a.x = fmaf(t, v.x, a.x); a.y = fmaf(t, v.y, a.y); a.z = fmaf(t, v.z, a.z); a.w = fmaf(t, v.w, a.w);
+  }
+  if (b_lo > 0 && phase == 0) {
+    float t = 0.f;
+    for (int k = 0; k < b_lo; ++k) t += taps[k];
+    const float4 v = *reinterpret_cast<const float4*>(samples + (0 - lo) * stride);
+    a.x = fmaf(t, v.x, a.x); a.y = fmaf(t, v.y, a.y); a.z = fmaf(t, v.z, a.z); a.w = fmaf(t, v.w, a.w);
+  }
+  if (b_hi < len - 1 && (n_hr - 1 - phase) % S_ == 0) {
+    float t = 0.f;
+    for (int k = b_hi + 1; k < len; ++k) t += taps[k];
+    const float4 v = *reinterpret_cast<const float4*>(samples + (n_lr - 1 - lo) * stride);
+    a.x = fmaf(t, v.x, a.x); a.y = fmaf(t, v.y, a.y); a.z = fmaf(t, v.z, a.z); a.w = fmaf(t, v.w, a.w);
+  }
+  return a;
+}
+
 template <int S_>
 __global__ void __launch_bounds__(256)
 cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g, int hl, int wl, int phase, const float* __restrict__ kv,
@@ -254,9 +284,8 @@ cem_up_add_fast_kernel(const float* __restrict__ f, const float* __restrict__ g,
     const int Y = Y0 + ty + 8 * k;
     const int yo = Y - crop;
     if (yo >= ho || Y >= hh) continue;
-    float acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = up_axis<S_>(tv, len, r, phase, Y, hh, hl, ilo, hb + 4 * xg + q, kUpTX);
+    const float4 a4 = up_axis4<S_>(tv, len, r, phase, Y, hh, hl, ilo, hb + 4 * xg, kUpTX);
+    const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
     const float* gp = g ? g + (size_t)nc * hh * wh + (size_t)Y * wh + X : nullptr;
     float* op = out + (size_t)nc * ho * wo + (size_t)yo * wo + (X - crop);
     if (vec) {

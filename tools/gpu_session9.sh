@@ -1,5 +1,5 @@
 #!/bin/bash
-OUT=gpurun_out/s9
+OUT=gpurun_out/s10
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -s -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1
 echo "pytest rc=$?" > $OUT/summary.txt
