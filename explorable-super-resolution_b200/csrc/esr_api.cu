@@ -156,6 +156,7 @@ RowsKernelFn select_rows_kernel(int nbn, bool bwd, int epi) {
     case 32 * 8 + 2: return esr::conv3x3_rows_kernel<32, false, 2>;
     case 32 * 8 + 4: return esr::conv3x3_rows_kernel<32, false, 4>;
     case 32 * 8 + 5: return esr::conv3x3_rows_kernel<32, false, 5>;
+    case 64 * 8 + 4: return esr::conv3x3_rows_kernel<64, false, 4>;
     case 64 * 8 + 5: return esr::conv3x3_rows_kernel<64, false, 5>;
     case 64 * 8 + 0: return esr::conv3x3_rows_kernel<64, false, 0>;
     case 64 * 8 + 1: return esr::conv3x3_rows_kernel<64, false, 1>;
@@ -196,7 +197,7 @@ int launch_conv(const void* kern, int grid, uint32_t smem_bytes, void* stream, v
 }
 
 struct WgradPlan {
-  int gyp, nbn, cpb, n_blocks, mt, rb;
+  int gyp, nbn, cpb, n_blocks, mt, rb, gstages;
   uint32_t slot_bytes, gstage_bytes, ring_bytes, smem_bytes;
 };
 // tiling of the weight-gradient kernel for (cin_planes, cout); returns false when it does not fit
@@ -213,6 +214,7 @@ bool wgrad_plan(int cp, int cout, WgradPlan* w) {
   const uint32_t group = esr::kWgBox * 16u;
   w->slot_bytes = (uint32_t)cp * group;
   w->gstage_bytes = 3u * w->cpb * group;
+  // activation ring as deep as fits next to three gradient stages, then as many more gradient stages as fit (v1 always uses three)
   int rb = esr::kWgMaxRing;
   for (; rb >= 4; --rb) {
     w->ring_bytes = (uint32_t)(rb + 2) * w->slot_bytes + 16u * group;   // + slack for the last M chunk
@@ -220,6 +222,12 @@ bool wgrad_plan(int cp, int cout, WgradPlan* w) {
     if (w->smem_bytes <= kSmemMax) break;
   }
   if (rb < 4) return false;
+  w->gstages = esr::kWgGStages;
+  const int max_stages = w->cpb > 4 ? 4 : 8;      // at most one outstanding stage grant per loader warp: stages x plane groups <= 8
+  while (w->gstages < max_stages && w->smem_bytes + esr::kWgNB * w->gstage_bytes <= kSmemMax) {
+    w->gstages++;
+    w->smem_bytes += esr::kWgNB * w->gstage_bytes;
+  }
   w->rb = rb;
   return true;
 }
@@ -398,7 +406,7 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
 
   const bool bwd = p.lead_planes > 0 || p.mask16 != nullptr || p.res3 != nullptr || p.tail_first > 0;
   // (the gradient-slice launches of the dense-block backward have the forward-type fast epilogue: same width rule as forward launches)
-  const bool mask_only_shape = bwd && a->rows_nbn == 32 && a->cout % 32 == 0 && a->mask16 && a->out16 && !a->lead_planes && !a->res1 && !a->res2 &&
+  const bool mask_only_shape = bwd && a->rows_nbn >= 32 && a->cout % 32 == 0 && a->mask16 && a->out16 && !a->lead_planes && !a->res1 && !a->res2 &&
                                !a->res3 && !a->out32 && !a->out_nchw && !a->out16_up2 && !a->out16_pixel_shuffle && a->tail_first_plane == 0 &&
                                a->alpha == 1.0f && !a->lrelu;
   const bool closing_shape = bwd && a->rows_nbn >= 32 && a->cout % 32 == 0 && !a->mask16 && !a->lead_planes && a->res3 && !a->res2 && a->out32 && a->out16 &&
@@ -417,12 +425,12 @@ int esr_conv3x3_fwd(const esr_conv3x3_args* a, void* stream) {
     }
     if (!bwd && nbn == 16 && p.out_nchw && p.out_nchw_c <= 8 && !p.out16 && !p.out32 && !p.res1 && !p.res2 && !p.res3) epi = 3;
     // gradient slice of the dense-block backward: mask * acc -> 16-bit planes, nothing else
-    const bool mask_only = bwd && nbn == 32 && a->cout % 32 == 0 && p.mask16 && p.out16 && !p.lead_planes && !p.res1 && !p.res2 && !p.res3 &&
+    const bool mask_only = bwd && nbn >= 32 && a->cout % 32 == 0 && p.mask16 && p.out16 && !p.lead_planes && !p.res1 && !p.res2 && !p.res3 &&
                            !p.out32 && !p.out_nchw && !p.out16_up2 && !p.out16_ps && p.tail_first == 0 && p.alpha == 1.0f && !p.lrelu;
     // closing launch of the dense-block backward: acc + beta3*res3 (+ beta1*res1 fp32) -> fp32 planes and 16-bit planes
     const bool closing = bwd && nbn >= 32 && a->cout % 32 == 0 && !p.mask16 && !p.lead_planes && p.res3 && !p.res2 && p.out32 && p.out16 && !p.out_nchw &&
                          !p.out16_up2 && !p.out16_ps && p.tail_first == 0 && p.alpha == 1.0f && !p.lrelu && (!p.res1 || !p.res1_is16);
-    RowsKernelFn rk = mask_only ? select_rows_kernel(32, false, 4) : (closing ? select_rows_kernel(nbn, false, 5) : select_rows_kernel(nbn, bwd, epi));
+    RowsKernelFn rk = mask_only ? select_rows_kernel(nbn, false, 4) : (closing ? select_rows_kernel(nbn, false, 5) : select_rows_kernel(nbn, bwd, epi));
     if (!rk) return fail(ESR_ERR_INVALID, "conv3x3: no row kernel for N block %d", nbn);
     p.nb_n = nbn;
     p.n_blocks = (a->cout + nbn - 1) / nbn;
@@ -601,7 +609,7 @@ int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* 
 size_t esr_conv3x3_wgrad_workspace(int cin_planes, int cout) {
   WgradPlan w;
   if (!wgrad_plan(cin_planes, cout, &w)) return 0;
-  return (size_t)num_sms() * w.mt * 128 * 3 * w.nbn * sizeof(float);
+  return (size_t)num_sms() * (w.mt * 128 * 3 * w.nbn + esr::kWgBiasStride) * sizeof(float);
 }
 
 int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
@@ -637,6 +645,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
   if (!wgrad_plan(cp, a->cout, &w)) return fail(ESR_ERR_INVALID, "wgrad: (cin %d, cout %d) does not fit the tensor-core tiling", a->cin, a->cout);
   if (a->gy_plane_off + w.gyp > a->gy_planes_total) return fail(ESR_ERR_INVALID, "wgrad: gradient planes out of range");
   cudaStream_t st = (cudaStream_t)stream;
+  bool fused_bias = false;
   if (a->dw) {
     esr::WgradParams p;
     memset(&p, 0, sizeof(p));
@@ -659,14 +668,19 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     p.slot_bytes = w.slot_bytes; p.gstage_bytes = w.gstage_bytes; p.ring_bytes = w.ring_bytes;
     // D=f32, A/B = f16|bf16, both MN-major (bits 15, 16), N = 3*nbn, M = 128
     p.issuers = deterministic() ? 1 : esr::kWgIssuers;
+    p.gstages = w.gstages; p.ngroups = w.cpb > 4 ? 2 : 1;
     p.idesc = (1u << 4) | ((uint32_t)a->dtype << 7) | ((uint32_t)a->dtype << 10) | (1u << 15) | (1u << 16) |
               ((uint32_t)((3 * w.nbn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int grid = ranges * w.n_blocks;
-    const size_t need = (size_t)grid * w.mt * 128 * 3 * w.nbn * sizeof(float);
+    const size_t part_floats = (size_t)grid * w.mt * 128 * 3 * w.nbn;
+    const size_t need = (part_floats + (size_t)grid * esr::kWgBiasStride) * sizeof(float);
     if (a->workspace_bytes < need) return fail(ESR_ERR_INVALID, "wgrad: workspace of %zu bytes needed, %zu given", need, a->workspace_bytes);
     p.part = a->workspace;
-    int rc = set_max_smem_once((const void*)esr::conv3x3_wgrad_kernel);
-    if (rc) return rc;
+    p.dtype = a->dtype;
+    // v2 (default): the gradient row crosses L2 -> SM once and the bias gradient is summed on the way; ESR_WGRAD_V1=1: three TMA copies
+    static const bool v1 = [] { const char* e = getenv("ESR_WGRAD_V1"); return e && atoi(e) != 0; }();
+    fused_bias = !v1 && a->db != nullptr;
+    p.bias_part = fused_bias ? a->workspace + part_floats : nullptr;
     // tensor maps over the planar-8 buffers: dims (8ch*W, H, planes, N); box = (8*32 elements, 1 row, planes of the operand, 1)
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail(ESR_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -679,24 +693,34 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
       CUresult cr = encode(&tmx, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed with CUresult %d", (int)cr);
-      cuuint64_t gdim2[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->gy_planes_total, (cuuint64_t)a->n};
-      cuuint64_t gstr2[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->gy_planes_total};
-      cuuint32_t box2[4] = {(cuuint32_t)esr::kWgBox * 8, 1, (cuuint32_t)w.cpb, 1};
-      cr = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->gy), gdim2, gstr2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(gy) failed with CUresult %d", (int)cr);
+      if (v1) {
+        cuuint64_t gdim2[4] = {(cuuint64_t)a->w * 8, (cuuint64_t)a->h, (cuuint64_t)a->gy_planes_total, (cuuint64_t)a->n};
+        cuuint64_t gstr2[3] = {(cuuint64_t)a->w * 16, (cuuint64_t)a->w * a->h * 16, (cuuint64_t)a->w * a->h * 16 * a->gy_planes_total};
+        cuuint32_t box2[4] = {(cuuint32_t)esr::kWgBox * 8, 1, (cuuint32_t)w.cpb, 1};
+        cr = encode(&tmg, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(a->gy), gdim2, gstr2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return fail(ESR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(gy) failed with CUresult %d", (int)cr);
+      }
     }
-    esr::conv3x3_wgrad_kernel<<<grid, esr::kWgThreads, w.smem_bytes, st>>>(tmx, tmg, p);
+    if (v1) {
+      int rc = set_max_smem_once((const void*)esr::conv3x3_wgrad_kernel_v1);
+      if (rc) return rc;
+      esr::conv3x3_wgrad_kernel_v1<<<grid, esr::kWgThreadsV1, w.smem_bytes, st>>>(tmx, tmg, p);
+    } else {
+      int rc = set_max_smem_once((const void*)esr::conv3x3_wgrad_kernel);
+      if (rc) return rc;
+      esr::conv3x3_wgrad_kernel<<<grid, esr::kWgThreads, w.smem_bytes, st>>>(tmx, p);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     const int per_cta = w.mt * 128 * 3 * w.nbn;
     esr::wgrad_reduce_kernel<<<dim3((unsigned)((per_cta + 255) / 256), (unsigned)w.n_blocks), 256, 0, st>>>(
         a->workspace, ranges, w.n_blocks, w.mt, w.nbn, cp, a->cout, a->cin, a->lead, a->scale, a->accumulate, a->dw,
-        a->cin_total > 0 ? a->cin_total : a->cin, a->cin_off);
+        a->cin_total > 0 ? a->cin_total : a->cin, a->cin_off, p.bias_part, a->db);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  if (a->db) {
+  if (a->db && !fused_bias) {
     if (!a->accumulate) CUDA_TRY(cudaMemsetAsync(a->db, 0, sizeof(float) * a->cout, st));
     const size_t hw = (size_t)a->h * a->w;
     size_t chunks = ((size_t)a->n * hw + 255) / 256;

@@ -59,6 +59,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {   // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Watchdog state: [0] = flag, [1] = block, [2] = thread, [3] = barrier smem address, [4] = parity, [5] = tag
 __device__ unsigned int g_watchdog[8];
 

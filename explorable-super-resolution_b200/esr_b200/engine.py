@@ -19,6 +19,8 @@ kernel with transposed/rotated weights (`transpose_flip`), the dense-block gradi
 (in-place `res2 == out32`), LeakyReLU derivatives come from the saved 16-bit activations (`mask16`), and the latent
 channels' gradient is accumulated by every launch into one plane (`lead_acc`).
 """
+import os
+
 import torch
 
 from . import ops
@@ -387,10 +389,19 @@ class RRDBEngine:
         # gradient operands share the activations' format (tcgen05 kind::f16 traps on f16 x bf16): training runs the whole
         # engine in bf16 because fp16 gradients underflow (a dense block's inner gradients sit 3-4 decades below the trunk's)
         gdt = self.dtype
-        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        f16 = lambda n_, planes, hh, ww, _8: ops.alloc16(gdt, n_, planes, hh, ww, dev, zero=True)
-        gz_hr = f32(n, 1, H, W, 8) if z else None
-        gz_lr = f32(n, 1, h, w, 8) if z else None
+        # every gradient buffer below is fully written by the launch that produces it before anything reads it: no zero-fill (at C2 the
+        # memsets of the HR-resolution buffers alone were 10 GB per step).  ESR_POISON=1 fills them with NaN instead (tests).
+        poison = os.environ.get('ESR_POISON', '0') == '1'
+
+        def f32(*s):
+            t = torch.empty(s, dtype=torch.float32, device=dev)
+            return t.fill_(float('nan')) if poison else t
+
+        def f16(n_, planes, hh, ww, _8):
+            t = ops.alloc16(gdt, n_, planes, hh, ww, dev)
+            return t.fill_(float('nan')) if poison else t
+        gz_hr = torch.zeros((n, 1, H, W, 8), dtype=torch.float32, device=dev) if z else None      # accumulated into by every launch that
+        gz_lr = torch.zeros((n, 1, h, w, 8), dtype=torch.float32, device=dev) if z else None      # reads the latent plane
         lead = dict(lead_planes=zp, lead_acc=gz_hr) if z else {}
         idx_lr = 1 + 15 * nb
         idx_hr0 = idx_lr + 1 + n_up

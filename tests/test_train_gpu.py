@@ -24,9 +24,13 @@ def _watchdog():
     assert wd[0] == 0, 'pipeline watchdog fired: %r' % (wd,)
 
 
-@pytest.mark.parametrize('tag', ['plain', 'latent'])
-def test_weight_gradients_match_reference_autograd(tag):
+@pytest.mark.parametrize('tag,poison', [('plain', False), ('latent', False), ('latent', True)])
+def test_weight_gradients_match_reference_autograd(tag, poison, monkeypatch):
+    """poison: the backward's scratch gradient buffers start as NaN instead of recycled memory (engine.backward allocates them without a
+    zero-fill): a launch that read anything it had not written would poison the gradients"""
     from esr_b200 import ops
+    if poison:
+        monkeypatch.setenv('ESR_POISON', '1')
     from CEM.CEMnet import CEMnet, Get_CEM_Conf
     ops.device_check()
     g = golden('wgrad_kinkfree_%s_train' % tag)
