@@ -342,7 +342,8 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int img, x0, ya, yb;
       bool x_pending = wg_next_segment(p, u, u1, img, x0, ya, yb);
       int row = x_pending ? ya - 1 : 0;
-      unsigned long long t0 = globaltimer_ns();
+      unsigned long long t0 = 0ull;
+      uint32_t idle = 0u;
       while (x_pending || q < total) {
         bool progressed = false;
         if (x_pending && mbar_test_wait(bar_xempty + 8 * xr.j, xr.ph ^ 1u)) {
@@ -372,10 +373,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           progressed = true;
         }
         if (progressed) {
-          t0 = globaltimer_ns();
-        } else {
+          idle = 0;
+        } else if (++idle >= 4096u) {       // (reading the global timer costs more than a poll: only while nothing moves)
+          if (idle == 4096u) t0 = globaltimer_ns();
           if (*(volatile unsigned int*)&g_watchdog[0]) break;
-          if (globaltimer_ns() - t0 > 2000000000ull) {
+          if ((idle & 1023u) == 0u && globaltimer_ns() - t0 > 2000000000ull) {
             if (atomicExch(&g_watchdog[0], 1u) == 0u) {
               g_watchdog[1] = blockIdx.x; g_watchdog[2] = threadIdx.x; g_watchdog[3] = bar_xempty + 8 * xr.j; g_watchdog[4] = xr.ph ^ 1u;
               g_watchdog[5] = 7u;
@@ -468,68 +470,67 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const bool want_bias = p.bias_part != nullptr;
     const int pg = (gw % p.ngroups) * 4;          // first plane of this warp's group
     {
-      long long u = u0;
-      int img, x0, ya, yb;
-      long long t = 0;
-      int s = 0;
+      // this warp's items t = gw, gw + 8, ...: unit coordinates straight from the unit index (walking the other warps' units
+      // cost more instructions than loading its own: ncu, 8 x 130 dependent integer instructions per item)
+      const uint32_t nitems = (uint32_t)(u1 - u0) * (uint32_t)p.ngroups;
       uint32_t round = 0;                          // items this warp has taken so far
-      while (wg_next_segment(p, u, u1, img, x0, ya, yb)) {
-        for (int row = ya; row < yb; ++row) {
-          for (int g = 0; g < p.ngroups; ++g, ++t) {
-            if ((int)(t & (kWgLoaders - 1)) != gw) continue;
-            const uint32_t stage = gst0 + (uint32_t)s * kWgNB * p.gstage_bytes;
-            const uint16_t* grow = reinterpret_cast<const uint16_t*>(p.gy) +
-                                   (((size_t)img * p.gy_pt + p.gy_po + nblk * p.cpb + pg) * p.h + row) * (size_t)p.w * 8;
-            uint4 v[4][3];
+      for (uint32_t t = (uint32_t)gw; t < nitems; t += kWgLoaders, ++round) {
+        const uint32_t q = p.ngroups == 2 ? (t >> 1) : t;
+        const uint32_t U = (uint32_t)u0 + q;
+        const uint32_t col = U / (uint32_t)p.h;
+        const int row = (int)(U - col * (uint32_t)p.h);
+        const int img = (int)(col / (uint32_t)p.strips);
+        const int x0 = (int)(col - (uint32_t)img * (uint32_t)p.strips) * kWgPW;
+        const int s = (int)(q % (uint32_t)p.gstages);
+        const uint32_t stage = gst0 + (uint32_t)s * kWgNB * p.gstage_bytes;
+        const uint16_t* grow = reinterpret_cast<const uint16_t*>(p.gy) +
+                               (((size_t)img * p.gy_pt + p.gy_po + nblk * p.cpb + pg) * p.h + row) * (size_t)p.w * 8;
+        uint4 v[4][3];
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-              const bool okp = pg + pp < p.cpb && nblk * p.cpb + pg + pp < p.gyp;
+        for (int pp = 0; pp < 4; ++pp) {
+          const bool okp = pg + pp < p.cpb && nblk * p.cpb + pg + pp < p.gyp;
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const int j = lane + 32 * c - 1, gx = x0 + j;
-                v[pp][c] = make_uint4(0u, 0u, 0u, 0u);
-                if (okp && j <= kWgPW && gx >= 0 && gx < p.w) v[pp][c] = ldg_nc_v4(grow + (size_t)pp * plane_elems + (size_t)gx * 8);
-              }
-            }
-            mbar_wait(bar_go + 8 * gw, round & 1u, 5u);      // the stage is free (its previous MMAs have completed)
-            ++round;
+          for (int c = 0; c < 3; ++c) {
+            const int j = lane + 32 * c - 1, gx = x0 + j;
+            v[pp][c] = make_uint4(0u, 0u, 0u, 0u);
+            if (okp && j <= kWgPW && gx >= 0 && gx < p.w) v[pp][c] = ldg_nc_v4(grow + (size_t)pp * plane_elems + (size_t)gx * 8);
+          }
+        }
+        mbar_wait(bar_go + 8 * gw, round & 1u, 5u);      // the stage is free (its previous MMAs have completed)
 #pragma unroll
-            for (int pp = 0; pp < 4; ++pp) {
-              if (pg + pp < p.cpb) {
+        for (int pp = 0; pp < 4; ++pp) {
+          if (pg + pp < p.cpb) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  const int j = lane + 32 * c - 1;
-                  if (j <= kWgPW) {
+            for (int c = 0; c < 3; ++c) {
+              const int j = lane + 32 * c - 1;
+              if (j <= kWgPW) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                      const int k = j + kx - 1;
-                      if (k >= 0 && k < kWgPW)
-                        sts_v4(stage + (uint32_t)(k >> 5) * p.gstage_bytes + (uint32_t)((kx * p.cpb + pg + pp) * kWgBox + (k & 31)) * 16u, v[pp][c]);
-                    }
-                  }
-                }
-              }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_gfull + 8 * s);
-            if (want_bias) {      // the bias gradient from the registers, off the stage's critical path
-#pragma unroll
-              for (int pp = 0; pp < 4; ++pp) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  const int j = lane + 32 * c - 1;
-                  if (j >= 0 && j < kWgPW) {
-                    float a[8];
-                    unpack8(v[pp][c], p.dtype, a);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) bsum[pp][e] += a[e];
-                  }
+                for (int kx = 0; kx < 3; ++kx) {
+                  const int k = j + kx - 1;
+                  if (k >= 0 && k < kWgPW)
+                    sts_v4(stage + (uint32_t)(k >> 5) * p.gstage_bytes + (uint32_t)((kx * p.cpb + pg + pp) * kWgBox + (k & 31)) * 16u, v[pp][c]);
                 }
               }
             }
           }
-          if (++s == p.gstages) s = 0;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_gfull + 8 * s);
+        if (want_bias) {      // the bias gradient from the registers, off the stage's critical path
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int j = lane + 32 * c - 1;
+              if (j >= 0 && j < kWgPW) {
+                float a[8];
+                unpack8(v[pp][c], p.dtype, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bsum[pp][e] += a[e];
+              }
+            }
+          }
         }
       }
     }
@@ -594,13 +595,27 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int ranges, 
   const int per_cta = mt * 128 * N3;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int nblk = blockIdx.y;
-  if (bias_part && blockIdx.x == 0 && (int)threadIdx.x < nbn) {
-    const int co = nblk * nbn + threadIdx.x;
-    if (co < cout) {
-      float b = 0.f;
-      for (int rg = 0; rg < ranges; ++rg) b += __ldg(bias_part + (size_t)(rg * n_blocks + nblk) * kWgBiasStride + threadIdx.x);
-      b *= scale;
-      db[co] = accumulate ? db[co] + b : b;
+  if (bias_part && blockIdx.x == 0) {
+    // 64 channels x 4 interleaved slices of the CTA list, four loads in flight per thread; combined in a fixed order
+    __shared__ float bsh[4][kWgBiasStride];
+    const int ch = threadIdx.x & (kWgBiasStride - 1), sl = threadIdx.x >> 6;
+    float b4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ch < nbn) {
+      int rg = sl;
+      for (; rg + 12 < ranges; rg += 16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b4[k] += __ldg(bias_part + (size_t)((rg + 4 * k) * n_blocks + nblk) * kWgBiasStride + ch);
+      }
+      for (; rg < ranges; rg += 4) b4[0] += __ldg(bias_part + (size_t)(rg * n_blocks + nblk) * kWgBiasStride + ch);
+    }
+    bsh[sl][ch] = (b4[0] + b4[1]) + (b4[2] + b4[3]);
+    __syncthreads();
+    if (sl == 0 && ch < nbn) {
+      const int co = nblk * nbn + ch;
+      if (co < cout) {
+        const float b = ((bsh[0][ch] + bsh[1][ch]) + (bsh[2][ch] + bsh[3][ch])) * scale;
+        db[co] = accumulate ? db[co] + b : b;
+      }
     }
   }
   if (e >= per_cta) return;

@@ -652,6 +652,7 @@ int esr_conv3x3_wgrad(const esr_conv3x3_wgrad_args* a, void* stream) {
     p.n = a->n; p.h = a->h; p.w = a->w;
     p.strips = (a->w + esr::kWgPW - 1) / esr::kWgPW;
     p.units = (long long)a->n * p.strips * a->h;
+    if (p.units > 0x3fffffffLL) return fail(ESR_ERR_INVALID, "wgrad: too many row units (%lld)", p.units);
     p.n_blocks = w.n_blocks;
     int ranges = num_sms() / w.n_blocks;
     if (ranges < 1) return fail(ESR_ERR_INVALID, "wgrad: too many n-blocks (%d)", w.n_blocks);
