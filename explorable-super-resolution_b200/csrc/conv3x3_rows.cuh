@@ -364,18 +364,68 @@ struct PackJob {
   float* bias_out; const float* bias_in; int cout_pad, bias_n;
 };
 
+// eight consecutive packed elements (one 16-byte core-matrix row: input channel positions i0 .. i0+7 of output position o at tap
+// (ky, kx)) -> one uint4.  The element decomposition (divisions by run-time extents) is paid once per eight elements.
+__device__ __forceinline__ uint4 pack_weights_vec8(const float* __restrict__ w, int cout, int cin, int lead, int dtype, int transpose_flip, int seg,
+                                                   int o, int i0, int ky, int kx) {
+  const int lc_out = transpose_flip ? cin : cout;
+  const int lc_in = transpose_flip ? cout : cin;
+  const int lead_pad = (lead + 7) / 8 * 8;
+  if (transpose_flip) {
+    if (o < lead_pad) o = o < lead ? o : -1;
+    else o = o - lead_pad + lead;
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int i = i0 + k;
+    if (!transpose_flip) {
+      if (i < lead_pad) i = i < lead ? i : -1;
+      else i = i - lead_pad + lead;
+    }
+    float val = 0.f;
+    if (o >= 0 && o < lc_out && i >= 0 && i < lc_in) {
+      if (!transpose_flip) val = __ldg(w + (((size_t)o * cin + i) * 3 + ky) * 3 + kx);
+      else val = __ldg(w + (((size_t)i * cin + o) * 3 + (2 - ky)) * 3 + (2 - kx));
+    }
+    h[k] = dtype == 2 ? (uint32_t)split_weight_bits(val, seg) : (pack2(val, 0.f, dtype) & 0xFFFFu);
+  }
+  return make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+}
+
 __global__ void pack_weights_batch_kernel(const PackJob* __restrict__ jobs) {
   const PackJob jb = jobs[blockIdx.y];
-  const size_t all = (size_t)jb.total + (size_t)jb.rows_total + (size_t)jb.cout_pad;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < all; idx += (size_t)gridDim.x * blockDim.x) {
-    if (idx < jb.total) {
-      jb.dst[idx] = pack_weights_elem(jb.w, jb.cout, jb.cin, jb.lead, jb.kcp, jb.nb_n, jb.nchunks, jb.dtype, jb.transpose_flip, idx);
-    } else if (idx < jb.total + jb.rows_total) {
-      const size_t k = idx - jb.total;
-      jb.rows_dst[k] = pack_weights_rows_elem(jb.w, jb.cout, jb.cin, jb.lead, jb.rows_nb_n, jb.rows_nchunks, jb.dtype, jb.transpose_flip, k);
+  const uint32_t v_tile = (uint32_t)(jb.total >> 3), v_rows = (uint32_t)(jb.rows_total >> 3);
+  const uint32_t all = v_tile + v_rows + (uint32_t)((jb.cout_pad + 7) >> 3);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < all; idx += gridDim.x * blockDim.x) {
+    if (idx < v_tile) {
+      // tile-kernel image: [n-block][chunk][tap][plane of the chunk][n][8 channels]
+      uint32_t r = idx;
+      const int n = r % jb.nb_n; r /= jb.nb_n;
+      const int j = r % jb.kcp; r /= jb.kcp;
+      const int tap = r % 9; r /= 9;
+      int c = r % jb.nchunks; r /= jb.nchunks;
+      int seg = 0;
+      if (jb.dtype == 2) { const int cps = jb.nchunks / 3; seg = c / cps; c -= seg * cps; }
+      reinterpret_cast<uint4*>(jb.dst)[idx] = pack_weights_vec8(jb.w, jb.cout, jb.cin, jb.lead, jb.dtype, jb.transpose_flip, seg,
+                                                                (int)r * jb.nb_n + n, (c * jb.kcp + j) * 8, tap / 3, tap % 3);
+    } else if (idx < v_tile + v_rows) {
+      // row-kernel image: [n-block][chunk][dx][plane of the chunk][(ky, n)][8 channels]
+      uint32_t r = idx - v_tile;
+      const int n3 = 3 * jb.rows_nb_n;
+      const int nn = r % n3; r /= n3;
+      const int j = r % kRowsKch; r /= kRowsKch;
+      const int dx = r % 3; r /= 3;
+      int c = r % jb.rows_nchunks; r /= jb.rows_nchunks;
+      int seg = 0;
+      if (jb.dtype == 2) { const int cps = jb.rows_nchunks / 3; seg = c / cps; c -= seg * cps; }
+      const int ky = nn / jb.rows_nb_n;
+      reinterpret_cast<uint4*>(jb.rows_dst)[idx - v_tile] = pack_weights_vec8(jb.w, jb.cout, jb.cin, jb.lead, jb.dtype, jb.transpose_flip, seg,
+                                                                             (int)r * jb.rows_nb_n + (nn - ky * jb.rows_nb_n),
+                                                                             (c * kRowsKch + j) * 8, ky, dx);
     } else {
-      const int k = (int)(idx - jb.total - jb.rows_total);
-      jb.bias_out[k] = (jb.bias_in && k < jb.bias_n) ? jb.bias_in[k] : 0.f;
+      const int k0 = (int)(idx - v_tile - v_rows) * 8;
+      for (int k = k0; k < k0 + 8 && k < jb.cout_pad; ++k) jb.bias_out[k] = (jb.bias_in && k < jb.bias_n) ? jb.bias_in[k] : 0.f;
     }
   }
 }

@@ -561,6 +561,8 @@ int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* 
     const esr_pack_item* it = items + i;
     if (failed_index) *failed_index = i;
     if (!it->w_oihw || !it->wpacked) return fail(ESR_ERR_INVALID, "pack batch: null pointer in item %d", i);
+    if (((uintptr_t)it->wpacked & 15) || ((uintptr_t)it->wpacked_rows & 15))
+      return fail(ESR_ERR_INVALID, "pack batch: packed images must be 16-byte aligned (item %d)", i);
     if (it->lead < 0 || it->lead > it->cin) return fail(ESR_ERR_INVALID, "pack batch: bad lead %d in item %d", it->lead, i);
     if (it->kcp != 2 && it->kcp != 4) return fail(ESR_ERR_INVALID, "pack batch: kcp must be 2 or 4 (item %d)", i);
     esr::PackJob& jb = jobs[(size_t)i];
@@ -599,7 +601,7 @@ int esr_pack_conv3x3_weights_batch(const esr_pack_item* items, int count, void* 
   CUDA_TRY(cudaMemcpyAsync(scratch, jobs.data(), sizeof(esr::PackJob) * (size_t)count, cudaMemcpyHostToDevice, st));
   for (int i0 = 0; i0 < count; i0 += 65535) {     // gridDim.y limit
     const int n = count - i0 < 65535 ? count - i0 : 65535;
-    esr::pack_weights_batch_kernel<<<dim3(8, (unsigned)n), 256, 0, st>>>((const esr::PackJob*)scratch + i0);
+    esr::pack_weights_batch_kernel<<<dim3(4, (unsigned)n), 256, 0, st>>>((const esr::PackJob*)scratch + i0);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
   }

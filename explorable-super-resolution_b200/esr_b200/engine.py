@@ -393,12 +393,14 @@ class RRDBEngine:
         # memsets of the HR-resolution buffers alone were 10 GB per step).  ESR_POISON=1 fills them with NaN instead (tests).
         poison = os.environ.get('ESR_POISON', '0') == '1'
 
+        zero = os.environ.get('ESR_ZERO_SCRATCH', '0') == '1'
+
         def f32(*s):
-            t = torch.empty(s, dtype=torch.float32, device=dev)
+            t = (torch.zeros if zero else torch.empty)(s, dtype=torch.float32, device=dev)
             return t.fill_(float('nan')) if poison else t
 
         def f16(n_, planes, hh, ww, _8):
-            t = ops.alloc16(gdt, n_, planes, hh, ww, dev)
+            t = ops.alloc16(gdt, n_, planes, hh, ww, dev, zero=zero)
             return t.fill_(float('nan')) if poison else t
         gz_hr = torch.zeros((n, 1, H, W, 8), dtype=torch.float32, device=dev) if z else None      # accumulated into by every launch that
         gz_lr = torch.zeros((n, 1, h, w, 8), dtype=torch.float32, device=dev) if z else None      # reads the latent plane
