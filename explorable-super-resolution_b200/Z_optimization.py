@@ -10,7 +10,8 @@ tcgen05 forward launches and, in backward, the dgrad launches + the exact CEM ad
 Objectives built: 'l1' (optionally masked), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' / 'STD_decrease' (global, or 'local_' over
 7x7 patches through ReturnPatchExtractionMat), 'Mag' (local magnitude), 'hist' / 'dict' (+ 'patch', 'noDC', 'no_localSTD', 'localSTD':
 SoftHistogramLoss on the esr_soft_hist kernels), 'VGG' (perceptual distance through the VGG19 engine), 'Adversarial' (the critic
-engine), 'random_l1' (+ '_limited').  Periodicity, scribble, desired_SVD and digit raise NotImplementedError."""
+engine), 'random_l1' (+ '_limited'), 'periodicity' (integer or 'nonInt' sub-pixel periods, optionally 'Plus' an STD increase).
+Scribble, desired_SVD and digit raise NotImplementedError."""
 import time
 
 import numpy as np
@@ -75,7 +76,25 @@ def TV_Loss(image):
     return (image[:, :, :, :-1] - image[:, :, :, 1:]).abs().mean(dim=(1, 2, 3)) + (image[:, :, :-1, :] - image[:, :, 1:, :]).abs().mean(dim=(1, 2, 3))
 
 
-_UNBUILT = ['periodicity', 'scribble', 'desired_SVD', 'digit']
+def _half_open(shift, negative=False):
+    """slice bound that drops |shift| rows / columns from one side (utils/util.py:260-264)"""
+    if negative:
+        return shift if shift < 0 else None
+    return shift if shift > 0 else None
+
+
+def Return_Translated_SubImage(image, translation):
+    """the part of `image` that overlaps its own copy translated by (dy, dx) (utils/util.py:266-273)"""
+    dy, dx = translation[0], translation[1]
+    return image[:, :, _half_open(dy):_half_open(dy, True), _half_open(dx):_half_open(dx, True)]
+
+
+def Return_Interpolated_SubImage(image, grid):
+    """bilinear samples of `image` on a normalised grid, for sub-pixel periods (utils/util.py:276-277)"""
+    return F.grid_sample(image, grid.repeat([image.size(0), 1, 1, 1]))
+
+
+_UNBUILT = ['scribble', 'desired_SVD', 'digit']
 
 
 class _SoftHistFn(torch.autograd.Function):
@@ -395,7 +414,7 @@ class Z_optimizer():
                 from models.modules.loss import GANLoss
                 self.netD = model.netD
                 self.loss = GANLoss('wgan-gp', 1.0, 0.0).to(self.device)
-            elif 'STD' in objective and 'TV' not in objective:
+            elif 'STD' in objective and not any(p in objective for p in ['periodicity', 'TV']):
                 assert self.objective.replace('local_', '') in ['max_STD', 'min_STD', 'STD_increase', 'STD_decrease']
                 if any(p in objective for p in ['increase', 'decrease']):
                     STD_CHANGE_FACTOR = 1.05
@@ -405,6 +424,40 @@ class Z_optimizer():
                     else:
                         self.desired_STD = self.desired_STD + (data['STD_increment'] if 'increase' in objective else -data['STD_increment'])
                         self.constraining_loss_weight = 255 / 10 * data['STD_increment'] ** 2
+            elif 'periodicity' in objective:      # the image should repeat itself at the given displacements (:470-504)
+                self.STD_PRESERVING_WEIGHT = 20
+                self.PLUS_MEANS_STD_INCREASE = True
+                if 'nonInt' in objective:
+                    image_size = list(self.initial_output.size()[2:])
+                    self.periodicity_points, self.half_period_points = [], []
+                    if 'Plus' in objective and self.PLUS_MEANS_STD_INCREASE:
+                        self.desired_STD = self.initial_STD + data['STD_increment']
+                    for point in data['periodicity_points']:
+                        point = np.array(point)
+                        self.periodicity_points.append([])
+                        self.half_period_points.append([])
+                        for half_period_round in range(1 + ('Plus' in objective and not self.PLUS_MEANS_STD_INCREASE)):
+                            for minus_point in range(2):
+                                cur_point = 1 * point
+                                if half_period_round:
+                                    cur_point = cur_point * 0.5
+                                if minus_point:
+                                    cur_point = cur_point * -1
+                                # sampling grid of the overlap between the image and its copy displaced by cur_point (x first, as grid_sample expects)
+                                y_range = [_half_open(cur_point[0]), _half_open(cur_point[0], True)]
+                                x_range = [_half_open(cur_point[1]), _half_open(cur_point[1], True)]
+                                ranges = []
+                                for axis, cur_range in enumerate([x_range, y_range]):
+                                    cur_range = [cur_range[0] if cur_range[0] is not None else 0,
+                                                 image_size[axis] + cur_range[1] if cur_range[1] is not None else image_size[axis]]
+                                    num = image_size[axis] - np.ceil(np.abs(np.array([0, image_size[axis]]) - cur_range)).astype(np.int16).max()
+                                    ranges.append(np.linspace(start=cur_range[0], stop=cur_range[1], num=num) / image_size[axis] * 2 - 1)
+                                grid = np.meshgrid(*ranges)
+                                grid = torch.from_numpy(np.stack(grid, -1)).view([1] + list(grid[0].shape) + [2]).type(
+                                    self.initial_output.dtype).to(self.initial_output.device)
+                                (self.half_period_points if half_period_round else self.periodicity_points)[-1].append(grid)
+                else:
+                    self.periodicity_points = [np.array(point) for point in data['periodicity_points']]
             elif 'TV' in objective:
                 self.STD_PRESERVING_WEIGHT = 100
             elif 'limited' in objective:
@@ -495,6 +548,10 @@ class Z_optimizer():
             Z_loss = torch.stack(values, 0)
         elif 'VGG' in self.objective:
             Z_loss = self.loss(self.model.netF(self.output_image).to(self.device), self.GT_HR_VGG)
+        elif 'periodicity' in self.objective:
+            Z_loss = self.PeriodicityLoss().to(self.device)
+            if 'Plus' in self.objective and self.PLUS_MEANS_STD_INCREASE:
+                Z_loss = Z_loss + self.STD_PRESERVING_WEIGHT * ((self.Masked_STD(first_image_only=False) - self.desired_STD) ** 2).mean()
         elif 'STD' in self.objective and 'TV' not in self.objective:
             Z_loss = self.Masked_STD(first_image_only=False)
             if any(p in self.objective for p in ['increase', 'decrease']):
@@ -535,7 +592,7 @@ class Z_optimizer():
         graph, static = None, None
         self._graph_ok = (self._own_optimizer and torch.cuda.is_available() and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0'
                           and not self.model_training and self.loggers is None
-                          and not any(p in self.objective for p in ['local', 'Mag', 'hist', 'dict'])      # (sparse products: eager iterations)
+                          and not any(p in self.objective for p in ['local', 'Mag', 'hist', 'dict', 'periodicity'])      # (sparse products, grid samples: eager iterations)
                           and (self.max_iters < 0 or self.max_iters >= self.GRAPH_WARMUP_ITERS + 4))
         if self._graph_ok:
             self._side_stream = torch.cuda.Stream()
@@ -597,6 +654,28 @@ class Z_optimizer():
             self.model.feed_data(self.data, need_GT=False)
             self.model.fake_H = self.model.netG(self.model.model_input)
         return Z_2_return
+
+    def PeriodicityLoss(self):
+        """mean |I(p + d/2) - I(p - d/2)| over the masked overlap, per requested displacement d (Z_optimization.py:799-814), plus the
+        term that keeps the region's STD where it started (dropped when the 'Plus' variant asks for an STD increase instead)"""
+        if 'Plus' in self.objective and self.PLUS_MEANS_STD_INCREASE:
+            loss = 0
+        else:
+            loss = (self.STD_PRESERVING_WEIGHT * (self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean()
+        image = self.output_image
+        mask = self.image_mask.unsqueeze(0).unsqueeze(0)
+        for point_num, point in enumerate(self.periodicity_points):
+            if 'nonInt' in self.objective:
+                cur_mask = Return_Interpolated_SubImage(mask, point[0]) * Return_Interpolated_SubImage(mask, point[1])
+                loss = loss + (cur_mask * (Return_Interpolated_SubImage(image, point[0]) - Return_Interpolated_SubImage(image, point[1])).abs()).mean(dim=(1, 2, 3))
+                if 'Plus' in self.objective and not self.PLUS_MEANS_STD_INCREASE:
+                    half = self.half_period_points[point_num]
+                    half_mask = Return_Interpolated_SubImage(mask, half[0]) * Return_Interpolated_SubImage(mask, half[1])
+                    loss = loss - (half_mask * (Return_Interpolated_SubImage(image, half[0]) - Return_Interpolated_SubImage(image, half[1])).abs()).mean(dim=(1, 2, 3))
+            else:
+                cur_mask = Return_Translated_SubImage(mask, point) * Return_Translated_SubImage(mask, -point)
+                loss = loss + (cur_mask * (Return_Translated_SubImage(image, point) - Return_Translated_SubImage(image, -point)).abs()).mean(dim=(1, 2, 3))
+        return loss
 
     def ReturnStatus(self):
         return self.cur_iter, self.Z_model.PreTanhZ()

@@ -139,6 +139,33 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, size_t nplanes,
   }
 }
 
+// adjoint of nn.PixelShuffle(2) (models/modules/block.py:287) on 16-bit planes: dst channel 4c + 2dy + dx at (y, x) = src channel c at
+// (2y + dy, 2x + dx).  One thread per (image, source plane, y, x): four 16 B loads (the 2x2 positions of 8 channels), four 16 B stores
+// (destination planes 4P .. 4P+3).  src [N][src_pt][2h][2w][8] from plane src_po, dst [N][dst_pt][h][w][8] from plane dst_po.
+__global__ void pixel_unshuffle2_kernel(const uint16_t* __restrict__ src, int n, int planes, int h, int w, int src_pt, int src_po,
+                                        uint16_t* __restrict__ dst, int dst_pt, int dst_po) {
+  const size_t total = (size_t)n * planes * h * w;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int x = r % w; r /= w;
+    const int y = r % h; r /= h;
+    const int P = r % planes; r /= planes;
+    const size_t img = r;
+    const uint16_t* sp = src + (((img * src_pt + src_po + P) * (2 * (size_t)h) + 2 * y) * (2 * (size_t)w) + 2 * x) * 8;
+    union { uint4 q; uint16_t e[8]; } in[2][2], out;
+    in[0][0].q = __ldg(reinterpret_cast<const uint4*>(sp));
+    in[0][1].q = __ldg(reinterpret_cast<const uint4*>(sp + 8));
+    in[1][0].q = __ldg(reinterpret_cast<const uint4*>(sp + 2 * (size_t)w * 8));
+    in[1][1].q = __ldg(reinterpret_cast<const uint4*>(sp + 2 * (size_t)w * 8 + 8));
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out.e[j] = in[(j >> 1) & 1][j & 1].e[2 * s4 + (j >> 2)];
+      *reinterpret_cast<uint4*>(dst + (((img * dst_pt + dst_po + 4 * P + s4) * (size_t)h + y) * w + x) * 8) = out.q;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // CEM filters (CEM/CEMnet.py:254-311).  All images NCHW fp32; one block per (tile, n*c).
 // Filters arrive as `rank` separable terms: K[a][b] = sum_r kv[r][a] * kh[r][b]  (rank 1 for the

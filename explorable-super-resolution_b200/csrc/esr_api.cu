@@ -847,6 +847,20 @@ int esr_unpack_planes32(const float* src32, int n, int c, int h, int w, int plan
   return ESR_OK;
 }
 
+int esr_pixel_unshuffle2_planes16(const void* src, int n, int planes, int h, int w, int src_planes_total, int src_plane_off, void* dst,
+                                  int dst_planes_total, int dst_plane_off, void* stream) {
+  if (!src || !dst || n <= 0 || planes <= 0 || h <= 0 || w <= 0) return fail(ESR_ERR_INVALID, "pixel_unshuffle: bad arguments");
+  if (src_plane_off < 0 || src_plane_off + planes > src_planes_total || dst_plane_off < 0 || dst_plane_off + 4 * planes > dst_planes_total)
+    return fail(ESR_ERR_INVALID, "pixel_unshuffle: planes out of range");
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return fail(ESR_ERR_INVALID, "pixel_unshuffle: pointers must be 16-byte aligned");
+  const size_t total = (size_t)n * planes * h * w;
+  esr::pixel_unshuffle2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, n, planes, h, w, src_planes_total,
+                                                                                     src_plane_off, (uint16_t*)dst, dst_planes_total, dst_plane_off);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ESR_OK;
+}
+
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream) {
   if (!src || !dst) return fail(ESR_ERR_INVALID, "upsample2x: null pointer");
   const size_t total = (size_t)n * planes * h * w;

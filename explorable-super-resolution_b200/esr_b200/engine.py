@@ -193,6 +193,8 @@ class RRDBEngine:
         for r in net.up_factors():
             s *= r
             b['up'].append(z16(n, nfp, h * s, w * s, 8))
+        if net.upsample_mode == 'pixelshuffle' and save:      # LR_conv + skip, the first shuffle stage's input (kept for its wgrad)
+            b['ps_in'] = z16(n, nfp, h, w, 8)
         b['hr_a'] = z16(n, nfp + zp, h * s, w * s, 8)
         b['hr_b'] = z16(n, nfp + zp, h * s, w * s, 8)
         if len(self._bufs) >= 2:  # keep at most two shapes alive (train + eval sizes)
@@ -246,13 +248,14 @@ class RRDBEngine:
                 else:  # the last upconv feeds HR_conv0, which sees the HR latent in plane 0 of hr_a
                     conv(ups[k], next(it), cin_planes=nfp, lrelu=True, slope=SLOPE, out16=B['hr_a'], out16_off=zp)
         else:
-            if save:
-                raise NotImplementedError('esr_b200: backward through the pixelshuffle upsampler is not built')
             # pixelshuffle_block (block.py:278-291): conv(nf -> 4nf) -> PixelShuffle(2) -> act; the shuffle is the
             # store addressing of the conv epilogue, the (elementwise) activation is applied before it
-            tmp = B['D'][2] if Dlast is not B['D'][2] else B['D'][0]
-            conv(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=tmp, out16_off=zp)
-            src, src_off = tmp, zp
+            if save:
+                tmp, tmp_off = B['ps_in'], 0
+            else:
+                tmp, tmp_off = (B['D'][2] if Dlast is not B['D'][2] else B['D'][0]), zp
+            conv(Dlast, next(it), cin_planes=zp + nfp, res1=F, beta1=1.0, out16=tmp, out16_off=tmp_off)
+            src, src_off = tmp, tmp_off
             for k in range(len(factors)):
                 dst, dst_off = (ups[k], 0) if k < len(factors) - 1 else (B['hr_a'], zp)
                 conv(src, next(it), in_plane_off=src_off, cin_planes=nfp, lrelu=True, slope=SLOPE, out16=dst, out16_off=dst_off,
@@ -418,10 +421,26 @@ class RRDBEngine:
         g_a = f16(n, nfp, H, W, 8)
         ops.conv3x3(g_b, wt[idx_hr0], mask16=B['hr_a'], mask_off=zp, mask_slope=SLOPE, out16=g_a, **lead)
         del g_b, g16
-        # upconvs: conv^T at the high resolution, then the adjoint of nearest x2 (2x2 sum)
         cur = g_a
         g_t32 = None
-        for k in range(n_up - 1, -1, -1):
+        if net.upsample_mode == 'pixelshuffle':
+            # pixelshuffle_block (block.py:278-291) in reverse: `cur` is the gradient of the stage's pre-activation output in the
+            # shuffled layout (the consumer's launch applied the LeakyReLU mask, which commutes with the permutation): un-shuffle it to
+            # the conv's 4nf output channels, then the ordinary transposed conv / weight gradient at the stage's input resolution
+            for k in range(n_up - 1, -1, -1):
+                hk, wk = h * 2 ** k, w * 2 ** k
+                gyu = ops.pixel_unshuffle2(cur, dtype=gdt)
+                src = B['ps_in'] if k == 0 else B['up'][k - 1]
+                wg(idx_lr + 1 + k, src, gyu)
+                if k > 0:   # the stage's input is the previous stage's activated output
+                    cur = f16(n, nfp, hk, wk, 8)
+                    ops.conv3x3(gyu, wt[idx_lr + 1 + k], mask16=src, mask_off=0, mask_slope=SLOPE, out16=cur)
+                else:       # ... or LR_conv + fea, no activation
+                    g_t32, cur = f32(n, nfp, h, w, 8), f16(n, nfp, h, w, 8)
+                    ops.conv3x3(gyu, wt[idx_lr + 1], out32=g_t32, out16=cur)
+                del gyu
+        # upconvs: conv^T at the high resolution, then the adjoint of nearest x2 (2x2 sum)
+        for k in (range(n_up - 1, -1, -1) if net.upsample_mode != 'pixelshuffle' else ()):
             hk, wk = h * 2 ** (k + 1), w * 2 ** (k + 1)
             wg(idx_lr + 1 + k, B['up'][k], cur)
             gu = f32(n, nfp, hk, wk, 8)

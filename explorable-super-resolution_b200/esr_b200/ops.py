@@ -372,6 +372,20 @@ def upsample2x(src16):
     return dst
 
 
+def pixel_unshuffle2(src16, dtype=None):
+    """adjoint of nn.PixelShuffle(2) on 16-bit planes [N, P, 2h, 2w, 8] -> [N, 4P, h, w, 8] (split tensors: both halves)"""
+    require_cuda(src16)
+    n, pt, h2, w2, _ = src16.shape
+    assert h2 % 2 == 0 and w2 % 2 == 0
+    h, w = h2 // 2, w2 // 2
+    split = dtype == SPLIT
+    planes = pt // 2 if split else pt
+    dst = torch.empty((n, 4 * pt, h, w, 8), dtype=src16.dtype, device=src16.device)
+    for half in range(2 if split else 1):
+        L.check(L.load().esr_pixel_unshuffle2_planes16(_ptr(src16), n, planes, h, w, pt, half * planes, _ptr(dst), 4 * pt, half * 4 * planes, _stream()))
+    return dst
+
+
 def latent_downscale(z_hr, s, pad_hr=0):
     require_cuda(z_hr)
     n, c, hh, wh = z_hr.shape

@@ -261,6 +261,11 @@ int esr_latent_grad(const float* gz_hr_planes32, const float* gz_lr_planes32, in
 
 /* nearest x2 of 16-bit planes (models/modules/block.py:299-300), for callers that cannot fold it */
 int esr_upsample2x_planes16(const void* src, int n, int planes, int h, int w, void* dst, void* stream);
+/* adjoint of nn.PixelShuffle(2) (models/modules/block.py:287, the 'pixelshuffle' upsample_mode of RRDBNet) on 16-bit planes: dst channel
+ * 4c + 2dy + dx at (y, x) = src channel c at (2y + dy, 2x + dx); src is [n][src_planes_total][2h][2w][8], dst [n][dst_planes_total][h][w][8],
+ * `planes` source planes from src_plane_off land in 4 * planes destination planes from dst_plane_off.  Bit-exact permutation. */
+int esr_pixel_unshuffle2_planes16(const void* src, int n, int planes, int h, int w, int src_planes_total, int src_plane_off, void* dst,
+                                  int dst_planes_total, int dst_plane_off, void* stream);
 
 /* Re-packing after an optimizer step: every conv of a network in ONE host call (the same two kernels per item as
  * esr_pack_conv3x3_weights / esr_pack_conv3x3_weights_rows; wpacked_rows == NULL skips the row-kernel image).  The packed

@@ -107,7 +107,8 @@ def test_z_optimizer_other_objectives_run(tmp_path):
     from Z_optimization import Z_optimizer
     model, g = _model(tmp_path)
     x_lr = torch.rand(1, 3, 16, 12, generator=torch.Generator().manual_seed(6)).cuda()
-    for objective, kw in (('max_STD', {}), ('TV', {}), ('STD_increase', {'STD_increment': 0.01}), ('random_l1', {})):
+    for objective, kw in (('max_STD', {}), ('TV', {}), ('STD_increase', {'STD_increment': 0.01}), ('random_l1', {}),
+                          ('periodicity', {'periodicity_points': [[3, 2]]}), ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01})):
         bs = 3 if 'random' in objective else 1
         data = {'LR': x_lr.expand(bs, -1, -1, -1).contiguous(), **kw}
         model.feed_data({'LR': data['LR'], 'Z': 0}, need_GT=False)
@@ -117,7 +118,7 @@ def test_z_optimizer_other_objectives_run(tmp_path):
         Z = zo.optimize()
         assert Z.shape == (bs, 3, 64, 48) and torch.isfinite(Z).all() and len(zo.loss_values) >= 1
     with pytest.raises(NotImplementedError):
-        Z_optimizer(objective='periodicity', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
+        Z_optimizer(objective='scribble', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
 
 
 def test_z_optimizer_graph_replay_matches_eager(tmp_path, monkeypatch):

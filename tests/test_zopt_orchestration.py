@@ -32,7 +32,10 @@ class GStand(nn.Module):
 
 CASES = [('max_STD', {}, 1, 6, False), ('min_STD', {}, 1, 6, False), ('TV', {}, 1, 6, False), ('STD_increase', {'STD_increment': 0.01}, 1, 6, False),
          ('STD_decrease', {'STD_increment': 0.02}, 1, 6, False), ('l1', {}, 2, 8, True),
-         ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False)]
+         ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False),
+         ('periodicity', {'periodicity_points': [[3, 2]]}, 1, 6, False),
+         ('nonInt_periodicity', {'periodicity_points': [[3.4, 1.7], [-2.2, 4.1]]}, 1, 6, False),
+         ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01}, 1, 5, False)]
 
 
 def _opt(tmp_path):
