@@ -1,11 +1,13 @@
 #!/bin/bash
-# full GPU suite + the default bench line
+# full GPU suite + the default bench line + the reference arm
 mkdir -p gpurun_out/full
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/full/tests.log 2>&1
 echo "tests rc=$?" > gpurun_out/full/summary.txt
 tail -4 gpurun_out/full/tests.log >> gpurun_out/full/summary.txt
 timeout 900 python bench.py > gpurun_out/full/bench_1gpu.json 2> gpurun_out/full/bench_1gpu.err
 echo "bench rc=$?" >> gpurun_out/full/summary.txt
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/full/bench_ref.json 2> gpurun_out/full/bench_ref.err
+echo "ref rc=$?" >> gpurun_out/full/summary.txt
 python - <<'PY' >> gpurun_out/full/summary.txt
 import json
 d = json.loads(open('gpurun_out/full/bench_1gpu.json').read().strip().splitlines()[-1])
