@@ -427,7 +427,8 @@ def main():
 
         def step_e2e():
             m2.feed_data(batch)            # pinned host -> device copies of LR and HR (SRRaGAN_model.feed_data)
-            m2.optimize_parameters()       # fwd + CEM + crop + L1 + bwd + all-reduce + Adam; reads the logged loss back to the host
+            m2.optimize_parameters()       # fwd + CEM + crop + L1 + bwd + all-reduce + Adam; the logged loss comes back through a pinned buffer
+                                           # (device->host copy every step, appended to log_dict when it has arrived / when the log is read)
         for _ in range(max(warmup, 3)):    # (the model's first iteration is the reference's idle one: SRRaGAN_model.py:351)
             step_e2e()
         barrier()

@@ -268,8 +268,50 @@ class SRRaGANModel(BaseModel):
             latent = latent.view([latent.size(0)] + [self.num_latent_channels] + [self.opt['scale'] * v for v in list(latent.size()[2:])])
         return latent
 
+    # ---------------------------------------------------------------- host <-> device traffic of a training step
+    def _to_device(self, t):
+        """`t.to(self.device)`.  A PINNED host batch is copied on a dedicated stream: the next step's images then travel while the
+        previous step still computes (the compute stream only waits for the copy's event).  ESR_SYNC_INPUT=1 keeps the blocking copy."""
+        if (not torch.is_tensor(t)) or t.is_cuda or self.device.type != 'cuda' or not t.is_pinned() or os.environ.get('ESR_SYNC_INPUT', '0') == '1':
+            return t.to(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            d = t.to(self.device, non_blocking=True)
+        cur.wait_stream(self._copy_stream)
+        d.record_stream(cur)
+        return d
+
+    def _resolve_logs(self, block):
+        """the logged scalars of the generator step come back through a pinned buffer and an event instead of a blocking .item():
+        append the ones that have arrived (all of them when `block`) to their lists, in order"""
+        pend = self.__dict__.get('_pending_logs')
+        while pend:
+            rec = pend[0]
+            if not rec['ev'].query():
+                if not block and len(pend) <= 4:
+                    break
+                rec['ev'].synchronize()
+            pend.pop(0)
+            vals = rec['host'].tolist()
+            for lst, v in zip(rec['lists'], vals):
+                lst.append(v)
+            for key, lst, step in rec['final']:
+                self._log_dict[key].append((step, np.mean(lst)))
+
+    @property
+    def log_dict(self):
+        self._resolve_logs(block=True)
+        return self._log_dict
+
+    @log_dict.setter
+    def log_dict(self, value):
+        self.__dict__.get('_pending_logs', [])[:] = []
+        self._log_dict = value
+
     def feed_data(self, data, need_GT=True, **kwargs):
-        self.var_L = data['LR'].to(self.device)
+        self.var_L = self._to_device(data['LR'])
         cur_Z = None
         if self.latent_input is not None:
             hr_size = [self.Z_size_factor * v for v in list(self.var_L.size()[2:])]
@@ -300,8 +342,8 @@ class SRRaGANModel(BaseModel):
             if self.is_train and getattr(self, 'add_quantization_noise', False):
                 # keeps the critic from telling real from generated images by their 8-bit quantisation (:272-273)
                 data['HR'] += (torch.rand_like(data['HR']) - 0.5) / 255
-            self.var_H = data['HR'].to(self.device)
-            self.var_ref = (data['ref'] if 'ref' in data else data['HR']).to(self.device)
+            self.var_H = self._to_device(data['HR'])
+            self.var_ref = self._to_device(data['ref']) if 'ref' in data else self.var_H
 
     @staticmethod
     def _batch_mean(t):
@@ -326,6 +368,7 @@ class SRRaGANModel(BaseModel):
         the VGG extractor, the CEM projection and the generator: dgrad + wgrad launches behind single autograd nodes)."""
         if not self.is_train:
             raise NotImplementedError('optimize_parameters needs a model built with is_train=True (no optimizer / losses exist)')
+        self._resolve_logs(block=False)
         self.gradient_step_num = self.step // self.max_accumulation_steps
         first_acc = self.step % self.grad_accumulation_steps_G == 0
         last_acc = self.step % self.grad_accumulation_steps_G == (self.grad_accumulation_steps_G - 1)
@@ -492,22 +535,32 @@ class SRRaGANModel(BaseModel):
                 terms = [(self.cri_fea, 'l_g_fea_grad_step', l_g_fea if self.cri_fea else None), (self.cri_pix, 'l_g_pix_grad_step', l_g_pix if self.cri_pix else None),
                          (self.cri_gan, 'l_g_gan_grad_step', l_g_gan if self.cri_gan else None), (self.cri_range, 'l_g_range_grad_step', l_g_range if self.cri_range else None)]
                 terms = [(name, v) for on, name, v in terms if on]
+                deferred = None
                 if terms:
-                    vals = torch.stack([v.detach().float().reshape(()) for _, v in terms]).cpu().tolist()
-                    for (name, _), v in zip(terms, vals):
-                        getattr(self, name).append(v)
+                    stacked = torch.stack([v.detach().float().reshape(()) for _, v in terms])
+                    if stacked.is_cuda and os.environ.get('ESR_SYNC_LOGS', '0') != '1':
+                        # one small device->host copy per step, read when it has arrived (or when someone looks at the logs)
+                        host = torch.empty(len(terms), dtype=torch.float32, pin_memory=True)
+                        host.copy_(stacked, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        deferred = {'ev': ev, 'host': host, 'lists': [getattr(self, name) for name, _ in terms], 'final': []}
+                        self.__dict__.setdefault('_pending_logs', []).append(deferred)
+                    else:
+                        for (name, _), v in zip(terms, stacked.cpu().tolist()):
+                            getattr(self, name).append(v)
                 if last_acc and last_dual:
                     parallel.average_gradients([p for p in self.netG.parameters() if p.requires_grad], optimizer=self.optimizer_G)
                     self.optimizer_G.step()
                     self.generator_changed = True
-                    if self.cri_pix:
-                        self.log_dict['l_g_pix'].append((self.gradient_step_num, np.mean(self.l_g_pix_grad_step)))
-                    if self.cri_fea:
-                        self.log_dict['l_g_fea'].append((self.gradient_step_num, np.mean(self.l_g_fea_grad_step)))
-                    if self.cri_range:
-                        self.log_dict['l_g_range'].append((self.gradient_step_num, np.mean(self.l_g_range_grad_step)))
-                    if self.cri_gan:
-                        self.log_dict['l_g_gan'].append((self.gradient_step_num, np.mean(self.l_g_gan_grad_step)))
+                    for on, key, lst in ((self.cri_pix, 'l_g_pix', self.l_g_pix_grad_step), (self.cri_fea, 'l_g_fea', self.l_g_fea_grad_step),
+                                         (self.cri_range, 'l_g_range', self.l_g_range_grad_step), (self.cri_gan, 'l_g_gan', self.l_g_gan_grad_step)):
+                        if not on:
+                            continue
+                        if deferred is not None:
+                            deferred['final'].append((key, lst, self.gradient_step_num))
+                        else:
+                            self.log_dict[key].append((self.gradient_step_num, np.mean(lst)))
                     if self.cri_latent:
                         for ch in range(self.num_latent_channels):
                             self.log_dict['l_g_latent_%d' % ch].append((self.gradient_step_num, np.mean([v[ch] for v in self.l_g_latent_grad_step])))
