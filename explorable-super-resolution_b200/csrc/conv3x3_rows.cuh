@@ -135,59 +135,73 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_rows_kernel(const __g
       // ------------------------------------------------------------------ producer (bulk copies)
       // One lane per plane of a stage: a single thread issuing all copies of a chunk (address arithmetic included)
       // takes longer than the MMAs of that chunk.
-      if (u0 < u1 && lane == 0) {
+      if (u0 < u1 && elect_one()) {
         mbar_expect_tx(bar_w, p.w_bytes);
         const uint8_t* wsrc = p.wts + (size_t)nblk * p.w_bytes;
         for (int c = 0; c < p.nchunks; ++c) bulk_load(wres + c * kChunkW, wsrc + (size_t)c * kChunkW, kChunkW, bar_w);
       }
       pdl_wait();  // weights do not depend on the previous launch, activations do
-      int s = 0;
-      uint32_t ph = 0;
-      const size_t plane16 = hw * 16;
-      // chunks per plane segment (split precision: three segments hi | lo | hi, else one); the last chunk of a segment may be
-      // partial.  K steps take plane pairs: an odd tail re-loads its last plane (zero weights)
-      const int cps = p.split ? p.cps : p.nchunks;
-      const int npl_last = p.cin_planes - (cps - 1) * kRowsKch;
-      const int nld_last = (npl_last + 1) & ~1;
-      const int lane_last = lane < npl_last ? lane : npl_last - 1;
-      const uint32_t lane_dst = (uint32_t)lane * kRowBytes;
-      int u_img, x0, ya, yb;
-      long long u = u0;
-      while (rows_next_segment(p, u, u1, u_img, x0, ya, yb)) {
-        const int yi0 = ya > 0 ? ya - 1 : 0, yi1 = yb < p.h ? yb : p.h - 1;
-        const int xs = x0 > 0 ? x0 - 1 : 0, xe = x0 + 129 < p.w ? x0 + 129 : p.w;
-        const uint32_t cnt_bytes = (uint32_t)(xe - xs) * 16u, dst_off = (uint32_t)(xs - (x0 - 1)) * 16u + lane_dst;
-        const bool zl = x0 == 0, zr = x0 + 129 > p.w;   // image border inside this strip: the halo pixel is zero padding
-        const uint32_t zr_off = (uint32_t)(p.w - (x0 - 1)) * 16u + lane_dst;
-        const uint8_t* colp = p.in + (((size_t)u_img * p.in_pt) * hw + xs) * 16;
-        int seg_uses = 0;
-        for (int yi = yi0; yi <= yi1; ++yi) {
-          const uint8_t* rowp = colp + (size_t)yi * p.w * 16;
-          int cc = 0, sg = 0;
-          for (int c = 0; c < p.nchunks; ++c) {
-            const bool last = cc == cps - 1;
-            const int nld = last ? nld_last : kRowsKch;
-            const int plane = (p.split ? p.seg_base[sg] : p.in_plane_off) + cc * kRowsKch + (last ? lane_last : lane);
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
-            const uint32_t sa = stage0 + s * kRowsStageBytes;
-            if ((zl || zr) && seg_uses < p.stages) {
-              // border pixels are never written by this segment's copies: zero each stage buffer once per segment
-              if (lane < kRowsKch) {
-                if (zl) st_shared_zero16(sa + lane_dst);
-                if (zr) st_shared_zero16(sa + zr_off);
+      // ONE thread issues every copy, with addresses advanced by additions only.  (One lane per plane looked parallel in the source
+      // but compiled into an ELECT loop that moved every lane's addresses into uniform registers: ~150 cycles per copy, and with 8-24
+      // copies per input row the producer warp - not the tensor pipe - set the pace of the whole kernel: ncu, round 2.)
+      if (elect_one()) {
+        int s = 0;
+        uint32_t ph = 0;
+        const size_t plane16 = hw * 16;
+        // chunks per plane segment (split precision: three segments hi | lo | hi, else one); the last chunk of a segment may be
+        // partial.  K steps take plane pairs: an odd tail re-loads its last plane (zero weights)
+        const int cps = p.split ? p.cps : p.nchunks;
+        const int npl_last = p.cin_planes - (cps - 1) * kRowsKch;
+        const int nld_last = (npl_last + 1) & ~1;
+        int u_img, x0, ya, yb;
+        long long u = u0;
+        while (rows_next_segment(p, u, u1, u_img, x0, ya, yb)) {
+          const int yi0 = ya > 0 ? ya - 1 : 0, yi1 = yb < p.h ? yb : p.h - 1;
+          const int xs = x0 > 0 ? x0 - 1 : 0, xe = x0 + 129 < p.w ? x0 + 129 : p.w;
+          const uint32_t cnt_bytes = (uint32_t)(xe - xs) * 16u, dst_off = (uint32_t)(xs - (x0 - 1)) * 16u;
+          const bool zl = x0 == 0, zr = x0 + 129 > p.w;   // image border inside this strip: the halo pixel is zero padding
+          const uint32_t zr_off = (uint32_t)(p.w - (x0 - 1)) * 16u;
+          const uint8_t* colp = p.in + (((size_t)u_img * p.in_pt) * hw + xs) * 16;
+          int seg_uses = 0;
+          for (int yi = yi0; yi <= yi1; ++yi) {
+            const uint8_t* rowp = colp + (size_t)yi * p.w * 16;
+            int cc = 0, sg = 0;
+            for (int c = 0; c < p.nchunks; ++c) {
+              const bool last = cc == cps - 1;
+              const int nld = last ? nld_last : kRowsKch;
+              const int npl = last ? npl_last : kRowsKch;
+              const int plane0 = (p.split ? p.seg_base[sg] : p.in_plane_off) + cc * kRowsKch;
+              mbar_wait(bar_empty + 8 * s, ph ^ 1u, 1u);
+              const uint32_t sa = stage0 + s * kRowsStageBytes;
+              if ((zl || zr) && seg_uses < p.stages) {
+                // border pixels are never written by this segment's copies: zero each stage buffer once per segment
+#pragma unroll
+                for (int k = 0; k < kRowsKch; ++k) {
+                  if (zl) st_shared_zero16(sa + (uint32_t)k * kRowBytes);
+                  if (zr) st_shared_zero16(sa + zr_off + (uint32_t)k * kRowBytes);
+                }
                 fence_proxy_async();
               }
-              __syncwarp();
+              const uint32_t full = bar_full + 8 * s;
+              mbar_expect_tx(full, (uint32_t)nld * cnt_bytes);
+              const uint8_t* src = rowp + (size_t)plane0 * plane16;
+              uint32_t dst = sa + dst_off;
+#pragma unroll
+              for (int k = 0; k < kRowsKch; ++k) {
+                if (k < nld) {
+                  bulk_load(dst, src, cnt_bytes, full);
+                  dst += kRowBytes;
+                  if (k + 1 < npl) src += plane16;       // (the odd tail re-loads the last plane)
+                }
+              }
+              ++seg_uses;
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+              if (++cc == cps) { cc = 0; ++sg; }
             }
-            if (lane == 0) mbar_expect_tx(bar_full + 8 * s, (uint32_t)nld * cnt_bytes);
-            __syncwarp();
-            if (lane < nld) bulk_load(sa + dst_off, rowp + (size_t)plane * plane16, cnt_bytes, bar_full + 8 * s);
-            ++seg_uses;
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
-            if (++cc == cps) { cc = 0; ++sg; }
           }
         }
       }
+      __syncwarp();
     } else {
       // ------------------------------------------------------------------ MMA issuers: ONE thread per warp runs the role.
       // A single thread cannot issue (and book-keep) as fast as the tensor pipe retires N=96 MMAs, so up to three warps

@@ -545,8 +545,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (elect.sync, not lane == 0: the compiler then keeps the
+    // copy operands in uniform registers instead of an ELECT + R2UR.BROADCAST sequence in front of every TMA instruction)
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       if (p.w_resident && (int)blockIdx.x < total_items) {

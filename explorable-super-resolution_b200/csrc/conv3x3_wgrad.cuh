@@ -327,7 +327,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ------------------------------------------------------------------ activation rows: one TMA tensor load per box row (box = 32
     // pixels x cp planes, landing as [plane][pixel] = consecutive M groups); rows / pixels outside the image are zero-filled by the
     // TMA unit, which is exactly the convolution's zero padding.
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmX);
       // Two independent duties polled by this one thread: (a) the next activation row as soon as its ring slot is free, (b) the next
       // gradient stage to the loader of the next row unit as soon as the MMAs have released it.  The stages are handed out here, in
