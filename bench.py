@@ -254,7 +254,8 @@ def supervise(rank, world, out_fd, max_attempts=3):
     """Every rank runs the benchmark in a CHILD process (fresh CUDA context) and keeps no GPU state itself.  A rare device exception
     ('unspecified launch failure', DESIGN.md section 5: seen in the first backward passes of a fresh process, never in steady state) is
     sticky for its process: when rank 0's child ends without having printed the line, every rank starts a fresh child - at most
-    twice, and the line says so ('attempt').  The ranks' parents agree through a small TCP store next to the rendezvous port."""
+    twice, and the line says so ('attempt').  The ranks' parents agree through a small TCP store (MASTER_PORT + 1717; the children
+    rendezvous on MASTER_PORT + 1718 + attempt, away from the ports a driver may use for its next run)."""
     import subprocess
     base = int(os.environ.get('MASTER_PORT', '29500'))
     addr = os.environ.get('MASTER_ADDR', '127.0.0.1')
@@ -262,16 +263,27 @@ def supervise(rank, world, out_fd, max_attempts=3):
     if world > 1:
         import datetime as _dt
         from torch.distributed import TCPStore
-        store = TCPStore(addr, base + 1, world, is_master=(rank == 0), timeout=_dt.timedelta(seconds=1800))
+        store = TCPStore(addr, base + 1717, world, is_master=(rank == 0), timeout=_dt.timedelta(seconds=1800))
     rc = 1
     for a in range(max_attempts):
-        env = dict(os.environ, ESR_BENCH_WORKER='1', ESR_BENCH_ATTEMPT=str(a), MASTER_ADDR=addr, MASTER_PORT=str(base + 2 + a))
+        env = dict(os.environ, ESR_BENCH_WORKER='1', ESR_BENCH_ATTEMPT=str(a), MASTER_ADDR=addr, MASTER_PORT=str(base + 1718 + a))
         env.pop('TORCHELASTIC_USE_AGENT_STORE', None)      # the children rendezvous on their own store (fresh port per attempt)
         rc = subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=out_fd)
         if world > 1:
-            if rank == 0:
-                store.set('esr_bench_attempt_%d' % a, str(rc))
-            rc0 = int(store.get('esr_bench_attempt_%d' % a).decode())
+            key = 'esr_bench_attempt_%d' % a
+            try:
+                if rank == 0:
+                    store.set(key, str(rc))
+                    rc0 = rc
+                    t0 = time.time()      # the store lives in this process: stay until every other rank has read the verdict
+                    while store.add(key + '_ack', 0) < world - 1 and time.time() - t0 < 300:
+                        time.sleep(0.05)
+                else:
+                    rc0 = int(store.get(key).decode())
+                    store.add(key + '_ack', 1)
+            except Exception as e:      # the store's host is gone: act on the own child's result
+                log('rank %d: supervisor store: %r' % (rank, e))
+                rc0 = rc
         else:
             rc0 = rc
         if rc0 == 0:
