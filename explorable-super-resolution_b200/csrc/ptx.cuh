@@ -82,12 +82,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 // Bounded wait: a protocol bug records where it was stuck and lets every role fall through (the launch
 // finishes with garbage and the host reports ESR_ERR_CUDA) instead of hanging the GPU.
+// The bound is counted on the SM's own cycle counter (clock64: monotonic, untouched by anything outside the SM) and is generous
+// (~20 s): %globaltimer, which the first version used with a 2 s bound, is a device-wide wall clock that the driver may step, and a
+// waiter that is legitimately held up (a dependency behind a slow first launch of a fresh process) must not be declared dead -
+// falling through a live pipeline is a guaranteed device exception.
+constexpr long long kWatchdogCycles = 40000000000ll;      // 20 s at 2 GHz
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = globaltimer_ns();
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*(volatile unsigned int*)&g_watchdog[0]) return;
-    if (globaltimer_ns() - t0 > 2000000000ull) {
+    if (clock64() - t0 > kWatchdogCycles) {
       if (atomicExch(&g_watchdog[0], 1u) == 0u) {
         g_watchdog[1] = blockIdx.x; g_watchdog[2] = threadIdx.x; g_watchdog[3] = bar; g_watchdog[4] = parity;
         g_watchdog[5] = tag;
