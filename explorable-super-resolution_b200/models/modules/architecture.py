@@ -157,6 +157,11 @@ class Discriminator_VGG_128(nn.Module):
         if norm_type != 'batch' or act_type != 'leakyrelu' or mode != 'CNA':
             raise NotImplementedError('esr_b200 Discriminator_VGG_128: only batch norm + leakyrelu(0.2) in CNA order is built')
         self.num_2_strides = 5
+        if int(input_patch_size) % 32 != 0:
+            # every 4x4 stride-2 conv runs over the 2x2 space-to-depth image: its input must be even, five times over (the reference
+            # sizes its classifier with ceil((s - 1) / 2) and accepts odd sizes, architecture.py:457-487)
+            raise NotImplementedError('esr_b200 Discriminator_VGG_128: input_patch_size must be a multiple of 32 (got %d); with the CEM the '
+                                      'critic sees patch_size - 2 * invalidity_margins_HR pixels' % int(input_patch_size))
         size = 1 * input_patch_size
         chans = [(in_nc, base_nf, 3), (base_nf, base_nf, 4), (base_nf, base_nf * 2, 3), (base_nf * 2, base_nf * 2, 4),
                  (base_nf * 2, base_nf * 4, 3), (base_nf * 4, base_nf * 4, 4), (base_nf * 4, base_nf * 8, 3), (base_nf * 8, base_nf * 8, 4),

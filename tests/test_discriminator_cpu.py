@@ -63,6 +63,8 @@ def test_mirror_state_dict_matches_reference_keys():
     assert sum(p.numel() for p in big.parameters()) == 14502281
     with pytest.raises(NotImplementedError):
         arch.Discriminator_VGG_128(3, 8, num_2_strides=3)
+    with pytest.raises(NotImplementedError, match='multiple of 32'):      # 128 - 2 * 20: refused at construction, not at the first step
+        arch.Discriminator_VGG_128(3, 8, input_patch_size=88)
 
 
 def test_k4s2_weight_reindexing_is_exact():
