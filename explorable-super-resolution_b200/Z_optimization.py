@@ -10,8 +10,9 @@ tcgen05 forward launches and, in backward, the dgrad launches + the exact CEM ad
 Objectives built: 'l1' (optionally masked), 'TV', 'max_STD' / 'min_STD' / 'STD_increase' / 'STD_decrease' (global, or 'local_' over
 7x7 patches through ReturnPatchExtractionMat), 'Mag' (local magnitude), 'hist' / 'dict' (+ 'patch', 'noDC', 'no_localSTD', 'localSTD':
 SoftHistogramLoss on the esr_soft_hist kernels), 'VGG' (perceptual distance through the VGG19 engine), 'Adversarial' (the critic
-engine), 'random_l1' (+ '_limited'), 'periodicity' (integer or 'nonInt' sub-pixel periods, optionally 'Plus' an STD increase).
-Scribble, desired_SVD and digit raise NotImplementedError."""
+engine), 'random_l1' (+ '_limited'), 'periodicity' (integer or 'nonInt' sub-pixel periods, optionally 'Plus' an STD increase), 'scribble'
+(masked l1 towards the scribbled colours, brightened / darkened regions through the V channel, total variation inside the smoothing
+scribbles).  desired_SVD and digit raise NotImplementedError."""
 import time
 
 import numpy as np
@@ -94,7 +95,7 @@ def Return_Interpolated_SubImage(image, grid):
     return F.grid_sample(image, grid.repeat([image.size(0), 1, 1, 1]))
 
 
-_UNBUILT = ['scribble', 'desired_SVD', 'digit']
+_UNBUILT = ['desired_SVD', 'digit']
 
 
 class _SoftHistFn(torch.autograd.Function):
@@ -376,11 +377,14 @@ class Z_optimizer():
             self.initial_STD = self.Masked_STD(first_image_only=True)
             print('Initial STD: %.3e' % (self.initial_STD.mean().item()))
         if existing_optimizer is None:
-            if 'l1' in objective and 'random' not in objective:
+            if any(p in objective for p in ['l1', 'scribble']) and 'random' not in objective:
                 if data is not None and 'desired' in data.keys():
                     self.desired_im = data['desired']
                 if self.image_mask is None:
                     self.loss = torch.nn.L1Loss()
+                elif 'scribble' in objective:
+                    self._init_scribble(data)
+                    self.constraining_loss_weight = 1
                 else:
                     loss_mask = (self.image_mask > 0).type(self.image_mask.dtype)
                     self.loss = lambda produced_im, GT_im: torch.stack(
@@ -480,6 +484,54 @@ class Z_optimizer():
             else 'allButFirst' if (initial_pre_tanh_Z is not None and initial_pre_tanh_Z.size(0) < batch_size) else False
         self.HR_unpadder = HR_unpadder
 
+    def _init_scribble(self, data):
+        """The scribble tool (Z_optimization.py:408-449).  data['scribble_mask'] labels every pixel: 0 untouched, 1 colour scribble (l1 towards
+        data['desired']), 2 / 3 brighten / darken (the current output's V channel times 1 +- data['brightness_factor'], smoothed over a 3x3
+        neighbourhood, becomes the target there), > 3 smoothing scribbles (one label per region: total variation between neighbours that both
+        carry the label)."""
+        from scipy.signal import convolve2d
+        from esr_b200.colors import hsv2rgb, rgb2hsv
+        loss_mask = (self.image_mask > 0).type(self.image_mask.dtype)
+        SMOOTHING_MARGIN = 1
+        labels = np.asarray(data['scribble_mask'])
+        scribble_mask_tensor = torch.from_numpy(labels).type(loss_mask.dtype).to(loss_mask.device)
+        scribble_multiplier = np.ones_like(labels).astype(np.float32)
+        scribble_multiplier += data['brightness_factor'] * (labels == 2) - data['brightness_factor'] * (labels == 3)
+        if SMOOTHING_MARGIN > 0:
+            k = 2 * SMOOTHING_MARGIN + 1
+            scribble_multiplier = convolve2d(np.pad(scribble_multiplier, ((SMOOTHING_MARGIN,) * 2,) * 2, mode='edge'), np.ones([k, k]) / k ** 2, mode='valid')
+        L1_loss_mask = loss_mask * ((scribble_mask_tensor > 0) * (scribble_mask_tensor < 4)).float()
+        TV_loss_masks = [loss_mask * (scribble_mask_tensor == i).float().unsqueeze(0).unsqueeze(0) for i in torch.unique(scribble_mask_tensor * loss_mask) if i > 3]
+        cur_HSV = rgb2hsv(np.clip(255 * self.initial_output[0].data.cpu().numpy().transpose((1, 2, 0)).copy(), 0, 255))
+        cur_HSV[:, :, 2] = cur_HSV[:, :, 2] * scribble_multiplier
+        desired_RGB = np.expand_dims(hsv2rgb(cur_HSV).transpose((2, 0, 1)), 0) / 255
+        desired_RGB_mask = ((scribble_mask_tensor == 2) | (scribble_mask_tensor == 3)).float()
+        self.desired_im = self.desired_im.to(loss_mask.device) * (1 - desired_RGB_mask) + \
+            desired_RGB_mask * torch.from_numpy(desired_RGB).type(loss_mask.dtype).to(loss_mask.device)
+
+        def Scribble_TV_Loss(produced_im):
+            loss = 0
+            for TV_loss_mask in TV_loss_masks:
+                # differences to the 8 neighbours, each unordered pair once: (dy, dx) in {(-1,-1), (-1,0), (0,-1), (1,-1)}
+                for y_shift in [-1, 0, 1]:
+                    for x_shift in [-1, 0]:
+                        if y_shift in [0, 1] and x_shift == 0:
+                            continue
+                        point = np.array([y_shift, x_shift])
+                        cur_mask = Return_Translated_SubImage(TV_loss_mask, point) * Return_Translated_SubImage(TV_loss_mask, -point)
+                        loss = loss + (cur_mask * (Return_Translated_SubImage(produced_im, point) -
+                                                   Return_Translated_SubImage(produced_im, -point)).abs()).mean(dim=(1, 2, 3))
+            return loss
+
+        def Scribble_Loss(produced_im, GT_im):
+            loss_per_im = []
+            for im_num in range(produced_im.size(0)):
+                loss_per_im.append(F.l1_loss(input=produced_im[im_num].unsqueeze(0) * L1_loss_mask, target=GT_im * L1_loss_mask))
+                if len(TV_loss_masks) > 0:
+                    loss_per_im[-1] = loss_per_im[-1] + Scribble_TV_Loss(produced_im[im_num].unsqueeze(0))
+            return torch.stack(loss_per_im, 0)
+        self.loss = Scribble_Loss
+
     def Masked_STD(self, first_image_only=False):
         model_output = self.model.Output_Batch(within_0_1=True)
         if 'local' in self.objective:      # STD of every 7x7 patch inside the mask (+ of the pixels no patch covers), per image (:618-625)
@@ -532,7 +584,7 @@ class Z_optimizer():
             Z_loss = -1 * Z_loss.mean(dim=(1, 2, 3))
             if 'local' in self.objective:
                 Z_loss = Z_loss + self.STD_PRESERVING_WEIGHT * ((self.Masked_STD(first_image_only=False) - self.initial_STD) ** 2).mean()
-        elif 'l1' in self.objective:
+        elif any(p in self.objective for p in ['l1', 'scribble']):
             Z_loss = self.loss(self.output_image.to(self.device), self.desired_im.to(self.device))
         elif any(p in self.objective for p in ['hist', 'dict']):
             Z_loss = self.loss(self.output_image.to(self.device))
@@ -592,7 +644,7 @@ class Z_optimizer():
         graph, static = None, None
         self._graph_ok = (self._own_optimizer and torch.cuda.is_available() and os.environ.get('ESR_ZOPT_GRAPH', '1') != '0'
                           and not self.model_training and self.loggers is None
-                          and not any(p in self.objective for p in ['local', 'Mag', 'hist', 'dict', 'periodicity'])      # (sparse products, grid samples: eager iterations)
+                          and not any(p in self.objective for p in ['local', 'Mag', 'hist', 'dict', 'periodicity', 'scribble'])      # (sparse products, grid samples: eager iterations)
                           and (self.max_iters < 0 or self.max_iters >= self.GRAPH_WARMUP_ITERS + 4))
         if self._graph_ok:
             self._side_stream = torch.cuda.Stream()

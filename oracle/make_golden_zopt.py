@@ -53,7 +53,22 @@ CASES = [('max_STD', {}, 1, 6, False), ('min_STD', {}, 1, 6, False), ('TV', {}, 
          ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False),
          ('periodicity', {'periodicity_points': [[3, 2]]}, 1, 6, False),
          ('nonInt_periodicity', {'periodicity_points': [[3.4, 1.7], [-2.2, 4.1]]}, 1, 6, False),
-         ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01}, 1, 5, False)]
+         ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01}, 1, 5, False),
+         ('scribble', {'_masks': True, 'brightness_factor': 0.3}, 1, 6, False)]
+
+
+def scribble_inputs():
+    """region masks and scribble labels of the 'scribble' case: 1 colour, 2 brighten, 3 darken, 4 / 5 two smoothing regions"""
+    image_mask = np.zeros((SCALE * H, SCALE * W), dtype=np.float32)
+    image_mask[6:42, 4:36] = 1
+    labels = np.zeros((SCALE * H, SCALE * W), dtype=np.int64)
+    labels[8:14, 6:20] = 1
+    labels[16:22, 8:18] = 2
+    labels[16:22, 22:32] = 3
+    labels[26:34, 6:16] = 4
+    labels[28:38, 20:34] = 5
+    labels[2:6, 2:10] = 1          # outside the region mask: must not count
+    return image_mask, 1 * image_mask, labels
 
 
 def build_model(model_cls, networks, tmp):
@@ -83,6 +98,13 @@ def main():
         def device(self, *a, **k):
             return torch.device('cpu')
     Zmod.torch = TorchProxy()
+    # the scribble tool takes rgb2hsv / hsv2rgb from skimage (absent here: the standard hexcone conversion of esr_b200.colors is lent to the
+    # reference) and subtracts comparison results from 1, which the torch of its day (uint8 masks) allowed
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'explorable-super-resolution_b200', 'esr_b200'))
+    import colors as _colors
+    Zmod.rgb2hsv, Zmod.hsv2rgb = _colors.rgb2hsv, _colors.hsv2rgb
+    _rsub = torch.Tensor.__rsub__
+    torch.Tensor.__rsub__ = lambda self, other: _rsub(self.to(torch.uint8) if self.dtype == torch.bool else self, other)
     g = torch.Generator().manual_seed(41)
     x_lr = torch.rand(1, 3, H, W, generator=g)
     desired = torch.rand(1, 3, SCALE * H, SCALE * W, generator=g)
@@ -91,8 +113,16 @@ def main():
         model = build_model(SRRaGANModel, networks, tmp)
         arrays.update({'w:' + k: v.detach().numpy() for k, v in model.netG.state_dict().items()})
         for idx, (objective, extra, bs, iters, training) in enumerate(CASES):
+            extra = dict(extra)
+            mask_kw = {}
+            if extra.pop('_masks', False):
+                image_mask, Z_mask, labels = scribble_inputs()
+                mask_kw = dict(image_mask=image_mask, Z_mask=Z_mask)
+                extra['scribble_mask'] = labels
             data = {'LR': x_lr.expand(bs, -1, -1, -1).contiguous(), 'desired': desired, **extra}
             model.feed_data({'LR': data['LR'], 'Z': torch.zeros(bs, 3, SCALE * H, SCALE * W)}, need_GT=False)
+            if mask_kw:               # a partial Z mask needs the current latent as the value outside the mask (GUI: initial_Z)
+                mask_kw['initial_Z'] = 1 * model.GetLatent()
             if training is True:      # training-time use (SRRaGAN_model.py:108-112): no image mask, random initial Z drawn inside optimize()
                 model.__dict__.pop('fake_H', None)
             else:
@@ -100,7 +130,8 @@ def main():
             torch.manual_seed(17 + idx)
             with contextlib.redirect_stdout(io.StringIO()):
                 zo = Zmod.Z_optimizer(objective=objective, Z_size=[SCALE * H, SCALE * W], model=model, Z_range=1.0, max_iters=iters, data=data,
-                                      initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random')
+                                      initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random',
+                                      **mask_kw)
                 Z = zo.optimize()
             arrays['%d:loss' % idx] = np.array([float(v) for v in zo.loss_values], dtype=np.float64)
             arrays['%d:Z' % idx] = Z.detach().cpu().numpy()

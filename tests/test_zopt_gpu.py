@@ -118,7 +118,7 @@ def test_z_optimizer_other_objectives_run(tmp_path):
         Z = zo.optimize()
         assert Z.shape == (bs, 3, 64, 48) and torch.isfinite(Z).all() and len(zo.loss_values) >= 1
     with pytest.raises(NotImplementedError):
-        Z_optimizer(objective='scribble', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
+        Z_optimizer(objective='desired_SVD', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
 
 
 def test_z_optimizer_graph_replay_matches_eager(tmp_path, monkeypatch):

@@ -35,7 +35,22 @@ CASES = [('max_STD', {}, 1, 6, False), ('min_STD', {}, 1, 6, False), ('TV', {}, 
          ('random_l1', {}, 3, 5, 'random'), ('max_STD', {}, 1, -4, False), ('min_STD', {}, 1, -2, False),
          ('periodicity', {'periodicity_points': [[3, 2]]}, 1, 6, False),
          ('nonInt_periodicity', {'periodicity_points': [[3.4, 1.7], [-2.2, 4.1]]}, 1, 6, False),
-         ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01}, 1, 5, False)]
+         ('nonInt_periodicity_Plus', {'periodicity_points': [[2.5, 3.3]], 'STD_increment': 0.01}, 1, 5, False),
+         ('scribble', {'_masks': True, 'brightness_factor': 0.3}, 1, 6, False)]
+
+
+def scribble_inputs():
+    """region masks and scribble labels of the 'scribble' case: 1 colour, 2 brighten, 3 darken, 4 / 5 two smoothing regions"""
+    image_mask = np.zeros((SCALE * H, SCALE * W), dtype=np.float32)
+    image_mask[6:42, 4:36] = 1
+    labels = np.zeros((SCALE * H, SCALE * W), dtype=np.int64)
+    labels[8:14, 6:20] = 1
+    labels[16:22, 8:18] = 2
+    labels[16:22, 22:32] = 3
+    labels[26:34, 6:16] = 4
+    labels[28:38, 20:34] = 5
+    labels[2:6, 2:10] = 1          # outside the region mask: must not count
+    return image_mask, 1 * image_mask, labels
 
 
 def _opt(tmp_path):
@@ -65,8 +80,16 @@ def test_z_optimizer_loop_matches_reference(monkeypatch, tmp_path, idx):
         assert np.array_equal(v.numpy(), g['w:' + k]), k
     objective, extra, bs, iters, training = CASES[idx]
     x_lr, desired = torch.from_numpy(g['x_lr']), torch.from_numpy(g['desired'])
+    extra = dict(extra)
+    mask_kw = {}
+    if extra.pop('_masks', False):
+        image_mask, Z_mask, labels = scribble_inputs()
+        mask_kw = dict(image_mask=image_mask, Z_mask=Z_mask)
+        extra['scribble_mask'] = labels
     data = {'LR': x_lr.expand(bs, -1, -1, -1).contiguous(), 'desired': desired, **extra}
     model.feed_data({'LR': data['LR'], 'Z': torch.zeros(bs, 3, SCALE * H, SCALE * W)}, need_GT=False)
+    if mask_kw:
+        mask_kw['initial_Z'] = 1 * model.GetLatent()
     if training is True:
         model.__dict__.pop('fake_H', None)
     else:
@@ -74,7 +97,8 @@ def test_z_optimizer_loop_matches_reference(monkeypatch, tmp_path, idx):
     torch.manual_seed(17 + idx)
     with contextlib.redirect_stdout(io.StringIO()):
         zo = Zmod.Z_optimizer(objective=objective, Z_size=[SCALE * H, SCALE * W], model=model, Z_range=1.0, max_iters=iters, data=data,
-                              initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random')
+                              initial_LR=0.1, batch_size=bs, HR_unpadder=(lambda t: t) if training is True else None, random_Z_inits=training == 'random',
+                              **mask_kw)
         Z = zo.optimize()
     ref_loss = g['%d:loss' % idx]
     own_loss = np.array([float(v) for v in zo.loss_values])
