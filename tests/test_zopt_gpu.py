@@ -117,6 +117,20 @@ def test_z_optimizer_other_objectives_run(tmp_path):
                          random_Z_inits='random' in objective)
         Z = zo.optimize()
         assert Z.shape == (bs, 3, 64, 48) and torch.isfinite(Z).all() and len(zo.loss_values) >= 1
+    # the scribble tool on the device: region masks, labels 1 (colour) / 2 / 3 (brighten / darken) / 4 (smoothing), the loss must go down
+    import numpy as np
+    image_mask = np.zeros((64, 48), dtype=np.float32)
+    image_mask[8:56, 6:42] = 1
+    labels = np.zeros((64, 48), dtype=np.int64)
+    labels[10:20, 8:30], labels[24:30, 8:20], labels[24:30, 24:38], labels[36:50, 10:36] = 1, 2, 3, 4
+    data = {'LR': x_lr, 'desired': torch.rand(1, 3, 64, 48, generator=torch.Generator().manual_seed(8)).cuda(), 'scribble_mask': labels,
+            'brightness_factor': 0.3}
+    model.feed_data({'LR': x_lr, 'Z': 0}, need_GT=False)
+    model.test()
+    zo = Z_optimizer(objective='scribble', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=8, data=data, initial_LR=0.1, batch_size=1,
+                     image_mask=image_mask, Z_mask=1 * image_mask, initial_Z=1 * model.GetLatent())
+    Z = zo.optimize()
+    assert torch.isfinite(Z).all() and zo.loss_values[-1] <= zo.loss_values[0]
     with pytest.raises(NotImplementedError):
         Z_optimizer(objective='desired_SVD', Z_size=[64, 48], model=model, Z_range=1.0, max_iters=4, data={}, initial_LR=0.1)
 
