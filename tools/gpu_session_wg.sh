@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out/wg
-timeout 300 python tools/debug_wgrad_v2.py > gpurun_out/wg/debug.txt 2>&1
+timeout 300 python tools/check_wgrad.py > gpurun_out/wg/debug.txt 2>&1
 echo "debug rc=$?" > gpurun_out/wg/summary.txt
 cat gpurun_out/wg/debug.txt >> gpurun_out/wg/summary.txt
 if grep -q "nan [1-9]\|Error\|error" gpurun_out/wg/debug.txt; then cat gpurun_out/wg/summary.txt; exit 0; fi
