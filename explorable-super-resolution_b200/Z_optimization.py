@@ -77,6 +77,22 @@ def TV_Loss(image):
     return (image[:, :, :, :-1] - image[:, :, :, 1:]).abs().mean(dim=(1, 2, 3)) + (image[:, :, :-1, :] - image[:, :, 1:, :]).abs().mean(dim=(1, 2, 3))
 
 
+def _dilate_rect(mask, k):
+    """grey-scale dilation with a k x k rectangle, as cv2.dilate(mask, np.ones([k, k])) computes it (Z_optimization.py:358, the editable
+    region of the non-local mode): anchor at the centre (k // 2), i.e. out[y, x] = max over dy, dx in [-(k // 2), k - 1 - k // 2] of
+    mask[y + dy, x + dx], pixels outside the image ignored."""
+    mask = np.asarray(mask)
+    a = k // 2
+    padded = np.full((mask.shape[0] + k - 1, mask.shape[1] + k - 1), -np.inf, dtype=np.float64)
+    padded[a:a + mask.shape[0], a:a + mask.shape[1]] = mask
+    out = np.full(mask.shape, -np.inf, dtype=np.float64)
+    for dy in range(k):
+        rows = padded[dy:dy + mask.shape[0]]
+        for dx in range(k):
+            out = np.maximum(out, rows[:, dx:dx + mask.shape[1]])
+    return out.astype(mask.dtype)
+
+
 def _half_open(shift, negative=False):
     """slice bound that drops |shift| rows / columns from one side (utils/util.py:260-264)"""
     if negative:
@@ -341,11 +357,10 @@ class Z_optimizer():
         if not self.model_training:
             self.initial_output = model.Output_Batch(within_0_1=True)
         if self.non_local_Z_optimization:
-            from cv2 import dilate
             NON_EDIT_MARGINS = 24
             new_Z_mask = np.zeros_like(Z_mask)
             new_Z_mask[NON_EDIT_MARGINS:-NON_EDIT_MARGINS, NON_EDIT_MARGINS:-NON_EDIT_MARGINS] = 1
-            Z_mask = np.minimum(1, new_Z_mask + dilate(image_mask, np.ones([16, 16])))
+            Z_mask = np.minimum(1, new_Z_mask + _dilate_rect(image_mask, 16))
         self.Z_model = Optimizable_Z(Z_shape=[batch_size, model.num_latent_channels] + list(Z_size), Z_range=Z_range,
                                      initial_pre_tanh_Z=initial_pre_tanh_Z, Z_mask=Z_mask,
                                      random_perturbations=(random_Z_inits and 'random' not in objective) or ('random' in objective and 'limited' in objective))
