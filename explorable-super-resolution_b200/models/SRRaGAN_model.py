@@ -50,9 +50,31 @@ def _psnr(img1, img2):
 
 
 def _save_png(img, path):
-    import cv2                      # utils/util.py:231-232 (BGR array -> file)
+    """utils/util.py:231-232 (cv2.imwrite of a BGR uint8 array).  Without OpenCV the same image is written by a minimal PNG encoder
+    (8-bit RGB / grey, no filtering): validation collages do not depend on an optional package."""
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    cv2.imwrite(path, img)
+    try:
+        import cv2
+        cv2.imwrite(path, img)
+        return
+    except ImportError:
+        pass
+    import struct
+    import zlib
+    a = np.ascontiguousarray(np.clip(np.asarray(img), 0, 255).astype(np.uint8))
+    if a.ndim == 3 and a.shape[2] == 1:
+        a = a[:, :, 0]
+    if a.ndim == 3:
+        a = np.ascontiguousarray(a[:, :, 2::-1])          # BGR -> RGB
+    h, w = a.shape[:2]
+    colour_type = 2 if a.ndim == 3 else 0
+    raw = b''.join(b'\x00' + a[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        return struct.pack('>I', len(data)) + tag + data + struct.pack('>I', zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, 'wb') as f:
+        f.write(b'\x89PNG\r\n\x1a\n' + chunk(b'IHDR', struct.pack('>IIBBBBB', w, h, 8, colour_type, 0, 0, 0)) +
+                chunk(b'IDAT', zlib.compress(raw, 6)) + chunk(b'IEND', b''))
 
 
 class SRRaGANModel(BaseModel):
