@@ -11,6 +11,28 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_base():
+    """a MASTER_PORT whose supervisor ports (base + 1717 .. + 1720) are free right now"""
+    import socket
+    for _ in range(50):
+        with socket.socket() as a:
+            a.bind(('127.0.0.1', 0))
+            port = a.getsockname()[1]
+        if port < 3000 or port > 65000:
+            continue
+        ok = True
+        for k in range(4):
+            with socket.socket() as b:
+                try:
+                    b.bind(('127.0.0.1', port + k))
+                except OSError:
+                    ok = False
+                    break
+        if ok:
+            return port - 1717
+    return 29871
+
+
 def _run(env_extra, port):
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), **env_extra)
     env.pop('ESR_BENCH_WORKER', None)
@@ -20,7 +42,8 @@ def _run(env_extra, port):
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='needs a machine without a GPU: the children must fail')
 def test_supervisor_restarts_all_ranks_and_gives_up_after_three_attempts():
-    procs = [_run({'RANK': str(r), 'LOCAL_RANK': str(r), 'WORLD_SIZE': '2'}, 29871) for r in range(2)]
+    base = _free_base()
+    procs = [_run({'RANK': str(r), 'LOCAL_RANK': str(r), 'WORLD_SIZE': '2'}, base) for r in range(2)]
     outs = [p.communicate(timeout=300) for p in procs]
     for r, (p, (out, err)) in enumerate(zip(procs, outs)):
         assert p.returncode != 0
@@ -31,6 +54,6 @@ def test_supervisor_restarts_all_ranks_and_gives_up_after_three_attempts():
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='needs a machine without a GPU: the children must fail')
 def test_supervisor_single_process():
-    p = _run({}, 29881)
+    p = _run({}, _free_base())
     out, err = p.communicate(timeout=300)
     assert p.returncode != 0 and out.strip() == '' and err.count('ended without a result') == 3
